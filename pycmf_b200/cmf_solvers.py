@@ -1,0 +1,338 @@
+"""B200 solvers behind the reference's solver seam.
+
+Same classes, constructor arguments, methods and error behaviour as the reference's
+pycmf/cmf_solvers.py (`_IterativeCMFSolver` :45-195, `MUSolver` :198-263, `NewtonSolver` :319-522):
+`fit_iterative_update(X, Y, U, V, Z) -> (U, V, Z, n_iter)` updates the caller's factor arrays in
+place, `update_step` / `compute_error` are the sub-seams.  The arithmetic runs in libpycmf_b200.so;
+this file only orchestrates phases, collectives and the convergence test (the host loop the
+reference also keeps in Python, :170-187).
+
+Backend-only knobs (extra keyword arguments, all optional): `dtype` ('float32' | 'float64'),
+`device`, `comm` (sharding.Comm), `sampler` ('numpy' | 'device' | 'auto'), `backend_options`.
+"""
+import numbers
+import time
+import warnings
+
+import numpy as np
+import scipy.sparse as sp
+
+from .sharding import Comm, default_comm, localize_indices, row_range
+
+EPSILON = np.finfo(np.float32).eps
+INTEGER_TYPES = (numbers.Integral, np.integer)
+
+
+def _beta_loss_to_float(beta_loss):
+    """sklearn.decomposition._nmf._beta_loss_to_float (used at cmf_solvers.py:106)."""
+    table = {"frobenius": 2, "kullback-leibler": 1, "itakura-saito": 0}
+    if isinstance(beta_loss, str):
+        if beta_loss not in table:
+            raise ValueError("Invalid beta_loss parameter: got %r instead of one of %r, or a float."
+                             % (beta_loss, list(table.keys())))
+        return table[beta_loss]
+    if not isinstance(beta_loss, numbers.Number):
+        raise ValueError("Invalid beta_loss parameter: got %r instead of one of %r, or a float."
+                         % (beta_loss, list(table.keys())))
+    return beta_loss
+
+
+class FitState:
+    """Everything one rank keeps in HBM during a fit: its row shard of X and U, replicated Y / V / Z."""
+
+    def __init__(self, backend, comm, X, Y, U, V, Z, n_total, rows):
+        self.be, self.comm = backend, comm
+        self.X, self.Y = X, Y
+        self.U, self.V, self.Z = U, V, Z
+        self.n_total = n_total
+        self.r0, self.r1 = rows
+        self.iteration = 0
+
+    @property
+    def shapes(self):
+        return self.n_total, self.V.shape[0], self.Z.shape[0], self.V.shape[1]
+
+
+class _IterativeCMFSolver:
+    """Boilerplate for the iterative solvers (reference cmf_solvers.py:45-195)."""
+
+    def __init__(self, max_iter=200, tol=1e-4, beta_loss="frobenius",
+                 l1_reg=0, l2_reg=0, alpha=0.5, verbose=0,
+                 U_non_negative=True, V_non_negative=True, Z_non_negative=True,
+                 update_U=True, update_V=True, update_Z=True,
+                 x_link="linear", y_link="linear", hessian_pertubation=0.2,
+                 sg_sample_ratio=1., random_state=None,
+                 dtype="float32", device=None, comm=None, sampler="auto", backend=None, backend_options=None):
+        self.max_iter = max_iter
+        self.tol = tol
+        self.beta_loss = _beta_loss_to_float(beta_loss)
+        self.l1_reg = l1_reg
+        self.l2_reg = l2_reg
+        self.alpha = alpha
+        self.verbose = verbose
+        self.U_non_negative = U_non_negative
+        self.V_non_negative = V_non_negative
+        self.Z_non_negative = Z_non_negative
+        self.update_U = update_U
+        self.update_V = update_V
+        self.update_Z = update_Z
+        self.x_link = x_link
+        self.y_link = y_link
+        self.hessian_pertubation = hessian_pertubation
+        self.sg_sample_ratio = sg_sample_ratio
+        self.random_state = random_state
+        if random_state is not None and isinstance(random_state, INTEGER_TYPES + (np.ndarray, list)):
+            np.random.seed(random_state)           # cmf_solvers.py:121-122 (global legacy RNG)
+        if self.beta_loss != 2:
+            raise NotImplementedError("only the Frobenius loss (beta_loss=2) is implemented, as in the reference")
+        self.dtype = np.dtype(dtype)
+        self.device = device
+        self.comm = comm
+        self.sampler = sampler
+        self.backend_options = backend_options
+        self._backend = backend
+        self.masks_per_iter = None     # test hook: list of per-iteration mask dicts (global indices)
+        self.history = None            # test hook: list receiving the objective after every iteration
+
+    # ---- backend / ingest ------------------------------------------------------------------------
+    def _get_backend(self):
+        if self._backend is None:
+            from .device import CudaBackend
+            self._backend = CudaBackend(device=self.device, dtype=self.dtype, options=self.backend_options)
+        return self._backend
+
+    def prepare(self, X, Y, U, V, Z):
+        """Host inputs -> FitState in HBM (row shard of X / U for this rank)."""
+        be = self._get_backend()
+        comm = self.comm if self.comm is not None else default_comm()
+        n_total = X.shape[0] if X is not None else np.shape(U)[0]
+        r0, r1 = row_range(n_total, comm.rank, comm.world)
+        Xd = None
+        if X is not None:
+            if sp.issparse(X):
+                Xd = be.ingest(sp.csr_matrix(X)[r0:r1])
+            else:
+                Xd = be.ingest(np.asarray(X)[r0:r1])
+        Yd = None
+        if Y is not None:
+            Yd = be.ingest(Y.toarray() if sp.issparse(Y) else Y)
+        Ud = be.to_device(np.asarray(U)[r0:r1])
+        Vd = be.to_device(np.asarray(V))
+        Zd = be.to_device(np.asarray(Z))
+        return FitState(be, comm, Xd, Yd, Ud, Vd, Zd, n_total, (r0, r1))
+
+    # ---- seam ------------------------------------------------------------------------------------
+    def update_step(self, X, Y, U, V, Z, l1_reg, l2_reg, alpha):
+        """A single update step for all the matrices in the factorization."""
+        raise NotImplementedError("Implement in concrete subclass to use")
+
+    def _step(self, st):
+        raise NotImplementedError("Implement in concrete subclass to use")
+
+    def _error_links(self):
+        return self.x_link, self.y_link
+
+    def device_error(self, st):
+        """alpha ||X - f(UV^T)||_F + (1 - alpha) ||Y - f(VZ^T)||_F  (cmf_solvers.py:128-130)."""
+        be = st.be
+        x_link, y_link = self._error_links()
+        parts = be.zeros(2, dtype=be.torch.float64)
+        if st.X is not None:
+            parts[0:1] = be.sqerr(st.U, st.V, st.X, x_link)
+        st.comm.all_reduce_sum(parts[0:1])
+        if st.Y is not None:
+            parts[1:2] = be.sqerr(st.V, st.Z, st.Y, y_link)
+        ex, ey = np.sqrt(np.maximum(be.to_host(parts), 0.0))
+        return float(self.alpha * ex + (1 - self.alpha) * ey)
+
+    def compute_error(self, X, Y, U, V, Z):
+        if isinstance(X, FitState):
+            return self.device_error(X)
+        st = self.prepare(X, Y, U, V, Z)
+        return self.device_error(st)
+
+    def fit_device(self, st):
+        """The loop of cmf_solvers.py:165-195 on device-resident state. Returns n_iter."""
+        start_time = time.time()
+        check = self.tol > 0
+        previous_error = error_at_init = self.device_error(st) if check else None
+        n_iter = 0
+        for n_iter in range(1, self.max_iter + 1):
+            st.iteration = n_iter
+            self._step(st)
+            if self.history is not None:
+                self.history.append(self.device_error(st))
+            if check and n_iter % 10 == 0:
+                error = self.device_error(st)
+                if self.verbose:
+                    print("Epoch %02d reached after %.3f seconds, error: %f" %
+                          (n_iter, time.time() - start_time, error))
+                if (previous_error - error) / error_at_init < self.tol:
+                    break
+                previous_error = error
+        if self.verbose and (self.tol == 0 or n_iter % 10 != 0):
+            st.be.synchronize()
+            print("Epoch %02d reached after %.3f seconds." % (n_iter, time.time() - start_time))
+        return n_iter
+
+    def fit_iterative_update(self, X, Y, U, V, Z):
+        """Compute CMF with iterative methods (reference cmf_solvers.py:132-195).
+
+        X (n x d, ndarray or scipy sparse), Y (d x l), U (n x k), V (d x k), Z (l x k) live on the host;
+        the factors are updated in place and returned by identity together with n_iter.
+        """
+        st = self.prepare(X, Y, U, V, Z)
+        n_iter = self.fit_device(st)
+        be = st.be
+        U_full = st.comm.all_gather_rows(st.U, st.n_total)
+        for host, dev in ((U, U_full), (V, st.V), (Z, st.Z)):
+            host[...] = be.to_host(dev)
+        return U, V, Z, n_iter
+
+
+class MUSolver(_IterativeCMFSolver):
+    """Multiplicative-update solver (reference cmf_solvers.py:198-263): order V, U, Z; links,
+    alpha and the non-negativity flags are ignored exactly as in the reference."""
+
+    def _error_links(self):
+        return "linear", "linear"
+
+    def _step(self, st):
+        be = st.be
+        if self.update_V:                                        # :252-255
+            buf = be.mu_v_partial(st.X, st.U)                    # [X^T U ; U^T U] of this shard
+            st.comm.all_reduce_sum(buf)
+            be.mu_v_apply(st.V, buf, st.Y, st.Z, self.l1_reg, self.l2_reg)
+        if self.update_U:                                        # :257-259
+            be.mu_left(st.U, st.V, st.X, self.l1_reg, self.l2_reg)
+        if self.update_Z:                                        # :261-263
+            be.mu_left(st.Z, st.V, st.Y, self.l1_reg, self.l2_reg, trans=True)
+
+    def update_step(self, X, Y, U, V, Z, l1_reg, l2_reg, alpha):
+        st = X if isinstance(X, FitState) else self.prepare(X, Y, U, V, Z)
+        keep = self.l1_reg, self.l2_reg
+        self.l1_reg, self.l2_reg = l1_reg, l2_reg
+        try:
+            self._step(st)
+        finally:
+            self.l1_reg, self.l2_reg = keep
+        if st is not X:
+            self._write_back(st, U, V, Z)
+
+    def _write_back(self, st, U, V, Z):
+        be = st.be
+        U[...] = be.to_host(st.comm.all_gather_rows(st.U, st.n_total))
+        V[...] = be.to_host(st.V)
+        Z[...] = be.to_host(st.Z)
+
+
+def _draw_masks_numpy(n, d, l, ratio, update_U, update_Z, update_V):
+    """Per-row sample sets from NumPy's global legacy RNG in the reference's call order
+    (cmf_solvers.py:328-344 called from :414 [U], :494 [Z], :455-456 [V: rows of U, then columns of Y])."""
+    s_d, s_n, s_l = int(d * ratio), int(n * ratio), int(l * ratio)
+    out = {}
+    perm = np.random.permutation
+    if update_U:
+        out["U"] = np.array([perm(np.arange(d))[:s_d] for _ in range(n)], dtype=np.int32).reshape(n, s_d)
+    if update_Z:
+        out["Z"] = np.array([perm(np.arange(d))[:s_d] for _ in range(l)], dtype=np.int32).reshape(l, s_d)
+    if update_V:
+        vx = np.empty((d, s_n), dtype=np.int32)
+        vy = np.empty((d, s_l), dtype=np.int32)
+        for j in range(d):
+            vx[j] = perm(np.arange(n))[:s_n]
+            vy[j] = perm(np.arange(l))[:s_l]
+        out["Vx"], out["Vy"] = vx, vy
+    return out
+
+
+class NewtonSolver(_IterativeCMFSolver):
+    """Row-wise Newton-Raphson solver (reference cmf_solvers.py:319-522): order U, Z, V."""
+
+    NUMPY_SAMPLER_LIMIT = 5e7   # 'auto' uses the reference's NumPy RNG stream up to this many drawn indices
+
+    def _masks(self, st):
+        """Sample index sets for this iteration as device tensors (or None when sg_sample_ratio == 1)."""
+        ratio = self.sg_sample_ratio
+        if ratio >= 1.:
+            return None
+        n, d, l, _ = st.shapes
+        be = st.be
+        if self.masks_per_iter is not None:
+            host = self.masks_per_iter[st.iteration - 1]
+        else:
+            mode = self.sampler
+            if mode == "auto":
+                draws = (n * d if self.update_U else 0) + (l * d if self.update_Z else 0) + \
+                        (d * (n + l) if self.update_V else 0)
+                mode = "numpy" if draws <= self.NUMPY_SAMPLER_LIMIT else "device"
+                if mode == "device":
+                    warnings.warn("sg_sample_ratio < 1 on a large problem: sampling on device (statistically "
+                                  "equivalent to, but not the same stream as, the reference's np.random draws)")
+            if mode == "device":
+                return self._masks_device(st)
+            host = _draw_masks_numpy(n, d, l, ratio, self.update_U, self.update_Z, self.update_V)
+        dev = {}
+        for key, val in host.items():
+            val = np.asarray(val)
+            if key == "U":
+                val = val[st.r0:st.r1]
+            elif key == "Vx" and st.comm.world > 1:
+                val = localize_indices(val, st.r0, st.r1)
+            dev[key] = be.to_device(val, np.int32)
+        return dev
+
+    def _masks_device(self, st):
+        n, d, l, _ = st.shapes
+        be, ratio = st.be, self.sg_sample_ratio
+        if st.comm.world > 1:
+            raise NotImplementedError("device sampler with row-sharded X: pass masks or use sampler='numpy'")
+        seed = 0 if self.random_state is None or not isinstance(self.random_state, INTEGER_TYPES) \
+            else int(self.random_state)
+        it = st.iteration
+        s_d, s_n, s_l = int(d * ratio), int(n * ratio), int(l * ratio)
+        out = {}
+        if self.update_U:
+            out["U"] = be.sample_indices(n, d, s_d, seed, 4 * it + 0)
+        if self.update_Z:
+            out["Z"] = be.sample_indices(l, d, s_d, seed, 4 * it + 1)
+        if self.update_V:
+            out["Vx"] = be.sample_indices(d, n, s_n, seed, 4 * it + 2)
+            out["Vy"] = be.sample_indices(d, l, s_l, seed, 4 * it + 3)
+        return out
+
+    def _step(self, st):
+        be = st.be
+        m = self._masks(st) or {}
+        alpha, l1, l2, pert = self.alpha, self.l1_reg, self.l2_reg, self.hessian_pertubation
+        if self.update_U:                                        # :511-513 -> _newton_update_U :394-430
+            be.newton_left(st.U, st.V, st.X, alpha, l1, l2, self.x_link, self.U_non_negative, pert,
+                           l2_in_logit_hessian=False, idx=m.get("U"))
+        if self.update_Z:                                        # :515-517 -> _newton_update_Z :488-508
+            be.newton_left(st.Z, st.V, st.Y, 1 - alpha, l1, l2, self.y_link, self.Z_non_negative, pert,
+                           l2_in_logit_hessian=True, idx=m.get("Z"), trans=True)
+        if self.update_V:                                        # :519-522 -> _newton_update_V :432-486
+            d, k = st.V.shape
+            idx_x, idx_y = m.get("Vx"), m.get("Vy")
+            per_row = be.newton_v_needs_per_row(self.x_link, idx_x is not None)
+            step = be.v_chunk_rows(d, k, per_row)
+            for j0 in range(0, d, step):
+                j1 = min(d, j0 + step)
+                gx, Hx, pr = be.newton_v_xpart(st.V, st.U, st.X, j0, j1, self.x_link, alpha,
+                                               idx=None if idx_x is None else idx_x[j0:j1])
+                st.comm.all_reduce_sum(gx)
+                st.comm.all_reduce_sum(Hx)
+                be.newton_v_finish(st.V, st.Z, st.Y, j0, j1, self.y_link, alpha, l1, l2, gx, Hx, pr,
+                                   self.V_non_negative, pert, idx=None if idx_y is None else idx_y[j0:j1])
+
+    def update_step(self, X, Y, U, V, Z, l1_reg, l2_reg, alpha):
+        st = X if isinstance(X, FitState) else self.prepare(X, Y, U, V, Z)
+        keep = self.l1_reg, self.l2_reg, self.alpha
+        self.l1_reg, self.l2_reg, self.alpha = l1_reg, l2_reg, alpha
+        try:
+            st.iteration += 1
+            self._step(st)
+        finally:
+            self.l1_reg, self.l2_reg, self.alpha = keep
+        if st is not X:
+            MUSolver._write_back(self, st, U, V, Z)

@@ -1,0 +1,170 @@
+// Shared declarations for libpycmf_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <stdexcept>
+
+#include "../../include/pycmf_b200.h"
+
+namespace pycmf {
+
+constexpr double kEpsF32 = 1.1920928955078125e-07;  // np.finfo(np.float32).eps, cmf_solvers.py:12
+
+struct Scratch {
+    void* ptr = nullptr;
+    size_t bytes = 0;
+};
+
+}  // namespace pycmf
+
+struct pycmf_ctx {
+    int device = 0;
+    int num_sms = 148;
+    int max_smem_optin = 0;
+    cudaStream_t stream = 0;
+    int64_t launches = 0;
+    // options
+    int chol_fastpath = 1;
+    int dense_path = 1;
+    size_t max_scratch = size_t(2) << 30;
+    // scratch arenas (grown on demand; growth synchronises the stream)
+    pycmf::Scratch arena[8];
+};
+
+namespace pycmf {
+
+void set_error(const std::string& msg);
+
+struct Error : public std::runtime_error {
+    explicit Error(const std::string& m) : std::runtime_error(m) {}
+};
+
+#define PYCMF_CHECK(cond, msg)                                                        \
+    do {                                                                              \
+        if (!(cond)) throw pycmf::Error(std::string(msg) + " [" #cond "]");           \
+    } while (0)
+
+#define PYCMF_CUDA(expr)                                                              \
+    do {                                                                              \
+        cudaError_t _e = (expr);                                                      \
+        if (_e != cudaSuccess)                                                        \
+            throw pycmf::Error(std::string("CUDA error: ") + cudaGetErrorString(_e) + \
+                               " at " __FILE__ ":" + std::to_string(__LINE__));       \
+    } while (0)
+
+#define PYCMF_LAUNCH_CHECK(ctx)                                                       \
+    do {                                                                              \
+        (ctx)->launches++;                                                            \
+        PYCMF_CUDA(cudaGetLastError());                                               \
+    } while (0)
+
+// scratch arena `slot`, at least `bytes` large (256-B aligned by cudaMalloc)
+void* scratch(pycmf_ctx* ctx, int slot, size_t bytes);
+
+static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+template <typename T> struct DType;
+template <> struct DType<float> { static constexpr int code = PYCMF_F32; };
+template <> struct DType<double> { static constexpr int code = PYCMF_F64; };
+
+// ---- device helpers -----------------------------------------------------------------------
+template <typename T> __device__ __forceinline__ T sigmoid_(T x);
+template <> __device__ __forceinline__ float sigmoid_<float>(float x) { return 1.0f / (1.0f + expf(-x)); }
+template <> __device__ __forceinline__ double sigmoid_<double>(double x) { return 1.0 / (1.0 + exp(-x)); }
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// block-wide sum of doubles; result valid in thread 0. `red` is >= 32 doubles of shared memory.
+__device__ __forceinline__ double block_sum(double v, double* red) {
+    v = warp_sum(v);
+    int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    __syncthreads();
+    if (lane == 0) red[w] = v;
+    __syncthreads();
+    double r = 0.0;
+    if (w == 0) {
+        int nw = (blockDim.x + 31) >> 5;
+        r = lane < nw ? red[lane] : 0.0;
+        r = warp_sum(r);
+    }
+    return r;
+}
+
+// ---- internal launchers (implemented across the .cu files; all enqueue on ctx->stream) -----
+// dense.cu
+template <typename T>
+void gemm(pycmf_ctx* ctx, bool trans_a, int64_t m, int64_t q, int64_t p, const T* A, int64_t lda,
+          const T* B, int64_t ldb, T* C, int64_t ldc, T alpha, T beta);
+// C (m x q, ldc) = alpha * sum_z part[z] (each m x q contiguous) + beta * C
+template <typename T>
+void reduce_parts(pycmf_ctx* ctx, int64_t m, int64_t q, int splits, const T* part, T* C, int64_t ldc, T alpha, T beta);
+// F *= N / (D + l1 + l2 F) with zero guard (cmf_solvers.py:212-228); all (rows x k) contiguous, ld given
+template <typename T>
+void mu_apply(pycmf_ctx* ctx, int64_t rows, int64_t k, T* F, const T* N, const T* D, double l1, double l2);
+template <typename T>
+void transpose(pycmf_ctx* ctx, int64_t rows, int64_t cols, const T* A, int64_t lda, T* At, int64_t ldat);
+// out[i] = alpha*a[i] + beta*b[i]
+template <typename T>
+void axpby(pycmf_ctx* ctx, int64_t n, T alpha, const T* a, T beta, const T* b, T* out);
+// *out = sum a[i]*b[i] (double accumulation), out is a device double; accumulate adds to *out
+template <typename T>
+void dot_f64(pycmf_ctx* ctx, int64_t n, const T* a, const T* b, double scale, double* out, bool accumulate);
+
+template <typename T>
+void broadcast_add(pycmf_ctx* ctx, int64_t rows, int64_t kk, T* H, const T* Hs, T scale, bool overwrite);
+// G (k x k float64) = A^T A accumulated in float64
+template <typename T>
+void gram_f64(pycmf_ctx* ctx, int64_t rows, int64_t k, const T* A, double* G);
+
+// *out = (accumulate ? *out : 0) + scale * sum(part[0..nparts))
+void final_sum(pycmf_ctx* ctx, int nparts, const double* part, double scale, double* out, bool accumulate);
+
+// sparse.cu
+template <typename T>
+void spmm(pycmf_ctx* ctx, int64_t rows, const int32_t* rowptr, const int32_t* colidx, const T* vals,
+          const T* B, int64_t ldb, int64_t k, T* C, int64_t ldc, T alpha, T beta);
+// mode 0: out += scale * sum_nz t_ij (a_i . b_j)
+// mode 1: out += scale * sum_nz [ (t_ij - s_ij)^2 - s_ij^2 ],  s_ij = sigmoid(a_i . b_j)
+// mode 2: out += scale * sum_nz t_ij^2
+template <typename T>
+void sddmm_reduce(pycmf_ctx* ctx, int mode, int64_t rows, const int32_t* rowptr, const int32_t* colidx,
+                  const T* vals, const T* A, const T* B, int64_t k, double scale, double* out);
+
+// resid.cu : R = f(A B^T) - Tgt (Tgt may be null);  outL = R B (ra x k), outR = R^T A (rb x k),
+// *sq += sum R^2.  Any of outL / outR / sq may be null.  Tgt is (ra x rb, ldt) or, if trans_t,
+// stored (rb x ra, ldt).
+template <typename T>
+void resid_pass(pycmf_ctx* ctx, int64_t ra, int64_t rb, int64_t k, const T* A, const T* B,
+                const T* Tgt, int64_t ldt, bool trans_t, int link, T* outL, T* outR, double* sq);
+
+// newton.cu
+// Per-row gradient / Hessian accumulation for rows of A against (sampled) rows of B.
+//   g_i (+)= w * sum_{j in s_i} (f(a_i.b_j) - t_ij) b_j ;  H_i (+)= w * sum_{j in s_i} f'(a_i.b_j) b_j b_j^T
+// target: dense T (element (i,j) at T[i*ldt + j], or T[j*ldt + i] if trans_t), CSR row i lookup, or none (t = 0).
+template <typename T>
+void row_grad_hess(pycmf_ctx* ctx, int64_t rows, int64_t m, int64_t k, const T* A, const T* B,
+                   const T* Tgt, int64_t ldt, bool trans_t,
+                   const int32_t* rowptr, const int32_t* colidx, const T* vals,
+                   int link, double w, const int32_t* idx, int64_t n_sample,
+                   T* g, T* H, bool accumulate);
+// F_i <- F_i - (g_i + l1 sign(F_i) + l2 F_i) S(H_i + l2_diag I); clamp. H: (rows x k x k) or shared (h_stride 0)
+template <typename T>
+void newton_solve_rows(pycmf_ctx* ctx, int64_t rows, int64_t k, T* F, const T* g, const T* H, int64_t h_stride,
+                       double l1, double l2, double l2_diag, double pert, bool non_negative);
+void safe_solve_f64(pycmf_ctx* ctx, int64_t batch, int64_t k, const double* H, int64_t h_stride,
+                    const double* g, double* x, double pert);
+void sample_indices(pycmf_ctx* ctx, int64_t rows, int64_t N, int64_t n_sample, uint64_t seed,
+                    uint64_t stream_id, int32_t* idx);
+
+}  // namespace pycmf

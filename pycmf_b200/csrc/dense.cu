@@ -1,0 +1,365 @@
+// Generic dense kernels (fp32 / fp64 FMA pipes): tiled GEMM with split-K, MU ratio epilogue,
+// transpose, axpby, dot.  These are the exact-precision path; the tcgen05 TF32 kernels in
+// tc_dense.cu take over the large fp32 contractions when ctx->dense_path != 0.
+#include "common.cuh"
+
+namespace pycmf {
+
+namespace {
+
+constexpr int BM = 64, BN = 64, BK = 16, PAD = 4;
+
+template <typename T> __device__ __forceinline__ void load4(const T* p, T (&v)[4]);
+template <> __device__ __forceinline__ void load4<float>(const float* p, float (&v)[4]) {
+    float4 t = *reinterpret_cast<const float4*>(p);
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+}
+template <> __device__ __forceinline__ void load4<double>(const double* p, double (&v)[4]) {
+    double2 a = *reinterpret_cast<const double2*>(p);
+    double2 b = *reinterpret_cast<const double2*>(p + 2);
+    v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+}
+
+// C_part[z] (m x q) = op(A)[:, pz0:pz1] * B[pz0:pz1, :]
+template <typename T, bool TRANS_A>
+__global__ void __launch_bounds__(256)
+gemm_kernel(int64_t m, int64_t q, int64_t p, int64_t p_per_split,
+            const T* __restrict__ A, int64_t lda, const T* __restrict__ B, int64_t ldb,
+            T* __restrict__ C, int64_t ldc, int64_t c_split_stride, T alpha, T beta, bool direct) {
+    __shared__ __align__(16) T As[BK][BM + PAD];
+    __shared__ __align__(16) T Bs[BK][BN + PAD];
+    const int tid = threadIdx.x;
+    const int tx = tid & 15, ty = tid >> 4;
+    const int64_t row0 = int64_t(blockIdx.y) * BM, col0 = int64_t(blockIdx.x) * BN;
+    const int64_t pz0 = int64_t(blockIdx.z) * p_per_split;
+    const int64_t pz1 = min(p, pz0 + p_per_split);
+
+    T acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) acc[i][j] = T(0);
+
+    for (int64_t k0 = pz0; k0 < pz1; k0 += BK) {
+        // ---- stage A tile as As[kk][row]
+        if (TRANS_A) {
+            // A stored (p x m): element op(A)[row][kk] = A[kk*lda + row]; coalesced along row
+#pragma unroll
+            for (int it = 0; it < (BM * BK) / 256; it++) {
+                int e = tid + it * 256;
+                int kk = e / BM, r = e % BM;
+                int64_t gk = k0 + kk, gr = row0 + r;
+                As[kk][r] = (gk < pz1 && gr < m) ? A[gk * lda + gr] : T(0);
+            }
+        } else {
+            // A stored (m x p): coalesced along kk
+#pragma unroll
+            for (int it = 0; it < (BM * BK) / 256; it++) {
+                int e = tid + it * 256;
+                int r = e / BK, kk = e % BK;
+                int64_t gk = k0 + kk, gr = row0 + r;
+                As[kk][r] = (gk < pz1 && gr < m) ? A[gr * lda + gk] : T(0);
+            }
+        }
+#pragma unroll
+        for (int it = 0; it < (BN * BK) / 256; it++) {
+            int e = tid + it * 256;
+            int kk = e / BN, c = e % BN;
+            int64_t gk = k0 + kk, gc = col0 + c;
+            Bs[kk][c] = (gk < pz1 && gc < q) ? B[gk * ldb + gc] : T(0);
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < BK; kk++) {
+            T a[4], b[4];
+            load4<T>(&As[kk][ty * 4], a);
+            load4<T>(&Bs[kk][tx * 4], b);
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+#pragma unroll
+                for (int j = 0; j < 4; j++) acc[i][j] = fma(a[i], b[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+    T* Cz = C + int64_t(blockIdx.z) * c_split_stride;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        int64_t gr = row0 + ty * 4 + i;
+        if (gr >= m) continue;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            int64_t gc = col0 + tx * 4 + j;
+            if (gc >= q) continue;
+            if (direct) {
+                T prev = beta != T(0) ? Cz[gr * ldc + gc] : T(0);
+                Cz[gr * ldc + gc] = alpha * acc[i][j] + beta * prev;
+            } else {
+                Cz[gr * ldc + gc] = acc[i][j];
+            }
+        }
+    }
+}
+
+template <typename T>
+__global__ void splitk_reduce_kernel(int64_t m, int64_t q, int splits, const T* __restrict__ part,
+                                     T* __restrict__ C, int64_t ldc, T alpha, T beta) {
+    int64_t e = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (e >= m * q) return;
+    T s = T(0);
+    for (int z = 0; z < splits; z++) s += part[int64_t(z) * m * q + e];
+    int64_t r = e / q, c = e % q;
+    T prev = beta != T(0) ? C[r * ldc + c] : T(0);
+    C[r * ldc + c] = alpha * s + beta * prev;
+}
+
+template <typename T>
+__global__ void mu_apply_kernel(int64_t n, T* __restrict__ F, const T* __restrict__ N,
+                                const T* __restrict__ D, T l1, T l2, T eps) {
+    int64_t e = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    T f = F[e];
+    T den = D[e];
+    if (l1 > T(0)) den += l1;
+    if (l2 > T(0)) den = den + l2 * f;
+    if (den == T(0)) den = eps;
+    F[e] = f * (N[e] / den);
+}
+
+template <typename T>
+__global__ void transpose_kernel(int64_t rows, int64_t cols, const T* __restrict__ A, int64_t lda,
+                                 T* __restrict__ At, int64_t ldat) {
+    __shared__ T tile[32][33];
+    int64_t c0 = int64_t(blockIdx.x) * 32, r0 = int64_t(blockIdx.y) * 32;
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        int64_t r = r0 + i, c = c0 + threadIdx.x;
+        tile[i][threadIdx.x] = (r < rows && c < cols) ? A[r * lda + c] : T(0);
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        int64_t c = c0 + i, r = r0 + threadIdx.x;
+        if (r < rows && c < cols) At[c * ldat + r] = tile[threadIdx.x][i];
+    }
+}
+
+template <typename T>
+__global__ void axpby_kernel(int64_t n, T alpha, const T* __restrict__ a, T beta, const T* __restrict__ b,
+                             T* __restrict__ out) {
+    int64_t e = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    T v = alpha * a[e];
+    if (b != nullptr) v += beta * b[e];
+    out[e] = v;
+}
+
+template <typename T>
+__global__ void dot_partial_kernel(int64_t n, const T* __restrict__ a, const T* __restrict__ b,
+                                   double* __restrict__ part) {
+    __shared__ double red[32];
+    double s = 0.0;
+    for (int64_t e = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; e < n; e += int64_t(gridDim.x) * blockDim.x)
+        s += double(a[e]) * double(b[e]);
+    s = block_sum(s, red);
+    if (threadIdx.x == 0) part[blockIdx.x] = s;
+}
+
+__global__ void final_sum_kernel(int nparts, const double* __restrict__ part, double scale, double* out,
+                                 bool accumulate) {
+    __shared__ double red[32];
+    double s = 0.0;
+    for (int i = threadIdx.x; i < nparts; i += blockDim.x) s += part[i];
+    s = block_sum(s, red);
+    if (threadIdx.x == 0) *out = (accumulate ? *out : 0.0) + scale * s;
+}
+
+
+// H[i] (kk elements each) = (overwrite ? 0 : H[i]) + scale * Hs
+template <typename T>
+__global__ void broadcast_add_kernel(int64_t rows, int64_t kk, T* __restrict__ H, const T* __restrict__ Hs,
+                                     T scale, bool overwrite) {
+    int64_t e = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (e >= rows * kk) return;
+    T v = scale * Hs[e % kk];
+    H[e] = overwrite ? v : H[e] + v;
+}
+
+// Gram matrix with float64 accumulation: part[blockIdx] (k x k doubles) = sum over the CTA's rows a_r a_r^T
+template <typename T, int HB>
+__global__ void __launch_bounds__(256)
+gram_f64_kernel(int64_t rows, int k, const T* __restrict__ A, double* __restrict__ part, int a_off, int b_off) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T* A_s = reinterpret_cast<T*>(smem_raw);  // 32 x (k+1)
+    const int kp = k + 1;
+    const int tid = threadIdx.x, ta = tid >> 4, tb = tid & 15;
+    double acc[HB][HB];
+#pragma unroll
+    for (int x = 0; x < HB; x++)
+#pragma unroll
+        for (int y = 0; y < HB; y++) acc[x][y] = 0.0;
+    for (int64_t r0 = int64_t(blockIdx.x) * 32; r0 < rows; r0 += int64_t(gridDim.x) * 32) {
+        __syncthreads();
+        for (int e = tid; e < 32 * k; e += 256) {
+            int rr = e / k, c = e % k;
+            A_s[rr * kp + c] = (r0 + rr < rows) ? A[(r0 + rr) * k + c] : T(0);
+        }
+        __syncthreads();
+        for (int rr = 0; rr < 32; rr++) {
+            double av[HB], bv[HB];
+#pragma unroll
+            for (int x = 0; x < HB; x++) { int a = a_off + ta + 16 * x; av[x] = a < k ? double(A_s[rr * kp + a]) : 0.0; }
+#pragma unroll
+            for (int y = 0; y < HB; y++) { int b = b_off + tb + 16 * y; bv[y] = b < k ? double(A_s[rr * kp + b]) : 0.0; }
+#pragma unroll
+            for (int x = 0; x < HB; x++)
+#pragma unroll
+                for (int y = 0; y < HB; y++) acc[x][y] = fma(av[x], bv[y], acc[x][y]);
+        }
+    }
+    double* P = part + int64_t(blockIdx.x) * k * k;
+#pragma unroll
+    for (int x = 0; x < HB; x++) {
+        int a = a_off + ta + 16 * x;
+        if (a >= k) continue;
+#pragma unroll
+        for (int y = 0; y < HB; y++) {
+            int b = b_off + tb + 16 * y;
+            if (b < k) P[a * k + b] = acc[x][y];
+        }
+    }
+}
+
+}  // namespace
+
+void final_sum(pycmf_ctx* ctx, int nparts, const double* part, double scale, double* out, bool accumulate) {
+    final_sum_kernel<<<1, 256, 0, ctx->stream>>>(nparts, part, scale, out, accumulate);
+    PYCMF_LAUNCH_CHECK(ctx);
+}
+
+template <typename T>
+void gemm(pycmf_ctx* ctx, bool trans_a, int64_t m, int64_t q, int64_t p, const T* A, int64_t lda,
+          const T* B, int64_t ldb, T* C, int64_t ldc, T alpha, T beta) {
+    if (m <= 0 || q <= 0) return;
+    int64_t tiles = ceil_div(m, BM) * ceil_div(q, BN);
+    int splits = 1;
+    if (p > 0 && tiles < 2 * ctx->num_sms) {
+        int64_t want = ceil_div(int64_t(4) * ctx->num_sms, tiles);
+        int64_t maxs = ceil_div(p, 256);
+        splits = int(std::max<int64_t>(1, std::min(want, maxs)));
+    }
+    int64_t p_per = ceil_div(std::max<int64_t>(p, 1), splits);
+    p_per = ceil_div(p_per, BK) * BK;
+    splits = int(std::max<int64_t>(1, ceil_div(std::max<int64_t>(p, 1), p_per)));
+    dim3 grid((unsigned)ceil_div(q, BN), (unsigned)ceil_div(m, BM), (unsigned)splits);
+    PYCMF_CHECK(grid.y <= 65535u * 32u, "gemm: too many row tiles");
+    if (grid.y > 65535u) {
+        // fold: process in row chunks
+        int64_t chunk = int64_t(65535) * BM;
+        for (int64_t r = 0; r < m; r += chunk) {
+            int64_t mm = std::min(chunk, m - r);
+            gemm<T>(ctx, trans_a, mm, q, p, trans_a ? A + r : A + r * lda, lda, B, ldb, C + r * ldc, ldc, alpha, beta);
+        }
+        return;
+    }
+    if (splits == 1) {
+        if (trans_a)
+            gemm_kernel<T, true><<<grid, 256, 0, ctx->stream>>>(m, q, p, p_per, A, lda, B, ldb, C, ldc, 0, alpha, beta, true);
+        else
+            gemm_kernel<T, false><<<grid, 256, 0, ctx->stream>>>(m, q, p, p_per, A, lda, B, ldb, C, ldc, 0, alpha, beta, true);
+        PYCMF_LAUNCH_CHECK(ctx);
+    } else {
+        T* part = static_cast<T*>(scratch(ctx, 0, size_t(splits) * m * q * sizeof(T)));
+        if (trans_a)
+            gemm_kernel<T, true><<<grid, 256, 0, ctx->stream>>>(m, q, p, p_per, A, lda, B, ldb, part, q, m * q, T(1), T(0), false);
+        else
+            gemm_kernel<T, false><<<grid, 256, 0, ctx->stream>>>(m, q, p, p_per, A, lda, B, ldb, part, q, m * q, T(1), T(0), false);
+        PYCMF_LAUNCH_CHECK(ctx);
+        int64_t n = m * q;
+        splitk_reduce_kernel<T><<<(unsigned)ceil_div(n, 256), 256, 0, ctx->stream>>>(m, q, splits, part, C, ldc, alpha, beta);
+        PYCMF_LAUNCH_CHECK(ctx);
+    }
+}
+
+template <typename T>
+void reduce_parts(pycmf_ctx* ctx, int64_t m, int64_t q, int splits, const T* part, T* C, int64_t ldc, T alpha, T beta) {
+    int64_t n = m * q;
+    if (n <= 0) return;
+    splitk_reduce_kernel<T><<<(unsigned)ceil_div(n, 256), 256, 0, ctx->stream>>>(m, q, splits, part, C, ldc, alpha, beta);
+    PYCMF_LAUNCH_CHECK(ctx);
+}
+
+template <typename T>
+void mu_apply(pycmf_ctx* ctx, int64_t rows, int64_t k, T* F, const T* N, const T* D, double l1, double l2) {
+    int64_t n = rows * k;
+    if (n <= 0) return;
+    mu_apply_kernel<T><<<(unsigned)ceil_div(n, 256), 256, 0, ctx->stream>>>(n, F, N, D, T(l1), T(l2), T(kEpsF32));
+    PYCMF_LAUNCH_CHECK(ctx);
+}
+
+template <typename T>
+void transpose(pycmf_ctx* ctx, int64_t rows, int64_t cols, const T* A, int64_t lda, T* At, int64_t ldat) {
+    if (rows <= 0 || cols <= 0) return;
+    dim3 grid((unsigned)ceil_div(cols, 32), (unsigned)ceil_div(rows, 32));
+    PYCMF_CHECK(grid.y <= 65535u, "transpose: too many rows (tile over rows)");
+    transpose_kernel<T><<<grid, dim3(32, 8), 0, ctx->stream>>>(rows, cols, A, lda, At, ldat);
+    PYCMF_LAUNCH_CHECK(ctx);
+}
+
+template <typename T>
+void axpby(pycmf_ctx* ctx, int64_t n, T alpha, const T* a, T beta, const T* b, T* out) {
+    if (n <= 0) return;
+    axpby_kernel<T><<<(unsigned)ceil_div(n, 256), 256, 0, ctx->stream>>>(n, alpha, a, beta, b, out);
+    PYCMF_LAUNCH_CHECK(ctx);
+}
+
+template <typename T>
+void dot_f64(pycmf_ctx* ctx, int64_t n, const T* a, const T* b, double scale, double* out, bool accumulate) {
+    int blocks = int(std::max<int64_t>(1, std::min<int64_t>(ceil_div(std::max<int64_t>(n, 1), 1024), 4 * ctx->num_sms)));
+    double* part = static_cast<double*>(scratch(ctx, 1, size_t(blocks) * sizeof(double)));
+    dot_partial_kernel<T><<<blocks, 256, 0, ctx->stream>>>(n, a, b, part);
+    PYCMF_LAUNCH_CHECK(ctx);
+    final_sum(ctx, blocks, part, scale, out, accumulate);
+}
+
+
+template <typename T>
+void broadcast_add(pycmf_ctx* ctx, int64_t rows, int64_t kk, T* H, const T* Hs, T scale, bool overwrite) {
+    int64_t n = rows * kk;
+    if (n <= 0) return;
+    broadcast_add_kernel<T><<<(unsigned)ceil_div(n, 256), 256, 0, ctx->stream>>>(rows, kk, H, Hs, scale, overwrite);
+    PYCMF_LAUNCH_CHECK(ctx);
+}
+
+template <typename T>
+void gram_f64(pycmf_ctx* ctx, int64_t rows, int64_t k, const T* A, double* G) {
+    PYCMF_CHECK(k >= 1 && k <= 256, "n_components must be in [1, 256]");
+    int blocks = int(std::max<int64_t>(1, std::min<int64_t>(ceil_div(std::max<int64_t>(rows, 1), 128), 2 * ctx->num_sms)));
+    double* part = static_cast<double*>(scratch(ctx, 0, size_t(blocks) * k * k * sizeof(double)));
+    size_t smem = sizeof(T) * size_t(32) * (k + 1);
+    int hb = k <= 16 ? 1 : (k <= 32 ? 2 : (k <= 64 ? 4 : 8));
+    int quads = k > 128 ? 2 : 1;
+    for (int qa = 0; qa < quads; qa++)
+        for (int qb = 0; qb < quads; qb++) {
+#define LAUNCH(HB) gram_f64_kernel<T, HB><<<blocks, 256, smem, ctx->stream>>>(rows, int(k), A, part, qa * 128, qb * 128)
+            if (hb == 1) LAUNCH(1);
+            else if (hb == 2) LAUNCH(2);
+            else if (hb == 4) LAUNCH(4);
+            else LAUNCH(8);
+#undef LAUNCH
+            PYCMF_LAUNCH_CHECK(ctx);
+        }
+    reduce_parts<double>(ctx, k, k, blocks, part, G, k, 1.0, 0.0);
+}
+
+#define INSTANTIATE(T)                                                                                   \
+    template void gemm<T>(pycmf_ctx*, bool, int64_t, int64_t, int64_t, const T*, int64_t, const T*,     \
+                          int64_t, T*, int64_t, T, T);                                                   \
+    template void reduce_parts<T>(pycmf_ctx*, int64_t, int64_t, int, const T*, T*, int64_t, T, T);        \
+    template void broadcast_add<T>(pycmf_ctx*, int64_t, int64_t, T*, const T*, T, bool);                  \
+    template void gram_f64<T>(pycmf_ctx*, int64_t, int64_t, const T*, double*);                           \
+    template void mu_apply<T>(pycmf_ctx*, int64_t, int64_t, T*, const T*, const T*, double, double);     \
+    template void transpose<T>(pycmf_ctx*, int64_t, int64_t, const T*, int64_t, T*, int64_t);           \
+    template void axpby<T>(pycmf_ctx*, int64_t, T, const T*, T, const T*, T*);                          \
+    template void dot_f64<T>(pycmf_ctx*, int64_t, const T*, const T*, double, double*, bool);
+INSTANTIATE(float)
+INSTANTIATE(double)
+
+}  // namespace pycmf

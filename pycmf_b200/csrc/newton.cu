@@ -1,0 +1,552 @@
+// Newton-step kernels:
+//   row_grad_hess     per-row gradient / weighted-Gram Hessian over (sampled) rows of the other factor
+//   safe_solve        batched k x k eigenvalue-clamped solve  x = S(H) g   (reference _safe_invert,
+//                     cmf_solvers.py:346-356) : Cholesky fast path when lambda_min(H) >= pert,
+//                     one-sided Jacobi otherwise; always float64
+//   newton_solve_rows F_i <- F_i - (g_i + l1 sign F_i + l2 F_i) S(H_i + l2 I), optional clamp
+//   sample_indices    on-device per-row sampling without replacement (Feistel permutation prefix)
+#include "common.cuh"
+
+namespace pycmf {
+namespace {
+
+// =============================================================================================
+// row_grad_hess
+// =============================================================================================
+constexpr int TJ = 32;  // sampled rows of B staged per tile
+
+template <typename T, int HB>
+__global__ void __launch_bounds__(256)
+row_grad_hess_kernel(int64_t rows, int64_t m, int k, const T* __restrict__ A, const T* __restrict__ B,
+                     const T* __restrict__ Tgt, int64_t ldt, bool trans_t,
+                     const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx,
+                     const T* __restrict__ vals, int link, T w,
+                     const int32_t* __restrict__ idx, int64_t n_sample,
+                     T* __restrict__ g, T* __restrict__ H, bool accumulate, int a_off, int b_off) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int kp = k + 1;
+    T* a_s = reinterpret_cast<T*>(smem_raw);          // k
+    T* B_s = a_s + ((k + 3) & ~3);                    // TJ x kp
+    T* r_s = B_s + TJ * kp;                           // TJ   (w * residual)
+    T* w_s = r_s + TJ;                                // TJ   (w * f')
+    const int64_t i = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int ta = tid >> 4, tb = tid & 15;
+    const bool want_g = g != nullptr, want_h = H != nullptr;
+
+    for (int c = tid; c < k; c += 256) a_s[c] = A[i * k + c];
+    T gacc = T(0);
+    T hacc[HB][HB];
+#pragma unroll
+    for (int x = 0; x < HB; x++)
+#pragma unroll
+        for (int y = 0; y < HB; y++) hacc[x][y] = T(0);
+
+    const int64_t total = idx != nullptr ? n_sample : m;
+    int lo = 0, hi = 0;
+    if (rowptr != nullptr) { lo = rowptr[i]; hi = rowptr[i + 1]; }
+
+    for (int64_t t0 = 0; t0 < total; t0 += TJ) {
+        const int64_t rem_t = total - t0;
+        const int cnt = rem_t < TJ ? int(rem_t) : TJ;
+        __syncthreads();
+        // stage the sampled rows of B
+        for (int e = tid; e < TJ * k; e += 256) {
+            int jj = e / k, c = e % k;
+            T v = T(0);
+            if (jj < cnt) {
+                int64_t j = idx != nullptr ? int64_t(idx[i * n_sample + t0 + jj]) : t0 + jj;
+                if (j >= 0) v = B[j * k + c];   // j < 0: sample lives on another shard
+            }
+            B_s[jj * kp + c] = v;
+        }
+        __syncthreads();
+        // estimates: each warp takes TJ / 8 sampled rows
+        for (int jj = warp; jj < TJ; jj += 8) {
+            T d = T(0);
+            for (int c = lane; c < k; c += 32) d = fma(a_s[c], B_s[jj * kp + c], d);
+            d = warp_sum(d);
+            if (lane == 0) {
+                T rr = T(0), ww = T(0);
+                int64_t j = -1;
+                if (jj < cnt) j = idx != nullptr ? int64_t(idx[i * n_sample + t0 + jj]) : t0 + jj;
+                if (j >= 0) {
+                    T est = d, fp = T(1);
+                    if (link == PYCMF_LOGIT) { est = sigmoid_<T>(d); fp = est * (T(1) - est); }
+                    T tg = T(0);
+                    if (want_g) {
+                        if (Tgt != nullptr) {
+                            tg = trans_t ? Tgt[j * ldt + i] : Tgt[i * ldt + j];
+                        } else if (rowptr != nullptr) {
+                            int l = lo, h = hi;
+                            while (l < h) {
+                                int mid = (l + h) >> 1;
+                                if (colidx[mid] < int(j)) l = mid + 1; else h = mid;
+                            }
+                            if (l < hi && colidx[l] == int(j)) tg = vals[l];
+                        }
+                    }
+                    rr = w * (est - tg);
+                    ww = w * fp;
+                }
+                r_s[jj] = rr;
+                w_s[jj] = ww;
+            }
+        }
+        __syncthreads();
+        if (want_g && tid < k) {
+#pragma unroll 8
+            for (int jj = 0; jj < TJ; jj++) gacc = fma(r_s[jj], B_s[jj * kp + tid], gacc);
+        }
+        if (want_h) {
+            for (int jj = 0; jj < cnt; jj++) {
+                T wa[HB], bb[HB];
+                const T wj = w_s[jj];
+#pragma unroll
+                for (int x = 0; x < HB; x++) {
+                    int a = a_off + ta + 16 * x;
+                    wa[x] = a < k ? wj * B_s[jj * kp + a] : T(0);
+                }
+#pragma unroll
+                for (int y = 0; y < HB; y++) {
+                    int b = b_off + tb + 16 * y;
+                    bb[y] = b < k ? B_s[jj * kp + b] : T(0);
+                }
+#pragma unroll
+                for (int x = 0; x < HB; x++)
+#pragma unroll
+                    for (int y = 0; y < HB; y++) hacc[x][y] = fma(wa[x], bb[y], hacc[x][y]);
+            }
+        }
+    }
+    if (want_g && tid < k) {
+        T prev = accumulate ? g[i * k + tid] : T(0);
+        g[i * k + tid] = prev + gacc;
+    }
+    if (want_h) {
+        T* Hi = H + i * int64_t(k) * k;
+#pragma unroll
+        for (int x = 0; x < HB; x++) {
+            int a = a_off + ta + 16 * x;
+            if (a >= k) continue;
+#pragma unroll
+            for (int y = 0; y < HB; y++) {
+                int b = b_off + tb + 16 * y;
+                if (b >= k) continue;
+                T prev = accumulate ? Hi[a * k + b] : T(0);
+                Hi[a * k + b] = prev + hacc[x][y];
+            }
+        }
+    }
+}
+
+// =============================================================================================
+// eigenvalue-clamped solve
+// =============================================================================================
+struct SolveShared {
+    int flag;
+    int fail;
+};
+
+// Load the LOWER triangle of H (row-major, like scipy.linalg.eigh(lower=True)) into W (column-major
+// == row-major for a symmetric matrix), adding `diag` on the diagonal.
+template <typename T>
+__device__ __forceinline__ void load_sym(double* W, const T* __restrict__ H, int k, double diag) {
+    for (int e = threadIdx.x; e < k * k; e += blockDim.x) {
+        int r = e / k, c = e % k;
+        int hi = r > c ? r : c, lo = r > c ? c : r;
+        double v = double(H[hi * k + lo]);
+        if (r == c) v += diag;
+        W[e] = v;
+    }
+}
+
+// In-place right-looking Cholesky of the lower triangle of W (element (r,c) at W[r*k+c]).
+// Returns false (uniformly) when a pivot is not safely positive.
+__device__ bool cholesky_inplace(double* W, int k, SolveShared* sh, double pivot_floor) {
+    for (int j = 0; j < k; j++) {
+        __syncthreads();
+        double piv = W[j * k + j];
+        if (!(piv > pivot_floor)) return false;  // uniform: every thread reads the same value
+        double inv = 1.0 / sqrt(piv);
+        __syncthreads();
+        for (int r = j + threadIdx.x; r < k; r += blockDim.x) W[r * k + j] *= inv;
+        __syncthreads();
+        // W[j][j] now holds piv * inv = sqrt(piv)
+        const int rem = k - j - 1;
+        for (int e = threadIdx.x; e < rem * rem; e += blockDim.x) {
+            int r = j + 1 + e / rem, c = j + 1 + e % rem;
+            if (c <= r) W[r * k + c] -= W[r * k + j] * W[c * k + j];
+        }
+    }
+    __syncthreads();
+    return true;
+}
+
+// Solve L L^T x = b in place on b (length k, shared memory), L in the lower triangle of W.
+__device__ void chol_solve(const double* W, int k, double* b) {
+    for (int j = 0; j < k; j++) {
+        __syncthreads();
+        double yj = b[j] / W[j * k + j];
+        __syncthreads();
+        if (threadIdx.x == 0) b[j] = yj;
+        for (int r = j + 1 + threadIdx.x; r < k; r += blockDim.x) b[r] -= W[r * k + j] * yj;
+    }
+    for (int j = k - 1; j >= 0; j--) {
+        __syncthreads();
+        double xj = b[j] / W[j * k + j];
+        __syncthreads();
+        if (threadIdx.x == 0) b[j] = xj;
+        for (int r = threadIdx.x; r < j; r += blockDim.x) b[r] -= W[j * k + r] * xj;
+    }
+    __syncthreads();
+}
+
+// One-sided (Hestenes) Jacobi on the columns of W (column p = W[p*k .. p*k+k), W symmetric on entry so
+// row-major == column-major).  On exit the columns are mutually orthogonal: W = Q diag(lambda) (up to
+// column order / sign), so x = S(H) g = g/p + sum_{sigma_i >= p} (1/sigma_i - 1/p) (w_i.g)/sigma_i^2 w_i.
+__device__ void jacobi_clamped_solve(double* W, int k, const double* g, double* x, double* xpart,
+                                     SolveShared* sh, double pert) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int kk = (k + 1) & ~1;
+    const double tol = 1e-15;
+    const double skip2 = (1e-3 * pert) * (1e-3 * pert);
+    for (int sweep = 0; sweep < 60; sweep++) {
+        __syncthreads();
+        if (threadIdx.x == 0) sh->flag = 0;
+        __syncthreads();
+        for (int step = 0; step < kk - 1; step++) {
+            for (int mth = warp; mth < kk / 2; mth += nwarps) {
+                int p, q;
+                if (mth == 0) { p = step; q = kk - 1; }
+                else { p = (step + mth) % (kk - 1); q = (step - mth + (kk - 1)) % (kk - 1); }
+                if (p >= k || q >= k) continue;
+                double* wp = W + p * k;
+                double* wq = W + q * k;
+                double al = 0.0, be = 0.0, ga = 0.0;
+                for (int r = lane; r < k; r += 32) {
+                    double a = wp[r], b = wq[r];
+                    al = fma(a, a, al); be = fma(b, b, be); ga = fma(a, b, ga);
+                }
+                al = warp_sum(al); be = warp_sum(be); ga = warp_sum(ga);
+                if (ga == 0.0 || fmax(al, be) < skip2) continue;
+                if (fabs(ga) <= tol * sqrt(al * be)) continue;
+                double zeta = (be - al) / (2.0 * ga);
+                double t = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+                double c = 1.0 / sqrt(1.0 + t * t), s = c * t;
+                for (int r = lane; r < k; r += 32) {
+                    double a = wp[r], b = wq[r];
+                    wp[r] = c * a - s * b;
+                    wq[r] = s * a + c * b;
+                }
+                if (lane == 0) sh->flag = 1;
+            }
+            __syncthreads();
+        }
+        if (sh->flag == 0) break;
+    }
+    __syncthreads();
+    // accumulate x
+    const int per = (k + 31) / 32;  // <= 8
+    double acc[8];
+#pragma unroll
+    for (int u = 0; u < 8; u++) acc[u] = 0.0;
+    for (int i = warp; i < k; i += nwarps) {
+        const double* wi = W + i * k;
+        double al = 0.0, dg = 0.0;
+        for (int r = lane; r < k; r += 32) { double a = wi[r]; al = fma(a, a, al); dg = fma(a, g[r], dg); }
+        al = warp_sum(al); dg = warp_sum(dg);
+        double sigma = sqrt(al);
+        if (sigma >= pert) {
+            double coef = (1.0 / sigma - 1.0 / pert) * dg / al;
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                int r = lane + 32 * u;
+                if (u < per && r < k) acc[u] = fma(coef, wi[r], acc[u]);
+            }
+        }
+    }
+    // cross-warp reduction through xpart (nwarps x k)
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+        int r = lane + 32 * u;
+        if (u < per && r < k) xpart[warp * k + r] = acc[u];
+    }
+    __syncthreads();
+    for (int r = threadIdx.x; r < k; r += blockDim.x) {
+        double s = g[r] / pert;
+        for (int wv = 0; wv < nwarps; wv++) s += xpart[wv * k + r];
+        x[r] = s;
+    }
+    __syncthreads();
+}
+
+// The whole clamped solve for one matrix; H is (re)loaded from global memory as needed.
+template <typename T>
+__device__ void safe_solve_one(double* W, const T* __restrict__ H, int k, double diag, const double* g,
+                               double* x, double* xpart, SolveShared* sh, double pert, bool chol_fastpath) {
+    bool done = false;
+    if (chol_fastpath) {
+        // lambda_min(H) > pert  <=>  H - pert I is positive definite  <=>  its Cholesky succeeds
+        load_sym<T>(W, H, k, diag - pert);
+        __syncthreads();
+        double tr = 0.0;
+        for (int r = 0; r < k; r++) tr += fabs(W[r * k + r]);   // every thread, same value (k <= 256)
+        bool ok = cholesky_inplace(W, k, sh, 1e-13 * (tr + pert));
+        __syncthreads();
+        if (ok) {
+            load_sym<T>(W, H, k, diag);
+            __syncthreads();
+            ok = cholesky_inplace(W, k, sh, 0.0);
+            if (ok) {
+                for (int r = threadIdx.x; r < k; r += blockDim.x) x[r] = g[r];
+                __syncthreads();
+                chol_solve(W, k, x);
+                done = true;
+            }
+        }
+        __syncthreads();
+    }
+    if (!done) {
+        load_sym<T>(W, H, k, diag);
+        __syncthreads();
+        jacobi_clamped_solve(W, k, g, x, xpart, sh, pert);
+    }
+}
+
+// MODE 0: x_b = S(H_b) g_b (all float64).  MODE 1: Newton row update on F.
+template <typename T, int MODE>
+__global__ void __launch_bounds__(256)
+safe_solve_kernel(int64_t batch, int k, const T* __restrict__ H, int64_t h_stride, const T* __restrict__ g,
+                  T* __restrict__ out, double l1, double l2, double l2_diag, double pert, bool non_negative,
+                  bool chol_fastpath, double* __restrict__ Wglobal) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int nwarps = blockDim.x >> 5;
+    double* gv = reinterpret_cast<double*>(smem_raw);   // k
+    double* xv = gv + k;                                // k
+    double* xpart = xv + k;                             // nwarps * k
+    SolveShared* sh = reinterpret_cast<SolveShared*>(xpart + nwarps * k);
+    double* W = Wglobal != nullptr ? Wglobal + int64_t(blockIdx.x) * k * k
+                                   : reinterpret_cast<double*>(sh + 2);
+    for (int64_t b = blockIdx.x; b < batch; b += gridDim.x) {
+        __syncthreads();
+        for (int r = threadIdx.x; r < k; r += blockDim.x) {
+            double gr = double(g[b * k + r]);
+            if (MODE == 1) {
+                double f = double(out[b * k + r]);
+                double sg = f > 0.0 ? 1.0 : (f < 0.0 ? -1.0 : 0.0);
+                gr += l1 * sg + l2 * f;
+            }
+            gv[r] = gr;
+        }
+        __syncthreads();
+        safe_solve_one<T>(W, H + b * h_stride, k, l2_diag, gv, xv, xpart, sh, pert, chol_fastpath);
+        __syncthreads();
+        for (int r = threadIdx.x; r < k; r += blockDim.x) {
+            if (MODE == 0) {
+                out[b * k + r] = T(xv[r]);
+            } else {
+                double f = double(out[b * k + r]) - xv[r];
+                if (non_negative && f < 0.0) f = 0.0;
+                out[b * k + r] = T(f);
+            }
+        }
+    }
+}
+
+// F (rows x k) <- F - (G + l1 sign F + l2 F) Hinv  (shared inverse, read through L1/L2), optional clamp
+template <typename T>
+__global__ void __launch_bounds__(256)
+apply_shared_inverse_kernel(int64_t rows, int k, T* __restrict__ F, const T* __restrict__ G,
+                            const double* __restrict__ Hinv, double l1, double l2, bool non_negative) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double* gs = reinterpret_cast<double*>(smem_raw);   // RPB x k
+    const int RPB = 8;
+    const int64_t r0 = int64_t(blockIdx.x) * RPB;
+    for (int e = threadIdx.x; e < RPB * k; e += blockDim.x) {
+        int64_t r = r0 + e / k;
+        int c = e % k;
+        double v = 0.0;
+        if (r < rows) {
+            double f = double(F[r * k + c]);
+            double sg = f > 0.0 ? 1.0 : (f < 0.0 ? -1.0 : 0.0);
+            v = double(G[r * k + c]) + l1 * sg + l2 * f;
+        }
+        gs[e] = v;
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < RPB * k; e += blockDim.x) {
+        int rr = e / k, c = e % k;
+        int64_t r = r0 + rr;
+        if (r >= rows) continue;
+        double s = 0.0;
+        for (int a = 0; a < k; a++) s = fma(gs[rr * k + a], __ldg(&Hinv[a * k + c]), s);
+        double f = double(F[r * k + c]) - s;
+        if (non_negative && f < 0.0) f = 0.0;
+        F[r * k + c] = T(f);
+    }
+}
+
+__global__ void identity_kernel(int k, double* I) {
+    int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e < k * k) I[e] = (e / k == e % k) ? 1.0 : 0.0;
+}
+
+template <typename T>
+__global__ void cast_to_f64_kernel(int64_t n, const T* __restrict__ a, double* __restrict__ b) {
+    int64_t e = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (e < n) b[e] = double(a[e]);
+}
+
+// =============================================================================================
+// sampler
+// =============================================================================================
+__device__ __forceinline__ uint32_t mix32(uint32_t x) {
+    x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16;
+    return x;
+}
+
+__global__ void sample_indices_kernel(int64_t rows, int64_t N, int64_t n_sample, uint64_t seed,
+                                      uint64_t stream_id, int32_t* __restrict__ idx) {
+    int64_t e = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (e >= rows * n_sample) return;
+    int64_t row = e / n_sample;
+    uint32_t t = uint32_t(e % n_sample);
+    int bits = 2;
+    while ((int64_t(1) << bits) < N) bits += 2;   // even number of bits
+    const int half = bits / 2;
+    const uint32_t hmask = (1u << half) - 1u;
+    uint32_t key0 = mix32(uint32_t(seed) ^ mix32(uint32_t(seed >> 32) + 0x9e3779b9U));
+    key0 = mix32(key0 ^ uint32_t(stream_id) * 0x85ebca6bU);
+    key0 = mix32(key0 ^ uint32_t(row) * 0xc2b2ae35U ^ uint32_t(uint64_t(row) >> 32));
+    uint32_t v = t;
+    do {
+        uint32_t L = v >> half, R = v & hmask;
+#pragma unroll
+        for (int round = 0; round < 4; round++) {
+            uint32_t f = mix32(R ^ key0 ^ (0x9e3779b9U * uint32_t(round + 1))) & hmask;
+            uint32_t nl = R, nr = L ^ f;
+            L = nl; R = nr;
+        }
+        v = (L << half) | R;
+    } while (int64_t(v) >= N);
+    idx[e] = int32_t(v);
+}
+
+size_t solve_smem_bytes(int k, int nthreads, bool w_in_smem) {
+    int nwarps = nthreads / 32;
+    size_t b = sizeof(double) * (size_t(2) * k + size_t(nwarps) * k) + 2 * sizeof(SolveShared);
+    b = (b + 15) & ~size_t(15);
+    if (w_in_smem) b += sizeof(double) * size_t(k) * k;
+    return b + 16;
+}
+
+template <typename T, int MODE>
+void launch_solve(pycmf_ctx* ctx, int64_t batch, int64_t k, const T* H, int64_t h_stride, const T* g, T* out,
+                  double l1, double l2, double l2_diag, double pert, bool non_negative) {
+    if (batch <= 0) return;
+    PYCMF_CHECK(k >= 1 && k <= 256, "n_components must be in [1, 256] for the Newton solve");
+    PYCMF_CHECK(pert > 0.0, "hessian_pertubation must be > 0");
+    int nthreads = k <= 32 ? 64 : (k <= 64 ? 128 : 256);
+    bool w_in_smem = solve_smem_bytes(int(k), nthreads, true) <= size_t(ctx->max_smem_optin);
+    size_t smem = solve_smem_bytes(int(k), nthreads, w_in_smem);
+    auto kern = safe_solve_kernel<T, MODE>;
+    PYCMF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    int64_t grid = batch;
+    double* Wg = nullptr;
+    if (!w_in_smem) {
+        grid = std::min<int64_t>(batch, 2 * ctx->num_sms);
+        Wg = static_cast<double*>(scratch(ctx, 2, size_t(grid) * k * k * sizeof(double)));
+    } else {
+        grid = std::min<int64_t>(batch, int64_t(1) << 30);
+    }
+    kern<<<(unsigned)grid, nthreads, smem, ctx->stream>>>(batch, int(k), H, h_stride, g, out, l1, l2, l2_diag,
+                                                         pert, non_negative, ctx->chol_fastpath != 0, Wg);
+    PYCMF_LAUNCH_CHECK(ctx);
+}
+
+}  // namespace
+
+template <typename T>
+void row_grad_hess(pycmf_ctx* ctx, int64_t rows, int64_t m, int64_t k, const T* A, const T* B,
+                   const T* Tgt, int64_t ldt, bool trans_t,
+                   const int32_t* rowptr, const int32_t* colidx, const T* vals,
+                   int link, double w, const int32_t* idx, int64_t n_sample,
+                   T* g, T* H, bool accumulate) {
+    if (rows <= 0) return;
+    PYCMF_CHECK(k >= 1 && k <= 256, "n_components must be in [1, 256] for the per-row Newton kernels");
+    size_t smem = sizeof(T) * (size_t((k + 3) & ~3) + size_t(TJ) * (k + 1) + 2 * TJ);
+    int hb = k <= 16 ? 1 : (k <= 32 ? 2 : (k <= 64 ? 4 : 8));
+    int quads = k > 128 ? 2 : 1;
+    for (int qa = 0; qa < quads; qa++) {
+        for (int qb = 0; qb < quads; qb++) {
+            bool first = (qa == 0 && qb == 0);
+            T* gq = first ? g : nullptr;
+            if (!first && H == nullptr) continue;
+#define LAUNCH(HB)                                                                                        \
+    do {                                                                                                  \
+        auto kern = row_grad_hess_kernel<T, HB>;                                                          \
+        PYCMF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));   \
+        kern<<<(unsigned)rows, 256, smem, ctx->stream>>>(rows, m, int(k), A, B, Tgt, ldt, trans_t, rowptr, \
+                                                         colidx, vals, link, T(w), idx, n_sample, gq, H,  \
+                                                         accumulate, qa * 128, qb * 128);                 \
+    } while (0)
+            if (hb == 1) LAUNCH(1);
+            else if (hb == 2) LAUNCH(2);
+            else if (hb == 4) LAUNCH(4);
+            else LAUNCH(8);
+#undef LAUNCH
+            PYCMF_LAUNCH_CHECK(ctx);
+        }
+    }
+}
+
+void safe_solve_f64(pycmf_ctx* ctx, int64_t batch, int64_t k, const double* H, int64_t h_stride,
+                    const double* g, double* x, double pert) {
+    launch_solve<double, 0>(ctx, batch, k, H, h_stride, g, x, 0.0, 0.0, 0.0, pert, false);
+}
+
+template <typename T>
+void newton_solve_rows(pycmf_ctx* ctx, int64_t rows, int64_t k, T* F, const T* g, const T* H, int64_t h_stride,
+                       double l1, double l2, double l2_diag, double pert, bool non_negative) {
+    if (rows <= 0) return;
+    if (h_stride != 0) {
+        launch_solve<T, 1>(ctx, rows, k, H, h_stride, g, F, l1, l2, l2_diag, pert, non_negative);
+        return;
+    }
+    // shared Hessian: invert once (k unit right-hand sides), then one small GEMM-like pass over the rows
+    double* buf = static_cast<double*>(scratch(ctx, 3, sizeof(double) * size_t(3) * k * k));
+    double *H64 = buf, *I64 = buf + k * k, *Hinv = buf + 2 * k * k;
+    int64_t n = k * k;
+    cast_to_f64_kernel<T><<<(unsigned)ceil_div(n, 256), 256, 0, ctx->stream>>>(n, H, H64);
+    PYCMF_LAUNCH_CHECK(ctx);
+    identity_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, ctx->stream>>>(int(k), I64);
+    PYCMF_LAUNCH_CHECK(ctx);
+    // column c of Hinv = S(H + l2_diag I) e_c ; S symmetric, so rows of the result are its columns
+    launch_solve<double, 0>(ctx, k, k, H64, 0, I64, Hinv, 0.0, 0.0, l2_diag, pert, false);
+    size_t smem = sizeof(double) * size_t(8) * k;
+    auto kern = apply_shared_inverse_kernel<T>;
+    kern<<<(unsigned)ceil_div(rows, 8), 256, smem, ctx->stream>>>(rows, int(k), F, g, Hinv, l1, l2, non_negative);
+    PYCMF_LAUNCH_CHECK(ctx);
+}
+
+void sample_indices(pycmf_ctx* ctx, int64_t rows, int64_t N, int64_t n_sample, uint64_t seed,
+                    uint64_t stream_id, int32_t* idx) {
+    int64_t n = rows * n_sample;
+    if (n <= 0) return;
+    PYCMF_CHECK(n_sample <= N, "cannot sample more indices than the population");
+    PYCMF_CHECK(N < (int64_t(1) << 31), "population too large for int32 indices");
+    sample_indices_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, ctx->stream>>>(rows, N, n_sample, seed, stream_id, idx);
+    PYCMF_LAUNCH_CHECK(ctx);
+}
+
+#define INSTANTIATE(T)                                                                                          \
+    template void row_grad_hess<T>(pycmf_ctx*, int64_t, int64_t, int64_t, const T*, const T*, const T*, int64_t, \
+                                   bool, const int32_t*, const int32_t*, const T*, int, double, const int32_t*, \
+                                   int64_t, T*, T*, bool);                                                      \
+    template void newton_solve_rows<T>(pycmf_ctx*, int64_t, int64_t, T*, const T*, const T*, int64_t, double,   \
+                                       double, double, double, bool);
+INSTANTIATE(float)
+INSTANTIATE(double)
+
+}  // namespace pycmf

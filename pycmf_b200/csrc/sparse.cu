@@ -1,0 +1,139 @@
+// CSR kernels: SpMM (C = alpha * S * B + beta * C) and SDDMM-style reductions over the nonzeros.
+// Warp-per-row; the nonzeros of a row are fetched coalesced (lane-strided) and broadcast by
+// shuffle; sub-warp groups of G lanes walk different nonzeros when k < 32 so no lane idles.
+#include "common.cuh"
+
+namespace pycmf {
+namespace {
+
+constexpr int MAXT = 8;  // columns per lane: k <= 32 * MAXT = 256
+
+template <typename T, int G>
+__global__ void __launch_bounds__(256)
+spmm_kernel(int64_t rows, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx,
+            const T* __restrict__ vals, const T* __restrict__ B, int64_t ldb, int k,
+            T* __restrict__ C, int64_t ldc, T alpha, T beta) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    if (row >= rows) return;
+    constexpr int NG = 32 / G;            // nonzeros in flight per warp
+    const int gl = lane % G, gid = lane / G;
+    T acc[MAXT];
+#pragma unroll
+    for (int t = 0; t < MAXT; t++) acc[t] = T(0);
+    const int start = rowptr[row], end = rowptr[row + 1];
+    for (int base = start; base < end; base += 32) {
+        int cnt = min(32, end - base);
+        int c = 0; T v = T(0);
+        if (lane < cnt) { c = colidx[base + lane]; v = vals[base + lane]; }
+        for (int j = 0; j < cnt; j += NG) {
+            int src = j + gid;
+            int cj = __shfl_sync(0xffffffffu, c, src & 31);
+            T vj = __shfl_sync(0xffffffffu, v, src & 31);
+            if (src < cnt) {
+                const T* brow = B + int64_t(cj) * ldb;
+#pragma unroll
+                for (int t = 0; t < MAXT; t++) {
+                    int col = gl + t * G;
+                    if (col < k) acc[t] = fma(vj, brow[col], acc[t]);
+                }
+            }
+        }
+    }
+    // reduce across the NG groups
+#pragma unroll
+    for (int t = 0; t < MAXT; t++) {
+#pragma unroll
+        for (int o = 16; o >= G; o >>= 1) acc[t] += __shfl_xor_sync(0xffffffffu, acc[t], o);
+    }
+    if (gid == 0) {
+#pragma unroll
+        for (int t = 0; t < MAXT; t++) {
+            int col = gl + t * G;
+            if (col < k) {
+                T prev = beta != T(0) ? C[row * ldc + col] : T(0);
+                C[row * ldc + col] = alpha * acc[t] + beta * prev;
+            }
+        }
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+sddmm_reduce_kernel(int mode, int64_t rows, const int32_t* __restrict__ rowptr,
+                    const int32_t* __restrict__ colidx, const T* __restrict__ vals,
+                    const T* __restrict__ A, const T* __restrict__ B, int k, double* __restrict__ part) {
+    __shared__ double red[32];
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = (int64_t(gridDim.x) * blockDim.x) >> 5;
+    double s = 0.0;
+    for (int64_t row = warp0; row < rows; row += nwarps) {
+        const int start = rowptr[row], end = rowptr[row + 1];
+        if (mode == 2) {
+            for (int e = start + lane; e < end; e += 32) { double v = double(vals[e]); s += v * v; }
+            continue;
+        }
+        T a[MAXT];
+#pragma unroll
+        for (int t = 0; t < MAXT; t++) { int col = lane + 32 * t; a[t] = col < k ? A[row * k + col] : T(0); }
+        for (int e = start; e < end; e++) {
+            const T* brow = B + int64_t(colidx[e]) * k;
+            T d = T(0);
+#pragma unroll
+            for (int t = 0; t < MAXT; t++) { int col = lane + 32 * t; if (col < k) d = fma(a[t], brow[col], d); }
+            d = warp_sum(d);
+            if (lane == 0) {
+                double x = double(vals[e]);
+                if (mode == 0) {
+                    s += x * double(d);
+                } else {
+                    double sg = 1.0 / (1.0 + exp(-double(d)));
+                    s += (x - sg) * (x - sg) - sg * sg;
+                }
+            }
+        }
+    }
+    s = block_sum(s, red);
+    if (threadIdx.x == 0) part[blockIdx.x] = s;
+}
+
+}  // namespace
+
+template <typename T>
+void spmm(pycmf_ctx* ctx, int64_t rows, const int32_t* rowptr, const int32_t* colidx, const T* vals,
+          const T* B, int64_t ldb, int64_t k, T* C, int64_t ldc, T alpha, T beta) {
+    if (rows <= 0 || k <= 0) return;
+    PYCMF_CHECK(k <= 32 * MAXT, "spmm: n_components > 256 is not supported");
+    unsigned blocks = (unsigned)ceil_div(rows * 32, 256);
+#define LAUNCH(G) spmm_kernel<T, G><<<blocks, 256, 0, ctx->stream>>>(rows, rowptr, colidx, vals, B, ldb, int(k), C, ldc, alpha, beta)
+    if (k <= 1) LAUNCH(1);
+    else if (k <= 2) LAUNCH(2);
+    else if (k <= 4) LAUNCH(4);
+    else if (k <= 8) LAUNCH(8);
+    else if (k <= 16) LAUNCH(16);
+    else LAUNCH(32);
+#undef LAUNCH
+    PYCMF_LAUNCH_CHECK(ctx);
+}
+
+template <typename T>
+void sddmm_reduce(pycmf_ctx* ctx, int mode, int64_t rows, const int32_t* rowptr, const int32_t* colidx,
+                  const T* vals, const T* A, const T* B, int64_t k, double scale, double* out) {
+    PYCMF_CHECK(k <= 32 * MAXT, "sddmm: n_components > 256 is not supported");
+    int blocks = int(std::max<int64_t>(1, std::min<int64_t>(ceil_div(std::max<int64_t>(rows, 1), 8), 8 * ctx->num_sms)));
+    double* part = static_cast<double*>(scratch(ctx, 1, size_t(blocks) * sizeof(double)));
+    sddmm_reduce_kernel<T><<<blocks, 256, 0, ctx->stream>>>(mode, rows, rowptr, colidx, vals, A, B, int(k), part);
+    PYCMF_LAUNCH_CHECK(ctx);
+    final_sum(ctx, blocks, part, scale, out, true);
+}
+
+#define INSTANTIATE(T)                                                                                        \
+    template void spmm<T>(pycmf_ctx*, int64_t, const int32_t*, const int32_t*, const T*, const T*, int64_t,   \
+                          int64_t, T*, int64_t, T, T);                                                        \
+    template void sddmm_reduce<T>(pycmf_ctx*, int, int64_t, const int32_t*, const int32_t*, const T*,         \
+                                  const T*, const T*, int64_t, double, double*);
+INSTANTIATE(float)
+INSTANTIATE(double)
+
+}  // namespace pycmf

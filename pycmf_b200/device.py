@@ -1,0 +1,307 @@
+"""Device side of the fit loop: ingest of X / Y into HBM and the CUDA backend object.
+
+`CudaBackend` is a thin, typed veneer over the C ABI (include/pycmf_b200.h): every method maps to one
+entry point and passes torch-owned device pointers.  torch is used for device memory, streams and
+(in sharding.py) torch.distributed only.
+"""
+import ctypes as C
+
+import numpy as np
+import scipy.sparse as sp
+
+from . import _lib
+
+_NP2CODE = {np.dtype("float32"): _lib.F32, np.dtype("float64"): _lib.F64}
+LINKS = {"linear": _lib.LINEAR, "logit": _lib.LOGIT}
+
+
+def link_code(link):
+    """Reference strings -> ABI codes; same error as cmf_solvers.py:33."""
+    try:
+        return LINKS[link]
+    except KeyError:
+        raise ValueError("Invalid link function {}".format(link))
+
+
+class DenseMatrix:
+    """Row-major dense matrix in HBM (rows x cols)."""
+    is_sparse = False
+
+    def __init__(self, tensor):
+        self.t = tensor
+        self.shape = tuple(tensor.shape)
+
+
+class SparseMatrix:
+    """CSR (row access) + CSC (column access) copies of one matrix in HBM, int32 indices, sorted.
+
+    The CSC arrays are the CSR arrays of the transpose: the MU V update (X^T U, cmf_solvers.py:244)
+    and the Newton V update (column j of X, :459) read them.
+    """
+    is_sparse = True
+
+    def __init__(self, shape, rowptr, colidx, vals, colptr, rowidx, cvals):
+        self.shape = tuple(shape)
+        self.rowptr, self.colidx, self.vals = rowptr, colidx, vals
+        self.colptr, self.rowidx, self.cvals = colptr, rowidx, cvals
+        self.nnz = int(vals.shape[0])
+
+
+def _ptr(t):
+    return 0 if t is None else t.data_ptr()
+
+
+class CudaBackend:
+    """One context (= one rank, one GPU, one stream)."""
+
+    def __init__(self, device=None, dtype="float32", options=None):
+        import torch
+        self.torch = torch
+        self.lib = _lib.load()
+        if not torch.cuda.is_available():
+            raise _lib.BackendError("pycmf_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        if device is None:
+            device = torch.cuda.current_device()
+        self.device = torch.device("cuda", device if isinstance(device, int) else torch.device(device).index or 0)
+        self.np_dtype = np.dtype(dtype)
+        if self.np_dtype not in _NP2CODE:
+            raise ValueError("dtype must be float32 or float64, got %r" % (dtype,))
+        self.code = _NP2CODE[self.np_dtype]
+        self.tdtype = torch.float32 if self.code == _lib.F32 else torch.float64
+        handle = C.c_void_p()
+        _lib.check(self.lib.pycmf_create(self.device.index, C.byref(handle)))
+        self.ctx = handle
+        self.use_stream(torch.cuda.current_stream(self.device))
+        for key, val in (options or {}).items():
+            self.set_option(key, val)
+
+    # ---- lifecycle ---------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "ctx", None) is not None:
+            self.lib.pycmf_destroy(self.ctx)
+            self.ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def use_stream(self, stream):
+        self.stream = stream
+        _lib.check(self.lib.pycmf_set_stream(self.ctx, C.c_void_p(stream.cuda_stream)))
+
+    def set_option(self, key, value):
+        _lib.check(self.lib.pycmf_set_option(self.ctx, key.encode(), float(value)))
+
+    def launch_count(self):
+        return int(self.lib.pycmf_launch_count(self.ctx))
+
+    def synchronize(self):
+        self.torch.cuda.synchronize(self.device)
+
+    # ---- memory ------------------------------------------------------------------------------
+    def empty(self, *shape, dtype=None):
+        return self.torch.empty(*shape, dtype=dtype or self.tdtype, device=self.device)
+
+    def zeros(self, *shape, dtype=None):
+        return self.torch.zeros(*shape, dtype=dtype or self.tdtype, device=self.device)
+
+    def to_device(self, a, dtype=None, pinned=False):
+        """Host ndarray -> contiguous device tensor of the compute dtype."""
+        torch = self.torch
+        a = np.ascontiguousarray(a, dtype=self.np_dtype if dtype is None else dtype)
+        t = torch.from_numpy(a)
+        if pinned:
+            t = t.pin_memory()
+        return t.to(self.device, non_blocking=pinned)
+
+    def to_host(self, t):
+        return t.detach().to("cpu").numpy()
+
+    def ingest(self, M):
+        """Host matrix (ndarray / scipy sparse) -> DenseMatrix or SparseMatrix in HBM.
+        Replaces check_array(..., accept_sparse=('csr','csc'), dtype=float) of cmf.py:386-388."""
+        if isinstance(M, (DenseMatrix, SparseMatrix)):
+            return M
+        if sp.issparse(M):
+            csr = sp.csr_matrix(M, dtype=self.np_dtype)
+            csr.sum_duplicates()
+            csr.sort_indices()
+            if csr.nnz >= 2 ** 31 or max(csr.shape) >= 2 ** 31:
+                raise ValueError("sparse matrix too large for int32 indices")
+            csc = csr.T.tocsr()
+            csc.sort_indices()
+            i32 = self.torch.int32
+            return SparseMatrix(
+                csr.shape,
+                self.to_device(csr.indptr, np.int32), self.to_device(csr.indices, np.int32), self.to_device(csr.data),
+                self.to_device(csc.indptr, np.int32), self.to_device(csc.indices, np.int32), self.to_device(csc.data))
+        M = np.asarray(M)
+        if M.ndim != 2:
+            raise ValueError("Expected 2D array, got %dD array instead" % M.ndim)
+        return DenseMatrix(self.to_device(M))
+
+    def row_slice(self, M, r0, r1):
+        """Rows [r0, r1) of an ingested matrix (view for dense, re-based copy for sparse)."""
+        if not M.is_sparse:
+            return DenseMatrix(M.t[r0:r1])
+        torch = self.torch
+        rp = M.rowptr[r0:r1 + 1].clone()
+        lo, hi = int(rp[0]), int(rp[-1])
+        rp -= lo
+        colidx, vals = M.colidx[lo:hi].clone(), M.vals[lo:hi].clone()
+        # CSC of the slice, built on device by a stable sort on the column index
+        rows_of = torch.repeat_interleave(torch.arange(r1 - r0, device=self.device, dtype=torch.int32),
+                                          (rp[1:] - rp[:-1]).to(torch.int64))
+        order = torch.sort(colidx.to(torch.int64), stable=True).indices
+        counts = torch.bincount(colidx.to(torch.int64), minlength=M.shape[1])
+        colptr = torch.zeros(M.shape[1] + 1, dtype=torch.int32, device=self.device)
+        colptr[1:] = torch.cumsum(counts, 0).to(torch.int32)
+        return SparseMatrix((r1 - r0, M.shape[1]), rp, colidx, vals, colptr, rows_of[order].contiguous(),
+                            vals[order].contiguous())
+
+    # ---- target argument packing ---------------------------------------------------------------
+    def _target_args(self, T, trans=False, rows=None):
+        """(dense ptr, ld, trans, rowptr, colidx, vals) for a left-factor target."""
+        if T.is_sparse:
+            if trans:
+                return 0, 0, 0, _ptr(T.colptr), _ptr(T.rowidx), _ptr(T.cvals)
+            return 0, 0, 0, _ptr(T.rowptr), _ptr(T.colidx), _ptr(T.vals)
+        t = T.t
+        assert t.stride(1) == 1
+        return t.data_ptr(), t.stride(0), int(bool(trans)), 0, 0, 0
+
+    # ---- objective -----------------------------------------------------------------------------
+    def sqerr(self, A, B, T, link, trans=False):
+        """sum (T - f(A B^T))^2 as a 0-d float64 device tensor (cmf_solvers.py:36-42)."""
+        out = self.zeros(1, dtype=self.torch.float64)
+        rows, k = A.shape
+        m = B.shape[0]
+        tp, ld, tr, rp, ci, vl = self._target_args(T, trans)
+        _lib.check(self.lib.pycmf_sqerr(self.ctx, self.code, rows, m, k, _ptr(A), _ptr(B), tp, ld, tr, rp, ci, vl,
+                                        link_code(link), _ptr(out)))
+        return out
+
+    # ---- MU ------------------------------------------------------------------------------------
+    def mu_v_partial(self, X, U, out=None):
+        n, k = U.shape
+        d = X.shape[1]
+        if out is None:
+            out = self.empty(d + k, k)
+        if X.is_sparse:
+            args = (0, 0, _ptr(X.colptr), _ptr(X.rowidx), _ptr(X.cvals))
+        else:
+            args = (X.t.data_ptr(), X.t.stride(0), 0, 0, 0)
+        _lib.check(self.lib.pycmf_mu_v_partial(self.ctx, self.code, n, d, k, *args, _ptr(U), _ptr(out)))
+        return out
+
+    def mu_v_apply(self, V, buf, Y, Z, l1, l2):
+        d, k = V.shape
+        l = Z.shape[0]
+        _lib.check(self.lib.pycmf_mu_v_apply(self.ctx, self.code, d, l, k, _ptr(V), _ptr(buf), Y.t.data_ptr(),
+                                             Y.t.stride(0), _ptr(Z), float(l1), float(l2)))
+
+    def mu_left(self, F, B, T, l1, l2, trans=False):
+        rows, k = F.shape
+        m = B.shape[0]
+        tp, ld, tr, rp, ci, vl = self._target_args(T, trans)
+        _lib.check(self.lib.pycmf_mu_left(self.ctx, self.code, rows, m, k, _ptr(F), _ptr(B), tp, ld, tr, rp, ci, vl,
+                                          float(l1), float(l2)))
+
+    # ---- Newton --------------------------------------------------------------------------------
+    def _idx_args(self, idx):
+        if idx is None:
+            return 0, 0
+        assert idx.dtype == self.torch.int32 and idx.is_contiguous()
+        n_sample = int(idx.shape[1])
+        # a non-NULL pointer is required even for an empty sample set (n_sample == 0 kills the data term)
+        return (idx.data_ptr() if n_sample > 0 else self._dummy().data_ptr()), n_sample
+
+    def _dummy(self):
+        if not hasattr(self, "_dummy_t"):
+            self._dummy_t = self.zeros(4, dtype=self.torch.int32)
+        return self._dummy_t
+
+    def newton_left(self, F, B, T, weight, l1, l2, link, non_negative, pert, l2_in_logit_hessian,
+                    idx=None, trans=False):
+        rows, k = F.shape
+        m = B.shape[0]
+        tp, ld, tr, rp, ci, vl = self._target_args(T, trans)
+        ip, ns = self._idx_args(idx)
+        _lib.check(self.lib.pycmf_newton_left(self.ctx, self.code, rows, m, k, _ptr(F), _ptr(B), tp, ld, tr, rp, ci, vl,
+                                              float(weight), float(l1), float(l2), link_code(link),
+                                              int(bool(non_negative)), float(pert), int(bool(l2_in_logit_hessian)),
+                                              ip, ns))
+
+    def newton_v_needs_per_row(self, x_link, sampled):
+        return bool(sampled) or x_link == "logit"
+
+    def newton_v_xpart(self, V, U, X, j0, j1, x_link, alpha, idx=None):
+        """X part of the V update for V rows [j0, j1): returns (gx, Hx, per_row)."""
+        n, k = U.shape
+        rows = j1 - j0
+        per_row = self.newton_v_needs_per_row(x_link, idx is not None)
+        gx = self.empty(rows, k)
+        Hx = self.empty(rows if per_row else 1, k, k)
+        if X.is_sparse:
+            xargs = (0, 0, X.colptr[j0:].data_ptr(), _ptr(X.rowidx), _ptr(X.cvals))
+        else:
+            xargs = (X.t[:, j0:].data_ptr(), X.t.stride(0), 0, 0, 0)
+        ip, ns = self._idx_args(idx)
+        flag = C.c_int(0)
+        _lib.check(self.lib.pycmf_newton_v_xpart(self.ctx, self.code, rows, n, k, V[j0:j1].data_ptr(), _ptr(U), *xargs,
+                                                 link_code(x_link), float(alpha), ip, ns, _ptr(gx), _ptr(Hx),
+                                                 C.byref(flag)))
+        assert bool(flag.value) == per_row
+        return gx, Hx, per_row
+
+    def newton_v_finish(self, V, Z, Y, j0, j1, y_link, alpha, l1, l2, gx, Hx, per_row, non_negative, pert, idx=None):
+        k = V.shape[1]
+        l = Z.shape[0]
+        ip, ns = self._idx_args(idx)
+        _lib.check(self.lib.pycmf_newton_v_finish(self.ctx, self.code, j1 - j0, l, k, V[j0:j1].data_ptr(), _ptr(Z),
+                                                  Y.t[j0:j1].data_ptr(), Y.t.stride(0), link_code(y_link), float(alpha),
+                                                  float(l1), float(l2), ip, ns, _ptr(gx), _ptr(Hx), int(per_row),
+                                                  int(bool(non_negative)), float(pert)))
+
+    def v_chunk_rows(self, d, k, per_row, budget_bytes=1 << 30):
+        if not per_row:
+            return d
+        return max(1, min(d, budget_bytes // (k * k * self.np_dtype.itemsize)))
+
+    # ---- utilities -----------------------------------------------------------------------------
+    def safe_solve(self, H, g, pert):
+        """x = S(H) g for float64 tensors H (batch x k x k or k x k shared) and g (batch x k)."""
+        batch, k = g.shape
+        x = self.empty(batch, k, dtype=self.torch.float64)
+        stride = 0 if H.dim() == 2 else k * k
+        _lib.check(self.lib.pycmf_safe_solve(self.ctx, batch, k, _ptr(H), stride, _ptr(g), _ptr(x), float(pert)))
+        return x
+
+    def sample_indices(self, rows, N, n_sample, seed, stream_id):
+        idx = self.empty(rows, n_sample, dtype=self.torch.int32)
+        _lib.check(self.lib.pycmf_sample_indices(self.ctx, rows, N, n_sample, int(seed) & (2 ** 64 - 1),
+                                                 int(stream_id), _ptr(idx)))
+        return idx
+
+    def gemm(self, A, B, trans_a=False, alpha=1.0, beta=0.0, out=None):
+        m = A.shape[1] if trans_a else A.shape[0]
+        p = A.shape[0] if trans_a else A.shape[1]
+        q = B.shape[1]
+        if out is None:
+            out = self.zeros(m, q)
+        _lib.check(self.lib.pycmf_gemm(self.ctx, self.code, int(trans_a), m, q, p, _ptr(A), A.stride(0), _ptr(B),
+                                       B.stride(0), _ptr(out), out.stride(0), float(alpha), float(beta)))
+        return out
+
+    def spmm(self, S, B, transposed=False, alpha=1.0, beta=0.0, out=None):
+        rows = S.shape[1] if transposed else S.shape[0]
+        k = B.shape[1]
+        if out is None:
+            out = self.zeros(rows, k)
+        rp, ci, vl = (S.colptr, S.rowidx, S.cvals) if transposed else (S.rowptr, S.colidx, S.vals)
+        _lib.check(self.lib.pycmf_spmm(self.ctx, self.code, rows, S.shape[0] if transposed else S.shape[1],
+                                       _ptr(rp), _ptr(ci), _ptr(vl), _ptr(B), B.stride(0), k, _ptr(out),
+                                       out.stride(0), float(alpha), float(beta)))
+        return out

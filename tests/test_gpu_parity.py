@@ -1,0 +1,201 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the reference-generated golden
+fixtures and the CPU oracle.  Tolerances are north_star's: fp32 objective 1e-4 rel / factors 1e-3
+rel Frobenius; fp64 1e-9 for both."""
+import zlib
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from helpers import CASES, draw_masks_for_case, load_golden, rel_fro, run_oracle
+from oracle import cmf_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+TOL = {"float32": (1e-4, 1e-3), "float64": (1e-9, 1e-9)}
+
+
+def run_ours(case, dtype, masks=None, **extra):
+    from pycmf_b200.cmf_solvers import MUSolver, NewtonSolver
+    p = dict(case["params"])
+    solver = p.pop("solver")
+    cls = MUSolver if solver == "mu" else NewtonSolver
+    s = cls(max_iter=case["iters"], tol=0, random_state=case["rng_seed"], dtype=dtype, **p, **extra)
+    s.history = []
+    s.masks_per_iter = masks
+    U, V, Z = case["U0"].copy(), case["V0"].copy(), case["Z0"].copy()
+    e0 = s.compute_error(case["X"], case["Y"], U, V, Z)
+    U2, V2, Z2, n_iter = s.fit_iterative_update(case["X"], case["Y"], U, V, Z)
+    assert U2 is U and V2 is V and Z2 is Z and n_iter == case["iters"]
+    return np.asarray([e0] + s.history), U, V, Z
+
+
+def assert_parity(hist, U, V, Z, ref_hist, rU, rV, rZ, dtype):
+    otol, ftol = TOL[dtype]
+    rel = np.abs(hist - ref_hist) / np.abs(ref_hist)
+    assert rel.max() < otol, "objective rel err %.3e at iter %d" % (rel.max(), rel.argmax())
+    for name, got, ref in (("U", U, rU), ("V", V, rV), ("Z", Z, rZ)):
+        assert rel_fro(got, ref) < ftol, "%s rel fro %.3e" % (name, rel_fro(got, ref))
+
+
+@pytest.mark.parametrize("dtype", ["float64", "float32"])
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_golden_parity(name, dtype):
+    case, g = load_golden(name)
+    masks = draw_masks_for_case(case)
+    hist, U, V, Z = run_ours(case, dtype, masks)
+    assert_parity(hist, U, V, Z, g["objective"], g["U"], g["V"], g["Z"], dtype)
+
+
+@pytest.mark.parametrize("name", ["nt_logit_logit", "nt_noreg_clamp", "nt_lin_logit"])
+def test_jacobi_only_matches_cholesky_fastpath(name):
+    case, g = load_golden(name)
+    hist, U, V, Z = run_ours(case, "float64", backend_options={"chol_fastpath": 0})
+    assert_parity(hist, U, V, Z, g["objective"], g["U"], g["V"], g["Z"], "float64")
+
+
+def _mid_case(solver, n, d, l, k, sparse, seed, **params):
+    rng = np.random.RandomState(seed)
+    Ut, Vt, Zt = 0.6 * np.abs(rng.randn(n, k)), 0.6 * np.abs(rng.randn(d, k)), 0.6 * rng.randn(l, k)
+    x_logit = params.get("x_link") == "logit"
+    X = O.expit(Ut @ Vt.T - 1.0) if x_logit else Ut @ Vt.T + 0.05 * np.abs(rng.randn(n, d))
+    if sparse:
+        X = sp.csr_matrix(X * (rng.rand(n, d) < 0.05))
+    Y = O.expit(Vt @ Zt.T) if params.get("y_link") == "logit" else np.abs(Vt @ Zt.T)
+    sx, sy = np.sqrt(np.abs(X.mean()) / k), np.sqrt(np.abs(Y.mean()) / k)
+    U0, V0 = sx * np.abs(rng.randn(n, k)), (sx * np.abs(rng.randn(d, k)) + sy * np.abs(rng.randn(d, k))) / 2
+    Z0 = sy * rng.randn(l, k) if params.get("Z_non_negative") is False else sy * np.abs(rng.randn(l, k))
+    return dict(X=X, Y=Y, U0=U0, V0=V0, Z0=Z0, params=dict(solver=solver, **params), iters=params.pop("iters", 8),
+                rng_seed=seed)
+
+
+NT = dict(alpha=0.4, l1_reg=0.01, l2_reg=0.1, Z_non_negative=False)
+MID = {
+    "mu_dense_k32": ("mu", 700, 300, 12, 32, False, dict(l1_reg=0.01, l2_reg=0.01)),
+    "mu_csr_k64": ("mu", 900, 400, 6, 64, True, dict()),
+    "mu_dense_k130": ("mu", 300, 280, 9, 130, False, dict()),
+    "mu_dense_k256": ("mu", 520, 300, 5, 256, False, dict()),
+    "nt_lin_logit_k32": ("newton", 600, 250, 10, 32, False, dict(NT, y_link="logit")),
+    "nt_logit_logit_k16": ("newton", 300, 200, 6, 16, False, dict(NT, x_link="logit", y_link="logit")),
+    "nt_csr_lin_lin_k24": ("newton", 500, 300, 6, 24, True, dict(NT)),
+    "nt_csr_logit_logit_k20": ("newton", 260, 180, 5, 20, True, dict(NT, x_link="logit", y_link="logit")),
+    "nt_lin_lin_k130": ("newton", 400, 300, 8, 130, False, dict(NT)),
+    "nt_logit_lin_k72": ("newton", 150, 140, 4, 72, False, dict(NT, x_link="logit")),
+}
+
+
+@pytest.mark.parametrize("dtype", ["float64", "float32"])
+@pytest.mark.parametrize("name", sorted(MID))
+def test_midsize_parity_vs_oracle(name, dtype):
+    solver, n, d, l, k, sparse, params = MID[name]
+    case = _mid_case(solver, n, d, l, k, sparse, seed=zlib.crc32(name.encode()) % 1000, **params)
+    case["iters"] = 6
+    ref_hist, rU, rV, rZ = run_oracle(case)
+    hist, U, V, Z = run_ours(case, dtype)
+    assert_parity(hist, U, V, Z, ref_hist, rU, rV, rZ, dtype)
+
+
+@pytest.mark.parametrize("dtype", ["float64", "float32"])
+def test_sampled_midsize_parity(dtype):
+    case = _mid_case("newton", 120, 90, 7, 12, False, seed=5, **dict(NT, x_link="logit", y_link="logit",
+                                                                      sg_sample_ratio=0.4))
+    case["iters"] = 4
+    masks = draw_masks_for_case(case)
+    ref_hist, rU, rV, rZ = run_oracle(case, masks_per_iter=masks)
+    hist, U, V, Z = run_ours(case, dtype, masks)
+    assert_parity(hist, U, V, Z, ref_hist, rU, rV, rZ, dtype)
+
+
+# ---- primitives ---------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def be64():
+    from pycmf_b200.device import CudaBackend
+    return CudaBackend(dtype="float64")
+
+
+@pytest.mark.parametrize("shape", [(1, 1, 1), (70, 33, 129), (5, 300, 4000), (257, 64, 64)])
+@pytest.mark.parametrize("trans", [False, True])
+def test_gemm(be64, shape, trans):
+    m, q, p = shape
+    rng = np.random.RandomState(0)
+    A = rng.randn(p, m) if trans else rng.randn(m, p)
+    B = rng.randn(p, q)
+    got = be64.to_host(be64.gemm(be64.to_device(A), be64.to_device(B), trans_a=trans))
+    ref = (A.T if trans else A) @ B
+    assert np.allclose(got, ref, rtol=1e-11, atol=1e-11)
+
+
+@pytest.mark.parametrize("k", [1, 3, 10, 32, 64, 100, 256])
+def test_spmm_and_transpose(be64, k):
+    rng = np.random.RandomState(k)
+    S = sp.random(200, 150, density=0.05, random_state=rng, format="csr")
+    S[7, :] = 0
+    S.eliminate_zeros()
+    Sd = be64.ingest(S)
+    B, A = rng.randn(150, k), rng.randn(200, k)
+    assert np.allclose(be64.to_host(be64.spmm(Sd, be64.to_device(B))), S @ B, atol=1e-12)
+    assert np.allclose(be64.to_host(be64.spmm(Sd, be64.to_device(A), transposed=True)), S.T @ A, atol=1e-12)
+
+
+@pytest.mark.parametrize("k", [1, 2, 7, 32, 33, 64, 128, 150])
+@pytest.mark.parametrize("chol", [0, 1])
+def test_safe_solve_matches_eigh_clamp(k, chol):
+    from pycmf_b200.device import CudaBackend
+    be = CudaBackend(dtype="float64", options={"chol_fastpath": chol})
+    rng = np.random.RandomState(k)
+    batch = 9
+    H = np.empty((batch, k, k))
+    for b in range(batch):
+        r = max(1, (b * k) // batch)                      # ranks from deficient to full
+        A = rng.randn(k, r)
+        H[b] = A @ A.T * (0.05 if b % 3 == 0 else 1.0)
+        if b == 4:
+            H[b] -= 0.7 * np.eye(k)                       # indefinite: abs() of negative eigenvalues
+        if b == 5:
+            H[b] += 3.0 * np.eye(k)                       # safely positive definite: Cholesky path
+    g = rng.randn(batch, k)
+    ref = np.einsum('bij,bj->bi', O.safe_invert(H, 0.2), g)
+    got = be.to_host(be.safe_solve(be.to_device(H), be.to_device(g), 0.2))
+    assert np.abs(got - ref).max() / np.abs(ref).max() < 1e-10
+
+
+def test_sqerr_dense_and_sparse(be64):
+    rng = np.random.RandomState(3)
+    A, B = rng.rand(90, 11), rng.rand(70, 11)
+    T = rng.rand(90, 70) * (rng.rand(90, 70) < 0.2)
+    for link in ("linear", "logit"):
+        ref = O.compute_factorization_error(T, A, B.T, link) ** 2
+        for tgt in (T, sp.csr_matrix(T)):
+            got = float(be64.to_host(be64.sqerr(be64.to_device(A), be64.to_device(B), be64.ingest(tgt), link))[0])
+            assert abs(got - ref) / ref < 1e-11
+
+
+def test_device_sampler_draws_distinct_in_range(be64):
+    idx = be64.to_host(be64.sample_indices(50, 1000, 300, seed=7, stream_id=3))
+    assert idx.min() >= 0 and idx.max() < 1000
+    assert all(len(set(r)) == 300 for r in idx)
+    idx2 = be64.to_host(be64.sample_indices(50, 1000, 300, seed=7, stream_id=4))
+    assert (idx != idx2).mean() > 0.9
+    # roughly uniform marginals
+    counts = np.bincount(idx.ravel(), minlength=1000)
+    assert counts.max() < 40 and counts.min() >= 2
+
+
+def test_cmf_api_end_to_end():
+    """The reference's own usage (tests/test_cmf.py:56-64, :271-291): CMF.fit_transform, dense == sparse."""
+    from pycmf_b200 import CMF
+    rng = np.random.mtrand.RandomState(42)
+    X = np.abs(rng.randn(10, 8))
+    X[:, 2 * np.arange(4)] = 0
+    Y = np.abs(rng.randn(8, 5))
+    for solver in ("mu", "newton"):
+        est1 = CMF(solver=solver, n_components=5, x_init='random', y_init='random', random_state=0, tol=1e-2,
+                   dtype="float64")
+        est2 = CMF(solver=solver, n_components=5, x_init='random', y_init='random', random_state=0, tol=1e-2,
+                   dtype="float64")
+        U1, V1, Z1 = est1.fit_transform(X, Y)
+        U2, V2, Z2 = est2.fit_transform(sp.csr_matrix(X), Y)
+        for a, b in ((U1, U2), (V1, V2), (Z1, Z2)):
+            np.testing.assert_array_almost_equal(a, b, decimal=6)
+        assert est1.reconstruction_err_ > 0 and est1.n_iter_ >= 1
+        assert not ((U1 < 0).any() or (V1 < 0).any() or (Z1 < 0).any())
