@@ -53,6 +53,13 @@ int pycmf_set_option(pycmf_ctx* ctx, const char* key, double value);
 /* number of kernels this context launched since creation (bench.py's gpu_launches) */
 int64_t pycmf_launch_count(pycmf_ctx* ctx);
 
+/* per-kernel-family device timers (bench.py's live roofline): enable, run, then query by family name
+ * ("resid_left", "resid_right", "gemm", "spmm", "row_grad_hess", "safe_solve", "tc_xv", "tc_xtu", ...).
+ * query synchronises the stream; total_ms / count cover everything since the last reset. */
+int pycmf_profile_enable(pycmf_ctx* ctx, int on);
+int pycmf_profile_query(pycmf_ctx* ctx, const char* family, double* total_ms, int64_t* count);
+int pycmf_profile_reset(pycmf_ctx* ctx);
+
 /* ---- primitives (used by the phases below; exported for tests and composition) ---------- */
 /* C (m x q) = alpha * op(A) * B + beta * C;  op(A) = A (m x p) or A^T with A stored (p x m).
  * Replaces np.dot / safe_sparse_dot on dense operands (cmf_solvers.py:232-245). */

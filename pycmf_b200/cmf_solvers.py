@@ -62,7 +62,8 @@ class _IterativeCMFSolver:
                  update_U=True, update_V=True, update_Z=True,
                  x_link="linear", y_link="linear", hessian_pertubation=0.2,
                  sg_sample_ratio=1., random_state=None,
-                 dtype="float32", device=None, comm=None, sampler="auto", backend=None, backend_options=None):
+                 dtype="float32", device=None, comm=None, sampler="auto", backend=None, backend_options=None,
+                 sharded_input=False):
         self.max_iter = max_iter
         self.tol = tol
         self.beta_loss = _beta_loss_to_float(beta_loss)
@@ -91,6 +92,7 @@ class _IterativeCMFSolver:
         self.sampler = sampler
         self.backend_options = backend_options
         self._backend = backend
+        self.sharded_input = sharded_input   # X / U handed in are already this rank's row block
         self.masks_per_iter = None     # test hook: list of per-iteration mask dicts (global indices)
         self.history = None            # test hook: list receiving the objective after every iteration
 
@@ -105,18 +107,29 @@ class _IterativeCMFSolver:
         """Host inputs -> FitState in HBM (row shard of X / U for this rank)."""
         be = self._get_backend()
         comm = self.comm if self.comm is not None else default_comm()
-        n_total = X.shape[0] if X is not None else np.shape(U)[0]
-        r0, r1 = row_range(n_total, comm.rank, comm.world)
+        n_local = X.shape[0] if X is not None else np.shape(U)[0]
+        if self.sharded_input and comm.world > 1:
+            counts = be.torch.zeros(comm.world, dtype=be.torch.int64, device=be.device)
+            counts[comm.rank] = n_local
+            counts = be.to_host(comm.all_reduce_sum(counts))
+            n_total = int(counts.sum())
+            r0 = int(counts[:comm.rank].sum())
+            r1 = r0 + n_local
+            take = slice(None)
+        else:
+            n_total = n_local
+            r0, r1 = row_range(n_total, comm.rank, comm.world)
+            take = slice(r0, r1)
         Xd = None
         if X is not None:
             if sp.issparse(X):
-                Xd = be.ingest(sp.csr_matrix(X)[r0:r1])
+                Xd = be.ingest(sp.csr_matrix(X)[take])
             else:
-                Xd = be.ingest(np.asarray(X)[r0:r1])
+                Xd = be.ingest(np.asarray(X)[take])
         Yd = None
         if Y is not None:
             Yd = be.ingest(Y.toarray() if sp.issparse(Y) else Y)
-        Ud = be.to_device(np.asarray(U)[r0:r1])
+        Ud = be.to_device(np.asarray(U)[take])
         Vd = be.to_device(np.asarray(V))
         Zd = be.to_device(np.asarray(Z))
         return FitState(be, comm, Xd, Yd, Ud, Vd, Zd, n_total, (r0, r1))
@@ -184,8 +197,8 @@ class _IterativeCMFSolver:
         st = self.prepare(X, Y, U, V, Z)
         n_iter = self.fit_device(st)
         be = st.be
-        U_full = st.comm.all_gather_rows(st.U, st.n_total)
-        for host, dev in ((U, U_full), (V, st.V), (Z, st.Z)):
+        U_out = st.U if self.sharded_input else st.comm.all_gather_rows(st.U, st.n_total)
+        for host, dev in ((U, U_out), (V, st.V), (Z, st.Z)):
             host[...] = be.to_host(dev)
         return U, V, Z, n_iter
 

@@ -279,6 +279,12 @@ static void check_link(int link) {
     if (link != PYCMF_LINEAR && link != PYCMF_LOGIT) throw pycmf::Error("Invalid link function code");
 }
 
+static void clear_timers(pycmf_ctx* ctx) {
+    for (auto& kv : ctx->timers)
+        for (auto& pr : kv.second) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
+    ctx->timers.clear();
+}
+
 extern "C" {
 
 int pycmf_abi_version(void) { return PYCMF_ABI_VERSION; }
@@ -315,6 +321,7 @@ int pycmf_destroy(pycmf_ctx* ctx) {
     if (!ctx) return 0;
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
+    clear_timers(ctx);
     for (auto& a : ctx->arena)
         if (a.ptr) cudaFree(a.ptr);
     delete ctx;
@@ -336,6 +343,36 @@ int pycmf_set_option(pycmf_ctx* ctx, const char* key, double value) {
 }
 
 int64_t pycmf_launch_count(pycmf_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int pycmf_profile_enable(pycmf_ctx* ctx, int on) {
+    return guarded(ctx, [&] { ctx->profile = on != 0; });
+}
+
+int pycmf_profile_reset(pycmf_ctx* ctx) {
+    return guarded(ctx, [&] {
+        PYCMF_CUDA(cudaStreamSynchronize(ctx->stream));
+        clear_timers(ctx);
+    });
+}
+
+int pycmf_profile_query(pycmf_ctx* ctx, const char* family, double* total_ms, int64_t* count) {
+    return guarded(ctx, [&] {
+        PYCMF_CUDA(cudaStreamSynchronize(ctx->stream));
+        double tot = 0.0;
+        int64_t n = 0;
+        auto it = ctx->timers.find(family ? family : "");
+        if (it != ctx->timers.end()) {
+            for (auto& pr : it->second) {
+                float ms = 0.f;
+                PYCMF_CUDA(cudaEventElapsedTime(&ms, pr.first, pr.second));
+                tot += ms;
+                n++;
+            }
+        }
+        if (total_ms) *total_ms = tot;
+        if (count) *count = n;
+    });
+}
 
 int pycmf_gemm(pycmf_ctx* ctx, int dtype, int trans_a, int64_t m, int64_t q, int64_t p, const void* A,
                int64_t lda, const void* B, int64_t ldb, void* C, int64_t ldc, double alpha, double beta) {

@@ -3,8 +3,11 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <map>
 #include <string>
 #include <stdexcept>
+#include <utility>
+#include <vector>
 
 #include "../../include/pycmf_b200.h"
 
@@ -31,6 +34,9 @@ struct pycmf_ctx {
     size_t max_scratch = size_t(2) << 30;
     // scratch arenas (grown on demand; growth synchronises the stream)
     pycmf::Scratch arena[8];
+    // optional per-kernel-family timers (cudaEvent pairs recorded on the stream around each launch)
+    int profile = 0;
+    std::map<std::string, std::vector<std::pair<cudaEvent_t, cudaEvent_t>>> timers;
 };
 
 namespace pycmf {
@@ -59,6 +65,23 @@ struct Error : public std::runtime_error {
         (ctx)->launches++;                                                            \
         PYCMF_CUDA(cudaGetLastError());                                               \
     } while (0)
+
+// RAII timer: when ctx->profile is on, brackets the enclosed launches with events on ctx->stream.
+struct Timed {
+    pycmf_ctx* ctx;
+    cudaEvent_t stop = nullptr;
+    Timed(pycmf_ctx* c, const char* name) : ctx(c) {
+        if (!c->profile) return;
+        cudaEvent_t start;
+        cudaEventCreate(&start);
+        cudaEventCreate(&stop);
+        cudaEventRecord(start, c->stream);
+        c->timers[name].emplace_back(start, stop);
+    }
+    ~Timed() {
+        if (stop) cudaEventRecord(stop, ctx->stream);
+    }
+};
 
 // scratch arena `slot`, at least `bytes` large (256-B aligned by cudaMalloc)
 void* scratch(pycmf_ctx* ctx, int slot, size_t bytes);

@@ -238,6 +238,7 @@ template <typename T>
 void gemm(pycmf_ctx* ctx, bool trans_a, int64_t m, int64_t q, int64_t p, const T* A, int64_t lda,
           const T* B, int64_t ldb, T* C, int64_t ldc, T alpha, T beta) {
     if (m <= 0 || q <= 0) return;
+    Timed timer(ctx, "gemm");
     int64_t tiles = ceil_div(m, BM) * ceil_div(q, BN);
     int splits = 1;
     if (p > 0 && tiles < 2 * ctx->num_sms) {

@@ -460,6 +460,7 @@ void launch_solve(pycmf_ctx* ctx, int64_t batch, int64_t k, const T* H, int64_t 
     } else {
         grid = std::min<int64_t>(batch, int64_t(1) << 30);
     }
+    Timed timer(ctx, "safe_solve");
     kern<<<(unsigned)grid, nthreads, smem, ctx->stream>>>(batch, int(k), H, h_stride, g, out, l1, l2, l2_diag,
                                                          pert, non_negative, ctx->chol_fastpath != 0, Wg);
     PYCMF_LAUNCH_CHECK(ctx);
@@ -478,6 +479,7 @@ void row_grad_hess(pycmf_ctx* ctx, int64_t rows, int64_t m, int64_t k, const T* 
     size_t smem = sizeof(T) * (size_t((k + 3) & ~3) + size_t(TJ) * (k + 1) + 2 * TJ);
     int hb = k <= 16 ? 1 : (k <= 32 ? 2 : (k <= 64 ? 4 : 8));
     int quads = k > 128 ? 2 : 1;
+    Timed timer(ctx, "row_grad_hess");
     for (int qa = 0; qa < quads; qa++) {
         for (int qb = 0; qb < quads; qb++) {
             bool first = (qa == 0 && qb == 0);

@@ -176,6 +176,7 @@ void launch_resid(pycmf_ctx* ctx, int64_t ra, int64_t rb, int64_t k, const T* A,
     int64_t nparts = own_blocks * splits;
     if (sq != nullptr) sq_part = static_cast<double*>(scratch(ctx, 1, size_t(nparts) * sizeof(double)));
     dim3 grid((unsigned)own_blocks, (unsigned)splits);
+    Timed timer(ctx, MODE == 0 ? "resid_left" : "resid_right");
     kern<<<grid, 256, smem, ctx->stream>>>(ra, rb, int(k), A, B, Tgt, ldt, trans_t, link, target, stride,
                                            tiles_per_split, sq_part, out != nullptr);
     PYCMF_LAUNCH_CHECK(ctx);

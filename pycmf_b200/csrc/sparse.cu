@@ -106,6 +106,7 @@ void spmm(pycmf_ctx* ctx, int64_t rows, const int32_t* rowptr, const int32_t* co
     if (rows <= 0 || k <= 0) return;
     PYCMF_CHECK(k <= 32 * MAXT, "spmm: n_components > 256 is not supported");
     unsigned blocks = (unsigned)ceil_div(rows * 32, 256);
+    Timed timer(ctx, "spmm");
 #define LAUNCH(G) spmm_kernel<T, G><<<blocks, 256, 0, ctx->stream>>>(rows, rowptr, colidx, vals, B, ldb, int(k), C, ldc, alpha, beta)
     if (k <= 1) LAUNCH(1);
     else if (k <= 2) LAUNCH(2);
@@ -123,6 +124,7 @@ void sddmm_reduce(pycmf_ctx* ctx, int mode, int64_t rows, const int32_t* rowptr,
     PYCMF_CHECK(k <= 32 * MAXT, "sddmm: n_components > 256 is not supported");
     int blocks = int(std::max<int64_t>(1, std::min<int64_t>(ceil_div(std::max<int64_t>(rows, 1), 8), 8 * ctx->num_sms)));
     double* part = static_cast<double*>(scratch(ctx, 1, size_t(blocks) * sizeof(double)));
+    Timed timer(ctx, "sddmm");
     sddmm_reduce_kernel<T><<<blocks, 256, 0, ctx->stream>>>(mode, rows, rowptr, colidx, vals, A, B, int(k), part);
     PYCMF_LAUNCH_CHECK(ctx);
     final_sum(ctx, blocks, part, scale, out, true);

@@ -100,6 +100,18 @@ class CudaBackend:
     def synchronize(self):
         self.torch.cuda.synchronize(self.device)
 
+    def profile(self, on=True):
+        _lib.check(self.lib.pycmf_profile_enable(self.ctx, int(bool(on))))
+
+    def profile_reset(self):
+        _lib.check(self.lib.pycmf_profile_reset(self.ctx))
+
+    def profile_query(self, family):
+        """(total milliseconds, launches) of one kernel family since the last reset."""
+        ms, cnt = C.c_double(0.0), C.c_int64(0)
+        _lib.check(self.lib.pycmf_profile_query(self.ctx, family.encode(), C.byref(ms), C.byref(cnt)))
+        return ms.value, cnt.value
+
     # ---- memory ------------------------------------------------------------------------------
     def empty(self, *shape, dtype=None):
         return self.torch.empty(*shape, dtype=dtype or self.tdtype, device=self.device)
@@ -107,14 +119,26 @@ class CudaBackend:
     def zeros(self, *shape, dtype=None):
         return self.torch.zeros(*shape, dtype=dtype or self.tdtype, device=self.device)
 
-    def to_device(self, a, dtype=None, pinned=False):
-        """Host ndarray -> contiguous device tensor of the compute dtype."""
+    def to_device(self, a, dtype=None):
+        """Host ndarray -> contiguous device tensor of the compute dtype (or `dtype`).
+
+        The bytes are copied as they are (asynchronously when the array lives in pinned memory) and
+        the cast to the compute dtype happens on the GPU, so a float64 host matrix costs one PCIe
+        transfer and no host-side conversion pass."""
         torch = self.torch
-        a = np.ascontiguousarray(a, dtype=self.np_dtype if dtype is None else dtype)
+        want = np.dtype(self.np_dtype if dtype is None else dtype)
+        a = np.asarray(a)
+        if a.dtype not in (np.float32, np.float64, np.int32, np.int64):
+            a = a.astype(want)
+        if not a.flags.c_contiguous:
+            a = np.ascontiguousarray(a)
+        if not a.flags.writeable:
+            a = a.copy()
         t = torch.from_numpy(a)
-        if pinned:
-            t = t.pin_memory()
-        return t.to(self.device, non_blocking=pinned)
+        d = t.to(self.device, non_blocking=t.is_pinned())
+        tw = {np.dtype("float32"): torch.float32, np.dtype("float64"): torch.float64,
+              np.dtype("int32"): torch.int32, np.dtype("int64"): torch.int64}[want]
+        return d if d.dtype == tw else d.to(tw)
 
     def to_host(self, t):
         return t.detach().to("cpu").numpy()
