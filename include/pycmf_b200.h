@@ -48,7 +48,7 @@ int pycmf_destroy(pycmf_ctx* ctx);
 /* stream is a cudaStream_t (0 = legacy default stream) */
 int pycmf_set_stream(pycmf_ctx* ctx, void* stream);
 /* options: "chol_fastpath" (0/1, default 1), "dense_path" (0 = generic FMA kernels, 1 = tcgen05
- * 3xTF32, 2 = tcgen05 1xTF32; default 1 where available), "max_scratch_mb" */
+ * 3xTF32, 2 = tcgen05 1xTF32; default 1 where available), "max_scratch_mb", "tc_max_splits" (tests) */
 int pycmf_set_option(pycmf_ctx* ctx, const char* key, double value);
 /* number of kernels this context launched since creation (bench.py's gpu_launches) */
 int64_t pycmf_launch_count(pycmf_ctx* ctx);

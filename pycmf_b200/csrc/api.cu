@@ -2,6 +2,7 @@
 #include <algorithm>
 #include <cstring>
 #include <mutex>
+#include <type_traits>
 
 #include "common.cuh"
 
@@ -89,7 +90,14 @@ template <typename T>
 void mu_v_partial_impl(pycmf_ctx* ctx, int64_t n, int64_t d, int64_t k, const T* X, int64_t ldx,
                        const int32_t* colptr, const int32_t* rowidx, const T* cvals, const T* U, T* out) {
     if (X != nullptr) {
-        gemm<T>(ctx, true, d, k, n, X, ldx, U, k, out, k, T(1), T(0));
+        bool done = false;
+        if constexpr (std::is_same<T, float>::value) {
+            if (tc_dense_eligible(ctx, n, d, k, X, ldx, false)) {
+                tc_xmul(ctx, true, n, d, X, ldx, U, out);
+                done = true;
+            }
+        }
+        if (!done) gemm<T>(ctx, true, d, k, n, X, ldx, U, k, out, k, T(1), T(0));
     } else {
         PYCMF_CHECK(colptr && rowidx && cvals, "mu_v_partial: neither dense X nor CSC arrays given");
         spmm<T>(ctx, d, colptr, rowidx, cvals, U, k, k, out, k, T(1), T(0));
@@ -118,7 +126,14 @@ void mu_left_impl(pycmf_ctx* ctx, int64_t rows, int64_t m, int64_t k, T* F, cons
     T* D = static_cast<T*>(scratch(ctx, SLOT_T1, sizeof(T) * size_t(rows) * k));
     T* G = static_cast<T*>(scratch(ctx, SLOT_T2, sizeof(T) * size_t(k) * k));
     if (Tg != nullptr) {
-        gemm<T>(ctx, trans_t, rows, k, m, Tg, ldt, B, k, N, k, T(1), T(0));
+        bool done = false;
+        if constexpr (std::is_same<T, float>::value) {
+            if (tc_dense_eligible(ctx, rows, m, k, Tg, ldt, trans_t)) {
+                tc_xmul(ctx, false, rows, m, Tg, ldt, B, N);
+                done = true;
+            }
+        }
+        if (!done) gemm<T>(ctx, trans_t, rows, k, m, Tg, ldt, B, k, N, k, T(1), T(0));
     } else {
         PYCMF_CHECK(rowptr && colidx && vals, "mu_left: neither dense target nor CSR arrays given");
         spmm<T>(ctx, rows, rowptr, colidx, vals, B, k, k, N, k, T(1), T(0));
@@ -337,6 +352,7 @@ int pycmf_set_option(pycmf_ctx* ctx, const char* key, double value) {
         std::string k(key ? key : "");
         if (k == "chol_fastpath") ctx->chol_fastpath = value != 0.0;
         else if (k == "dense_path") ctx->dense_path = int(value);
+        else if (k == "tc_max_splits") ctx->tc_max_splits = int(value);
         else if (k == "max_scratch_mb") ctx->max_scratch = size_t(std::max(16.0, value)) << 20;
         else throw pycmf::Error("unknown option: " + k);
     });

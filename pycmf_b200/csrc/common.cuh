@@ -31,6 +31,7 @@ struct pycmf_ctx {
     // options
     int chol_fastpath = 1;
     int dense_path = 1;
+    int tc_max_splits = 0;   // > 0: cap the split count of the tcgen05 passes (tests use 1 to get long tile loops)
     size_t max_scratch = size_t(2) << 30;
     // scratch arenas (grown on demand; growth synchronises the stream)
     pycmf::Scratch arena[8];
@@ -170,6 +171,13 @@ void sddmm_reduce(pycmf_ctx* ctx, int mode, int64_t rows, const int32_t* rowptr,
 template <typename T>
 void resid_pass(pycmf_ctx* ctx, int64_t ra, int64_t rb, int64_t k, const T* A, const T* B,
                 const T* Tgt, int64_t ldt, bool trans_t, int link, T* outL, T* outR, double* sq);
+
+// tc_resid.cu : tcgen05 / TMEM / TMA versions of the dense passes over X (fp32, n_components == 32)
+bool tc_dense_eligible(pycmf_ctx* ctx, int64_t ra, int64_t rb, int64_t k, const float* X, int64_t ldx, bool trans_t);
+void tc_resid_pass(pycmf_ctx* ctx, int64_t ra, int64_t rb, const float* A, const float* B, const float* X, int64_t ldx,
+                   int link, float* outL, float* outR, double* sq);
+void tc_xmul(pycmf_ctx* ctx, bool trans, int64_t rows, int64_t cols, const float* X, int64_t ldx, const float* Q,
+             float* out);
 
 // newton.cu
 // Per-row gradient / Hessian accumulation for rows of A against (sampled) rows of B.

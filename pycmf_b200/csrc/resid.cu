@@ -6,6 +6,8 @@
 // second product into register accumulators.  This is the reference's
 //     res = inverse(np.dot(U, V.T), link) - X ;  np.dot(res, V) / np.dot(res.T, U)
 // (cmf_solvers.py:399-400, :436-440) and the dense objective (:36-42) without the n x d temporary.
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace pycmf {
@@ -204,6 +206,12 @@ void resid_pass(pycmf_ctx* ctx, int64_t ra, int64_t rb, int64_t k, const T* A, c
         if (outL && ra > 0) PYCMF_CUDA(cudaMemsetAsync(outL, 0, size_t(ra) * k * sizeof(T), ctx->stream));
         if (outR && rb > 0) PYCMF_CUDA(cudaMemsetAsync(outR, 0, size_t(rb) * k * sizeof(T), ctx->stream));
         return;
+    }
+    if constexpr (std::is_same<T, float>::value) {
+        if ((outL != nullptr || outR != nullptr) && tc_dense_eligible(ctx, ra, rb, k, Tgt, ldt, trans_t)) {
+            tc_resid_pass(ctx, ra, rb, A, B, Tgt, ldt, link, outL, outR, sq);
+            return;
+        }
     }
     if (outL != nullptr || (outR == nullptr && sq != nullptr))
         dispatch_kc<T, 0>(ctx, ra, rb, k, A, B, Tgt, ldt, trans_t, link, outL, sq);

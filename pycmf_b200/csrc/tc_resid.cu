@@ -1,0 +1,542 @@
+// tcgen05 / TMEM / TMA version of the dense streaming passes over X (fp32 data, TF32 tensor cores).
+//
+// One kernel template covers the four dense hot loops of the fit (n_components == 32):
+//   RESID, LEFT  : outL = (f(A B^T) - X)   B     Newton U gradient   (cmf_solvers.py:399-400)
+//   RESID, RIGHT : outR = (f(A B^T) - X)^T A     Newton V gradient   (cmf_solvers.py:436-440)
+//   COPY,  LEFT  : out  = X   B                  MU numerator X V    (cmf_solvers.py:232)
+//   COPY,  RIGHT : out  = X^T A                  MU numerator X^T U  (cmf_solvers.py:244)
+//
+// A CTA owns 128 "own" rows (rows of X for LEFT, columns of X for RIGHT) and walks the other
+// dimension in tiles of 64.  Per tile:
+//   TMA        : X tile (128 x 64 fp32, SWIZZLE_128B) + the 64 x 32 factor tile Q (tf32 hi / lo parts)
+//   tcgen05.mma: S[128 x 64] = P Q^T          (GEMM1, accumulator in TMEM, 3xTF32: hi*hi + hi*lo + lo*hi)
+//   epilogue   : tcgen05.ld S -> f() -> minus X -> R (hi / lo) written back to swizzled shared memory
+//   tcgen05.mma: OUT[128 x 32] += R Q         (GEMM2, Q read MN-major from the same shared tile)
+// so neither U V^T nor the residual ever touches HBM.  GEMM1 of tile t+1 is issued before GEMM2 of
+// tile t (two S buffers in TMEM) so the tensor pipe works while the epilogue warps convert tile t.
+//
+// Warp roles (256 threads): warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator,
+// warps 4-7 = epilogue (thread i <-> TMEM lane i <-> own row i).
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace pycmf {
+namespace {
+
+constexpr int OWN = 128;      // own rows per CTA  (UMMA M)
+constexpr int OTH = 64;       // other rows per tile (GEMM1 N, GEMM2 K)
+constexpr int KC = 32;        // n_components handled by this kernel (one 128-byte swizzle span)
+constexpr int NSTAGE = 2;
+constexpr int TMEM_COLS = 256;
+constexpr int TMEM_OUT_COL = 128;
+
+constexpr uint32_t P_BYTES = OWN * 128;          // 16 KB  (128 rows x 32 fp32)
+constexpr uint32_t Q_BYTES = OTH * 128;          //  8 KB
+constexpr uint32_t X_BYTES = OWN * OTH * 4;      // 32 KB
+constexpr uint32_t R_BYTES = OWN * OTH * 4;      // 32 KB  (two K-blocks of 128 rows x 128 B)
+
+struct SmemLayout {
+    // all tile buffers are 1024-byte aligned (SWIZZLE_128B atoms)
+    static constexpr uint32_t p_hi = 0;
+    static constexpr uint32_t p_lo = p_hi + P_BYTES;
+    static constexpr uint32_t stage0 = p_lo + P_BYTES;
+    static constexpr uint32_t q_hi = 0, q_lo = Q_BYTES, x = 2 * Q_BYTES;   // offsets inside a stage
+    static constexpr uint32_t stage_bytes = 2 * Q_BYTES + X_BYTES;
+    static constexpr uint32_t r_hi = stage0 + NSTAGE * stage_bytes;
+    static constexpr uint32_t r_lo = r_hi + R_BYTES;
+    static constexpr uint32_t bars = r_lo + R_BYTES;
+    static constexpr uint32_t total = bars + 256;
+};
+
+// barrier slots (8 bytes each) inside the `bars` region
+enum Bar { FULL0 = 0, EMPTY0 = FULL0 + NSTAGE, SFULL0 = EMPTY0 + NSTAGE, SEMPTY0 = SFULL0 + 2, RFULL = SEMPTY0 + 2,
+           REMPTY, PFULL, OUTFULL, NBARS };
+
+// ---- PTX wrappers ----------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return uint32_t(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+        "@P1 bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t"
+        "}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t"
+        "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; i++) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ float tf32_rna(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
+
+// shared-memory matrix descriptor, SWIZZLE_128B, version 1 (sm_100)
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= uint64_t((saddr >> 4) & 0x3FFF);
+    d |= uint64_t((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= uint64_t((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= uint64_t(1) << 46;
+    d |= uint64_t(2) << 61;
+    return d;
+}
+// instruction descriptor: D = F32, A = B = TF32
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn_major, int b_mn_major) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | (uint32_t(a_mn_major) << 15) | (uint32_t(b_mn_major) << 16) |
+           (uint32_t(N >> 3) << 17) | (uint32_t(M >> 4) << 24);
+}
+
+struct Params {
+    int64_t own_n, oth_n;       // extents of the own / other dimension
+    int64_t tiles_per_split;
+    int link;
+    float* out;                 // (own_n x 32) or split partials
+    int64_t out_split_stride;
+    double* sq_part;            // per-CTA partial of sum R^2 (may be null)
+};
+
+// MODE 0 = LEFT (own = rows of X), 1 = RIGHT (own = columns of X).  RESID: R = f(S) - X, else R = X.
+template <int MODE, bool RESID, int NSPLIT>
+__global__ void __launch_bounds__(256, 1)
+tc_pass_kernel(const __grid_constant__ CUtensorMap tm_p_hi, const __grid_constant__ CUtensorMap tm_p_lo,
+               const __grid_constant__ CUtensorMap tm_q_hi, const __grid_constant__ CUtensorMap tm_q_lo,
+               const __grid_constant__ CUtensorMap tm_x, const Params prm) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    // dynamic shared memory is only guaranteed 16-byte aligned: round up to 1024 for the swizzle atoms
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    unsigned char* gen = smem_raw + (base - smem_u32(smem_raw));
+    const uint32_t bars = base + SmemLayout::bars;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gen + SmemLayout::bars + NBARS * 8);
+    double* sq_slot = reinterpret_cast<double*>(gen + SmemLayout::bars + NBARS * 8 + 16);
+    auto bar = [&](int i) { return bars + 8u * uint32_t(i); };
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t own0 = int64_t(blockIdx.x) * OWN;
+    const int64_t n_tiles_total = (prm.oth_n + OTH - 1) / OTH;
+    const int64_t t_begin = int64_t(blockIdx.y) * prm.tiles_per_split;
+    const int64_t t_end = (t_begin + prm.tiles_per_split < n_tiles_total) ? t_begin + prm.tiles_per_split : n_tiles_total;
+    const int n_it = int(t_end - t_begin);
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < NSTAGE; s++) { mbar_init(bar(FULL0 + s), 1); mbar_init(bar(EMPTY0 + s), 1); }
+        for (int s = 0; s < 2; s++) { mbar_init(bar(SFULL0 + s), 1); mbar_init(bar(SEMPTY0 + s), 4); }
+        mbar_init(bar(RFULL), 4);
+        mbar_init(bar(REMPTY), 1);
+        mbar_init(bar(PFULL), 1);
+        mbar_init(bar(OUTFULL), 1);
+        *sq_slot = 0.0;
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        fence_async_smem();
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                     "r"(uint32_t(TMEM_COLS)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp == 0) {
+        // =============================== TMA producer ===============================
+        if (lane == 0) {
+            if (RESID) {
+                mbar_expect_tx(bar(PFULL), NSPLIT == 3 ? 2 * P_BYTES : P_BYTES);
+                tma_load_2d(base + SmemLayout::p_hi, &tm_p_hi, bar(PFULL), 0, int(own0));
+                if (NSPLIT == 3) tma_load_2d(base + SmemLayout::p_lo, &tm_p_lo, bar(PFULL), 0, int(own0));
+            }
+            for (int it = 0; it < n_it; it++) {
+                const int s = it % NSTAGE;
+                const uint32_t ph = uint32_t(it / NSTAGE) & 1u;
+                mbar_wait(bar(EMPTY0 + s), ph ^ 1u);
+                const uint32_t st = base + SmemLayout::stage0 + uint32_t(s) * SmemLayout::stage_bytes;
+                const int oth0 = int((t_begin + it) * OTH);
+                mbar_expect_tx(bar(FULL0 + s), (NSPLIT == 3 ? 2 * Q_BYTES : Q_BYTES) + X_BYTES);
+                tma_load_2d(st + SmemLayout::q_hi, &tm_q_hi, bar(FULL0 + s), 0, oth0);
+                if (NSPLIT == 3) tma_load_2d(st + SmemLayout::q_lo, &tm_q_lo, bar(FULL0 + s), 0, oth0);
+                if (MODE == 0) {
+                    // X tile: own rows x 64 other columns, two 32-column boxes of 128 rows
+                    tma_load_2d(st + SmemLayout::x, &tm_x, bar(FULL0 + s), oth0, int(own0));
+                    tma_load_2d(st + SmemLayout::x + OWN * 128, &tm_x, bar(FULL0 + s), oth0 + 32, int(own0));
+                } else {
+                    // X tile: 64 other rows x 128 own columns, four 32-column boxes of 64 rows
+#pragma unroll
+                    for (int b = 0; b < 4; b++)
+                        tma_load_2d(st + SmemLayout::x + uint32_t(b) * OTH * 128, &tm_x, bar(FULL0 + s),
+                                    int(own0) + 32 * b, oth0);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // =============================== MMA issuer ================================
+        if (lane == 0) {
+            constexpr uint32_t idesc1 = make_idesc(OWN, OTH, 0, 0);   // S   = P (K-major) x Q (K-major)
+            constexpr uint32_t idesc2 = make_idesc(OWN, KC, 0, 1);    // OUT = R (K-major) x Q (MN-major)
+            const uint32_t p_hi = base + SmemLayout::p_hi, p_lo = base + SmemLayout::p_lo;
+            const uint32_t r_hi = base + SmemLayout::r_hi, r_lo = base + SmemLayout::r_lo;
+            auto issue_g1 = [&](int it) {
+                const int s = it % NSTAGE, sb = it & 1;
+                mbar_wait(bar(FULL0 + s), uint32_t(it / NSTAGE) & 1u);
+                mbar_wait(bar(SEMPTY0 + sb), (uint32_t(it >> 1) & 1u) ^ 1u);
+                tc_fence_after();
+                const uint32_t st = base + SmemLayout::stage0 + uint32_t(s) * SmemLayout::stage_bytes;
+                const uint32_t d = tmem + uint32_t(sb * OTH);
+                uint32_t acc = 0;
+#pragma unroll
+                for (int term = 0; term < NSPLIT; term++) {
+                    const uint32_t pa = (term == 2) ? p_lo : p_hi;
+                    const uint32_t qa = st + ((term == 1) ? SmemLayout::q_lo : SmemLayout::q_hi);
+#pragma unroll
+                    for (int kk = 0; kk < KC / 8; kk++) {
+                        umma_tf32(d, make_desc(pa + kk * 32, 16, 1024), make_desc(qa + kk * 32, 16, 1024), idesc1, acc);
+                        acc = 1;
+                    }
+                }
+                umma_commit(bar(SFULL0 + sb));
+            };
+            if (RESID) {
+                mbar_wait(bar(PFULL), 0);
+                if (n_it > 0) issue_g1(0);
+            }
+            uint32_t out_acc = 0;
+            for (int it = 0; it < n_it; it++) {
+                const int s = it % NSTAGE;
+                if (RESID) {
+                    if (it + 1 < n_it) issue_g1(it + 1);
+                } else {
+                    mbar_wait(bar(FULL0 + s), uint32_t(it / NSTAGE) & 1u);
+                }
+                mbar_wait(bar(RFULL), uint32_t(it) & 1u);
+                tc_fence_after();
+                const uint32_t st = base + SmemLayout::stage0 + uint32_t(s) * SmemLayout::stage_bytes;
+                const uint32_t d = tmem + TMEM_OUT_COL;
+#pragma unroll
+                for (int term = 0; term < NSPLIT; term++) {
+                    const uint32_t ra = (term == 2) ? r_lo : r_hi;
+                    const uint32_t qa = st + ((term == 1) ? SmemLayout::q_lo : SmemLayout::q_hi);
+#pragma unroll
+                    for (int kk = 0; kk < OTH / 8; kk++) {
+                        const uint32_t a_addr = ra + uint32_t(kk / 4) * (OWN * 128) + uint32_t(kk % 4) * 32;
+                        const uint32_t b_addr = qa + uint32_t(kk) * 1024;
+                        umma_tf32(d, make_desc(a_addr, 16, 1024), make_desc(b_addr, OTH * 128, 1024), idesc2, out_acc);
+                        out_acc = 1;
+                    }
+                }
+                umma_commit(bar(REMPTY));
+                umma_commit(bar(EMPTY0 + s));
+            }
+            umma_commit(bar(OUTFULL));
+        }
+    } else if (warp >= 4) {
+        // ================================ epilogue ================================
+        const int q = warp - 4;                   // TMEM lane quadrant
+        const int i = q * 32 + lane;              // own row inside the tile == TMEM lane
+        const int64_t own_idx = own0 + i;
+        const bool own_ok = own_idx < prm.own_n;
+        const uint32_t lane_addr = tmem + (uint32_t(q * 32) << 16);
+        double sq = 0.0;
+        for (int it = 0; it < n_it; it++) {
+            const int s = it % NSTAGE, sb = it & 1;
+            const int64_t oth0 = (t_begin + it) * OTH;
+            mbar_wait(bar(FULL0 + s), uint32_t(it / NSTAGE) & 1u);
+            if (RESID) {
+                mbar_wait(bar(SFULL0 + sb), uint32_t(it >> 1) & 1u);
+                tc_fence_after();
+            }
+            const unsigned char* xs = gen + SmemLayout::stage0 + s * SmemLayout::stage_bytes + SmemLayout::x;
+            bool waited_r = false;
+#pragma unroll 1
+            for (int c = 0; c < OTH / 16; c++) {
+                float sv[16];
+                if (RESID) {
+                    tmem_ld16(lane_addr + uint32_t(sb * OTH + c * 16), sv);
+                }
+                float hi[16], lo[16];
+#pragma unroll
+                for (int g = 0; g < 4; g++) {
+                    // 4 consecutive other-indices j = 16c + 4g + e
+                    float xv[4];
+                    if (MODE == 0) {
+                        const int j = c * 16 + g * 4;
+                        const int blk = j >> 5, ch = (j & 31) >> 2;
+                        const float4 t4 = *reinterpret_cast<const float4*>(xs + blk * (OWN * 128) + i * 128 +
+                                                                           ((ch ^ (i & 7)) << 4));
+                        xv[0] = t4.x; xv[1] = t4.y; xv[2] = t4.z; xv[3] = t4.w;
+                    } else {
+                        const int blk = i >> 5, ch = (i & 31) >> 2, w = i & 3;
+#pragma unroll
+                        for (int e = 0; e < 4; e++) {
+                            const int j = c * 16 + g * 4 + e;
+                            xv[e] = *reinterpret_cast<const float*>(xs + blk * (OTH * 128) + j * 128 +
+                                                                    ((ch ^ (j & 7)) << 4) + w * 4);
+                        }
+                    }
+#pragma unroll
+                    for (int e = 0; e < 4; e++) {
+                        const int j = c * 16 + g * 4 + e;
+                        float r;
+                        if (RESID) {
+                            float est = sv[g * 4 + e];
+                            if (prm.link == PYCMF_LOGIT) est = 1.0f / (1.0f + __expf(-est));
+                            r = (own_ok && (oth0 + j) < prm.oth_n) ? est - xv[e] : 0.0f;
+                            sq += double(r) * double(r);
+                        } else {
+                            r = xv[e];                         // TMA zero-fills out-of-range elements
+                        }
+                        const float h = NSPLIT == 3 ? tf32_rna(r) : r;
+                        hi[g * 4 + e] = h;
+                        lo[g * 4 + e] = NSPLIT == 3 ? tf32_rna(r - h) : 0.0f;
+                    }
+                }
+                if (!waited_r) {
+                    mbar_wait(bar(REMPTY), (uint32_t(it) & 1u) ^ 1u);   // GEMM2 of the previous tile has drained R
+                    waited_r = true;
+                }
+                // R[i][16c .. 16c+15]: K-block (16c)/32, 16-byte chunks ((16c % 32)/4 + g) ^ (i & 7)
+                const int blk = (c * 16) >> 5;
+                unsigned char* rh = gen + SmemLayout::r_hi + blk * (OWN * 128) + i * 128;
+                unsigned char* rl = gen + SmemLayout::r_lo + blk * (OWN * 128) + i * 128;
+#pragma unroll
+                for (int g = 0; g < 4; g++) {
+                    const int ch = (((c * 16) & 31) >> 2) + g;
+                    const int off = (ch ^ (i & 7)) << 4;
+                    *reinterpret_cast<float4*>(rh + off) = make_float4(hi[g * 4], hi[g * 4 + 1], hi[g * 4 + 2], hi[g * 4 + 3]);
+                    if (NSPLIT == 3)
+                        *reinterpret_cast<float4*>(rl + off) = make_float4(lo[g * 4], lo[g * 4 + 1], lo[g * 4 + 2], lo[g * 4 + 3]);
+                }
+            }
+            fence_async_smem();            // generic-proxy writes of R -> visible to the tensor-core (async) proxy
+            if (RESID) tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+                if (RESID) mbar_arrive(bar(SEMPTY0 + sb));
+                mbar_arrive(bar(RFULL));
+            }
+        }
+        // ---- final: OUT (128 x 32) from TMEM to global
+        mbar_wait(bar(OUTFULL), 0);
+        tc_fence_after();
+        if (n_it > 0) {
+            float o[32];
+            {
+                float t16[16];
+                tmem_ld16(lane_addr + TMEM_OUT_COL, t16);
+#pragma unroll
+                for (int e = 0; e < 16; e++) o[e] = t16[e];
+                tmem_ld16(lane_addr + TMEM_OUT_COL + 16, t16);
+#pragma unroll
+                for (int e = 0; e < 16; e++) o[16 + e] = t16[e];
+            }
+            if (own_ok) {
+                float4* dst = reinterpret_cast<float4*>(prm.out + int64_t(blockIdx.y) * prm.out_split_stride + own_idx * KC);
+#pragma unroll
+                for (int e = 0; e < 8; e++) dst[e] = make_float4(o[4 * e], o[4 * e + 1], o[4 * e + 2], o[4 * e + 3]);
+            }
+        } else if (own_ok) {
+            float4* dst = reinterpret_cast<float4*>(prm.out + int64_t(blockIdx.y) * prm.out_split_stride + own_idx * KC);
+#pragma unroll
+            for (int e = 0; e < 8; e++) dst[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        if (RESID && prm.sq_part != nullptr) {
+            sq = warp_sum(sq);
+            if (lane == 0) atomicAdd(sq_slot, sq);
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (RESID && prm.sq_part != nullptr && threadIdx.x == 0)
+        prm.sq_part[blockIdx.y * gridDim.x + blockIdx.x] = *sq_slot;
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(uint32_t(TMEM_COLS)) : "memory");
+    }
+}
+
+__global__ void split_tf32_kernel(int64_t n, const float* __restrict__ x, float* __restrict__ hi,
+                                  float* __restrict__ lo) {
+    int64_t e = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    float v = x[e];
+    float h = tf32_rna(v);
+    hi[e] = h;
+    lo[e] = tf32_rna(v - h);
+}
+
+// ---- host side --------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (fn == nullptr) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        PYCMF_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres));
+        PYCMF_CHECK(p != nullptr && qres == cudaDriverEntryPointSuccess, "cuTensorMapEncodeTiled not available");
+        fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+// 2-D fp32 row-major tensor (rows x cols, row stride ld elements); box = (32 columns, box_rows), SWIZZLE_128B
+CUtensorMap make_map(const float* ptr, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+    CUtensorMap m;
+    cuuint64_t dims[2] = {cuuint64_t(cols), cuuint64_t(rows)};
+    cuuint64_t strides[1] = {cuuint64_t(ld) * sizeof(float)};
+    cuuint32_t box[2] = {32u, cuuint32_t(box_rows)};
+    cuuint32_t estr[2] = {1u, 1u};
+    CUresult r = encode_fn()(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims, strides, box, estr,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    PYCMF_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed");
+    return m;
+}
+
+template <int MODE, bool RESID, int NSPLIT>
+void launch_tc(pycmf_ctx* ctx, int64_t own_n, int64_t oth_n, const float* P_hi, const float* P_lo, const float* Q_hi,
+               const float* Q_lo, const float* X, int64_t x_rows, int64_t x_cols, int64_t ldx, int link, float* out,
+               double* sq) {
+    const int64_t own_tiles = ceil_div(own_n, OWN), loop_tiles = ceil_div(oth_n, OTH);
+    int64_t splits = 1;
+    if (own_tiles < 4 * ctx->num_sms)
+        splits = std::max<int64_t>(1, std::min(loop_tiles, ceil_div(int64_t(4) * ctx->num_sms, own_tiles)));
+    if (ctx->tc_max_splits > 0) splits = std::min<int64_t>(splits, ctx->tc_max_splits);
+    int64_t tiles_per_split = ceil_div(loop_tiles, splits);
+    splits = ceil_div(loop_tiles, tiles_per_split);
+    PYCMF_CHECK(splits <= 65535, "tc pass: too many splits");
+    CUtensorMap tm_p_hi = make_map(RESID ? P_hi : Q_hi, RESID ? own_n : oth_n, KC, KC, RESID ? OWN : OTH);
+    CUtensorMap tm_p_lo = make_map(RESID ? P_lo : Q_lo, RESID ? own_n : oth_n, KC, KC, RESID ? OWN : OTH);
+    CUtensorMap tm_q_hi = make_map(Q_hi, oth_n, KC, KC, OTH);
+    CUtensorMap tm_q_lo = make_map(Q_lo, oth_n, KC, KC, OTH);
+    CUtensorMap tm_x = make_map(X, x_rows, x_cols, ldx, MODE == 0 ? OWN : OTH);
+    Params prm;
+    prm.own_n = own_n;
+    prm.oth_n = oth_n;
+    prm.tiles_per_split = tiles_per_split;
+    prm.link = link;
+    prm.out = out;
+    prm.out_split_stride = 0;
+    if (splits > 1) {
+        prm.out = static_cast<float*>(scratch(ctx, 0, size_t(splits) * own_n * KC * sizeof(float)));
+        prm.out_split_stride = own_n * KC;
+    }
+    prm.sq_part = nullptr;
+    const int64_t nparts = own_tiles * splits;
+    if (RESID && sq != nullptr) prm.sq_part = static_cast<double*>(scratch(ctx, 1, size_t(nparts) * sizeof(double)));
+    auto kern = tc_pass_kernel<MODE, RESID, NSPLIT>;
+    const size_t smem = SmemLayout::total + 1024;
+    PYCMF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    dim3 grid((unsigned)own_tiles, (unsigned)splits);
+    {
+        Timed timer(ctx, RESID ? (MODE == 0 ? "tc_resid_left" : "tc_resid_right") : (MODE == 0 ? "tc_xv" : "tc_xtu"));
+        kern<<<grid, 256, smem, ctx->stream>>>(tm_p_hi, tm_p_lo, tm_q_hi, tm_q_lo, tm_x, prm);
+        PYCMF_LAUNCH_CHECK(ctx);
+    }
+    if (splits > 1) reduce_parts<float>(ctx, own_n, KC, int(splits), prm.out, out, KC, 1.0f, 0.0f);
+    if (prm.sq_part != nullptr) final_sum(ctx, int(nparts), prm.sq_part, 1.0, sq, true);
+}
+
+void split_factor(pycmf_ctx* ctx, int64_t rows, const float* F, float* hi, float* lo) {
+    int64_t n = rows * KC;
+    split_tf32_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, ctx->stream>>>(n, F, hi, lo);
+    PYCMF_LAUNCH_CHECK(ctx);
+}
+
+}  // namespace
+
+bool tc_dense_eligible(pycmf_ctx* ctx, int64_t ra, int64_t rb, int64_t k, const float* X, int64_t ldx, bool trans_t) {
+    if (ctx->dense_path == 0 || trans_t || X == nullptr) return false;
+    if (k != KC) return false;
+    if ((reinterpret_cast<uintptr_t>(X) & 15) != 0 || (ldx % 4) != 0) return false;
+    if (ra * rb < (int64_t(1) << 16)) return false;      // tiny problems: the generic kernel has less setup
+    return ra >= 1 && rb >= 1 && ra < (int64_t(1) << 31) && rb < (int64_t(1) << 31);
+}
+
+// R = f(A B^T) - X (RESID) : outL = R B and / or outR = R^T A, *sq += sum R^2.   A: ra x 32, B: rb x 32, X: ra x rb.
+void tc_resid_pass(pycmf_ctx* ctx, int64_t ra, int64_t rb, const float* A, const float* B, const float* X, int64_t ldx,
+                   int link, float* outL, float* outR, double* sq) {
+    const bool three = ctx->dense_path != 2;
+    float* buf = static_cast<float*>(scratch(ctx, 3, sizeof(float) * size_t(2) * (ra + rb) * KC));
+    float *A_hi = buf, *A_lo = buf + ra * KC, *B_hi = buf + 2 * ra * KC, *B_lo = buf + (2 * ra + rb) * KC;
+    if (three) {
+        split_factor(ctx, ra, A, A_hi, A_lo);
+        split_factor(ctx, rb, B, B_hi, B_lo);
+    }
+    const float *Ah = three ? A_hi : A, *Al = three ? A_lo : A, *Bh = three ? B_hi : B, *Bl = three ? B_lo : B;
+    if (outL != nullptr || (outR == nullptr && sq != nullptr)) {
+        PYCMF_CHECK(outL != nullptr, "tc_resid_pass: objective-only passes use the generic kernel");
+        if (three) launch_tc<0, true, 3>(ctx, ra, rb, Ah, Al, Bh, Bl, X, ra, rb, ldx, link, outL, sq);
+        else launch_tc<0, true, 1>(ctx, ra, rb, Ah, Al, Bh, Bl, X, ra, rb, ldx, link, outL, sq);
+    }
+    if (outR != nullptr) {
+        double* s2 = outL == nullptr ? sq : nullptr;
+        if (three) launch_tc<1, true, 3>(ctx, rb, ra, Bh, Bl, Ah, Al, X, ra, rb, ldx, link, outR, s2);
+        else launch_tc<1, true, 1>(ctx, rb, ra, Bh, Bl, Ah, Al, X, ra, rb, ldx, link, outR, s2);
+    }
+}
+
+// out = X Q (trans == false: X is rows x cols, Q is cols x 32, out rows x 32)
+//       X^T Q (trans == true : Q is rows x 32, out cols x 32)
+void tc_xmul(pycmf_ctx* ctx, bool trans, int64_t rows, int64_t cols, const float* X, int64_t ldx, const float* Q,
+             float* out) {
+    const bool three = ctx->dense_path != 2;
+    const int64_t qn = trans ? rows : cols;
+    float* buf = static_cast<float*>(scratch(ctx, 3, sizeof(float) * size_t(2) * qn * KC));
+    float *Q_hi = buf, *Q_lo = buf + qn * KC;
+    if (three) split_factor(ctx, qn, Q, Q_hi, Q_lo);
+    const float *Qh = three ? Q_hi : Q, *Ql = three ? Q_lo : Q;
+    if (!trans) {
+        if (three) launch_tc<0, false, 3>(ctx, rows, cols, nullptr, nullptr, Qh, Ql, X, rows, cols, ldx, 0, out, nullptr);
+        else launch_tc<0, false, 1>(ctx, rows, cols, nullptr, nullptr, Qh, Ql, X, rows, cols, ldx, 0, out, nullptr);
+    } else {
+        if (three) launch_tc<1, false, 3>(ctx, cols, rows, nullptr, nullptr, Qh, Ql, X, rows, cols, ldx, 0, out, nullptr);
+        else launch_tc<1, false, 1>(ctx, cols, rows, nullptr, nullptr, Qh, Ql, X, rows, cols, ldx, 0, out, nullptr);
+    }
+}
+
+}  // namespace pycmf

@@ -206,3 +206,61 @@ def test_cmf_api_end_to_end():
             np.testing.assert_array_almost_equal(a, b, decimal=6)
         assert est1.reconstruction_err_ > 0 and est1.n_iter_ >= 1
         assert not ((U1 < 0).any() or (V1 < 0).any() or (Z1 < 0).any())
+
+
+# ---- tcgen05 dense path (fp32, k == 32) ------------------------------------------------------------
+def _tc_backend(path, splits=0):
+    from pycmf_b200.device import CudaBackend
+    opts = {"dense_path": path}
+    if splits:
+        opts["tc_max_splits"] = splits
+    return CudaBackend(dtype="float32", options=opts)
+
+
+@pytest.mark.parametrize("shape", [(1000, 520), (300, 2052), (4100, 260)])
+@pytest.mark.parametrize("path,tol", [(0, 3e-6), (1, 3e-6), (2, 3e-3)])
+@pytest.mark.parametrize("splits", [0, 1])
+def test_tc_mu_products_match_numpy(shape, path, tol, splits):
+    """X^T U and X V on the tensor cores (3xTF32 ~ fp32 accuracy, 1xTF32 ~ 1e-3) vs float64 NumPy."""
+    n, d = shape
+    rng = np.random.RandomState(n + d)
+    X, U, V = rng.randn(n, d), rng.randn(n, 32), rng.randn(d, 32)
+    be = _tc_backend(path, splits)
+    Xd = be.ingest(X)
+    buf = be.to_host(be.mu_v_partial(Xd, be.to_device(U)))
+    assert rel_fro(buf[:d], X.T @ U) < tol
+    assert rel_fro(buf[d:], U.T @ U) < 3e-6
+    # X V through the MU left update: F <- F * (X V) / (F (V^T V)) with F = 1  =>  X V = F_new * (1 (V^T V))
+    F = np.ones((n, 32))
+    Fd = be.to_device(F)
+    be.mu_left(Fd, be.to_device(V), Xd, 0.0, 0.0)
+    got = be.to_host(Fd) * (F @ (V.T @ V))
+    assert rel_fro(got, X @ V) < max(tol, 1e-5)
+
+
+@pytest.mark.parametrize("link", ["linear", "logit"])
+@pytest.mark.parametrize("path,tol", [(0, 5e-6), (1, 5e-6), (2, 5e-3)])
+@pytest.mark.parametrize("splits", [0, 1])
+def test_tc_fused_residual_right_matches_numpy(link, path, tol, splits):
+    """gx = alpha (f(U V^T) - X)^T U from the fused tcgen05 kernel vs float64 NumPy (X never leaves fp32)."""
+    n, d = 1100, 516
+    rng = np.random.RandomState(7)
+    U, V = 0.3 * rng.randn(n, 32), 0.3 * rng.randn(d, 32)
+    X = (O.expit(U @ V.T) if link == "logit" else U @ V.T) + 0.05 * rng.randn(n, d)
+    be = _tc_backend(path, splits)
+    gx, Hx, per_row = be.newton_v_xpart(be.to_device(V), be.to_device(U), be.ingest(X), 0, d, link, 0.7)
+    ref = 0.7 * (O.inverse(U @ V.T, link) - X.astype(np.float32).astype(np.float64)).T @ U
+    assert rel_fro(be.to_host(gx), ref) < tol
+
+
+@pytest.mark.parametrize("path", [1, 2])
+def test_tc_long_tile_loop_newton_step(path):
+    """Single split => every CTA walks all tiles (multi-phase mbarrier ring); one Newton step vs the oracle."""
+    case = _mid_case("newton", 700, 1300, 9, 32, False, seed=11, **dict(NT, y_link="logit"))
+    case["iters"] = 3
+    ref_hist, rU, rV, rZ = run_oracle(case)
+    hist, U, V, Z = run_ours(case, "float32", backend_options={"dense_path": path, "tc_max_splits": 1})
+    otol, ftol = (1e-4, 1e-3) if path == 1 else (2e-3, 2e-2)
+    assert (np.abs(hist - ref_hist) / np.abs(ref_hist)).max() < otol
+    for got, ref in ((U, rU), (V, rV), (Z, rZ)):
+        assert rel_fro(got, ref) < ftol
