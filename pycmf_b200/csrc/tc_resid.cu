@@ -11,7 +11,9 @@
 //   TMA        : X tile (128 x 64 fp32, SWIZZLE_128B) + the 64 x 32 factor tile Q (tf32 hi / lo parts)
 //   tcgen05.mma: S[128 x 64] = P Q^T          (GEMM1, accumulator in TMEM, 3xTF32: hi*hi + hi*lo + lo*hi)
 //   epilogue   : tcgen05.ld S -> f() -> minus X -> R (hi / lo) written back to swizzled shared memory
-//   tcgen05.mma: OUT[128 x 32] += R Q         (GEMM2, Q read MN-major from the same shared tile)
+//   tcgen05.mma: OUT[128 x 32] += R Q         (GEMM2; its B operand is a K-major tile of Q^T, loaded by TMA from a
+//                                              transposed tf32 copy of the factor: MN-major tf32 operands would need the
+//                                              128B_BASE32B swizzle, which the K-major GEMM1 read of the same tile cannot share)
 // so neither U V^T nor the residual ever touches HBM.  GEMM1 of tile t+1 is issued before GEMM2 of
 // tile t (two S buffers in TMEM) so the tensor pipe works while the epilogue warps convert tile t.
 //
@@ -41,8 +43,9 @@ struct SmemLayout {
     static constexpr uint32_t p_hi = 0;
     static constexpr uint32_t p_lo = p_hi + P_BYTES;
     static constexpr uint32_t stage0 = p_lo + P_BYTES;
-    static constexpr uint32_t q_hi = 0, q_lo = Q_BYTES, x = 2 * Q_BYTES;   // offsets inside a stage
-    static constexpr uint32_t stage_bytes = 2 * Q_BYTES + X_BYTES;
+    // offsets inside a stage: Q (64 x 32, K-major for GEMM1), Q^T (32 x 64 as two 32 x 32 K-blocks, GEMM2), X tile
+    static constexpr uint32_t q_hi = 0, q_lo = Q_BYTES, qt_hi = 2 * Q_BYTES, qt_lo = 3 * Q_BYTES, x = 4 * Q_BYTES;
+    static constexpr uint32_t stage_bytes = 4 * Q_BYTES + X_BYTES;
     static constexpr uint32_t r_hi = stage0 + NSTAGE * stage_bytes;
     static constexpr uint32_t r_lo = r_hi + R_BYTES;
     static constexpr uint32_t bars = r_lo + R_BYTES;
@@ -143,6 +146,7 @@ template <int MODE, bool RESID, int NSPLIT>
 __global__ void __launch_bounds__(256, 1)
 tc_pass_kernel(const __grid_constant__ CUtensorMap tm_p_hi, const __grid_constant__ CUtensorMap tm_p_lo,
                const __grid_constant__ CUtensorMap tm_q_hi, const __grid_constant__ CUtensorMap tm_q_lo,
+               const __grid_constant__ CUtensorMap tm_qt_hi, const __grid_constant__ CUtensorMap tm_qt_lo,
                const __grid_constant__ CUtensorMap tm_x, const Params prm) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     // dynamic shared memory is only guaranteed 16-byte aligned: round up to 1024 for the swizzle atoms
@@ -195,9 +199,17 @@ tc_pass_kernel(const __grid_constant__ CUtensorMap tm_p_hi, const __grid_constan
                 mbar_wait(bar(EMPTY0 + s), ph ^ 1u);
                 const uint32_t st = base + SmemLayout::stage0 + uint32_t(s) * SmemLayout::stage_bytes;
                 const int oth0 = int((t_begin + it) * OTH);
-                mbar_expect_tx(bar(FULL0 + s), (NSPLIT == 3 ? 2 * Q_BYTES : Q_BYTES) + X_BYTES);
-                tma_load_2d(st + SmemLayout::q_hi, &tm_q_hi, bar(FULL0 + s), 0, oth0);
-                if (NSPLIT == 3) tma_load_2d(st + SmemLayout::q_lo, &tm_q_lo, bar(FULL0 + s), 0, oth0);
+                mbar_expect_tx(bar(FULL0 + s), (RESID ? 2u : 1u) * (NSPLIT == 3 ? 2 * Q_BYTES : Q_BYTES) + X_BYTES);
+                if (RESID) {
+                    tma_load_2d(st + SmemLayout::q_hi, &tm_q_hi, bar(FULL0 + s), 0, oth0);
+                    if (NSPLIT == 3) tma_load_2d(st + SmemLayout::q_lo, &tm_q_lo, bar(FULL0 + s), 0, oth0);
+                }
+#pragma unroll
+                for (int b = 0; b < 2; b++) {
+                    tma_load_2d(st + SmemLayout::qt_hi + uint32_t(b) * (KC * 128), &tm_qt_hi, bar(FULL0 + s), oth0 + 32 * b, 0);
+                    if (NSPLIT == 3)
+                        tma_load_2d(st + SmemLayout::qt_lo + uint32_t(b) * (KC * 128), &tm_qt_lo, bar(FULL0 + s), oth0 + 32 * b, 0);
+                }
                 if (MODE == 0) {
                     // X tile: own rows x 64 other columns, two 32-column boxes of 128 rows
                     tma_load_2d(st + SmemLayout::x, &tm_x, bar(FULL0 + s), oth0, int(own0));
@@ -215,7 +227,7 @@ tc_pass_kernel(const __grid_constant__ CUtensorMap tm_p_hi, const __grid_constan
         // =============================== MMA issuer ================================
         if (lane == 0) {
             constexpr uint32_t idesc1 = make_idesc(OWN, OTH, 0, 0);   // S   = P (K-major) x Q (K-major)
-            constexpr uint32_t idesc2 = make_idesc(OWN, KC, 0, 1);    // OUT = R (K-major) x Q (MN-major)
+            constexpr uint32_t idesc2 = make_idesc(OWN, KC, 0, 0);    // OUT = R (K-major) x Q^T tile (K-major)
             const uint32_t p_hi = base + SmemLayout::p_hi, p_lo = base + SmemLayout::p_lo;
             const uint32_t r_hi = base + SmemLayout::r_hi, r_lo = base + SmemLayout::r_lo;
             auto issue_g1 = [&](int it) {
@@ -257,12 +269,12 @@ tc_pass_kernel(const __grid_constant__ CUtensorMap tm_p_hi, const __grid_constan
 #pragma unroll
                 for (int term = 0; term < NSPLIT; term++) {
                     const uint32_t ra = (term == 2) ? r_lo : r_hi;
-                    const uint32_t qa = st + ((term == 1) ? SmemLayout::q_lo : SmemLayout::q_hi);
+                    const uint32_t qa = st + ((term == 1) ? SmemLayout::qt_lo : SmemLayout::qt_hi);
 #pragma unroll
                     for (int kk = 0; kk < OTH / 8; kk++) {
                         const uint32_t a_addr = ra + uint32_t(kk / 4) * (OWN * 128) + uint32_t(kk % 4) * 32;
-                        const uint32_t b_addr = qa + uint32_t(kk) * 1024;
-                        umma_tf32(d, make_desc(a_addr, 16, 1024), make_desc(b_addr, OTH * 128, 1024), idesc2, out_acc);
+                        const uint32_t b_addr = qa + uint32_t(kk / 4) * (KC * 128) + uint32_t(kk % 4) * 32;
+                        umma_tf32(d, make_desc(a_addr, 16, 1024), make_desc(b_addr, 16, 1024), idesc2, out_acc);
                         out_acc = 1;
                     }
                 }
@@ -315,6 +327,7 @@ tc_pass_kernel(const __grid_constant__ CUtensorMap tm_p_hi, const __grid_constan
                                                                     ((ch ^ (j & 7)) << 4) + w * 4);
                         }
                     }
+#pragma unroll
 #pragma unroll
                     for (int e = 0; e < 4; e++) {
                         const int j = c * 16 + g * 4 + e;
@@ -396,14 +409,32 @@ tc_pass_kernel(const __grid_constant__ CUtensorMap tm_p_hi, const __grid_constan
     }
 }
 
-__global__ void split_tf32_kernel(int64_t n, const float* __restrict__ x, float* __restrict__ hi,
-                                  float* __restrict__ lo) {
-    int64_t e = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (e >= n) return;
-    float v = x[e];
-    float h = tf32_rna(v);
-    hi[e] = h;
-    lo[e] = tf32_rna(v - h);
+// tf32 hi / lo parts of a factor F (rows x 32), in the original layout and transposed (32 x ldt)
+__global__ void split_tf32_kernel(int64_t rows, int64_t ldt, const float* __restrict__ x, float* __restrict__ hi,
+                                  float* __restrict__ lo, float* __restrict__ hi_t, float* __restrict__ lo_t) {
+    __shared__ float th[32][33], tl[32][33];
+    const int64_t r0 = int64_t(blockIdx.x) * 32;
+    for (int rr = threadIdx.y; rr < 32; rr += blockDim.y) {
+        int64_t r = r0 + rr;
+        float h = 0.f, l = 0.f;
+        if (r < rows) {
+            float v = x[r * KC + threadIdx.x];
+            h = tf32_rna(v);
+            l = tf32_rna(v - h);
+            hi[r * KC + threadIdx.x] = h;
+            lo[r * KC + threadIdx.x] = l;
+        }
+        th[rr][threadIdx.x] = h;
+        tl[rr][threadIdx.x] = l;
+    }
+    __syncthreads();
+    for (int c = threadIdx.y; c < 32; c += blockDim.y) {
+        int64_t r = r0 + threadIdx.x;
+        if (r < ldt) {
+            hi_t[int64_t(c) * ldt + r] = th[threadIdx.x][c];
+            lo_t[int64_t(c) * ldt + r] = tl[threadIdx.x][c];
+        }
+    }
 }
 
 // ---- host side --------------------------------------------------------------------------------
@@ -437,10 +468,19 @@ CUtensorMap make_map(const float* ptr, int64_t rows, int64_t cols, int64_t ld, i
     return m;
 }
 
+// tf32 parts of one factor in HBM: hi / lo in the factor's own layout (rows x 32) and transposed (32 x ldt)
+struct FactorParts {
+    const float *hi, *lo, *hi_t, *lo_t;
+    int64_t rows, ldt;
+};
+
+// generic 2-D map: `cols` contiguous, box = (32, box_rows)
+CUtensorMap factor_map(const float* p, int64_t rows, int box_rows) { return make_map(p, rows, KC, KC, box_rows); }
+CUtensorMap factor_t_map(const float* p, int64_t rows, int64_t ldt) { return make_map(p, KC, rows, ldt, KC); }
+
 template <int MODE, bool RESID, int NSPLIT>
-void launch_tc(pycmf_ctx* ctx, int64_t own_n, int64_t oth_n, const float* P_hi, const float* P_lo, const float* Q_hi,
-               const float* Q_lo, const float* X, int64_t x_rows, int64_t x_cols, int64_t ldx, int link, float* out,
-               double* sq) {
+void launch_tc(pycmf_ctx* ctx, int64_t own_n, int64_t oth_n, const FactorParts& P, const FactorParts& Q,
+               const float* X, int64_t x_rows, int64_t x_cols, int64_t ldx, int link, float* out, double* sq) {
     const int64_t own_tiles = ceil_div(own_n, OWN), loop_tiles = ceil_div(oth_n, OTH);
     int64_t splits = 1;
     if (own_tiles < 4 * ctx->num_sms)
@@ -449,10 +489,13 @@ void launch_tc(pycmf_ctx* ctx, int64_t own_n, int64_t oth_n, const float* P_hi, 
     int64_t tiles_per_split = ceil_div(loop_tiles, splits);
     splits = ceil_div(loop_tiles, tiles_per_split);
     PYCMF_CHECK(splits <= 65535, "tc pass: too many splits");
-    CUtensorMap tm_p_hi = make_map(RESID ? P_hi : Q_hi, RESID ? own_n : oth_n, KC, KC, RESID ? OWN : OTH);
-    CUtensorMap tm_p_lo = make_map(RESID ? P_lo : Q_lo, RESID ? own_n : oth_n, KC, KC, RESID ? OWN : OTH);
-    CUtensorMap tm_q_hi = make_map(Q_hi, oth_n, KC, KC, OTH);
-    CUtensorMap tm_q_lo = make_map(Q_lo, oth_n, KC, KC, OTH);
+    const FactorParts& Pm = RESID ? P : Q;   // P is unused (but must be a valid map) in COPY mode
+    CUtensorMap tm_p_hi = factor_map(Pm.hi, Pm.rows, RESID ? OWN : OTH);
+    CUtensorMap tm_p_lo = factor_map(Pm.lo, Pm.rows, RESID ? OWN : OTH);
+    CUtensorMap tm_q_hi = factor_map(Q.hi, Q.rows, OTH);
+    CUtensorMap tm_q_lo = factor_map(Q.lo, Q.rows, OTH);
+    CUtensorMap tm_qt_hi = factor_t_map(Q.hi_t, Q.rows, Q.ldt);
+    CUtensorMap tm_qt_lo = factor_t_map(Q.lo_t, Q.rows, Q.ldt);
     CUtensorMap tm_x = make_map(X, x_rows, x_cols, ldx, MODE == 0 ? OWN : OTH);
     Params prm;
     prm.own_n = own_n;
@@ -470,21 +513,27 @@ void launch_tc(pycmf_ctx* ctx, int64_t own_n, int64_t oth_n, const float* P_hi, 
     if (RESID && sq != nullptr) prm.sq_part = static_cast<double*>(scratch(ctx, 1, size_t(nparts) * sizeof(double)));
     auto kern = tc_pass_kernel<MODE, RESID, NSPLIT>;
     const size_t smem = SmemLayout::total + 1024;
+    PYCMF_CHECK(smem <= size_t(ctx->max_smem_optin), "tc pass: shared memory budget exceeded");
     PYCMF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
     dim3 grid((unsigned)own_tiles, (unsigned)splits);
     {
         Timed timer(ctx, RESID ? (MODE == 0 ? "tc_resid_left" : "tc_resid_right") : (MODE == 0 ? "tc_xv" : "tc_xtu"));
-        kern<<<grid, 256, smem, ctx->stream>>>(tm_p_hi, tm_p_lo, tm_q_hi, tm_q_lo, tm_x, prm);
+        kern<<<grid, 256, smem, ctx->stream>>>(tm_p_hi, tm_p_lo, tm_q_hi, tm_q_lo, tm_qt_hi, tm_qt_lo, tm_x, prm);
         PYCMF_LAUNCH_CHECK(ctx);
     }
     if (splits > 1) reduce_parts<float>(ctx, own_n, KC, int(splits), prm.out, out, KC, 1.0f, 0.0f);
     if (prm.sq_part != nullptr) final_sum(ctx, int(nparts), prm.sq_part, 1.0, sq, true);
 }
 
-void split_factor(pycmf_ctx* ctx, int64_t rows, const float* F, float* hi, float* lo) {
-    int64_t n = rows * KC;
-    split_tf32_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, ctx->stream>>>(n, F, hi, lo);
+size_t parts_floats(int64_t rows) { return size_t(2) * rows * KC + size_t(2) * KC * ((rows + 3) & ~int64_t(3)); }
+
+// writes the four tf32 part arrays of F into `buf` (parts_floats(rows) floats)
+FactorParts split_factor(pycmf_ctx* ctx, int64_t rows, const float* F, float* buf) {
+    const int64_t ldt = (rows + 3) & ~int64_t(3);
+    float *hi = buf, *lo = hi + rows * KC, *hi_t = lo + rows * KC, *lo_t = hi_t + KC * ldt;
+    split_tf32_kernel<<<(unsigned)ceil_div(ldt, 32), dim3(32, 8), 0, ctx->stream>>>(rows, ldt, F, hi, lo, hi_t, lo_t);
     PYCMF_LAUNCH_CHECK(ctx);
+    return FactorParts{hi, lo, hi_t, lo_t, rows, ldt};
 }
 
 }  // namespace
@@ -500,23 +549,19 @@ bool tc_dense_eligible(pycmf_ctx* ctx, int64_t ra, int64_t rb, int64_t k, const 
 // R = f(A B^T) - X (RESID) : outL = R B and / or outR = R^T A, *sq += sum R^2.   A: ra x 32, B: rb x 32, X: ra x rb.
 void tc_resid_pass(pycmf_ctx* ctx, int64_t ra, int64_t rb, const float* A, const float* B, const float* X, int64_t ldx,
                    int link, float* outL, float* outR, double* sq) {
+    PYCMF_CHECK(outL != nullptr || outR != nullptr, "tc_resid_pass: objective-only passes use the generic kernel");
     const bool three = ctx->dense_path != 2;
-    float* buf = static_cast<float*>(scratch(ctx, 3, sizeof(float) * size_t(2) * (ra + rb) * KC));
-    float *A_hi = buf, *A_lo = buf + ra * KC, *B_hi = buf + 2 * ra * KC, *B_lo = buf + (2 * ra + rb) * KC;
-    if (three) {
-        split_factor(ctx, ra, A, A_hi, A_lo);
-        split_factor(ctx, rb, B, B_hi, B_lo);
-    }
-    const float *Ah = three ? A_hi : A, *Al = three ? A_lo : A, *Bh = three ? B_hi : B, *Bl = three ? B_lo : B;
-    if (outL != nullptr || (outR == nullptr && sq != nullptr)) {
-        PYCMF_CHECK(outL != nullptr, "tc_resid_pass: objective-only passes use the generic kernel");
-        if (three) launch_tc<0, true, 3>(ctx, ra, rb, Ah, Al, Bh, Bl, X, ra, rb, ldx, link, outL, sq);
-        else launch_tc<0, true, 1>(ctx, ra, rb, Ah, Al, Bh, Bl, X, ra, rb, ldx, link, outL, sq);
+    float* buf = static_cast<float*>(scratch(ctx, 3, sizeof(float) * (parts_floats(ra) + parts_floats(rb) + 64)));
+    FactorParts Ap = split_factor(ctx, ra, A, buf);
+    FactorParts Bp = split_factor(ctx, rb, B, buf + ((parts_floats(ra) + 31) & ~size_t(31)));
+    if (outL != nullptr) {
+        if (three) launch_tc<0, true, 3>(ctx, ra, rb, Ap, Bp, X, ra, rb, ldx, link, outL, sq);
+        else launch_tc<0, true, 1>(ctx, ra, rb, Ap, Bp, X, ra, rb, ldx, link, outL, sq);
     }
     if (outR != nullptr) {
         double* s2 = outL == nullptr ? sq : nullptr;
-        if (three) launch_tc<1, true, 3>(ctx, rb, ra, Bh, Bl, Ah, Al, X, ra, rb, ldx, link, outR, s2);
-        else launch_tc<1, true, 1>(ctx, rb, ra, Bh, Bl, Ah, Al, X, ra, rb, ldx, link, outR, s2);
+        if (three) launch_tc<1, true, 3>(ctx, rb, ra, Bp, Ap, X, ra, rb, ldx, link, outR, s2);
+        else launch_tc<1, true, 1>(ctx, rb, ra, Bp, Ap, X, ra, rb, ldx, link, outR, s2);
     }
 }
 
@@ -526,16 +571,14 @@ void tc_xmul(pycmf_ctx* ctx, bool trans, int64_t rows, int64_t cols, const float
              float* out) {
     const bool three = ctx->dense_path != 2;
     const int64_t qn = trans ? rows : cols;
-    float* buf = static_cast<float*>(scratch(ctx, 3, sizeof(float) * size_t(2) * qn * KC));
-    float *Q_hi = buf, *Q_lo = buf + qn * KC;
-    if (three) split_factor(ctx, qn, Q, Q_hi, Q_lo);
-    const float *Qh = three ? Q_hi : Q, *Ql = three ? Q_lo : Q;
+    float* buf = static_cast<float*>(scratch(ctx, 3, sizeof(float) * (parts_floats(qn) + 64)));
+    FactorParts Qp = split_factor(ctx, qn, Q, buf);
     if (!trans) {
-        if (three) launch_tc<0, false, 3>(ctx, rows, cols, nullptr, nullptr, Qh, Ql, X, rows, cols, ldx, 0, out, nullptr);
-        else launch_tc<0, false, 1>(ctx, rows, cols, nullptr, nullptr, Qh, Ql, X, rows, cols, ldx, 0, out, nullptr);
+        if (three) launch_tc<0, false, 3>(ctx, rows, cols, Qp, Qp, X, rows, cols, ldx, 0, out, nullptr);
+        else launch_tc<0, false, 1>(ctx, rows, cols, Qp, Qp, X, rows, cols, ldx, 0, out, nullptr);
     } else {
-        if (three) launch_tc<1, false, 3>(ctx, cols, rows, nullptr, nullptr, Qh, Ql, X, rows, cols, ldx, 0, out, nullptr);
-        else launch_tc<1, false, 1>(ctx, cols, rows, nullptr, nullptr, Qh, Ql, X, rows, cols, ldx, 0, out, nullptr);
+        if (three) launch_tc<1, false, 3>(ctx, cols, rows, Qp, Qp, X, rows, cols, ldx, 0, out, nullptr);
+        else launch_tc<1, false, 1>(ctx, cols, rows, Qp, Qp, X, rows, cols, ldx, 0, out, nullptr);
     }
 }
 

@@ -218,7 +218,7 @@ def _tc_backend(path, splits=0):
 
 
 @pytest.mark.parametrize("shape", [(1000, 520), (300, 2052), (4100, 260)])
-@pytest.mark.parametrize("path,tol", [(0, 3e-6), (1, 3e-6), (2, 3e-3)])
+@pytest.mark.parametrize("path,tol", [(0, 3e-6), (1, 2e-5), (2, 3e-3)])
 @pytest.mark.parametrize("splits", [0, 1])
 def test_tc_mu_products_match_numpy(shape, path, tol, splits):
     """X^T U and X V on the tensor cores (3xTF32 ~ fp32 accuracy, 1xTF32 ~ 1e-3) vs float64 NumPy."""
@@ -239,7 +239,7 @@ def test_tc_mu_products_match_numpy(shape, path, tol, splits):
 
 
 @pytest.mark.parametrize("link", ["linear", "logit"])
-@pytest.mark.parametrize("path,tol", [(0, 5e-6), (1, 5e-6), (2, 5e-3)])
+@pytest.mark.parametrize("path,tol", [(0, 5e-6), (1, 2e-5), (2, 5e-3)])
 @pytest.mark.parametrize("splits", [0, 1])
 def test_tc_fused_residual_right_matches_numpy(link, path, tol, splits):
     """gx = alpha (f(U V^T) - X)^T U from the fused tcgen05 kernel vs float64 NumPy (X never leaves fp32)."""
