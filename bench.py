@@ -230,7 +230,7 @@ def run_ours(args):
     clock_info = clocks.finish()
     fams = {}
     for fam in ("resid_left", "resid_right", "gemm", "spmm", "sddmm", "row_grad_hess", "safe_solve",
-                "tc_xv", "tc_xtu", "tc_resid_left", "tc_resid_right"):
+                "newton_finish_small", "tc_xv", "tc_xtu", "tc_resid_left", "tc_resid_right"):
         tot, cnt = be.profile_query(fam)
         if cnt:
             fams[fam] = (tot, cnt)
@@ -257,7 +257,10 @@ def run_ours(args):
     if fams:
         dom = max(fams, key=lambda f: fams[f][0])
         tot, cnt = fams[dom]
-        if cfg["sparse"]:
+        if dom in ("row_grad_hess", "safe_solve", "newton_finish_small"):
+            # factor-sized kernels (latency / ALU bound): bytes = factors in + out, label rows, per-row k x k where used
+            alg_bytes = (3 * d * k + d * l + k * k) * sb
+        elif cfg["sparse"]:
             nnz = data["X"].nnz
             alg_bytes = nnz * (sb + 4) + (n_loc + 1) * 4 + (n_loc + min(d, nnz)) * k * sb
         else:

@@ -180,9 +180,10 @@ void newton_left_impl(pycmf_ctx* ctx, int64_t rows, int64_t m, int64_t k, T* F, 
             spmm<T>(ctx, rows, rowptr, colidx, vals, B, k, k, g, k, T(-weight), T(1));
         }
         if (link == PYCMF_LINEAR) {
-            T* H = static_cast<T*>(scratch(ctx, SLOT_T1, sizeof(T) * size_t(k) * k));
-            gemm<T>(ctx, true, k, k, m, B, k, B, k, H, k, T(weight), T(0));
-            newton_solve_rows<T>(ctx, rows, k, F, g, H, 0, l1, l2, l2_diag, pert, non_negative);
+            // shared Hessian weight * B^T B + l2 I (cmf_solvers.py:407-410), Gram accumulated in float64
+            double* G64 = static_cast<double*>(scratch(ctx, SLOT_T1, sizeof(double) * size_t(k) * k));
+            gram_f64<T>(ctx, m, k, B, G64);
+            newton_solve_shared64<T>(ctx, rows, k, F, g, G64, weight, l1, l2, l2_diag, pert, non_negative);
             return;
         }
     }
@@ -248,6 +249,9 @@ void newton_v_finish_impl(pycmf_ctx* ctx, int64_t d_rows, int64_t l, int64_t k, 
     if (d_rows <= 0) return;
     const bool sampled = idx != nullptr;
     const double wy = 1.0 - alpha;
+    if (!sampled && newton_finish_small<T>(ctx, d_rows, l, k, V, Z, Yr, ldy, y_link, wy, gx, Hx, hx_per_row, l1, l2, l2,
+                                           pert, non_negative))
+        return;
     const bool per_row = hx_per_row || sampled || y_link == PYCMF_LOGIT;
     T* g = static_cast<T*>(scratch(ctx, SLOT_T0, sizeof(T) * size_t(d_rows) * k));
     T* H = static_cast<T*>(scratch(ctx, SLOT_T1, sizeof(T) * size_t(per_row ? d_rows : 1) * k * k));

@@ -193,6 +193,15 @@ void row_grad_hess(pycmf_ctx* ctx, int64_t rows, int64_t m, int64_t k, const T* 
 template <typename T>
 void newton_solve_rows(pycmf_ctx* ctx, int64_t rows, int64_t k, T* F, const T* g, const T* H, int64_t h_stride,
                        double l1, double l2, double l2_diag, double pert, bool non_negative);
+// shared Hessian given in float64 as h_scale * G (+ l2_diag I): invert once, apply to every row
+template <typename T>
+void newton_solve_shared64(pycmf_ctx* ctx, int64_t rows, int64_t k, T* F, const T* g, const double* G64, double h_scale,
+                           double l1, double l2, double l2_diag, double pert, bool non_negative);
+// newton_small.cu : fused warp-per-row finish of the V update for k <= 32 and a small label factor; false = not eligible
+template <typename T>
+bool newton_finish_small(pycmf_ctx* ctx, int64_t rows, int64_t l, int64_t k, T* F, const T* Z, const T* Y, int64_t ldy,
+                         int y_link, double wy, const T* gx, const T* Hx, bool hx_per_row, double l1, double l2,
+                         double l2_diag, double pert, bool non_negative);
 void safe_solve_f64(pycmf_ctx* ctx, int64_t batch, int64_t k, const double* H, int64_t h_stride,
                     const double* g, double* x, double pert);
 void sample_indices(pycmf_ctx* ctx, int64_t rows, int64_t N, int64_t n_sample, uint64_t seed,

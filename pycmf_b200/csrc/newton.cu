@@ -22,7 +22,8 @@ row_grad_hess_kernel(int64_t rows, int64_t m, int k, const T* __restrict__ A, co
                      const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx,
                      const T* __restrict__ vals, int link, T w,
                      const int32_t* __restrict__ idx, int64_t n_sample,
-                     T* __restrict__ g, T* __restrict__ H, bool accumulate, int a_off, int b_off) {
+                     T* __restrict__ g, T* __restrict__ H, bool accumulate, int a_off, int b_off,
+                     int64_t samples_per_split, int64_t g_split_stride, int64_t h_split_stride) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int kp = k + 1;
     T* a_s = reinterpret_cast<T*>(smem_raw);          // k
@@ -42,11 +43,15 @@ row_grad_hess_kernel(int64_t rows, int64_t m, int k, const T* __restrict__ A, co
 #pragma unroll
         for (int y = 0; y < HB; y++) hacc[x][y] = T(0);
 
-    const int64_t total = idx != nullptr ? n_sample : m;
+    const int64_t total_all = idx != nullptr ? n_sample : m;
+    const int64_t t_first = int64_t(blockIdx.y) * samples_per_split;
+    const int64_t total = t_first + samples_per_split < total_all ? t_first + samples_per_split : total_all;
+    if (g != nullptr) g += int64_t(blockIdx.y) * g_split_stride;
+    if (H != nullptr) H += int64_t(blockIdx.y) * h_split_stride;
     int lo = 0, hi = 0;
     if (rowptr != nullptr) { lo = rowptr[i]; hi = rowptr[i + 1]; }
 
-    for (int64_t t0 = 0; t0 < total; t0 += TJ) {
+    for (int64_t t0 = t_first; t0 < total; t0 += TJ) {
         const int64_t rem_t = total - t0;
         const int cnt = rem_t < TJ ? int(rem_t) : TJ;
         __syncthreads();
@@ -151,11 +156,11 @@ struct SolveShared {
 // Load the LOWER triangle of H (row-major, like scipy.linalg.eigh(lower=True)) into W (column-major
 // == row-major for a symmetric matrix), adding `diag` on the diagonal.
 template <typename T>
-__device__ __forceinline__ void load_sym(double* W, const T* __restrict__ H, int k, double diag) {
+__device__ __forceinline__ void load_sym(double* W, const T* __restrict__ H, int k, double diag, double scale) {
     for (int e = threadIdx.x; e < k * k; e += blockDim.x) {
         int r = e / k, c = e % k;
         int hi = r > c ? r : c, lo = r > c ? c : r;
-        double v = double(H[hi * k + lo]);
+        double v = scale * double(H[hi * k + lo]);
         if (r == c) v += diag;
         W[e] = v;
     }
@@ -284,18 +289,19 @@ __device__ void jacobi_clamped_solve(double* W, int k, const double* g, double* 
 // The whole clamped solve for one matrix; H is (re)loaded from global memory as needed.
 template <typename T>
 __device__ void safe_solve_one(double* W, const T* __restrict__ H, int k, double diag, const double* g,
-                               double* x, double* xpart, SolveShared* sh, double pert, bool chol_fastpath) {
+                               double* x, double* xpart, SolveShared* sh, double pert, bool chol_fastpath,
+                               double scale) {
     bool done = false;
     if (chol_fastpath) {
         // lambda_min(H) > pert  <=>  H - pert I is positive definite  <=>  its Cholesky succeeds
-        load_sym<T>(W, H, k, diag - pert);
+        load_sym<T>(W, H, k, diag - pert, scale);
         __syncthreads();
         double tr = 0.0;
         for (int r = 0; r < k; r++) tr += fabs(W[r * k + r]);   // every thread, same value (k <= 256)
         bool ok = cholesky_inplace(W, k, sh, 1e-13 * (tr + pert));
         __syncthreads();
         if (ok) {
-            load_sym<T>(W, H, k, diag);
+            load_sym<T>(W, H, k, diag, scale);
             __syncthreads();
             ok = cholesky_inplace(W, k, sh, 0.0);
             if (ok) {
@@ -308,7 +314,7 @@ __device__ void safe_solve_one(double* W, const T* __restrict__ H, int k, double
         __syncthreads();
     }
     if (!done) {
-        load_sym<T>(W, H, k, diag);
+        load_sym<T>(W, H, k, diag, scale);
         __syncthreads();
         jacobi_clamped_solve(W, k, g, x, xpart, sh, pert);
     }
@@ -319,7 +325,7 @@ template <typename T, int MODE>
 __global__ void __launch_bounds__(256)
 safe_solve_kernel(int64_t batch, int k, const T* __restrict__ H, int64_t h_stride, const T* __restrict__ g,
                   T* __restrict__ out, double l1, double l2, double l2_diag, double pert, bool non_negative,
-                  bool chol_fastpath, double* __restrict__ Wglobal) {
+                  bool chol_fastpath, double* __restrict__ Wglobal, double h_scale) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int nwarps = blockDim.x >> 5;
     double* gv = reinterpret_cast<double*>(smem_raw);   // k
@@ -340,7 +346,7 @@ safe_solve_kernel(int64_t batch, int k, const T* __restrict__ H, int64_t h_strid
             gv[r] = gr;
         }
         __syncthreads();
-        safe_solve_one<T>(W, H + b * h_stride, k, l2_diag, gv, xv, xpart, sh, pert, chol_fastpath);
+        safe_solve_one<T>(W, H + b * h_stride, k, l2_diag, gv, xv, xpart, sh, pert, chol_fastpath, h_scale);
         __syncthreads();
         for (int r = threadIdx.x; r < k; r += blockDim.x) {
             if (MODE == 0) {
@@ -443,7 +449,7 @@ size_t solve_smem_bytes(int k, int nthreads, bool w_in_smem) {
 
 template <typename T, int MODE>
 void launch_solve(pycmf_ctx* ctx, int64_t batch, int64_t k, const T* H, int64_t h_stride, const T* g, T* out,
-                  double l1, double l2, double l2_diag, double pert, bool non_negative) {
+                  double l1, double l2, double l2_diag, double pert, bool non_negative, double h_scale = 1.0) {
     if (batch <= 0) return;
     PYCMF_CHECK(k >= 1 && k <= 256, "n_components must be in [1, 256] for the Newton solve");
     PYCMF_CHECK(pert > 0.0, "hessian_pertubation must be > 0");
@@ -462,7 +468,7 @@ void launch_solve(pycmf_ctx* ctx, int64_t batch, int64_t k, const T* H, int64_t 
     }
     Timed timer(ctx, "safe_solve");
     kern<<<(unsigned)grid, nthreads, smem, ctx->stream>>>(batch, int(k), H, h_stride, g, out, l1, l2, l2_diag,
-                                                         pert, non_negative, ctx->chol_fastpath != 0, Wg);
+                                                         pert, non_negative, ctx->chol_fastpath != 0, Wg, h_scale);
     PYCMF_LAUNCH_CHECK(ctx);
 }
 
@@ -479,27 +485,52 @@ void row_grad_hess(pycmf_ctx* ctx, int64_t rows, int64_t m, int64_t k, const T* 
     size_t smem = sizeof(T) * (size_t((k + 3) & ~3) + size_t(TJ) * (k + 1) + 2 * TJ);
     int hb = k <= 16 ? 1 : (k <= 32 ? 2 : (k <= 64 ? 4 : 8));
     int quads = k > 128 ? 2 : 1;
-    Timed timer(ctx, "row_grad_hess");
-    for (int qa = 0; qa < quads; qa++) {
-        for (int qb = 0; qb < quads; qb++) {
-            bool first = (qa == 0 && qb == 0);
-            T* gq = first ? g : nullptr;
-            if (!first && H == nullptr) continue;
+    // few rows, many samples (e.g. the Z update: l rows against d samples): split the samples over CTAs
+    const int64_t total = idx != nullptr ? n_sample : m;
+    int64_t nsplit = 1;
+    if (quads == 1 && rows < 2 * ctx->num_sms && total >= 8 * TJ)
+        nsplit = std::max<int64_t>(1, std::min(ceil_div(total, 4 * TJ), ceil_div(int64_t(4) * ctx->num_sms, rows)));
+    int64_t per_split = ceil_div(ceil_div(std::max<int64_t>(total, 1), nsplit), TJ) * TJ;
+    nsplit = std::max<int64_t>(1, ceil_div(std::max<int64_t>(total, 1), per_split));
+    T *g_out = g, *H_out = H;
+    int64_t g_stride = 0, h_stride = 0;
+    bool acc_kernel = accumulate;
+    if (nsplit > 1) {
+        size_t gbytes = g ? size_t(nsplit) * rows * k * sizeof(T) : 0, hbytes = H ? size_t(nsplit) * rows * k * k * sizeof(T) : 0;
+        gbytes = (gbytes + 255) & ~size_t(255);
+        unsigned char* part = static_cast<unsigned char*>(scratch(ctx, 0, gbytes + hbytes + 256));
+        if (g) { g_out = reinterpret_cast<T*>(part); g_stride = rows * k; }
+        if (H) { H_out = reinterpret_cast<T*>(part + gbytes); h_stride = rows * k * k; }
+        acc_kernel = false;
+    }
+    {
+        Timed timer(ctx, "row_grad_hess");
+        for (int qa = 0; qa < quads; qa++) {
+            for (int qb = 0; qb < quads; qb++) {
+                bool first = (qa == 0 && qb == 0);
+                T* gq = first ? g_out : nullptr;
+                if (!first && H == nullptr) continue;
+                dim3 grid((unsigned)rows, (unsigned)nsplit);
 #define LAUNCH(HB)                                                                                        \
     do {                                                                                                  \
         auto kern = row_grad_hess_kernel<T, HB>;                                                          \
         PYCMF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));   \
-        kern<<<(unsigned)rows, 256, smem, ctx->stream>>>(rows, m, int(k), A, B, Tgt, ldt, trans_t, rowptr, \
-                                                         colidx, vals, link, T(w), idx, n_sample, gq, H,  \
-                                                         accumulate, qa * 128, qb * 128);                 \
+        kern<<<grid, 256, smem, ctx->stream>>>(rows, m, int(k), A, B, Tgt, ldt, trans_t, rowptr, colidx,  \
+                                               vals, link, T(w), idx, n_sample, gq, H_out, acc_kernel,    \
+                                               qa * 128, qb * 128, per_split, g_stride, h_stride);        \
     } while (0)
-            if (hb == 1) LAUNCH(1);
-            else if (hb == 2) LAUNCH(2);
-            else if (hb == 4) LAUNCH(4);
-            else LAUNCH(8);
+                if (hb == 1) LAUNCH(1);
+                else if (hb == 2) LAUNCH(2);
+                else if (hb == 4) LAUNCH(4);
+                else LAUNCH(8);
 #undef LAUNCH
-            PYCMF_LAUNCH_CHECK(ctx);
+                PYCMF_LAUNCH_CHECK(ctx);
+            }
         }
+    }
+    if (nsplit > 1) {
+        if (g) reduce_parts<T>(ctx, rows, k, int(nsplit), g_out, g, k, T(1), accumulate ? T(1) : T(0));
+        if (H) reduce_parts<T>(ctx, rows, k * k, int(nsplit), H_out, H, k * k, T(1), accumulate ? T(1) : T(0));
     }
 }
 
@@ -532,6 +563,22 @@ void newton_solve_rows(pycmf_ctx* ctx, int64_t rows, int64_t k, T* F, const T* g
     PYCMF_LAUNCH_CHECK(ctx);
 }
 
+template <typename T>
+void newton_solve_shared64(pycmf_ctx* ctx, int64_t rows, int64_t k, T* F, const T* g, const double* G64, double h_scale,
+                           double l1, double l2, double l2_diag, double pert, bool non_negative) {
+    if (rows <= 0) return;
+    double* buf = static_cast<double*>(scratch(ctx, 3, sizeof(double) * size_t(2) * k * k));
+    double *I64 = buf, *Hinv = buf + k * k;
+    int64_t n = k * k;
+    identity_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, ctx->stream>>>(int(k), I64);
+    PYCMF_LAUNCH_CHECK(ctx);
+    launch_solve<double, 0>(ctx, k, k, G64, 0, I64, Hinv, 0.0, 0.0, l2_diag, pert, false, h_scale);
+    size_t smem = sizeof(double) * size_t(8) * k;
+    apply_shared_inverse_kernel<T><<<(unsigned)ceil_div(rows, 8), 256, smem, ctx->stream>>>(rows, int(k), F, g, Hinv, l1, l2,
+                                                                                       non_negative);
+    PYCMF_LAUNCH_CHECK(ctx);
+}
+
 void sample_indices(pycmf_ctx* ctx, int64_t rows, int64_t N, int64_t n_sample, uint64_t seed,
                     uint64_t stream_id, int32_t* idx) {
     int64_t n = rows * n_sample;
@@ -547,7 +594,9 @@ void sample_indices(pycmf_ctx* ctx, int64_t rows, int64_t N, int64_t n_sample, u
                                    bool, const int32_t*, const int32_t*, const T*, int, double, const int32_t*, \
                                    int64_t, T*, T*, bool);                                                      \
     template void newton_solve_rows<T>(pycmf_ctx*, int64_t, int64_t, T*, const T*, const T*, int64_t, double,   \
-                                       double, double, double, bool);
+                                       double, double, double, bool);                                           \
+    template void newton_solve_shared64<T>(pycmf_ctx*, int64_t, int64_t, T*, const T*, const double*, double,   \
+                                           double, double, double, double, bool);
 INSTANTIATE(float)
 INSTANTIATE(double)
 

@@ -17,8 +17,10 @@
 // so neither U V^T nor the residual ever touches HBM.  GEMM1 of tile t+1 is issued before GEMM2 of
 // tile t (two S buffers in TMEM) so the tensor pipe works while the epilogue warps convert tile t.
 //
-// Warp roles (256 threads): warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator,
-// warps 4-7 = epilogue (thread i <-> TMEM lane i <-> own row i).
+// Warp roles (640 threads): warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator,
+// warps 4-19 = epilogue: warp w works on TMEM lane quadrant w % 4 (own rows 32 (w % 4) ..) and on the
+// 16-column chunk (w - 4) / 4 of the 64-wide tile, so every SM sub-partition has four epilogue warps to
+// hide the TMEM / shared-memory latencies.
 #include <cuda.h>
 
 #include "common.cuh"
@@ -32,6 +34,8 @@ constexpr int KC = 32;        // n_components handled by this kernel (one 128-by
 constexpr int NSTAGE = 2;
 constexpr int TMEM_COLS = 256;
 constexpr int TMEM_OUT_COL = 128;
+constexpr int EPI_WARPS = 16;
+constexpr int NTHREADS = 128 + 32 * EPI_WARPS;
 
 constexpr uint32_t P_BYTES = OWN * 128;          // 16 KB  (128 rows x 32 fp32)
 constexpr uint32_t Q_BYTES = OTH * 128;          //  8 KB
@@ -143,7 +147,7 @@ struct Params {
 
 // MODE 0 = LEFT (own = rows of X), 1 = RIGHT (own = columns of X).  RESID: R = f(S) - X, else R = X.
 template <int MODE, bool RESID, int NSPLIT>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(NTHREADS, 1)
 tc_pass_kernel(const __grid_constant__ CUtensorMap tm_p_hi, const __grid_constant__ CUtensorMap tm_p_lo,
                const __grid_constant__ CUtensorMap tm_q_hi, const __grid_constant__ CUtensorMap tm_q_lo,
                const __grid_constant__ CUtensorMap tm_qt_hi, const __grid_constant__ CUtensorMap tm_qt_lo,
@@ -166,8 +170,8 @@ tc_pass_kernel(const __grid_constant__ CUtensorMap tm_p_hi, const __grid_constan
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < NSTAGE; s++) { mbar_init(bar(FULL0 + s), 1); mbar_init(bar(EMPTY0 + s), 1); }
-        for (int s = 0; s < 2; s++) { mbar_init(bar(SFULL0 + s), 1); mbar_init(bar(SEMPTY0 + s), 4); }
-        mbar_init(bar(RFULL), 4);
+        for (int s = 0; s < 2; s++) { mbar_init(bar(SFULL0 + s), 1); mbar_init(bar(SEMPTY0 + s), EPI_WARPS); }
+        mbar_init(bar(RFULL), EPI_WARPS);
         mbar_init(bar(REMPTY), 1);
         mbar_init(bar(PFULL), 1);
         mbar_init(bar(OUTFULL), 1);
@@ -285,7 +289,8 @@ tc_pass_kernel(const __grid_constant__ CUtensorMap tm_p_hi, const __grid_constan
         }
     } else if (warp >= 4) {
         // ================================ epilogue ================================
-        const int q = warp - 4;                   // TMEM lane quadrant
+        const int q = warp & 3;                   // TMEM lane quadrant (hardware: warp id % 4)
+        const int cchunk = (warp - 4) >> 2;       // which 16-column chunk of the 64-wide tile this warp converts
         const int i = q * 32 + lane;              // own row inside the tile == TMEM lane
         const int64_t own_idx = own0 + i;
         const bool own_ok = own_idx < prm.own_n;
@@ -300,9 +305,9 @@ tc_pass_kernel(const __grid_constant__ CUtensorMap tm_p_hi, const __grid_constan
                 tc_fence_after();
             }
             const unsigned char* xs = gen + SmemLayout::stage0 + s * SmemLayout::stage_bytes + SmemLayout::x;
-            bool waited_r = false;
-#pragma unroll 1
-            for (int c = 0; c < OTH / 16; c++) {
+            float sq_tile = 0.0f;
+            {
+                const int c = cchunk;
                 float sv[16];
                 if (RESID) {
                     tmem_ld16(lane_addr + uint32_t(sb * OTH + c * 16), sv);
@@ -336,7 +341,7 @@ tc_pass_kernel(const __grid_constant__ CUtensorMap tm_p_hi, const __grid_constan
                             float est = sv[g * 4 + e];
                             if (prm.link == PYCMF_LOGIT) est = 1.0f / (1.0f + __expf(-est));
                             r = (own_ok && (oth0 + j) < prm.oth_n) ? est - xv[e] : 0.0f;
-                            sq += double(r) * double(r);
+                            sq_tile = fmaf(r, r, sq_tile);
                         } else {
                             r = xv[e];                         // TMA zero-fills out-of-range elements
                         }
@@ -345,10 +350,7 @@ tc_pass_kernel(const __grid_constant__ CUtensorMap tm_p_hi, const __grid_constan
                         lo[g * 4 + e] = NSPLIT == 3 ? tf32_rna(r - h) : 0.0f;
                     }
                 }
-                if (!waited_r) {
-                    mbar_wait(bar(REMPTY), (uint32_t(it) & 1u) ^ 1u);   // GEMM2 of the previous tile has drained R
-                    waited_r = true;
-                }
+                mbar_wait(bar(REMPTY), (uint32_t(it) & 1u) ^ 1u);   // GEMM2 of the previous tile has drained R
                 // R[i][16c .. 16c+15]: K-block (16c)/32, 16-byte chunks ((16c % 32)/4 + g) ^ (i & 7)
                 const int blk = (c * 16) >> 5;
                 unsigned char* rh = gen + SmemLayout::r_hi + blk * (OWN * 128) + i * 128;
@@ -362,6 +364,7 @@ tc_pass_kernel(const __grid_constant__ CUtensorMap tm_p_hi, const __grid_constan
                         *reinterpret_cast<float4*>(rl + off) = make_float4(lo[g * 4], lo[g * 4 + 1], lo[g * 4 + 2], lo[g * 4 + 3]);
                 }
             }
+            sq += double(sq_tile);
             fence_async_smem();            // generic-proxy writes of R -> visible to the tensor-core (async) proxy
             if (RESID) tc_fence_before();
             __syncwarp();
@@ -373,26 +376,20 @@ tc_pass_kernel(const __grid_constant__ CUtensorMap tm_p_hi, const __grid_constan
         // ---- final: OUT (128 x 32) from TMEM to global
         mbar_wait(bar(OUTFULL), 0);
         tc_fence_after();
-        if (n_it > 0) {
-            float o[32];
-            {
-                float t16[16];
-                tmem_ld16(lane_addr + TMEM_OUT_COL, t16);
+        if (cchunk < KC / 16) {                   // two warps per quadrant write the two 16-column halves of OUT
+            float o[16];
+            if (n_it > 0) {
+                tmem_ld16(lane_addr + TMEM_OUT_COL + cchunk * 16, o);
+            } else {
 #pragma unroll
-                for (int e = 0; e < 16; e++) o[e] = t16[e];
-                tmem_ld16(lane_addr + TMEM_OUT_COL + 16, t16);
-#pragma unroll
-                for (int e = 0; e < 16; e++) o[16 + e] = t16[e];
+                for (int e = 0; e < 16; e++) o[e] = 0.0f;
             }
             if (own_ok) {
-                float4* dst = reinterpret_cast<float4*>(prm.out + int64_t(blockIdx.y) * prm.out_split_stride + own_idx * KC);
+                float4* dst = reinterpret_cast<float4*>(prm.out + int64_t(blockIdx.y) * prm.out_split_stride +
+                                                        own_idx * KC + cchunk * 16);
 #pragma unroll
-                for (int e = 0; e < 8; e++) dst[e] = make_float4(o[4 * e], o[4 * e + 1], o[4 * e + 2], o[4 * e + 3]);
+                for (int e = 0; e < 4; e++) dst[e] = make_float4(o[4 * e], o[4 * e + 1], o[4 * e + 2], o[4 * e + 3]);
             }
-        } else if (own_ok) {
-            float4* dst = reinterpret_cast<float4*>(prm.out + int64_t(blockIdx.y) * prm.out_split_stride + own_idx * KC);
-#pragma unroll
-            for (int e = 0; e < 8; e++) dst[e] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
         if (RESID && prm.sq_part != nullptr) {
             sq = warp_sum(sq);
@@ -518,7 +515,7 @@ void launch_tc(pycmf_ctx* ctx, int64_t own_n, int64_t oth_n, const FactorParts& 
     dim3 grid((unsigned)own_tiles, (unsigned)splits);
     {
         Timed timer(ctx, RESID ? (MODE == 0 ? "tc_resid_left" : "tc_resid_right") : (MODE == 0 ? "tc_xv" : "tc_xtu"));
-        kern<<<grid, 256, smem, ctx->stream>>>(tm_p_hi, tm_p_lo, tm_q_hi, tm_q_lo, tm_qt_hi, tm_qt_lo, tm_x, prm);
+        kern<<<grid, NTHREADS, smem, ctx->stream>>>(tm_p_hi, tm_p_lo, tm_q_hi, tm_q_lo, tm_qt_hi, tm_qt_lo, tm_x, prm);
         PYCMF_LAUNCH_CHECK(ctx);
     }
     if (splits > 1) reduce_parts<float>(ctx, own_n, KC, int(splits), prm.out, out, KC, 1.0f, 0.0f);
