@@ -197,7 +197,9 @@ void newton_left_impl(pycmf_ctx* ctx, int64_t rows, int64_t m, int64_t k, T* F, 
         const int32_t* ix = idx ? idx + r0 * n_sample : nullptr;
         row_grad_hess<T>(ctx, rc, m, k, F + r0 * k, B, Tc, ldt, trans_t, rp, colidx, vals, link, weight, ix,
                          n_sample, sampled ? g + r0 * k : nullptr, H, false);
-        newton_solve_rows<T>(ctx, rc, k, F + r0 * k, g + r0 * k, H, k * k, l1, l2, l2_diag, pert, non_negative);
+        // H_i = weight * (PSD weighted Gram) + l2_diag I: lambda_min >= l2_diag, so the clamp test can be skipped
+        newton_solve_rows<T>(ctx, rc, k, F + r0 * k, g + r0 * k, H, k * k, l1, l2, l2_diag, pert, non_negative,
+                             weight >= 0.0 && l2_diag >= pert);
     }
 }
 

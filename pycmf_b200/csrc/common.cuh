@@ -192,7 +192,7 @@ void row_grad_hess(pycmf_ctx* ctx, int64_t rows, int64_t m, int64_t k, const T* 
 // F_i <- F_i - (g_i + l1 sign(F_i) + l2 F_i) S(H_i + l2_diag I); clamp. H: (rows x k x k) or shared (h_stride 0)
 template <typename T>
 void newton_solve_rows(pycmf_ctx* ctx, int64_t rows, int64_t k, T* F, const T* g, const T* H, int64_t h_stride,
-                       double l1, double l2, double l2_diag, double pert, bool non_negative);
+                       double l1, double l2, double l2_diag, double pert, bool non_negative, bool known_pd = false);
 // shared Hessian given in float64 as h_scale * G (+ l2_diag I): invert once, apply to every row
 template <typename T>
 void newton_solve_shared64(pycmf_ctx* ctx, int64_t rows, int64_t k, T* F, const T* g, const double* G64, double h_scale,
@@ -205,7 +205,7 @@ bool newton_finish_small(pycmf_ctx* ctx, int64_t rows, int64_t l, int64_t k, T* 
 // warp-per-matrix clamped solve for k <= 32 (false = not eligible). MODE 0: x = S(.) g ; MODE 1: Newton row update
 template <typename T, int MODE>
 bool safe_solve_small(pycmf_ctx* ctx, int64_t batch, int64_t k, const T* H, int64_t h_stride, const T* g, T* out,
-                      double l1, double l2, double l2_diag, double pert, bool non_negative, double h_scale);
+                      double l1, double l2, double l2_diag, double pert, bool non_negative, double h_scale, bool known_pd);
 void safe_solve_f64(pycmf_ctx* ctx, int64_t batch, int64_t k, const double* H, int64_t h_stride,
                     const double* g, double* x, double pert);
 void sample_indices(pycmf_ctx* ctx, int64_t rows, int64_t N, int64_t n_sample, uint64_t seed,

@@ -449,11 +449,14 @@ size_t solve_smem_bytes(int k, int nthreads, bool w_in_smem) {
 
 template <typename T, int MODE>
 void launch_solve(pycmf_ctx* ctx, int64_t batch, int64_t k, const T* H, int64_t h_stride, const T* g, T* out,
-                  double l1, double l2, double l2_diag, double pert, bool non_negative, double h_scale = 1.0) {
+                  double l1, double l2, double l2_diag, double pert, bool non_negative, double h_scale = 1.0,
+                  bool known_pd = false) {
     if (batch <= 0) return;
     PYCMF_CHECK(k >= 1 && k <= 256, "n_components must be in [1, 256] for the Newton solve");
     PYCMF_CHECK(pert > 0.0, "hessian_pertubation must be > 0");
-    if (safe_solve_small<T, MODE>(ctx, batch, k, H, h_stride, g, out, l1, l2, l2_diag, pert, non_negative, h_scale)) return;
+    if (safe_solve_small<T, MODE>(ctx, batch, k, H, h_stride, g, out, l1, l2, l2_diag, pert, non_negative, h_scale,
+                                  known_pd))
+        return;
     int nthreads = k <= 32 ? 64 : (k <= 64 ? 128 : 256);
     bool w_in_smem = solve_smem_bytes(int(k), nthreads, true) <= size_t(ctx->max_smem_optin);
     size_t smem = solve_smem_bytes(int(k), nthreads, w_in_smem);
@@ -542,10 +545,10 @@ void safe_solve_f64(pycmf_ctx* ctx, int64_t batch, int64_t k, const double* H, i
 
 template <typename T>
 void newton_solve_rows(pycmf_ctx* ctx, int64_t rows, int64_t k, T* F, const T* g, const T* H, int64_t h_stride,
-                       double l1, double l2, double l2_diag, double pert, bool non_negative) {
+                       double l1, double l2, double l2_diag, double pert, bool non_negative, bool known_pd) {
     if (rows <= 0) return;
     if (h_stride != 0) {
-        launch_solve<T, 1>(ctx, rows, k, H, h_stride, g, F, l1, l2, l2_diag, pert, non_negative);
+        launch_solve<T, 1>(ctx, rows, k, H, h_stride, g, F, l1, l2, l2_diag, pert, non_negative, 1.0, known_pd);
         return;
     }
     // shared Hessian: invert once (k unit right-hand sides), then one small GEMM-like pass over the rows
@@ -595,7 +598,7 @@ void sample_indices(pycmf_ctx* ctx, int64_t rows, int64_t N, int64_t n_sample, u
                                    bool, const int32_t*, const int32_t*, const T*, int, double, const int32_t*, \
                                    int64_t, T*, T*, bool);                                                      \
     template void newton_solve_rows<T>(pycmf_ctx*, int64_t, int64_t, T*, const T*, const T*, int64_t, double,   \
-                                       double, double, double, bool);                                           \
+                                       double, double, double, bool, bool);                                        \
     template void newton_solve_shared64<T>(pycmf_ctx*, int64_t, int64_t, T*, const T*, const double*, double,   \
                                            double, double, double, double, bool);
 INSTANTIATE(float)

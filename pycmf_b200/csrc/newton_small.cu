@@ -18,56 +18,58 @@ using wsolve::shfl_d;
 constexpr int WARPS = 4;
 constexpr int LMAX = 128;         // max rows of the small factor (labels)
 
+// pd_mode: 0 = test every row (Cholesky of H - pert I), 1 = read the shared verdict from *pd_flag, 2 = known PD
 template <typename T>
 __global__ void __launch_bounds__(WARPS * 32)
 newton_finish_small_kernel(int64_t rows, int l, int k, T* __restrict__ F, const T* __restrict__ Z,
-                           const T* __restrict__ Y, int64_t ldy, int y_link, double wy,
+                           const T* __restrict__ Y, int64_t ldy, int y_link, T wy,
                            const T* __restrict__ gx, const T* __restrict__ Hx, int64_t hx_stride,
-                           double l1, double l2, double l2_diag, double pert, bool non_negative, bool chol_fastpath) {
+                           double l1, double l2, double l2_diag, double pert, bool non_negative, bool chol_fastpath,
+                           int pd_mode, const int* __restrict__ pd_flag) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    double* Zs = reinterpret_cast<double*>(smem_raw);            // l x (k + 1)
-    double* Hs = Zs + size_t(l) * (k + 1);                       // k x k   (shared Hessian part, if hx_stride == 0)
-    double* Wall = Hs + KS * KS;                                 // WARPS x KS x WLD (Jacobi fallback tiles)
+    double* Wall = reinterpret_cast<double*>(smem_raw);          // WARPS x KS x WLD solve tiles
+    T* Zs = reinterpret_cast<T*>(Wall + WARPS * KS * WLD);       // l x (k + 1)
+    T* Hs = Zs + size_t(l) * (k + 1);                            // k x k (shared Hessian part, if hx_stride == 0)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int kz = k + 1;
-    for (int e = threadIdx.x; e < l * k; e += blockDim.x) Zs[(e / k) * kz + (e % k)] = double(Z[e]);
+    for (int e = threadIdx.x; e < l * k; e += blockDim.x) Zs[(e / k) * kz + (e % k)] = Z[e];
     if (hx_stride == 0)
         for (int e = threadIdx.x; e < k * k; e += blockDim.x) {
             int r = e / k, c = e % k;
-            Hs[e] = double(Hx[(r > c ? r : c) * k + (r > c ? c : r)]);   // lower triangle, like eigh
+            Hs[e] = Hx[(r > c ? r : c) * k + (r > c ? c : r)];   // lower triangle, like eigh
         }
     __syncthreads();
     double* W = Wall + warp * (KS * WLD);
     const bool act = lane < k;
+    const bool known_pd = pd_mode == 2 || (pd_mode == 1 && *pd_flag != 0);
     for (int64_t row = int64_t(blockIdx.x) * WARPS + warp; row < rows; row += int64_t(gridDim.x) * WARPS) {
-        const double v = act ? double(F[row * k + lane]) : 0.0;
-        double g = act ? double(gx[row * k + lane]) : 0.0;
+        const T v = act ? F[row * k + lane] : T(0);
+        T g = act ? gx[row * k + lane] : T(0);
         // ---- estimates for the labels c2 = lane + 32 t
-        double res[LMAX / 32], wgt[LMAX / 32];
+        T res[LMAX / 32], wgt[LMAX / 32];
 #pragma unroll
         for (int t = 0; t < LMAX / 32; t++) {
             const int c2 = lane + 32 * t;
-            if (32 * t >= l) { res[t] = 0.0; wgt[t] = 0.0; continue; }
-            double d = 0.0;
-            for (int a = 0; a < k; a++) d = fma(shfl_d(v, a), (c2 < l) ? Zs[c2 * kz + a] : 0.0, d);
-            double est = d, fp = 1.0;
-            if (y_link == PYCMF_LOGIT) { est = 1.0 / (1.0 + exp(-d)); fp = est * (1.0 - est); }
-            const double y = (c2 < l) ? double(Y[row * ldy + c2]) : 0.0;
-            res[t] = (c2 < l) ? wy * (est - y) : 0.0;
-            wgt[t] = (c2 < l) ? wy * fp : 0.0;
+            if (32 * t >= l) { res[t] = T(0); wgt[t] = T(0); continue; }
+            T d = T(0);
+            for (int a = 0; a < k; a++) d = fma(T(__shfl_sync(0xffffffffu, v, a)), (c2 < l) ? Zs[c2 * kz + a] : T(0), d);
+            T est = d, fp = T(1);
+            if (y_link == PYCMF_LOGIT) { est = sigmoid_<T>(d); fp = est * (T(1) - est); }
+            const T y = (c2 < l) ? Y[row * ldy + c2] : T(0);
+            res[t] = (c2 < l) ? wy * (est - y) : T(0);
+            wgt[t] = (c2 < l) ? wy * fp : T(0);
         }
-        // ---- row `lane` of the Hessian in registers
-        double Wr[KS];
+        // ---- row `lane` of the Hessian in registers (compute dtype)
+        T Wr[KS];
 #pragma unroll
         for (int c = 0; c < KS; c++) {
-            double h = 0.0;
+            T h = T(0);
             if (act && c < k) {
                 if (hx_stride == 0) h = Hs[lane * k + c];
                 else {
                     const int hi = lane > c ? lane : c, lo = lane > c ? c : lane;
-                    h = double(Hx[row * hx_stride + hi * k + lo]);
+                    h = Hx[row * hx_stride + hi * k + lo];
                 }
-                if (c == lane) h += l2_diag;
             }
             Wr[c] = h;
         }
@@ -76,25 +78,46 @@ newton_finish_small_kernel(int64_t rows, int l, int k, T* __restrict__ F, const 
             const int lim = min(32, l - 32 * t);
             for (int cc = 0; cc < lim; cc++) {
                 const int c2 = 32 * t + cc;
-                const double r = shfl_d(res[t], cc), w = shfl_d(wgt[t], cc);
-                const double za = act ? Zs[c2 * kz + lane] : 0.0;
+                const T r = __shfl_sync(0xffffffffu, res[t], cc), w = __shfl_sync(0xffffffffu, wgt[t], cc);
+                const T za = act ? Zs[c2 * kz + lane] : T(0);
                 g = fma(r, za, g);
-                const double wza = w * za;
+                const T wza = w * za;
 #pragma unroll
                 for (int c = 0; c < KS; c++)
                     if (c < k) Wr[c] = fma(wza, Zs[c2 * kz + c], Wr[c]);
             }
         }
-        const double sgn = v > 0.0 ? 1.0 : (v < 0.0 ? -1.0 : 0.0);
-        const double gfull = act ? g + l1 * sgn + l2 * v : 0.0;
-        // ---- solve (registers; Jacobi fallback in the per-warp tile)
-        const double x = wsolve::safe_solve_warp(Wr, k, lane, gfull, pert, chol_fastpath, W);
+        const double vd = double(v);
+        const double sgn = vd > 0.0 ? 1.0 : (vd < 0.0 ? -1.0 : 0.0);
+        const double gfull = act ? double(g) + l1 * sgn + l2 * vd : 0.0;
+        // ---- l2 on the diagonal, then the clamped solve in float64
+        double Wd[KS];
+#pragma unroll
+        for (int c = 0; c < KS; c++) Wd[c] = double(Wr[c]) + ((c == lane) ? l2_diag : 0.0);
+        const double x = wsolve::safe_solve_warp(Wd, k, lane, gfull, pert, chol_fastpath, known_pd, W);
         if (act) {
-            double f = v - x;
+            double f = vd - x;
             if (non_negative && f < 0.0) f = 0.0;
             F[row * k + lane] = T(f);
         }
     }
+}
+
+// *flag = 1 iff scale * H + (diag - pert) I is positive definite (one warp; H is k x k, lower triangle used)
+template <typename T>
+__global__ void pd_flag_kernel(int k, const T* __restrict__ H, double scale, double diag, double pert, int* flag) {
+    __shared__ double W[KS * WLD];
+    const int lane = threadIdx.x;
+    double tr = 0.0;
+    for (int c = 0; c <= lane && lane < k; c++) {
+        double h = scale * double(H[lane * k + c]) + (c == lane ? diag - pert : 0.0);
+        W[lane * WLD + c] = h;
+        if (c == lane) tr = fabs(h);
+    }
+    tr = warp_sum(tr);
+    __syncwarp();
+    const bool ok = wsolve::chol_tile(W, k, lane, 1e-13 * (tr + pert));
+    if (lane == 0) *flag = ok ? 1 : 0;
 }
 
 // Warp-per-matrix clamped solve for k <= 32.  MODE 0: x_b = S(scale H_b + diag I) g_b.  MODE 1: Newton row update.
@@ -102,7 +125,7 @@ template <typename T, int MODE>
 __global__ void __launch_bounds__(WARPS * 32)
 safe_solve_small_kernel(int64_t batch, int k, const T* __restrict__ H, int64_t h_stride, const T* __restrict__ g,
                         T* __restrict__ out, double l1, double l2, double l2_diag, double pert, bool non_negative,
-                        bool chol_fastpath, double h_scale) {
+                        bool chol_fastpath, double h_scale, bool known_pd) {
     __shared__ double Wall[WARPS * KS * WLD];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     double* W = Wall + warp * (KS * WLD);
@@ -126,7 +149,7 @@ safe_solve_small_kernel(int64_t batch, int k, const T* __restrict__ H, int64_t h
             f = double(out[b * k + lane]);
             gr += l1 * (f > 0.0 ? 1.0 : (f < 0.0 ? -1.0 : 0.0)) + l2 * f;
         }
-        const double x = wsolve::safe_solve_warp(Hr, k, lane, gr, pert, chol_fastpath, W);
+        const double x = wsolve::safe_solve_warp(Hr, k, lane, gr, pert, chol_fastpath, known_pd, W);
         if (act) {
             if (MODE == 0) {
                 out[b * k + lane] = T(x);
@@ -143,12 +166,12 @@ safe_solve_small_kernel(int64_t batch, int k, const T* __restrict__ H, int64_t h
 
 template <typename T, int MODE>
 bool safe_solve_small(pycmf_ctx* ctx, int64_t batch, int64_t k, const T* H, int64_t h_stride, const T* g, T* out,
-                      double l1, double l2, double l2_diag, double pert, bool non_negative, double h_scale) {
+                      double l1, double l2, double l2_diag, double pert, bool non_negative, double h_scale, bool known_pd) {
     if (k > KS || batch < 1) return false;
     int64_t grid = std::min<int64_t>(ceil_div(batch, WARPS), int64_t(16) * ctx->num_sms);
     Timed timer(ctx, "safe_solve");
     safe_solve_small_kernel<T, MODE><<<(unsigned)grid, WARPS * 32, 0, ctx->stream>>>(
-        batch, int(k), H, h_stride, g, out, l1, l2, l2_diag, pert, non_negative, ctx->chol_fastpath != 0, h_scale);
+        batch, int(k), H, h_stride, g, out, l1, l2, l2_diag, pert, non_negative, ctx->chol_fastpath != 0, h_scale, known_pd);
     PYCMF_LAUNCH_CHECK(ctx);
     return true;
 }
@@ -158,25 +181,40 @@ bool newton_finish_small(pycmf_ctx* ctx, int64_t rows, int64_t l, int64_t k, T* 
                          int y_link, double wy, const T* gx, const T* Hx, bool hx_per_row, double l1, double l2,
                          double l2_diag, double pert, bool non_negative) {
     if (k > KS || l > LMAX || l < 1 || rows < 1) return false;
-    size_t smem = sizeof(double) * (size_t(l) * (k + 1) + KS * KS + size_t(WARPS) * KS * WLD);
+    size_t smem = sizeof(double) * size_t(WARPS) * KS * WLD + sizeof(T) * (size_t(l) * (k + 1) + KS * KS);
     if (smem > size_t(ctx->max_smem_optin)) return false;
+    // Definiteness shortcut: H_j = Hx(_j) + wy Z^T D Z + l2 I with the label term PSD when wy >= 0.
+    //   l2 >= pert                      -> every H_j has lambda_min >= pert (pd_mode 2, if Hx is PSD: weights >= 0)
+    //   shared Hx: test Hx + l2 I once  -> verdict read by every row (pd_mode 1)
+    int pd_mode = 0;
+    int* flag = nullptr;
+    if (wy >= 0.0 && ctx->chol_fastpath) {
+        if (!hx_per_row) {
+            flag = static_cast<int*>(scratch(ctx, 2, 256));
+            pd_flag_kernel<T><<<1, 32, 0, ctx->stream>>>(int(k), Hx, 1.0, l2_diag, pert, flag);
+            PYCMF_LAUNCH_CHECK(ctx);
+            pd_mode = 1;
+        } else if (l2_diag >= pert) {
+            pd_mode = 2;
+        }
+    }
     auto kern = newton_finish_small_kernel<T>;
     PYCMF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-    int64_t grid = std::min<int64_t>(ceil_div(rows, WARPS), int64_t(8) * ctx->num_sms);
+    int64_t grid = std::min<int64_t>(ceil_div(rows, WARPS), int64_t(16) * ctx->num_sms);
     Timed timer(ctx, "newton_finish_small");
-    kern<<<(unsigned)grid, WARPS * 32, smem, ctx->stream>>>(rows, int(l), int(k), F, Z, Y, ldy, y_link, wy, gx, Hx,
+    kern<<<(unsigned)grid, WARPS * 32, smem, ctx->stream>>>(rows, int(l), int(k), F, Z, Y, ldy, y_link, T(wy), gx, Hx,
                                                            hx_per_row ? k * k : 0, l1, l2, l2_diag, pert, non_negative,
-                                                           ctx->chol_fastpath != 0);
+                                                           ctx->chol_fastpath != 0, pd_mode, flag);
     PYCMF_LAUNCH_CHECK(ctx);
     return true;
 }
 
 template bool safe_solve_small<float, 1>(pycmf_ctx*, int64_t, int64_t, const float*, int64_t, const float*, float*, double,
-                                         double, double, double, bool, double);
+                                         double, double, double, bool, double, bool);
 template bool safe_solve_small<double, 0>(pycmf_ctx*, int64_t, int64_t, const double*, int64_t, const double*, double*,
-                                          double, double, double, double, bool, double);
+                                          double, double, double, double, bool, double, bool);
 template bool safe_solve_small<double, 1>(pycmf_ctx*, int64_t, int64_t, const double*, int64_t, const double*, double*,
-                                          double, double, double, double, bool, double);
+                                          double, double, double, double, bool, double, bool);
 template bool newton_finish_small<float>(pycmf_ctx*, int64_t, int64_t, int64_t, float*, const float*, const float*,
                                          int64_t, int, double, const float*, const float*, bool, double, double, double,
                                          double, bool);

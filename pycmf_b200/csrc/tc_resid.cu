@@ -32,6 +32,7 @@ constexpr int OWN = 128;      // own rows per CTA  (UMMA M)
 constexpr int OTH = 64;       // other rows per tile (GEMM1 N, GEMM2 K)
 constexpr int KC = 32;        // n_components handled by this kernel (one 128-byte swizzle span)
 constexpr int NSTAGE = 2;
+constexpr int PREFETCH_DIST = 8;   // X tiles requested into L2 ahead of the shared-memory ring
 constexpr int TMEM_COLS = 256;
 constexpr int TMEM_OUT_COL = 128;
 constexpr int EPI_WARPS = 16;
@@ -87,6 +88,12 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
     asm volatile(
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
         ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+// TMA prefetch of one box into L2 only (no shared-memory slot needed): lets the producer run many tiles ahead of
+// the 2-stage shared-memory ring so the HBM latency is paid long before the real load
+__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* map, int c0, int c1) {
+    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];"
+                 ::"l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1) : "memory");
 }
 __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
                                           uint32_t accumulate) {
@@ -197,9 +204,21 @@ tc_pass_kernel(const __grid_constant__ CUtensorMap tm_p_hi, const __grid_constan
                 tma_load_2d(base + SmemLayout::p_hi, &tm_p_hi, bar(PFULL), 0, int(own0));
                 if (NSPLIT == 3) tma_load_2d(base + SmemLayout::p_lo, &tm_p_lo, bar(PFULL), 0, int(own0));
             }
+            auto prefetch_x = [&](int it) {
+                const int oth0 = int((t_begin + it) * OTH);
+                if (MODE == 0) {
+                    tma_prefetch_2d(&tm_x, oth0, int(own0));
+                    tma_prefetch_2d(&tm_x, oth0 + 32, int(own0));
+                } else {
+#pragma unroll
+                    for (int b = 0; b < 4; b++) tma_prefetch_2d(&tm_x, int(own0) + 32 * b, oth0);
+                }
+            };
+            for (int it = 0; it < PREFETCH_DIST && it < n_it; it++) prefetch_x(it);
             for (int it = 0; it < n_it; it++) {
                 const int s = it % NSTAGE;
                 const uint32_t ph = uint32_t(it / NSTAGE) & 1u;
+                if (it + PREFETCH_DIST < n_it) prefetch_x(it + PREFETCH_DIST);
                 mbar_wait(bar(EMPTY0 + s), ph ^ 1u);
                 const uint32_t st = base + SmemLayout::stage0 + uint32_t(s) * SmemLayout::stage_bytes;
                 const int oth0 = int((t_begin + it) * OTH);

@@ -1,9 +1,10 @@
-// Warp-level eigenvalue-clamped solve for small symmetric systems (k <= 32), all in float64.
+// Warp-level eigenvalue-clamped solve for small symmetric systems (k <= 32), float64.
 //   x = S(H) g,  S(H) = Q diag(1 / max(|lambda|, pert)) Q^T          (reference _safe_invert, cmf_solvers.py:346-356)
-// Lane r owns row r of H in REGISTERS (double A[32]); the Cholesky factorisation, both triangular solves and
-// the definiteness test (Cholesky of H - pert I succeeds <=> lambda_min(H) > pert <=> the clamp is inactive and
-// S(H) = H^-1) exchange data by warp shuffles only -- no shared-memory latency chains, no block barriers.
-// If the test fails the warp falls back to a one-sided Jacobi in a per-warp shared-memory tile.
+// One warp per matrix; the matrix lives in a per-warp shared-memory tile (lane == row, leading dimension 33 so a
+// column access is bank-conflict free).  Fast path: Cholesky of H - pert I succeeds  <=>  lambda_min(H) > pert  <=>
+// the clamp is inactive and S(H) = H^-1, solved with a Cholesky of H.  When the caller can prove lambda_min >= pert
+// (Hessian = PSD term + l2 I with l2 >= pert, or a shared lower bound tested once) the test factorisation is skipped.
+// Otherwise: one-sided Jacobi in the same tile.  Runtime loops only (small code: the I-cache matters here).
 #pragma once
 #include "common.cuh"
 
@@ -11,60 +12,57 @@ namespace pycmf {
 namespace wsolve {
 
 constexpr int KS = 32;
-constexpr int WLD = KS + 1;   // padded leading dimension of the Jacobi tile (doubles)
+constexpr int WLD = KS + 1;
 
 __device__ __forceinline__ double shfl_d(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
 
-// In-register Cholesky. On success A[c] (c <= lane) holds L[lane][c] and *dinv = 1 / L[lane][lane].
-// Uniform return value (false: a pivot was <= floor).
-__device__ __forceinline__ bool chol_reg(double (&A)[KS], int k, int lane, double floor, double* dinv) {
-    double my_inv = 0.0;
+// In-place Cholesky of the lower triangle of the tile.  On success W[r][c] (c < r) = L[r][c] and the DIAGONAL holds
+// 1 / L[r][r].  Uniform return value (false: a pivot was <= floor).
+__device__ __forceinline__ bool chol_tile(double* W, int k, int lane, double floor) {
+    for (int j = 0; j < k; j++) {
+        const double piv = W[j * WLD + j];
+        if (!(piv > floor)) return false;
+        const double inv = rsqrt(piv);
+        double lrj = 0.0;
+        if (lane > j && lane < k) {
+            lrj = W[lane * WLD + j] * inv;
+            W[lane * WLD + j] = lrj;
+        }
+        if (lane == j) W[j * WLD + j] = inv;
+        __syncwarp();
+        // trailing update of this lane's row: W[r][c] -= L[r][j] L[c][j] for j < c <= r (4 independent columns a time)
+        for (int c0 = j + 1; c0 < k; c0 += 4) {
+            double l4[4], w4[4];
 #pragma unroll
-    for (int j = 0; j < KS; j++) {
-        if (j < k) {
-            const double piv = shfl_d(A[j], j);
-            if (!(piv > floor)) return false;
-            const double inv = rsqrt(piv);
-            const double lrj = A[j] * inv;
-            A[j] = lrj;
-            if (lane == j) my_inv = inv;
+            for (int u = 0; u < 4; u++) {
+                const int c = c0 + u;
+                const bool on = c < k && c <= lane && lane < k;
+                // L[c][j] for c == lane is lrj itself; for c < lane it is row c, column j (broadcast read)
+                l4[u] = on ? (c == lane ? lrj : W[c * WLD + j]) : 0.0;
+                w4[u] = on ? W[lane * WLD + c] : 0.0;
+            }
 #pragma unroll
-            for (int c = j + 1; c < KS; c++) {
-                if (c < k) {
-                    const double lcj = shfl_d(lrj, c);
-                    A[c] = fma(-lrj, lcj, A[c]);
-                }
+            for (int u = 0; u < 4; u++) {
+                const int c = c0 + u;
+                if (c < k && c <= lane && lane < k) W[lane * WLD + c] = fma(-lrj, l4[u], w4[u]);
             }
         }
+        __syncwarp();
     }
-    *dinv = my_inv;
     return true;
 }
 
-// Solve L L^T x = b with L in registers (see chol_reg); lane r holds b_r on entry and x_r on return.
-__device__ __forceinline__ double chol_solve_reg(const double (&A)[KS], int k, int lane, double dinv, double b) {
-#pragma unroll
-    for (int j = 0; j < KS; j++) {
-        if (j < k) {
-            const double y = shfl_d(b * dinv, j);
-            if (lane == j) b = y;
-            if (lane > j) b = fma(-A[j], y, b);
-        }
+// Solve L L^T x = b with the factor left by chol_tile; lane r holds b_r on entry and x_r on return.
+__device__ __forceinline__ double chol_solve_tile(const double* W, int k, int lane, double b) {
+    for (int j = 0; j < k; j++) {
+        const double y = shfl_d(b, j) * W[j * WLD + j];
+        if (lane == j) b = y;
+        if (lane > j && lane < k) b = fma(-W[lane * WLD + j], y, b);
     }
-#pragma unroll
-    for (int j = KS - 1; j >= 0; j--) {
-        if (j < k) {
-            const double x = shfl_d(b * dinv, j);
-            if (lane == j) b = x;
-            // b_r -= L[j][r] x for r < j : L[j][r] is register r of lane j
-#pragma unroll
-            for (int r = 0; r < KS; r++) {
-                if (r < j) {
-                    const double ljr = shfl_d(A[r], j);
-                    if (lane == r) b = fma(-ljr, x, b);
-                }
-            }
-        }
+    for (int j = k - 1; j >= 0; j--) {
+        const double x = shfl_d(b, j) * W[j * WLD + j];
+        if (lane == j) b = x;
+        if (lane < j) b = fma(-W[j * WLD + lane], x, b);
     }
     return b;
 }
@@ -104,31 +102,47 @@ __device__ __forceinline__ double jacobi_solve_tile(double* W, int k, int lane, 
     return x;
 }
 
-// The full clamped solve.  H_row: row `lane` of the symmetric matrix (entries c <= lane are used, like
-// eigh(lower=True)); g: this lane's right-hand-side entry; W: per-warp tile of KS * WLD doubles (fallback only).
-__device__ __forceinline__ double safe_solve_warp(const double (&H_row)[KS], int k, int lane, double g, double pert,
-                                                  bool chol_fastpath, double* W) {
+// Writes row `lane` (lower part c <= lane) of the matrix into the tile, shifting the diagonal by `shift`.
+template <typename R>
+__device__ __forceinline__ void store_row_lower(double* W, const R (&H_row)[KS], int k, int lane, double shift) {
+#pragma unroll
+    for (int c = 0; c < KS; c++)
+        if (c < k && c <= lane && lane < k) W[lane * WLD + c] = double(H_row[c]) + (c == lane ? shift : 0.0);
+}
+
+// The full clamped solve.  H_row: row `lane` of the symmetric matrix in registers (entries c <= lane are used, like
+// eigh(lower=True)); g: this lane's right-hand-side entry; W: per-warp tile of KS * WLD doubles.
+// known_pd: the caller guarantees lambda_min(H) >= pert (skips the test factorisation).
+template <typename R>
+__device__ __forceinline__ double safe_solve_warp(const R (&H_row)[KS], int k, int lane, double g, double pert,
+                                                  bool chol_fastpath, bool known_pd, double* W) {
     const bool act = lane < k;
     if (chol_fastpath) {
-        double A[KS];
-        double tr = 0.0;
+        bool ok = known_pd;
+        if (!ok) {
+            double tr = 0.0;
 #pragma unroll
-        for (int c = 0; c < KS; c++) {
-            A[c] = H_row[c] - ((c == lane) ? pert : 0.0);
-            if (c == lane && act) tr = fabs(A[c]);
+            for (int c = 0; c < KS; c++)
+                if (c == lane && act) tr = fabs(double(H_row[c]) - pert);
+            tr = warp_sum(tr);
+            store_row_lower(W, H_row, k, lane, -pert);
+            __syncwarp();
+            ok = chol_tile(W, k, lane, 1e-13 * (tr + pert));
+            __syncwarp();
         }
-        tr = warp_sum(tr);
-        double dinv;
-        if (chol_reg(A, k, lane, 1e-13 * (tr + pert), &dinv)) {
-#pragma unroll
-            for (int c = 0; c < KS; c++) A[c] = H_row[c];
-            if (chol_reg(A, k, lane, 0.0, &dinv)) return chol_solve_reg(A, k, lane, dinv, act ? g : 0.0);
+        if (ok) {
+            store_row_lower(W, H_row, k, lane, 0.0);
+            __syncwarp();
+            if (chol_tile(W, k, lane, 0.0)) {
+                const double x = chol_solve_tile(W, k, lane, act ? g : 0.0);
+                __syncwarp();
+                return x;
+            }
+            __syncwarp();
         }
     }
     // eigenvalue clamp active (or fast path disabled): Jacobi on the symmetric tile built from the lower triangle
-#pragma unroll
-    for (int c = 0; c < KS; c++)
-        if (c < k && act && c <= lane) W[lane * WLD + c] = H_row[c];
+    store_row_lower(W, H_row, k, lane, 0.0);
     __syncwarp();
     for (int c = lane + 1; c < k; c++)
         if (act) W[lane * WLD + c] = W[c * WLD + lane];
