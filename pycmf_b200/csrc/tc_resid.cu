@@ -84,6 +84,17 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         "DONE_%=:\n\t"
         "}" ::"r"(bar), "r"(parity) : "memory");
 }
+// non-blocking probe: true once the phase with this parity has completed
+__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, P1;\n\t"
+        "}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
     asm volatile(
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
@@ -255,9 +266,6 @@ tc_pass_kernel(const __grid_constant__ CUtensorMap tm_p_hi, const __grid_constan
             const uint32_t r_hi = base + SmemLayout::r_hi, r_lo = base + SmemLayout::r_lo;
             auto issue_g1 = [&](int it) {
                 const int s = it % NSTAGE, sb = it & 1;
-                mbar_wait(bar(FULL0 + s), uint32_t(it / NSTAGE) & 1u);
-                mbar_wait(bar(SEMPTY0 + sb), (uint32_t(it >> 1) & 1u) ^ 1u);
-                tc_fence_after();
                 const uint32_t st = base + SmemLayout::stage0 + uint32_t(s) * SmemLayout::stage_bytes;
                 const uint32_t d = tmem + uint32_t(sb * OTH);
                 uint32_t acc = 0;
@@ -273,20 +281,9 @@ tc_pass_kernel(const __grid_constant__ CUtensorMap tm_p_hi, const __grid_constan
                 }
                 umma_commit(bar(SFULL0 + sb));
             };
-            if (RESID) {
-                mbar_wait(bar(PFULL), 0);
-                if (n_it > 0) issue_g1(0);
-            }
             uint32_t out_acc = 0;
-            for (int it = 0; it < n_it; it++) {
+            auto issue_g2 = [&](int it) {
                 const int s = it % NSTAGE;
-                if (RESID) {
-                    if (it + 1 < n_it) issue_g1(it + 1);
-                } else {
-                    mbar_wait(bar(FULL0 + s), uint32_t(it / NSTAGE) & 1u);
-                }
-                mbar_wait(bar(RFULL), uint32_t(it) & 1u);
-                tc_fence_after();
                 const uint32_t st = base + SmemLayout::stage0 + uint32_t(s) * SmemLayout::stage_bytes;
                 const uint32_t d = tmem + TMEM_OUT_COL;
 #pragma unroll
@@ -303,6 +300,24 @@ tc_pass_kernel(const __grid_constant__ CUtensorMap tm_p_hi, const __grid_constan
                 }
                 umma_commit(bar(REMPTY));
                 umma_commit(bar(EMPTY0 + s));
+            };
+            if (RESID) mbar_wait(bar(PFULL), 0);
+            // Event-driven issue: GEMM2(t) goes out as soon as the epilogue has published R(t); GEMM1(t') as soon as
+            // its operands have landed and its S buffer is free -- neither waits behind the other's barrier.
+            int g1 = RESID ? 0 : n_it, g2 = 0;
+            while (g2 < n_it) {
+                if (mbar_test(bar(RFULL), uint32_t(g2) & 1u) &&
+                    mbar_test(bar(FULL0 + g2 % NSTAGE), uint32_t(g2 / NSTAGE) & 1u)) {
+                    tc_fence_after();
+                    issue_g2(g2);
+                    g2++;
+                }
+                if (g1 < n_it && mbar_test(bar(FULL0 + g1 % NSTAGE), uint32_t(g1 / NSTAGE) & 1u) &&
+                    mbar_test(bar(SEMPTY0 + (g1 & 1)), (uint32_t(g1 >> 1) & 1u) ^ 1u)) {
+                    tc_fence_after();
+                    issue_g1(g1);
+                    g1++;
+                }
             }
             umma_commit(bar(OUTFULL));
         }

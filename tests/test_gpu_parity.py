@@ -83,7 +83,8 @@ MID = {
     "nt_lin_logit_k32": ("newton", 600, 250, 10, 32, False, dict(NT, y_link="logit")),
     "nt_logit_logit_k16": ("newton", 300, 200, 6, 16, False, dict(NT, x_link="logit", y_link="logit")),
     "nt_csr_lin_lin_k24": ("newton", 500, 300, 6, 24, True, dict(NT)),
-    "nt_csr_logit_logit_k20": ("newton", 260, 180, 5, 20, True, dict(NT, x_link="logit", y_link="logit")),
+    "nt_csr_logit_logit_k20": ("newton", 260, 180, 5, 20, True, dict(NT, x_link="logit", y_link="logit",
+                                                                        U_non_negative=False, V_non_negative=False)),
     "nt_lin_lin_k130": ("newton", 700, 600, 8, 130, False, dict(NT, l2_reg=1.0)),
     "nt_logit_lin_k72": ("newton", 150, 140, 4, 72, False, dict(NT, x_link="logit")),
     "nt_signed_l1_lin_logit_k32": ("newton", 400, 200, 8, 32, False, dict(NT_SIGNED_L1, y_link="logit")),
