@@ -340,13 +340,17 @@ tc_pass_kernel(const __grid_constant__ CUtensorMap tm_p_hi, const __grid_constan
             }
             const unsigned char* xs = gen + SmemLayout::stage0 + s * SmemLayout::stage_bytes + SmemLayout::x;
             float sq_tile = 0.0f;
+            // interior tiles need no bounds masks; the masked path only runs on the last row / column tiles
+            const bool interior = (own0 + OWN <= prm.own_n) && (oth0 + OTH <= prm.oth_n);
+            const int64_t oth_rem = prm.oth_n - oth0;
+            const int oth_left = oth_rem < OTH ? int(oth_rem) : OTH;   // valid other-indices in this tile
             {
                 const int c = cchunk;
                 float sv[16];
                 if (RESID) {
                     tmem_ld16(lane_addr + uint32_t(sb * OTH + c * 16), sv);
                 }
-                float hi[16], lo[16];
+                float rr[16];
 #pragma unroll
                 for (int g = 0; g < 4; g++) {
                     // 4 consecutive other-indices j = 16c + 4g + e
@@ -367,25 +371,31 @@ tc_pass_kernel(const __grid_constant__ CUtensorMap tm_p_hi, const __grid_constan
                         }
                     }
 #pragma unroll
-#pragma unroll
                     for (int e = 0; e < 4; e++) {
-                        const int j = c * 16 + g * 4 + e;
                         float r;
                         if (RESID) {
                             float est = sv[g * 4 + e];
                             if (prm.link == PYCMF_LOGIT) est = 1.0f / (1.0f + __expf(-est));
-                            r = (own_ok && (oth0 + j) < prm.oth_n) ? est - xv[e] : 0.0f;
-                            sq_tile = fmaf(r, r, sq_tile);
+                            r = est - xv[e];
                         } else {
                             r = xv[e];                         // TMA zero-fills out-of-range elements
                         }
-                        const float h = NSPLIT == 3 ? tf32_rna(r) : r;
-                        hi[g * 4 + e] = h;
-                        lo[g * 4 + e] = NSPLIT == 3 ? tf32_rna(r - h) : 0.0f;
+                        rr[g * 4 + e] = r;
                     }
                 }
+                if (RESID && !interior) {
+#pragma unroll
+                    for (int e = 0; e < 16; e++)
+                        if (!own_ok || c * 16 + e >= oth_left) rr[e] = 0.0f;
+                }
+                if (RESID) {
+#pragma unroll
+                    for (int e = 0; e < 16; e++) sq_tile = fmaf(rr[e], rr[e], sq_tile);
+                }
                 mbar_wait(bar(REMPTY), (uint32_t(it) & 1u) ^ 1u);   // GEMM2 of the previous tile has drained R
-                // R[i][16c .. 16c+15]: K-block (16c)/32, 16-byte chunks ((16c % 32)/4 + g) ^ (i & 7)
+                // R[i][16c .. 16c+15]: K-block (16c)/32, 16-byte chunks ((16c % 32)/4 + g) ^ (i & 7).
+                // tf32 split by truncation: hi = r with the 13 low mantissa bits cleared (exact tf32), lo = r - hi (exact
+                // in fp32; the tensor core reads its top 19 bits) -> hi*hi + hi*lo + lo*hi carries ~2^-20 relative error
                 const int blk = (c * 16) >> 5;
                 unsigned char* rh = gen + SmemLayout::r_hi + blk * (OWN * 128) + i * 128;
                 unsigned char* rl = gen + SmemLayout::r_lo + blk * (OWN * 128) + i * 128;
@@ -393,9 +403,14 @@ tc_pass_kernel(const __grid_constant__ CUtensorMap tm_p_hi, const __grid_constan
                 for (int g = 0; g < 4; g++) {
                     const int ch = (((c * 16) & 31) >> 2) + g;
                     const int off = (ch ^ (i & 7)) << 4;
-                    *reinterpret_cast<float4*>(rh + off) = make_float4(hi[g * 4], hi[g * 4 + 1], hi[g * 4 + 2], hi[g * 4 + 3]);
+                    float h[4];
+#pragma unroll
+                    for (int e = 0; e < 4; e++)
+                        h[e] = NSPLIT == 3 ? __uint_as_float(__float_as_uint(rr[g * 4 + e]) & 0xffffe000u) : rr[g * 4 + e];
+                    *reinterpret_cast<float4*>(rh + off) = make_float4(h[0], h[1], h[2], h[3]);
                     if (NSPLIT == 3)
-                        *reinterpret_cast<float4*>(rl + off) = make_float4(lo[g * 4], lo[g * 4 + 1], lo[g * 4 + 2], lo[g * 4 + 3]);
+                        *reinterpret_cast<float4*>(rl + off) = make_float4(rr[g * 4] - h[0], rr[g * 4 + 1] - h[1],
+                                                                           rr[g * 4 + 2] - h[2], rr[g * 4 + 3] - h[3]);
                 }
             }
             sq += double(sq_tile);
