@@ -242,7 +242,7 @@ def test_tc_mu_products_match_numpy(shape, path, tol, splits):
 
 
 @pytest.mark.parametrize("link", ["linear", "logit"])
-@pytest.mark.parametrize("path,tol", [(0, 5e-6), (1, 5e-5), (2, 5e-3)])
+@pytest.mark.parametrize("path,tol", [(0, 5e-6), (1, 5e-5), (2, 3e-2)])
 @pytest.mark.parametrize("splits", [0, 1])
 def test_tc_fused_residual_right_matches_numpy(link, path, tol, splits):
     """gx = alpha (f(U V^T) - X)^T U from the fused tcgen05 kernel vs float64 NumPy (X never leaves fp32)."""
