@@ -60,6 +60,11 @@ int pycmf_profile_enable(pycmf_ctx* ctx, int on);
 int pycmf_profile_query(pycmf_ctx* ctx, const char* family, double* total_ms, int64_t* count);
 int pycmf_profile_reset(pycmf_ctx* ctx);
 
+/* diagnostics: with option "tc_trace" = 1 every tcgen05 pass records clock64 stamps of its pipeline events
+ * (TMA issue, GEMM1 issue, S seen, R published, GEMM2 issue, stage freed, operands landed) for the first 32
+ * tiles of CTA (0,0); this copies the last trace (7 x 32 int64) to the host. */
+int pycmf_debug_tc_trace(pycmf_ctx* ctx, int64_t* host, int64_t max_words);
+
 /* ---- primitives (used by the phases below; exported for tests and composition) ---------- */
 /* C (m x q) = alpha * op(A) * B + beta * C;  op(A) = A (m x p) or A^T with A stored (p x m).
  * Replaces np.dot / safe_sparse_dot on dense operands (cmf_solvers.py:232-245). */
@@ -73,6 +78,12 @@ int pycmf_spmm(pycmf_ctx* ctx, int dtype, int64_t rows, int64_t cols,
                const int32_t* rowptr, const int32_t* colidx, const void* vals,
                const void* B, int64_t ldb, int64_t k, void* C, int64_t ldc,
                double alpha, double beta);
+
+/* Fused residual pass: R = f(A B^T) - T (never materialised);  outL = R B (rows x k), outR = R^T A (m x k),
+ * *sq += sum R^2 (device double).  Any of outL / outR / sq may be NULL.  This is the reference's
+ * `res = inverse(np.dot(U, V.T), link) - X; np.dot(res, V); np.dot(res.T, U)` (cmf_solvers.py:399-400, :436-440). */
+int pycmf_resid_pass(pycmf_ctx* ctx, int dtype, int64_t rows, int64_t m, int64_t k, const void* A, const void* B,
+                     const void* T, int64_t ldt, int trans_t, int link, void* outL, void* outR, double* sq);
 
 /* ---- objective (cmf_solvers.py:36-42; sklearn _beta_divergence beta=2) -------------------- */
 /* *out_sq (device double) = sum_ij (T_ij - f(a_i . b_j))^2 over ALL entries, for

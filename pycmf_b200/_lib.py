@@ -27,8 +27,10 @@ SIGNATURES = {
     "pycmf_profile_enable": (_int, [_vp, _int]),
     "pycmf_profile_query": (_int, [_vp, C.c_char_p, C.POINTER(_dbl), C.POINTER(_i64)]),
     "pycmf_profile_reset": (_int, [_vp]),
+    "pycmf_debug_tc_trace": (_int, [_vp, _vp, _i64]),
     "pycmf_gemm": (_int, [_vp, _int, _int, _i64, _i64, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _dbl, _dbl]),
     "pycmf_spmm": (_int, [_vp, _int, _i64, _i64, _i32p, _i32p, _vp, _vp, _i64, _i64, _vp, _i64, _dbl, _dbl]),
+    "pycmf_resid_pass": (_int, [_vp, _int, _i64, _i64, _i64, _vp, _vp, _vp, _i64, _int, _int, _vp, _vp, _vp]),
     "pycmf_sqerr": (_int, [_vp, _int, _i64, _i64, _i64, _vp, _vp, _vp, _i64, _int, _i32p, _i32p, _vp, _int, _vp]),
     "pycmf_mu_v_partial": (_int, [_vp, _int, _i64, _i64, _i64, _vp, _i64, _i32p, _i32p, _vp, _vp, _vp]),
     "pycmf_mu_v_apply": (_int, [_vp, _int, _i64, _i64, _i64, _vp, _vp, _vp, _i64, _vp, _dbl, _dbl]),

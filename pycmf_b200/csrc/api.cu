@@ -359,12 +359,22 @@ int pycmf_set_option(pycmf_ctx* ctx, const char* key, double value) {
         if (k == "chol_fastpath") ctx->chol_fastpath = value != 0.0;
         else if (k == "dense_path") ctx->dense_path = int(value);
         else if (k == "tc_max_splits") ctx->tc_max_splits = int(value);
+        else if (k == "tc_trace") ctx->tc_trace = int(value);
         else if (k == "max_scratch_mb") ctx->max_scratch = size_t(std::max(16.0, value)) << 20;
         else throw pycmf::Error("unknown option: " + k);
     });
 }
 
 int64_t pycmf_launch_count(pycmf_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int pycmf_debug_tc_trace(pycmf_ctx* ctx, int64_t* host, int64_t max_words) {
+    return guarded(ctx, [&] {
+        PYCMF_CUDA(cudaStreamSynchronize(ctx->stream));
+        PYCMF_CHECK(ctx->arena[2].ptr != nullptr, "no trace recorded (set option tc_trace = 1 first)");
+        int64_t n = std::min<int64_t>(max_words, tc_trace_words());
+        PYCMF_CUDA(cudaMemcpy(host, ctx->arena[2].ptr, sizeof(int64_t) * n, cudaMemcpyDeviceToHost));
+    });
+}
 
 int pycmf_profile_enable(pycmf_ctx* ctx, int on) {
     return guarded(ctx, [&] { ctx->profile = on != 0; });
@@ -417,6 +427,18 @@ int pycmf_spmm(pycmf_ctx* ctx, int dtype, int64_t rows, int64_t cols, const int3
                              float(alpha), float(beta)),
                  spmm<double>(ctx, rows, rowptr, colidx, (const double*)vals, (const double*)B, ldb, k, (double*)C,
                               ldc, alpha, beta));
+    });
+}
+
+int pycmf_resid_pass(pycmf_ctx* ctx, int dtype, int64_t rows, int64_t m, int64_t k, const void* A, const void* B,
+                     const void* T, int64_t ldt, int trans_t, int link, void* outL, void* outR, double* sq) {
+    return guarded(ctx, [&] {
+        check_link(link);
+        DISPATCH(dtype,
+                 resid_pass<float>(ctx, rows, m, k, (const float*)A, (const float*)B, (const float*)T, ldt, trans_t != 0,
+                                   link, (float*)outL, (float*)outR, sq),
+                 resid_pass<double>(ctx, rows, m, k, (const double*)A, (const double*)B, (const double*)T, ldt,
+                                    trans_t != 0, link, (double*)outL, (double*)outR, sq));
     });
 }
 

@@ -31,6 +31,7 @@ struct pycmf_ctx {
     // options
     int chol_fastpath = 1;
     int dense_path = 1;
+    int tc_trace = 0;        // diagnostics: record a pipeline trace of CTA (0,0) of every tcgen05 pass into arena 2
     int tc_max_splits = 0;   // > 0: cap the split count of the tcgen05 passes (tests use 1 to get long tile loops)
     size_t max_scratch = size_t(2) << 30;
     // scratch arenas (grown on demand; growth synchronises the stream)
@@ -173,6 +174,7 @@ void resid_pass(pycmf_ctx* ctx, int64_t ra, int64_t rb, int64_t k, const T* A, c
                 const T* Tgt, int64_t ldt, bool trans_t, int link, T* outL, T* outR, double* sq);
 
 // tc_resid.cu : tcgen05 / TMEM / TMA versions of the dense passes over X (fp32, n_components == 32)
+int tc_trace_words();
 bool tc_dense_eligible(pycmf_ctx* ctx, int64_t ra, int64_t rb, int64_t k, const float* X, int64_t ldx, bool trans_t);
 void tc_resid_pass(pycmf_ctx* ctx, int64_t ra, int64_t rb, const float* A, const float* B, const float* X, int64_t ldx,
                    int link, float* outL, float* outR, double* sq);

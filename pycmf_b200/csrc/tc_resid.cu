@@ -6,21 +6,23 @@
 //   COPY,  LEFT  : out  = X   B                  MU numerator X V    (cmf_solvers.py:232)
 //   COPY,  RIGHT : out  = X^T A                  MU numerator X^T U  (cmf_solvers.py:244)
 //
-// A CTA owns 128 "own" rows (rows of X for LEFT, columns of X for RIGHT) and walks the other
-// dimension in tiles of 64.  Per tile:
-//   TMA        : X tile (128 x 64 fp32, SWIZZLE_128B) + the 64 x 32 factor tile Q (tf32 hi / lo parts)
-//   tcgen05.mma: S[128 x 64] = P Q^T          (GEMM1, accumulator in TMEM, 3xTF32: hi*hi + hi*lo + lo*hi)
-//   epilogue   : tcgen05.ld S -> f() -> minus X -> R (hi / lo) written back to swizzled shared memory
-//   tcgen05.mma: OUT[128 x 32] += R Q         (GEMM2; its B operand is a K-major tile of Q^T, loaded by TMA from a
-//                                              transposed tf32 copy of the factor: MN-major tf32 operands would need the
-//                                              128B_BASE32B swizzle, which the K-major GEMM1 read of the same tile cannot share)
-// so neither U V^T nor the residual ever touches HBM.  GEMM1 of tile t+1 is issued before GEMM2 of
-// tile t (two S buffers in TMEM) so the tensor pipe works while the epilogue warps convert tile t.
+// A CTA owns 128 "own" rows (rows of X for LEFT, columns of X for RIGHT) and walks the other dimension in
+// tiles of 64.  Per tile:
+//   TMA        : X tile (128 x 64 fp32, SWIZZLE_128B) + the 64 x 32 factor tile Q and its transpose Q^T
+//                (tf32 hi / lo parts) into a 3-stage shared-memory ring; X is also prefetched into L2 8 tiles ahead
+//   tcgen05.mma: S[128 x 64]  = P Q^T     GEMM1, A operand P resident in TENSOR MEMORY for the whole CTA
+//   epilogue   : tcgen05.ld S -> f() -> minus X -> R (tf32 hi / lo) -> tcgen05.st back into TENSOR MEMORY
+//   tcgen05.mma: OUT[128 x 32] += R Q     GEMM2, A operand R read from tensor memory, B = K-major Q^T tile
+// Neither U V^T nor the residual ever touches HBM -- or shared memory: with N = 32..64 the MMAs have too little
+// operand reuse for shared-memory A operands (a 128 x 8 tf32 A slice is 4 KB per instruction: at 128 B/clk the
+// SS form was measured shared-memory-bound at ~60 clk per MMA), so both A operands live in TMEM (TS form) and
+// shared memory only carries the TMA ring and the small B slices.  3xTF32: hi*hi + hi*lo + lo*hi.
+// GEMM1 of tile t+1 is issued before GEMM2 of tile t (two S buffers, two R buffers in TMEM); the MMA thread
+// issues whichever GEMM has its inputs ready (event-driven, non-blocking mbarrier probes).
 //
 // Warp roles (640 threads): warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator,
 // warps 4-19 = epilogue: warp w works on TMEM lane quadrant w % 4 (own rows 32 (w % 4) ..) and on the
-// 16-column chunk (w - 4) / 4 of the 64-wide tile, so every SM sub-partition has four epilogue warps to
-// hide the TMEM / shared-memory latencies.
+// 16-column chunk (w - 4) / 4 of the 64-wide tile, so every SM sub-partition has four epilogue warps.
 #include <cuda.h>
 
 #include "common.cuh"
@@ -31,35 +33,36 @@ namespace {
 constexpr int OWN = 128;      // own rows per CTA  (UMMA M)
 constexpr int OTH = 64;       // other rows per tile (GEMM1 N, GEMM2 K)
 constexpr int KC = 32;        // n_components handled by this kernel (one 128-byte swizzle span)
-constexpr int NSTAGE = 2;
+constexpr int NSTAGE = 3;
 constexpr int PREFETCH_DIST = 8;   // X tiles requested into L2 ahead of the shared-memory ring
-constexpr int TMEM_COLS = 256;
-constexpr int TMEM_OUT_COL = 128;
 constexpr int EPI_WARPS = 16;
 constexpr int NTHREADS = 128 + 32 * EPI_WARPS;
 
-constexpr uint32_t P_BYTES = OWN * 128;          // 16 KB  (128 rows x 32 fp32)
-constexpr uint32_t Q_BYTES = OTH * 128;          //  8 KB
+// tensor-memory columns (512 x 128 lanes x 32 bit, all allocated: one CTA per SM)
+constexpr int TMEM_COLS = 512;
+constexpr int TM_S = 0;            // S[2]   : 2 x 64 columns
+constexpr int TM_OUT = 128;        // OUT    : 32 columns
+constexpr int TM_P_HI = 160;       // P hi   : 32 columns (A operand of GEMM1)
+constexpr int TM_P_LO = 192;       // P lo   : 32 columns
+constexpr int TM_OUT2 = 224;       // OUT2   : 32 columns, accumulates only the small hi*lo + lo*hi terms of GEMM2
+constexpr int TM_R = 256;          // R[2]   : 2 x (64 hi + 64 lo) columns (A operand of GEMM2)
+
+constexpr uint32_t Q_BYTES = OTH * 128;          //  8 KB (64 rows x 32 fp32; also 2 x 32 x 32 for Q^T)
 constexpr uint32_t X_BYTES = OWN * OTH * 4;      // 32 KB
-constexpr uint32_t R_BYTES = OWN * OTH * 4;      // 32 KB  (two K-blocks of 128 rows x 128 B)
 
 struct SmemLayout {
     // all tile buffers are 1024-byte aligned (SWIZZLE_128B atoms)
-    static constexpr uint32_t p_hi = 0;
-    static constexpr uint32_t p_lo = p_hi + P_BYTES;
-    static constexpr uint32_t stage0 = p_lo + P_BYTES;
     // offsets inside a stage: Q (64 x 32, K-major for GEMM1), Q^T (32 x 64 as two 32 x 32 K-blocks, GEMM2), X tile
     static constexpr uint32_t q_hi = 0, q_lo = Q_BYTES, qt_hi = 2 * Q_BYTES, qt_lo = 3 * Q_BYTES, x = 4 * Q_BYTES;
     static constexpr uint32_t stage_bytes = 4 * Q_BYTES + X_BYTES;
-    static constexpr uint32_t r_hi = stage0 + NSTAGE * stage_bytes;
-    static constexpr uint32_t r_lo = r_hi + R_BYTES;
-    static constexpr uint32_t bars = r_lo + R_BYTES;
+    static constexpr uint32_t stage0 = 0;
+    static constexpr uint32_t bars = stage0 + NSTAGE * stage_bytes;
     static constexpr uint32_t total = bars + 256;
 };
 
 // barrier slots (8 bytes each) inside the `bars` region
-enum Bar { FULL0 = 0, EMPTY0 = FULL0 + NSTAGE, SFULL0 = EMPTY0 + NSTAGE, SEMPTY0 = SFULL0 + 2, RFULL = SEMPTY0 + 2,
-           REMPTY, PFULL, OUTFULL, NBARS };
+enum Bar { FULL0 = 0, EMPTY0 = FULL0 + NSTAGE, SFULL0 = EMPTY0 + NSTAGE, SEMPTY0 = SFULL0 + 2, RFULL0 = SEMPTY0 + 2,
+           REMPTY0 = RFULL0 + 2, PFULL = REMPTY0 + 2, OUTFULL, NBARS };
 
 // ---- PTX wrappers ----------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return uint32_t(__cvta_generic_to_shared(p)); }
@@ -100,20 +103,30 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
         ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1) : "memory");
 }
-// TMA prefetch of one box into L2 only (no shared-memory slot needed): lets the producer run many tiles ahead of
-// the 2-stage shared-memory ring so the HBM latency is paid long before the real load
+// TMA prefetch of one box into L2 only (no shared-memory slot needed)
 __device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* map, int c0, int c1) {
     asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];"
                  ::"l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1) : "memory");
 }
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                          uint32_t accumulate) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t"
-        "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u) : "memory");
+// D (+)= A B with A in tensor memory (TS form), B through a shared-memory descriptor.  The accumulate flag is a
+// compile-time constant: issuing an MMA is an address add plus the instruction itself.
+template <bool ACC>
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc) {
+    if (ACC) {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "setp.eq.u32 p, 1, 1;\n\t"
+            "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, {%4, %4, %4, %4}, p;\n\t"
+            "}" ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(0u) : "memory");
+    } else {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "setp.ne.u32 p, 1, 1;\n\t"
+            "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, {%4, %4, %4, %4}, p;\n\t"
+            "}" ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(0u) : "memory");
+    }
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
@@ -129,6 +142,17 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
 #pragma unroll
     for (int i = 0; i < 16; i++) v[i] = __uint_as_float(r[i]);
 }
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float (&v)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+        ::"r"(taddr), "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])),
+          "r"(__float_as_uint(v[3])), "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])),
+          "r"(__float_as_uint(v[7])), "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])),
+          "r"(__float_as_uint(v[11])), "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])),
+          "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15]))
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -158,16 +182,25 @@ struct Params {
     int64_t own_n, oth_n;       // extents of the own / other dimension
     int64_t tiles_per_split;
     int link;
+    const float *p_hi, *p_lo;   // tf32 parts of the own-side factor (own_n x 32), RESID only
     float* out;                 // (own_n x 32) or split partials
     int64_t out_split_stride;
     double* sq_part;            // per-CTA partial of sum R^2 (may be null)
+    long long* trace;           // optional pipeline trace of CTA (0,0): [event][tile] clock64 stamps (diagnostics)
 };
+
+constexpr int TRACE_TILES = 32;
+enum TraceEvent { TR_TMA_ISSUE = 0, TR_G1_ISSUE, TR_S_SEEN, TR_R_DONE, TR_G2_ISSUE, TR_EMPTY_SEEN, TR_FULL_SEEN_EPI, TR_NEVENTS };
+#define TC_TRACE(ev, it)                                                                        \
+    do {                                                                                        \
+        if (prm.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && (it) < TRACE_TILES)   \
+            prm.trace[(ev) * TRACE_TILES + (it)] = clock64();                                   \
+    } while (0)
 
 // MODE 0 = LEFT (own = rows of X), 1 = RIGHT (own = columns of X).  RESID: R = f(S) - X, else R = X.
 template <int MODE, bool RESID, int NSPLIT>
 __global__ void __launch_bounds__(NTHREADS, 1)
-tc_pass_kernel(const __grid_constant__ CUtensorMap tm_p_hi, const __grid_constant__ CUtensorMap tm_p_lo,
-               const __grid_constant__ CUtensorMap tm_q_hi, const __grid_constant__ CUtensorMap tm_q_lo,
+tc_pass_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_constant__ CUtensorMap tm_q_lo,
                const __grid_constant__ CUtensorMap tm_qt_hi, const __grid_constant__ CUtensorMap tm_qt_lo,
                const __grid_constant__ CUtensorMap tm_x, const Params prm) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -188,10 +221,13 @@ tc_pass_kernel(const __grid_constant__ CUtensorMap tm_p_hi, const __grid_constan
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < NSTAGE; s++) { mbar_init(bar(FULL0 + s), 1); mbar_init(bar(EMPTY0 + s), 1); }
-        for (int s = 0; s < 2; s++) { mbar_init(bar(SFULL0 + s), 1); mbar_init(bar(SEMPTY0 + s), EPI_WARPS); }
-        mbar_init(bar(RFULL), EPI_WARPS);
-        mbar_init(bar(REMPTY), 1);
-        mbar_init(bar(PFULL), 1);
+        for (int s = 0; s < 2; s++) {
+            mbar_init(bar(SFULL0 + s), 1);
+            mbar_init(bar(SEMPTY0 + s), EPI_WARPS);
+            mbar_init(bar(RFULL0 + s), EPI_WARPS);
+            mbar_init(bar(REMPTY0 + s), 1);
+        }
+        mbar_init(bar(PFULL), EPI_WARPS);
         mbar_init(bar(OUTFULL), 1);
         *sq_slot = 0.0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -210,11 +246,6 @@ tc_pass_kernel(const __grid_constant__ CUtensorMap tm_p_hi, const __grid_constan
     if (warp == 0) {
         // =============================== TMA producer ===============================
         if (lane == 0) {
-            if (RESID) {
-                mbar_expect_tx(bar(PFULL), NSPLIT == 3 ? 2 * P_BYTES : P_BYTES);
-                tma_load_2d(base + SmemLayout::p_hi, &tm_p_hi, bar(PFULL), 0, int(own0));
-                if (NSPLIT == 3) tma_load_2d(base + SmemLayout::p_lo, &tm_p_lo, bar(PFULL), 0, int(own0));
-            }
             auto prefetch_x = [&](int it) {
                 const int oth0 = int((t_begin + it) * OTH);
                 if (MODE == 0) {
@@ -231,6 +262,7 @@ tc_pass_kernel(const __grid_constant__ CUtensorMap tm_p_hi, const __grid_constan
                 const uint32_t ph = uint32_t(it / NSTAGE) & 1u;
                 if (it + PREFETCH_DIST < n_it) prefetch_x(it + PREFETCH_DIST);
                 mbar_wait(bar(EMPTY0 + s), ph ^ 1u);
+                TC_TRACE(TR_EMPTY_SEEN, it);
                 const uint32_t st = base + SmemLayout::stage0 + uint32_t(s) * SmemLayout::stage_bytes;
                 const int oth0 = int((t_begin + it) * OTH);
                 mbar_expect_tx(bar(FULL0 + s), (RESID ? 2u : 1u) * (NSPLIT == 3 ? 2 * Q_BYTES : Q_BYTES) + X_BYTES);
@@ -255,66 +287,86 @@ tc_pass_kernel(const __grid_constant__ CUtensorMap tm_p_hi, const __grid_constan
                         tma_load_2d(st + SmemLayout::x + uint32_t(b) * OTH * 128, &tm_x, bar(FULL0 + s),
                                     int(own0) + 32 * b, oth0);
                 }
+                TC_TRACE(TR_TMA_ISSUE, it);
             }
         }
     } else if (warp == 1) {
         // =============================== MMA issuer ================================
         if (lane == 0) {
-            constexpr uint32_t idesc1 = make_idesc(OWN, OTH, 0, 0);   // S   = P (K-major) x Q (K-major)
-            constexpr uint32_t idesc2 = make_idesc(OWN, KC, 0, 0);    // OUT = R (K-major) x Q^T tile (K-major)
-            const uint32_t p_hi = base + SmemLayout::p_hi, p_lo = base + SmemLayout::p_lo;
-            const uint32_t r_hi = base + SmemLayout::r_hi, r_lo = base + SmemLayout::r_lo;
+            constexpr uint32_t idesc1 = make_idesc(OWN, OTH, 0, 0);   // S   = P (TMEM) x Q (K-major)
+            constexpr uint32_t idesc2 = make_idesc(OWN, KC, 0, 0);    // OUT = R (TMEM) x Q^T tile (K-major)
+            // B descriptors are built once per stage; inside a tile only the 14-bit start-address field changes,
+            // by small multiples of 16 bytes that cannot carry out of the field (all tiles live below 256 KB).
+            uint64_t dQ_hi[NSTAGE], dQ_lo[NSTAGE], dQt_hi[NSTAGE], dQt_lo[NSTAGE];
+#pragma unroll
+            for (int s = 0; s < NSTAGE; s++) {
+                const uint32_t st = base + SmemLayout::stage0 + uint32_t(s) * SmemLayout::stage_bytes;
+                dQ_hi[s] = make_desc(st + SmemLayout::q_hi, 16, 1024);
+                dQ_lo[s] = make_desc(st + SmemLayout::q_lo, 16, 1024);
+                dQt_hi[s] = make_desc(st + SmemLayout::qt_hi, 16, 1024);
+                dQt_lo[s] = make_desc(st + SmemLayout::qt_lo, 16, 1024);
+            }
+            auto pick = [&](const uint64_t (&d)[NSTAGE], int s) { return s == 0 ? d[0] : (s == 1 ? d[1] : d[2]); };
+            // Tensor-core accumulation into TMEM truncates (measured: ~2^-24 |acc| lost per MMA), so the order matters:
+            //  GEMM1: the small correction terms hi*lo, lo*hi first, the four hi*hi MMAs last;
+            //  GEMM2: corrections go to their own accumulator OUT2 (their rounding is relative to 2^-11 |OUT|), only the
+            //         eight hi*hi MMAs per tile extend the long chain in OUT; the epilogue adds OUT + OUT2.
             auto issue_g1 = [&](int it) {
                 const int s = it % NSTAGE, sb = it & 1;
-                const uint32_t st = base + SmemLayout::stage0 + uint32_t(s) * SmemLayout::stage_bytes;
-                const uint32_t d = tmem + uint32_t(sb * OTH);
-                uint32_t acc = 0;
+                const uint32_t d = tmem + uint32_t(TM_S + sb * OTH);
+                const uint64_t qh = pick(dQ_hi, s), ql = pick(dQ_lo, s);
 #pragma unroll
-                for (int term = 0; term < NSPLIT; term++) {
-                    const uint32_t pa = (term == 2) ? p_lo : p_hi;
-                    const uint32_t qa = st + ((term == 1) ? SmemLayout::q_lo : SmemLayout::q_hi);
+                for (int t = 0; t < NSPLIT; t++) {
+                    const int term = NSPLIT == 3 ? (t == 0 ? 1 : (t == 1 ? 2 : 0)) : 0;   // hi*lo, lo*hi, hi*hi
+                    const uint32_t pa = tmem + uint32_t((term == 2) ? TM_P_LO : TM_P_HI);
+                    const uint64_t qa = (term == 1) ? ql : qh;
 #pragma unroll
                     for (int kk = 0; kk < KC / 8; kk++) {
-                        umma_tf32(d, make_desc(pa + kk * 32, 16, 1024), make_desc(qa + kk * 32, 16, 1024), idesc1, acc);
-                        acc = 1;
+                        if (t == 0 && kk == 0) umma_tf32_ts<false>(d, pa, qa, idesc1);
+                        else umma_tf32_ts<true>(d, pa + uint32_t(kk * 8), qa + uint64_t(kk * 2), idesc1);
                     }
                 }
                 umma_commit(bar(SFULL0 + sb));
             };
-            uint32_t out_acc = 0;
-            auto issue_g2 = [&](int it) {
-                const int s = it % NSTAGE;
-                const uint32_t st = base + SmemLayout::stage0 + uint32_t(s) * SmemLayout::stage_bytes;
-                const uint32_t d = tmem + TMEM_OUT_COL;
+            auto issue_g2 = [&](int it, bool first) {
+                const int s = it % NSTAGE, rb = it & 1;
+                const uint32_t r_hi = tmem + uint32_t(TM_R + rb * 2 * OTH), r_lo = r_hi + OTH;
+                const uint64_t qh = pick(dQt_hi, s), ql = pick(dQt_lo, s);
 #pragma unroll
                 for (int term = 0; term < NSPLIT; term++) {
+                    const uint32_t d = tmem + uint32_t(term == 0 ? TM_OUT : TM_OUT2);
                     const uint32_t ra = (term == 2) ? r_lo : r_hi;
-                    const uint32_t qa = st + ((term == 1) ? SmemLayout::qt_lo : SmemLayout::qt_hi);
+                    const uint64_t qa = (term == 1) ? ql : qh;
 #pragma unroll
                     for (int kk = 0; kk < OTH / 8; kk++) {
-                        const uint32_t a_addr = ra + uint32_t(kk / 4) * (OWN * 128) + uint32_t(kk % 4) * 32;
-                        const uint32_t b_addr = qa + uint32_t(kk / 4) * (KC * 128) + uint32_t(kk % 4) * 32;
-                        umma_tf32(d, make_desc(a_addr, 16, 1024), make_desc(b_addr, 16, 1024), idesc2, out_acc);
-                        out_acc = 1;
+                        // K-step kk: 8 TMEM columns of R; Q^T K-block kk / 4 (32 rows x 128 B = 256 x 16 B)
+                        const uint64_t bd = qa + uint64_t((kk / 4) * (KC * 128 / 16) + (kk % 4) * 2);
+                        if (term <= 1 && kk == 0 && first) umma_tf32_ts<false>(d, ra, bd, idesc2);
+                        else umma_tf32_ts<true>(d, ra + uint32_t(kk * 8), bd, idesc2);
                     }
                 }
-                umma_commit(bar(REMPTY));
+                umma_commit(bar(REMPTY0 + rb));
                 umma_commit(bar(EMPTY0 + s));
             };
-            if (RESID) mbar_wait(bar(PFULL), 0);
+            if (RESID) {
+                mbar_wait(bar(PFULL), 0);      // epilogue warps have parked P in tensor memory
+                tc_fence_after();
+            }
             // Event-driven issue: GEMM2(t) goes out as soon as the epilogue has published R(t); GEMM1(t') as soon as
             // its operands have landed and its S buffer is free -- neither waits behind the other's barrier.
             int g1 = RESID ? 0 : n_it, g2 = 0;
             while (g2 < n_it) {
-                if (mbar_test(bar(RFULL), uint32_t(g2) & 1u) &&
+                if (mbar_test(bar(RFULL0 + (g2 & 1)), uint32_t(g2 >> 1) & 1u) &&
                     mbar_test(bar(FULL0 + g2 % NSTAGE), uint32_t(g2 / NSTAGE) & 1u)) {
                     tc_fence_after();
-                    issue_g2(g2);
+                    TC_TRACE(TR_G2_ISSUE, g2);
+                    if (g2 == 0) issue_g2(0, true); else issue_g2(g2, false);
                     g2++;
                 }
                 if (g1 < n_it && mbar_test(bar(FULL0 + g1 % NSTAGE), uint32_t(g1 / NSTAGE) & 1u) &&
                     mbar_test(bar(SEMPTY0 + (g1 & 1)), (uint32_t(g1 >> 1) & 1u) ^ 1u)) {
                     tc_fence_after();
+                    TC_TRACE(TR_G1_ISSUE, g1);
                     issue_g1(g1);
                     g1++;
                 }
@@ -329,26 +381,60 @@ tc_pass_kernel(const __grid_constant__ CUtensorMap tm_p_hi, const __grid_constan
         const int64_t own_idx = own0 + i;
         const bool own_ok = own_idx < prm.own_n;
         const uint32_t lane_addr = tmem + (uint32_t(q * 32) << 16);
+        if (RESID) {
+            // park this thread's 8 + 8 columns of P (tf32 hi / lo of the own-side factor row) in tensor memory
+            float ph[16];
+#pragma unroll
+            for (int e = 0; e < 16; e++) ph[e] = 0.0f;
+            if (own_ok) {
+                const float4* src_h = reinterpret_cast<const float4*>(prm.p_hi + own_idx * KC + cchunk * 8);
+                const float4* src_l = reinterpret_cast<const float4*>(prm.p_lo + own_idx * KC + cchunk * 8);
+                const float4 a0 = src_h[0], a1 = src_h[1];
+                ph[0] = a0.x; ph[1] = a0.y; ph[2] = a0.z; ph[3] = a0.w; ph[4] = a1.x; ph[5] = a1.y; ph[6] = a1.z; ph[7] = a1.w;
+                if (NSPLIT == 3) {
+                    const float4 b0 = src_l[0], b1 = src_l[1];
+                    ph[8] = b0.x; ph[9] = b0.y; ph[10] = b0.z; ph[11] = b0.w; ph[12] = b1.x; ph[13] = b1.y; ph[14] = b1.z; ph[15] = b1.w;
+                }
+            }
+            {
+                asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                             ::"r"(lane_addr + uint32_t(TM_P_HI + cchunk * 8)), "r"(__float_as_uint(ph[0])),
+                               "r"(__float_as_uint(ph[1])), "r"(__float_as_uint(ph[2])), "r"(__float_as_uint(ph[3])),
+                               "r"(__float_as_uint(ph[4])), "r"(__float_as_uint(ph[5])), "r"(__float_as_uint(ph[6])),
+                               "r"(__float_as_uint(ph[7])) : "memory");
+                asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                             ::"r"(lane_addr + uint32_t(TM_P_LO + cchunk * 8)), "r"(__float_as_uint(ph[8])),
+                               "r"(__float_as_uint(ph[9])), "r"(__float_as_uint(ph[10])), "r"(__float_as_uint(ph[11])),
+                               "r"(__float_as_uint(ph[12])), "r"(__float_as_uint(ph[13])), "r"(__float_as_uint(ph[14])),
+                               "r"(__float_as_uint(ph[15])) : "memory");
+            }
+            tmem_st_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar(PFULL));
+        }
         double sq = 0.0;
         for (int it = 0; it < n_it; it++) {
             const int s = it % NSTAGE, sb = it & 1;
             const int64_t oth0 = (t_begin + it) * OTH;
             mbar_wait(bar(FULL0 + s), uint32_t(it / NSTAGE) & 1u);
+            if (warp == 4 && lane == 0) TC_TRACE(TR_FULL_SEEN_EPI, it);
             if (RESID) {
                 mbar_wait(bar(SFULL0 + sb), uint32_t(it >> 1) & 1u);
                 tc_fence_after();
             }
+            if (warp == 4 && lane == 0) TC_TRACE(TR_S_SEEN, it);
             const unsigned char* xs = gen + SmemLayout::stage0 + s * SmemLayout::stage_bytes + SmemLayout::x;
             float sq_tile = 0.0f;
             // interior tiles need no bounds masks; the masked path only runs on the last row / column tiles
             const bool interior = (own0 + OWN <= prm.own_n) && (oth0 + OTH <= prm.oth_n);
             const int64_t oth_rem = prm.oth_n - oth0;
-            const int oth_left = oth_rem < OTH ? int(oth_rem) : OTH;   // valid other-indices in this tile
+            const int oth_left = oth_rem < OTH ? int(oth_rem) : OTH;
             {
                 const int c = cchunk;
                 float sv[16];
                 if (RESID) {
-                    tmem_ld16(lane_addr + uint32_t(sb * OTH + c * 16), sv);
+                    tmem_ld16(lane_addr + uint32_t(TM_S + sb * OTH + c * 16), sv);
                 }
                 float rr[16];
 #pragma unroll
@@ -392,34 +478,29 @@ tc_pass_kernel(const __grid_constant__ CUtensorMap tm_p_hi, const __grid_constan
 #pragma unroll
                     for (int e = 0; e < 16; e++) sq_tile = fmaf(rr[e], rr[e], sq_tile);
                 }
-                mbar_wait(bar(REMPTY), (uint32_t(it) & 1u) ^ 1u);   // GEMM2 of the previous tile has drained R
-                // R[i][16c .. 16c+15]: K-block (16c)/32, 16-byte chunks ((16c % 32)/4 + g) ^ (i & 7).
                 // tf32 split by truncation: hi = r with the 13 low mantissa bits cleared (exact tf32), lo = r - hi (exact
                 // in fp32; the tensor core reads its top 19 bits) -> hi*hi + hi*lo + lo*hi carries ~2^-20 relative error
-                const int blk = (c * 16) >> 5;
-                unsigned char* rh = gen + SmemLayout::r_hi + blk * (OWN * 128) + i * 128;
-                unsigned char* rl = gen + SmemLayout::r_lo + blk * (OWN * 128) + i * 128;
+                float hi[16], lo[16];
 #pragma unroll
-                for (int g = 0; g < 4; g++) {
-                    const int ch = (((c * 16) & 31) >> 2) + g;
-                    const int off = (ch ^ (i & 7)) << 4;
-                    float h[4];
-#pragma unroll
-                    for (int e = 0; e < 4; e++)
-                        h[e] = NSPLIT == 3 ? __uint_as_float(__float_as_uint(rr[g * 4 + e]) & 0xffffe000u) : rr[g * 4 + e];
-                    *reinterpret_cast<float4*>(rh + off) = make_float4(h[0], h[1], h[2], h[3]);
-                    if (NSPLIT == 3)
-                        *reinterpret_cast<float4*>(rl + off) = make_float4(rr[g * 4] - h[0], rr[g * 4 + 1] - h[1],
-                                                                           rr[g * 4 + 2] - h[2], rr[g * 4 + 3] - h[3]);
+                for (int e = 0; e < 16; e++) {
+                    hi[e] = NSPLIT == 3 ? __uint_as_float(__float_as_uint(rr[e]) & 0xffffe000u) : rr[e];
+                    lo[e] = rr[e] - hi[e];
                 }
+                // R buffer it & 1 in tensor memory: GEMM2 of tile it - 2 must have drained it
+                mbar_wait(bar(REMPTY0 + sb), (uint32_t(it >> 1) & 1u) ^ 1u);
+                tc_fence_after();
+                const uint32_t r_hi = lane_addr + uint32_t(TM_R + sb * 2 * OTH + c * 16);
+                tmem_st16(r_hi, hi);
+                if (NSPLIT == 3) tmem_st16(r_hi + OTH, lo);
+                tmem_st_wait();
             }
             sq += double(sq_tile);
-            fence_async_smem();            // generic-proxy writes of R -> visible to the tensor-core (async) proxy
-            if (RESID) tc_fence_before();
+            tc_fence_before();
             __syncwarp();
             if (lane == 0) {
                 if (RESID) mbar_arrive(bar(SEMPTY0 + sb));
-                mbar_arrive(bar(RFULL));
+                mbar_arrive(bar(RFULL0 + sb));
+                if (warp == 4) TC_TRACE(TR_R_DONE, it);
             }
         }
         // ---- final: OUT (128 x 32) from TMEM to global
@@ -428,7 +509,13 @@ tc_pass_kernel(const __grid_constant__ CUtensorMap tm_p_hi, const __grid_constan
         if (cchunk < KC / 16) {                   // two warps per quadrant write the two 16-column halves of OUT
             float o[16];
             if (n_it > 0) {
-                tmem_ld16(lane_addr + TMEM_OUT_COL + cchunk * 16, o);
+                tmem_ld16(lane_addr + uint32_t(TM_OUT + cchunk * 16), o);
+                if (NSPLIT == 3) {
+                    float o2[16];
+                    tmem_ld16(lane_addr + uint32_t(TM_OUT2 + cchunk * 16), o2);
+#pragma unroll
+                    for (int e = 0; e < 16; e++) o[e] += o2[e];
+                }
             } else {
 #pragma unroll
                 for (int e = 0; e < 16; e++) o[e] = 0.0f;
@@ -532,15 +619,12 @@ void launch_tc(pycmf_ctx* ctx, int64_t own_n, int64_t oth_n, const FactorParts& 
     if (own_tiles < 4 * ctx->num_sms)
         splits = std::max<int64_t>(1, std::min(loop_tiles, ceil_div(int64_t(4) * ctx->num_sms, own_tiles)));
     // TMEM accumulation is fp32 without round-to-nearest: bound the chain length per accumulator (measured: 65 tiles
-    // of random-sign data -> 3e-5 relative, 8 tiles -> 7e-7) and let the fp32 split reduction add the partials
-    splits = std::max(splits, ceil_div(loop_tiles, int64_t(32)));
+    // of random-sign data -> 3e-5 relative, 8 tiles -> 7e-7): at most 16 tiles, the fp32 split reduction adds the partials
+    splits = std::max(splits, ceil_div(loop_tiles, int64_t(16)));
     if (ctx->tc_max_splits > 0) splits = std::min<int64_t>(splits, ctx->tc_max_splits);
     int64_t tiles_per_split = ceil_div(loop_tiles, splits);
     splits = ceil_div(loop_tiles, tiles_per_split);
     PYCMF_CHECK(splits <= 65535, "tc pass: too many splits");
-    const FactorParts& Pm = RESID ? P : Q;   // P is unused (but must be a valid map) in COPY mode
-    CUtensorMap tm_p_hi = factor_map(Pm.hi, Pm.rows, RESID ? OWN : OTH);
-    CUtensorMap tm_p_lo = factor_map(Pm.lo, Pm.rows, RESID ? OWN : OTH);
     CUtensorMap tm_q_hi = factor_map(Q.hi, Q.rows, OTH);
     CUtensorMap tm_q_lo = factor_map(Q.lo, Q.rows, OTH);
     CUtensorMap tm_qt_hi = factor_t_map(Q.hi_t, Q.rows, Q.ldt);
@@ -551,6 +635,8 @@ void launch_tc(pycmf_ctx* ctx, int64_t own_n, int64_t oth_n, const FactorParts& 
     prm.oth_n = oth_n;
     prm.tiles_per_split = tiles_per_split;
     prm.link = link;
+    prm.p_hi = P.hi;
+    prm.p_lo = P.lo;
     prm.out = out;
     prm.out_split_stride = 0;
     if (splits > 1) {
@@ -558,6 +644,7 @@ void launch_tc(pycmf_ctx* ctx, int64_t own_n, int64_t oth_n, const FactorParts& 
         prm.out_split_stride = own_n * KC;
     }
     prm.sq_part = nullptr;
+    prm.trace = ctx->tc_trace ? static_cast<long long*>(scratch(ctx, 2, sizeof(long long) * TR_NEVENTS * TRACE_TILES)) : nullptr;
     const int64_t nparts = own_tiles * splits;
     if (RESID && sq != nullptr) prm.sq_part = static_cast<double*>(scratch(ctx, 1, size_t(nparts) * sizeof(double)));
     auto kern = tc_pass_kernel<MODE, RESID, NSPLIT>;
@@ -567,7 +654,7 @@ void launch_tc(pycmf_ctx* ctx, int64_t own_n, int64_t oth_n, const FactorParts& 
     dim3 grid((unsigned)own_tiles, (unsigned)splits);
     {
         Timed timer(ctx, RESID ? (MODE == 0 ? "tc_resid_left" : "tc_resid_right") : (MODE == 0 ? "tc_xv" : "tc_xtu"));
-        kern<<<grid, NTHREADS, smem, ctx->stream>>>(tm_p_hi, tm_p_lo, tm_q_hi, tm_q_lo, tm_qt_hi, tm_qt_lo, tm_x, prm);
+        kern<<<grid, NTHREADS, smem, ctx->stream>>>(tm_q_hi, tm_q_lo, tm_qt_hi, tm_qt_lo, tm_x, prm);
         PYCMF_LAUNCH_CHECK(ctx);
     }
     if (splits > 1) reduce_parts<float>(ctx, own_n, KC, int(splits), prm.out, out, KC, 1.0f, 0.0f);
@@ -586,6 +673,8 @@ FactorParts split_factor(pycmf_ctx* ctx, int64_t rows, const float* F, float* bu
 }
 
 }  // namespace
+
+int tc_trace_words() { return TR_NEVENTS * TRACE_TILES; }
 
 bool tc_dense_eligible(pycmf_ctx* ctx, int64_t ra, int64_t rb, int64_t k, const float* X, int64_t ldx, bool trans_t) {
     if (ctx->dense_path == 0 || trans_t || X == nullptr) return false;
