@@ -103,21 +103,122 @@ newton_finish_small_kernel(int64_t rows, int l, int k, T* __restrict__ F, const 
     }
 }
 
-// *flag = 1 iff scale * H + (diag - pert) I is positive definite (one warp; H is k x k, lower triangle used)
-template <typename T>
-__global__ void pd_flag_kernel(int k, const T* __restrict__ H, double scale, double diag, double pert, int* flag) {
-    __shared__ double W[KS * WLD];
-    const int lane = threadIdx.x;
-    double tr = 0.0;
-    for (int c = 0; c <= lane && lane < k; c++) {
-        double h = scale * double(H[lane * k + c]) + (c == lane ? diag - pert : 0.0);
-        W[lane * WLD + c] = h;
-        if (c == lane) tr = fabs(h);
+// ---- CTA-cooperative variants (32 x 32 threads, thread (r, c) owns one matrix element): used when there are only a
+// few matrices, where the one-warp-per-matrix kernels are pure latency (~30 us for a 32 x 32 factorisation).
+// LDL^T without square roots: step j updates W[r][c] -= W[r][j] W[c][j] / d_j for j < c <= r, then scales column j.
+// Returns false (uniformly) when a pivot is <= floor.  On success: unit-lower L below the diagonal, D on it.
+__device__ bool ldl_cta(double* W, int k, int r, int c, double floor) {
+    for (int j = 0; j < k; j++) {
+        __syncthreads();
+        const double piv = W[j * wsolve::WLD + j];
+        if (!(piv > floor)) return false;
+        if (r < k && c > j && c <= r) W[r * wsolve::WLD + c] -= W[r * wsolve::WLD + j] * W[c * wsolve::WLD + j] / piv;
+        __syncthreads();
+        if (c == j && r > j && r < k) W[r * wsolve::WLD + j] /= piv;
     }
+    __syncthreads();
+    return true;
+}
+
+template <typename T>
+__device__ void load_tile_cta(double* W, const T* __restrict__ H, int k, int r, int c, double scale, double diag) {
+    if (r < k && c <= r) W[r * wsolve::WLD + c] = scale * double(H[r * k + c]) + (r == c ? diag : 0.0);
+}
+
+// *flag = 1 iff scale * H + (diag - pert) I is positive definite (H is k x k, lower triangle used)
+template <typename T>
+__global__ void __launch_bounds__(1024)
+pd_flag_kernel(int k, const T* __restrict__ H, double scale, double diag, double pert, int* flag) {
+    __shared__ double W[KS * WLD];
+    __shared__ double red[32];
+    const int r = threadIdx.y, c = threadIdx.x;
+    load_tile_cta<T>(W, H, k, r, c, scale, diag - pert);
+    __syncthreads();
+    double tr = (r == 0 && c < k) ? fabs(W[c * WLD + c]) : 0.0;
     tr = warp_sum(tr);
-    __syncwarp();
-    const bool ok = wsolve::chol_tile(W, k, lane, 1e-13 * (tr + pert));
-    if (lane == 0) *flag = ok ? 1 : 0;
+    if (r == 0 && c == 0) red[0] = tr;
+    __syncthreads();
+    const bool ok = ldl_cta(W, k, r, c, 1e-13 * (red[0] + pert));
+    if (r == 0 && c == 0) *flag = ok ? 1 : 0;
+}
+
+// One CTA per matrix, nrhs right-hand sides per matrix (warp w takes rhs w, w + 32, ...).
+// MODE 0: X[b][q] = S(scale H_b + diag I) G[b][q].   MODE 1 (nrhs == 1): Newton row update of out[b].
+template <typename T, int MODE>
+__global__ void __launch_bounds__(1024)
+safe_solve_cta_kernel(int64_t batch, int k, const T* __restrict__ H, int64_t h_stride, const T* __restrict__ g,
+                      T* __restrict__ out, int nrhs, double l1, double l2, double l2_diag, double pert,
+                      bool non_negative, bool chol_fastpath, double h_scale, bool known_pd) {
+    __shared__ double W[KS * WLD];
+    __shared__ double red[32];
+    __shared__ int ok_s;
+    const int r = threadIdx.y, c = threadIdx.x, lane = c, warp = r;
+    const bool act = lane < k;
+    for (int64_t b = blockIdx.x; b < batch; b += gridDim.x) {
+        const T* Hb = H + b * h_stride;
+        bool ok = false;
+        __syncthreads();
+        if (chol_fastpath) {
+            ok = known_pd;
+            if (!ok) {
+                load_tile_cta<T>(W, Hb, k, r, c, h_scale, l2_diag - pert);
+                __syncthreads();
+                double tr = (r == 0 && c < k) ? fabs(W[c * WLD + c]) : 0.0;
+                tr = warp_sum(tr);
+                if (r == 0 && c == 0) red[0] = tr;
+                __syncthreads();
+                ok = ldl_cta(W, k, r, c, 1e-13 * (red[0] + pert));
+                __syncthreads();
+            }
+            if (ok) {
+                load_tile_cta<T>(W, Hb, k, r, c, h_scale, l2_diag);
+                ok = ldl_cta(W, k, r, c, 0.0);
+            }
+        }
+        if (!ok) {
+            // eigenvalue clamp active: symmetric tile, Jacobi sweeps by warp 0, then every warp applies it to its rhs
+            __syncthreads();
+            if (r < k && c < k) {
+                const int hi = r > c ? r : c, lo = r > c ? c : r;
+                W[r * WLD + c] = h_scale * double(Hb[hi * k + lo]) + (r == c ? l2_diag : 0.0);
+            }
+            __syncthreads();
+            if (warp == 0) wsolve::jacobi_sweeps_tile(W, k, lane, pert);
+            __syncthreads();
+        }
+        for (int q = warp; q < nrhs; q += 32) {
+            const int64_t gi = (b * nrhs + q) * k + lane;
+            double gr = act ? double(g[gi]) : 0.0, f = 0.0;
+            if (MODE == 1 && act) {
+                f = double(out[gi]);
+                gr += l1 * (f > 0.0 ? 1.0 : (f < 0.0 ? -1.0 : 0.0)) + l2 * f;
+            }
+            double x;
+            if (ok) {
+                double bv = gr;
+                for (int j = 0; j < k; j++) {                       // L y = b (unit lower)
+                    const double y = wsolve::shfl_d(bv, j);
+                    if (lane > j && act) bv = fma(-W[lane * WLD + j], y, bv);
+                }
+                if (act) bv /= W[lane * WLD + lane];                // D z = y
+                for (int j = k - 1; j >= 0; j--) {                  // L^T x = z
+                    const double xv = wsolve::shfl_d(bv, j);
+                    if (lane < j) bv = fma(-W[j * WLD + lane], xv, bv);
+                }
+                x = bv;
+            } else {
+                x = wsolve::jacobi_apply_tile(W, k, lane, gr, pert);
+            }
+            if (act) {
+                if (MODE == 0) out[gi] = T(x);
+                else {
+                    double fn = f - x;
+                    if (non_negative && fn < 0.0) fn = 0.0;
+                    out[gi] = T(fn);
+                }
+            }
+        }
+    }
 }
 
 // Warp-per-matrix clamped solve for k <= 32.  MODE 0: x_b = S(scale H_b + diag I) g_b.  MODE 1: Newton row update.
@@ -168,8 +269,19 @@ template <typename T, int MODE>
 bool safe_solve_small(pycmf_ctx* ctx, int64_t batch, int64_t k, const T* H, int64_t h_stride, const T* g, T* out,
                       double l1, double l2, double l2_diag, double pert, bool non_negative, double h_scale, bool known_pd) {
     if (k > KS || batch < 1) return false;
-    int64_t grid = std::min<int64_t>(ceil_div(batch, WARPS), int64_t(16) * ctx->num_sms);
     Timed timer(ctx, "safe_solve");
+    if (batch <= 2 * ctx->num_sms || (h_stride == 0 && MODE == 0)) {
+        // few matrices (or one matrix with many right-hand sides): CTA-cooperative factorisation
+        const bool shared = h_stride == 0 && MODE == 0;
+        const int64_t nb = shared ? 1 : batch;
+        const int nrhs = shared ? int(batch) : 1;
+        safe_solve_cta_kernel<T, MODE><<<(unsigned)nb, dim3(32, 32), 0, ctx->stream>>>(
+            nb, int(k), H, h_stride, g, out, nrhs, l1, l2, l2_diag, pert, non_negative, ctx->chol_fastpath != 0, h_scale,
+            known_pd);
+        PYCMF_LAUNCH_CHECK(ctx);
+        return true;
+    }
+    int64_t grid = std::min<int64_t>(ceil_div(batch, WARPS), int64_t(16) * ctx->num_sms);
     safe_solve_small_kernel<T, MODE><<<(unsigned)grid, WARPS * 32, 0, ctx->stream>>>(
         batch, int(k), H, h_stride, g, out, l1, l2, l2_diag, pert, non_negative, ctx->chol_fastpath != 0, h_scale, known_pd);
     PYCMF_LAUNCH_CHECK(ctx);
@@ -191,7 +303,7 @@ bool newton_finish_small(pycmf_ctx* ctx, int64_t rows, int64_t l, int64_t k, T* 
     if (wy >= 0.0 && ctx->chol_fastpath) {
         if (!hx_per_row) {
             flag = static_cast<int*>(scratch(ctx, 2, 256));
-            pd_flag_kernel<T><<<1, 32, 0, ctx->stream>>>(int(k), Hx, 1.0, l2_diag, pert, flag);
+            pd_flag_kernel<T><<<1, dim3(32, 32), 0, ctx->stream>>>(int(k), Hx, 1.0, l2_diag, pert, flag);
             PYCMF_LAUNCH_CHECK(ctx);
             pd_mode = 1;
         } else if (l2_diag >= pert) {

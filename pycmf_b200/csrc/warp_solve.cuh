@@ -67,8 +67,9 @@ __device__ __forceinline__ double chol_solve_tile(const double* W, int k, int la
     return b;
 }
 
-// One-sided (Hestenes) Jacobi on the columns of the symmetric tile W (lane == row).  Returns x_lane.
-__device__ __forceinline__ double jacobi_solve_tile(double* W, int k, int lane, double g, double pert) {
+// One-sided (Hestenes) Jacobi sweeps on the columns of the symmetric tile W (lane == row), executed by ONE warp.
+// On exit the columns are mutually orthogonal: W = Q diag(lambda) up to column order / sign.
+__device__ __forceinline__ void jacobi_sweeps_tile(double* W, int k, int lane, double pert) {
     const bool act = lane < k;
     const double tol = 1e-15, skip2 = (1e-3 * pert) * (1e-3 * pert);
     for (int sweep = 0; sweep < 60; sweep++) {
@@ -92,6 +93,11 @@ __device__ __forceinline__ double jacobi_solve_tile(double* W, int k, int lane, 
         __syncwarp();
         if (!rotated) break;
     }
+}
+
+// x = S(H) g from the orthogonalised tile:  x = g/p + sum_{sigma_i >= p} (1/sigma_i - 1/p) (w_i . g) / sigma_i^2  w_i
+__device__ __forceinline__ double jacobi_apply_tile(const double* W, int k, int lane, double g, double pert) {
+    const bool act = lane < k;
     double x = g / pert;
     for (int i = 0; i < k; i++) {
         const double w = act ? W[lane * WLD + i] : 0.0;
@@ -100,6 +106,11 @@ __device__ __forceinline__ double jacobi_solve_tile(double* W, int k, int lane, 
         if (sigma >= pert) x += (1.0 / sigma - 1.0 / pert) * dg / al * w;
     }
     return x;
+}
+
+__device__ __forceinline__ double jacobi_solve_tile(double* W, int k, int lane, double g, double pert) {
+    jacobi_sweeps_tile(W, k, lane, pert);
+    return jacobi_apply_tile(W, k, lane, g, pert);
 }
 
 // Writes row `lane` (lower part c <= lane) of the matrix into the tile, shifting the diagonal by `shift`.

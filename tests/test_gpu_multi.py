@@ -1,0 +1,63 @@
+"""Row-sharded fits over 2 GPUs (NCCL) must reproduce the single-GPU result (shard-count invariance)."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+_WORKER = r'''
+import os, sys
+sys.path.insert(0, sys.argv[1]); sys.path.insert(0, os.path.join(sys.argv[1], "tests"))
+import numpy as np, torch, torch.distributed as dist
+rank = int(os.environ["RANK"]); torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
+dist.init_process_group("nccl")
+from helpers import load_golden, draw_masks_for_case, rel_fro
+from test_gpu_parity import _mid_case, MID, NT
+import zlib
+from pycmf_b200.cmf_solvers import MUSolver, NewtonSolver
+from pycmf_b200.sharding import TorchComm, Comm
+
+def run(case, dtype, comm, masks=None):
+    p = dict(case["params"]); solver = p.pop("solver")
+    cls = MUSolver if solver == "mu" else NewtonSolver
+    s = cls(max_iter=case["iters"], tol=0, random_state=case["rng_seed"], dtype=dtype, comm=comm, **p)
+    s.history = []; s.masks_per_iter = masks
+    U, V, Z = case["U0"].copy(), case["V0"].copy(), case["Z0"].copy()
+    s.fit_iterative_update(case["X"], case["Y"], U, V, Z)
+    return np.asarray(s.history), U, V, Z
+
+names = ["mu_dense", "mu_csr_reg", "nt_lin_logit", "nt_logit_logit", "nt_csr_lin_logit", "nt_sg_logit_logit"]
+for name in names:
+    case, g = load_golden(name)
+    masks = draw_masks_for_case(case)
+    hist, U, V, Z = run(case, "float64", TorchComm(), masks)
+    assert np.allclose(hist, g["objective"][1:], rtol=1e-9, atol=1e-11), name
+    for got, ref in ((U, g["U"]), (V, g["V"]), (Z, g["Z"])):
+        assert rel_fro(got, ref) < 1e-9, name
+for name in ["mu_dense_k32", "nt_lin_logit_k32", "mu_csr_k64"]:
+    solver, n, d, l, k, sparse, params = MID[name]
+    case = _mid_case(solver, n, d, l, k, sparse, seed=zlib.crc32(name.encode()) % 1000, **params); case["iters"] = 4
+    h2, U2, V2, Z2 = run(case, "float32", TorchComm())
+    h1, U1, V1, Z1 = run(case, "float32", Comm())
+    assert np.abs(h2 - h1).max() / np.abs(h1).max() < 1e-5, (name, h1, h2)
+    for a, b in ((U1, U2), (V1, V2), (Z1, Z2)):
+        assert rel_fro(a, b) < 1e-4, name
+dist.barrier(); dist.destroy_process_group()
+if rank == 0: print("MULTI_OK")
+'''
+
+
+def test_two_gpu_row_sharding_matches_single_gpu(tmp_path):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    script = tmp_path / "worker.py"
+    script.write_text(_WORKER)
+    port = str(29600 + os.getpid() % 2000)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+           "--master-addr", "127.0.0.1", "--master-port", port, str(script), ROOT]
+    out = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900)
+    assert out.returncode == 0 and "MULTI_OK" in out.stdout, out.stdout[-4000:]

@@ -259,7 +259,10 @@ def test_tc_fused_residual_right_matches_numpy(link, path, tol, splits):
 @pytest.mark.parametrize("path", [1, 2])
 def test_tc_long_tile_loop_newton_step(path):
     """Single split => every CTA walks all tiles (multi-phase mbarrier ring); one Newton step vs the oracle."""
-    case = _mid_case("newton", 700, 1300, 9, 32, False, seed=11, **dict(NT, y_link="logit"))
+    # signed factors: with the projection this shape bounces (objective 1.8e3 -> 6.2e3 -> 6.8e2) and amplifies any
+    # rounding difference 5x per iteration, which tests the trajectory's conditioning rather than the kernel
+    case = _mid_case("newton", 700, 1300, 9, 32, False, seed=11,
+                     **dict(NT, y_link="logit", U_non_negative=False, V_non_negative=False))
     case["iters"] = 3
     ref_hist, rU, rV, rZ = run_oracle(case)
     hist, U, V, Z = run_ours(case, "float32", backend_options={"dense_path": path, "tc_max_splits": 1})
