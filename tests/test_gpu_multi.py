@@ -23,7 +23,10 @@ from pycmf_b200.sharding import TorchComm, Comm
 def run(case, dtype, comm, masks=None):
     p = dict(case["params"]); solver = p.pop("solver")
     cls = MUSolver if solver == "mu" else NewtonSolver
-    s = cls(max_iter=case["iters"], tol=0, random_state=case["rng_seed"], dtype=dtype, comm=comm, **p)
+    # dense_path 0: both shard counts use the same (FMA) arithmetic, so only the summation order differs; the tcgen05
+    # path switches on above a size threshold and would be compared against the FMA path on the smaller shards
+    s = cls(max_iter=case["iters"], tol=0, random_state=case["rng_seed"], dtype=dtype, comm=comm,
+            backend_options={"dense_path": 0}, **p)
     s.history = []; s.masks_per_iter = masks
     U, V, Z = case["U0"].copy(), case["V0"].copy(), case["Z0"].copy()
     s.fit_iterative_update(case["X"], case["Y"], U, V, Z)
@@ -37,7 +40,7 @@ for name in names:
     assert np.allclose(hist, g["objective"][1:], rtol=1e-9, atol=1e-11), name
     for got, ref in ((U, g["U"]), (V, g["V"]), (Z, g["Z"])):
         assert rel_fro(got, ref) < 1e-9, name
-for name in ["mu_dense_k32", "nt_lin_logit_k32", "mu_csr_k64"]:
+for name in ["mu_dense_k32", "nt_signed_l1_lin_logit_k32", "mu_csr_k64"]:   # contractive trajectories only
     solver, n, d, l, k, sparse, params = MID[name]
     case = _mid_case(solver, n, d, l, k, sparse, seed=zlib.crc32(name.encode()) % 1000, **params); case["iters"] = 4
     h2, U2, V2, Z2 = run(case, "float32", TorchComm())
@@ -60,4 +63,5 @@ def test_two_gpu_row_sharding_matches_single_gpu(tmp_path):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
            "--master-addr", "127.0.0.1", "--master-port", port, str(script), ROOT]
     out = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900)
-    assert out.returncode == 0 and "MULTI_OK" in out.stdout, out.stdout[-4000:]
+    errors = [ln for ln in out.stdout.splitlines() if "Error" in ln and "ChildFailed" not in ln]
+    assert out.returncode == 0 and "MULTI_OK" in out.stdout, "\n".join(errors[:6]) or out.stdout[-3000:]
