@@ -30,6 +30,7 @@ row_grad_hess_kernel(int64_t rows, int64_t m, int k, const T* __restrict__ A, co
     T* B_s = a_s + ((k + 3) & ~3);                    // TJ x kp
     T* r_s = B_s + TJ * kp;                           // TJ   (w * residual)
     T* w_s = r_s + TJ;                                // TJ   (w * f')
+    T* t_s = w_s + TJ;                                // TJ   targets of the staged samples
     const int64_t i = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int ta = tid >> 4, tb = tid & 15;
@@ -65,6 +66,26 @@ row_grad_hess_kernel(int64_t rows, int64_t m, int k, const T* __restrict__ A, co
             }
             B_s[jj * kp + c] = v;
         }
+        // targets of the tile, fetched in parallel (one thread per sample) instead of serially by lane 0 below
+        if (want_g && tid < TJ) {
+            T tg = T(0);
+            if (tid < cnt) {
+                const int64_t j = idx != nullptr ? int64_t(idx[i * n_sample + t0 + tid]) : t0 + tid;
+                if (j >= 0) {
+                    if (Tgt != nullptr) {
+                        tg = trans_t ? Tgt[j * ldt + i] : Tgt[i * ldt + j];
+                    } else if (rowptr != nullptr) {
+                        int l = lo, h = hi;
+                        while (l < h) {
+                            int mid = (l + h) >> 1;
+                            if (colidx[mid] < int(j)) l = mid + 1; else h = mid;
+                        }
+                        if (l < hi && colidx[l] == int(j)) tg = vals[l];
+                    }
+                }
+            }
+            t_s[tid] = tg;
+        }
         __syncthreads();
         // estimates: each warp takes TJ / 8 sampled rows
         for (int jj = warp; jj < TJ; jj += 8) {
@@ -78,19 +99,7 @@ row_grad_hess_kernel(int64_t rows, int64_t m, int k, const T* __restrict__ A, co
                 if (j >= 0) {
                     T est = d, fp = T(1);
                     if (link == PYCMF_LOGIT) { est = sigmoid_<T>(d); fp = est * (T(1) - est); }
-                    T tg = T(0);
-                    if (want_g) {
-                        if (Tgt != nullptr) {
-                            tg = trans_t ? Tgt[j * ldt + i] : Tgt[i * ldt + j];
-                        } else if (rowptr != nullptr) {
-                            int l = lo, h = hi;
-                            while (l < h) {
-                                int mid = (l + h) >> 1;
-                                if (colidx[mid] < int(j)) l = mid + 1; else h = mid;
-                            }
-                            if (l < hi && colidx[l] == int(j)) tg = vals[l];
-                        }
-                    }
+                    const T tg = want_g ? t_s[jj] : T(0);
                     rr = w * (est - tg);
                     ww = w * fp;
                 }
@@ -486,7 +495,7 @@ void row_grad_hess(pycmf_ctx* ctx, int64_t rows, int64_t m, int64_t k, const T* 
                    T* g, T* H, bool accumulate) {
     if (rows <= 0) return;
     PYCMF_CHECK(k >= 1 && k <= 256, "n_components must be in [1, 256] for the per-row Newton kernels");
-    size_t smem = sizeof(T) * (size_t((k + 3) & ~3) + size_t(TJ) * (k + 1) + 2 * TJ);
+    size_t smem = sizeof(T) * (size_t((k + 3) & ~3) + size_t(TJ) * (k + 1) + 3 * TJ);
     int hb = k <= 16 ? 1 : (k <= 32 ? 2 : (k <= 64 ? 4 : 8));
     int quads = k > 128 ? 2 : 1;
     // few rows, many samples (e.g. the Z update: l rows against d samples): split the samples over CTAs

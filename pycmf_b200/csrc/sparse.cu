@@ -1,6 +1,11 @@
 // CSR kernels: SpMM (C = alpha * S * B + beta * C) and SDDMM-style reductions over the nonzeros.
-// Warp-per-row; the nonzeros of a row are fetched coalesced (lane-strided) and broadcast by
-// shuffle; sub-warp groups of G lanes walk different nonzeros when k < 32 so no lane idles.
+// Work unit = a CHUNK of at most 512 nonzeros of one row, one warp per chunk (rows are split so that a hot row /
+// column of a tf-idf-like matrix -- 10^5 nonzeros in one CSC row is normal -- does not serialise on one warp);
+// chunk offsets come from a per-call count + exclusive scan, the kernel is grid-stride over the chunks so no host
+// synchronisation is needed.  The nonzeros of a chunk are fetched coalesced (lane-strided) and broadcast by shuffle;
+// sub-warp groups of G lanes walk different nonzeros when k < 32 so no lane idles.
+#include <cub/device/device_scan.cuh>
+
 #include "common.cuh"
 
 namespace pycmf {
@@ -8,51 +13,84 @@ namespace {
 
 constexpr int MAXT = 8;  // columns per lane: k <= 32 * MAXT = 256
 
+constexpr int CHUNK = 512;
+
+// chunks[r] = max(1, ceil(len_r / CHUNK)); rows that will be combined by atomics are pre-scaled by beta here
+template <typename T>
+__global__ void spmm_count_kernel(int64_t rows, const int32_t* __restrict__ rowptr, int* __restrict__ chunks,
+                                  T* __restrict__ C, int64_t ldc, int k, T beta) {
+    const int64_t r = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (r > rows) return;
+    if (r == rows) { chunks[r] = 0; return; }
+    const int len = rowptr[r + 1] - rowptr[r];
+    const int nc = len <= CHUNK ? 1 : (len + CHUNK - 1) / CHUNK;
+    chunks[r] = nc;
+    if (nc > 1)
+        for (int c = 0; c < k; c++) C[r * ldc + c] = beta != T(0) ? beta * C[r * ldc + c] : T(0);
+}
+
 template <typename T, int G>
 __global__ void __launch_bounds__(256)
 spmm_kernel(int64_t rows, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx,
             const T* __restrict__ vals, const T* __restrict__ B, int64_t ldb, int k,
-            T* __restrict__ C, int64_t ldc, T alpha, T beta) {
+            T* __restrict__ C, int64_t ldc, T alpha, T beta, const int* __restrict__ chunk_off) {
     const int lane = threadIdx.x & 31;
-    const int64_t row = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
-    if (row >= rows) return;
+    const int64_t warp0 = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = (int64_t(gridDim.x) * blockDim.x) >> 5;
+    const int64_t total = chunk_off[rows];
     constexpr int NG = 32 / G;            // nonzeros in flight per warp
     const int gl = lane % G, gid = lane / G;
-    T acc[MAXT];
+    for (int64_t ch = warp0; ch < total; ch += nwarps) {
+        // row of this chunk: last r with chunk_off[r] <= ch
+        int64_t lo = 0, hi = rows;
+        while (hi - lo > 1) {
+            const int64_t mid = (lo + hi) >> 1;
+            if (int64_t(chunk_off[mid]) <= ch) lo = mid; else hi = mid;
+        }
+        const int64_t row = lo;
+        const int ci = int(ch - chunk_off[row]);
+        const bool split = chunk_off[row + 1] - chunk_off[row] > 1;
+        T acc[MAXT];
 #pragma unroll
-    for (int t = 0; t < MAXT; t++) acc[t] = T(0);
-    const int start = rowptr[row], end = rowptr[row + 1];
-    for (int base = start; base < end; base += 32) {
-        int cnt = min(32, end - base);
-        int c = 0; T v = T(0);
-        if (lane < cnt) { c = colidx[base + lane]; v = vals[base + lane]; }
-        for (int j = 0; j < cnt; j += NG) {
-            int src = j + gid;
-            int cj = __shfl_sync(0xffffffffu, c, src & 31);
-            T vj = __shfl_sync(0xffffffffu, v, src & 31);
-            if (src < cnt) {
-                const T* brow = B + int64_t(cj) * ldb;
+        for (int t = 0; t < MAXT; t++) acc[t] = T(0);
+        const int start = rowptr[row] + ci * CHUNK;
+        const int end = min(rowptr[row + 1], start + CHUNK);
+        for (int base = start; base < end; base += 32) {
+            int cnt = min(32, end - base);
+            int c = 0; T v = T(0);
+            if (lane < cnt) { c = colidx[base + lane]; v = vals[base + lane]; }
+            for (int j = 0; j < cnt; j += NG) {
+                int src = j + gid;
+                int cj = __shfl_sync(0xffffffffu, c, src & 31);
+                T vj = __shfl_sync(0xffffffffu, v, src & 31);
+                if (src < cnt) {
+                    const T* brow = B + int64_t(cj) * ldb;
 #pragma unroll
-                for (int t = 0; t < MAXT; t++) {
-                    int col = gl + t * G;
-                    if (col < k) acc[t] = fma(vj, brow[col], acc[t]);
+                    for (int t = 0; t < MAXT; t++) {
+                        int col = gl + t * G;
+                        if (col < k) acc[t] = fma(vj, brow[col], acc[t]);
+                    }
                 }
             }
         }
-    }
-    // reduce across the NG groups
-#pragma unroll
-    for (int t = 0; t < MAXT; t++) {
-#pragma unroll
-        for (int o = 16; o >= G; o >>= 1) acc[t] += __shfl_xor_sync(0xffffffffu, acc[t], o);
-    }
-    if (gid == 0) {
+        // reduce across the NG groups
 #pragma unroll
         for (int t = 0; t < MAXT; t++) {
-            int col = gl + t * G;
-            if (col < k) {
-                T prev = beta != T(0) ? C[row * ldc + col] : T(0);
-                C[row * ldc + col] = alpha * acc[t] + beta * prev;
+#pragma unroll
+            for (int o = 16; o >= G; o >>= 1) acc[t] += __shfl_xor_sync(0xffffffffu, acc[t], o);
+        }
+        if (gid == 0) {
+#pragma unroll
+            for (int t = 0; t < MAXT; t++) {
+                int col = gl + t * G;
+                if (col < k) {
+                    if (split) {
+                        atomicAdd(&C[row * ldc + col], alpha * acc[t]);     // row pre-scaled by beta in the count pass
+                    } else {
+                        T prev = beta != T(0) ? C[row * ldc + col] : T(0);
+                        C[row * ldc + col] = alpha * acc[t] + beta * prev;
+                    }
+                }
             }
         }
     }
@@ -105,9 +143,22 @@ void spmm(pycmf_ctx* ctx, int64_t rows, const int32_t* rowptr, const int32_t* co
           const T* B, int64_t ldb, int64_t k, T* C, int64_t ldc, T alpha, T beta) {
     if (rows <= 0 || k <= 0) return;
     PYCMF_CHECK(k <= 32 * MAXT, "spmm: n_components > 256 is not supported");
-    unsigned blocks = (unsigned)ceil_div(rows * 32, 256);
+    PYCMF_CHECK(rows < (int64_t(1) << 31) - 1, "spmm: too many rows");
     Timed timer(ctx, "spmm");
-#define LAUNCH(G) spmm_kernel<T, G><<<blocks, 256, 0, ctx->stream>>>(rows, rowptr, colidx, vals, B, ldb, int(k), C, ldc, alpha, beta)
+    // chunk counts -> exclusive scan -> chunk offsets (rows + 1 ints), all on the stream
+    size_t cub_bytes = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, cub_bytes, (int*)nullptr, (int*)nullptr, int(rows + 1), ctx->stream);
+    const size_t off_bytes = ((size_t(rows) + 1) * sizeof(int) + 255) & ~size_t(255);
+    unsigned char* buf = static_cast<unsigned char*>(scratch(ctx, 2, 2 * off_bytes + cub_bytes + 256));
+    int* counts = reinterpret_cast<int*>(buf);
+    int* offsets = reinterpret_cast<int*>(buf + off_bytes);
+    void* cub_tmp = buf + 2 * off_bytes;
+    spmm_count_kernel<T><<<(unsigned)ceil_div(rows + 1, 256), 256, 0, ctx->stream>>>(rows, rowptr, counts, C, ldc, int(k), beta);
+    PYCMF_LAUNCH_CHECK(ctx);
+    PYCMF_CUDA(cub::DeviceScan::ExclusiveSum(cub_tmp, cub_bytes, counts, offsets, int(rows + 1), ctx->stream));
+    ctx->launches++;
+    const unsigned blocks = (unsigned)std::min<int64_t>(ceil_div(rows * 32, 256), int64_t(32) * ctx->num_sms);
+#define LAUNCH(G) spmm_kernel<T, G><<<blocks, 256, 0, ctx->stream>>>(rows, rowptr, colidx, vals, B, ldb, int(k), C, ldc, alpha, beta, offsets)
     if (k <= 1) LAUNCH(1);
     else if (k <= 2) LAUNCH(2);
     else if (k <= 4) LAUNCH(4);

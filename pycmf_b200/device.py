@@ -112,6 +112,21 @@ class CudaBackend:
         _lib.check(self.lib.pycmf_profile_query(self.ctx, family.encode(), C.byref(ms), C.byref(cnt)))
         return ms.value, cnt.value
 
+    def capture_step(self, fn):
+        """Runs fn() once under CUDA-graph capture (it executes on replay, not now) and returns the graph.
+        The library's launches follow torch's capture stream; event timers are off while capturing."""
+        torch = self.torch
+        prev_stream = self.stream
+        g = torch.cuda.CUDAGraph()
+        self.profile(False)
+        torch.cuda.synchronize(self.device)
+        with torch.cuda.graph(g):
+            self.use_stream(torch.cuda.current_stream(self.device))
+            fn()
+        self.use_stream(prev_stream)
+        g.replay()          # the captured iteration has not run yet: run it now
+        return g
+
     # ---- memory ------------------------------------------------------------------------------
     def empty(self, *shape, dtype=None):
         return self.torch.empty(*shape, dtype=dtype or self.tdtype, device=self.device)
