@@ -87,6 +87,8 @@ MID = {
                                                                         U_non_negative=False, V_non_negative=False)),
     "nt_lin_lin_k130": ("newton", 700, 600, 8, 130, False, dict(NT, l2_reg=1.0)),
     "nt_logit_lin_k72": ("newton", 150, 140, 4, 72, False, dict(NT, x_link="logit")),
+    # d >= 1024 with few label rows: the grouped-row Hessian kernel of the Z update (two row groups, ragged k)
+    "nt_lin_logit_d1100_k24": ("newton", 300, 1100, 20, 24, False, dict(NT_SIGNED_L1, y_link="logit", l1_reg=0.0)),
     "nt_signed_l1_lin_logit_k32": ("newton", 400, 200, 8, 32, False, dict(NT_SIGNED_L1, y_link="logit")),
     "nt_signed_l1_csr_logit_k16": ("newton", 300, 200, 6, 16, True, dict(NT_SIGNED_L1, x_link="logit", y_link="logit")),
 }
