@@ -156,6 +156,15 @@ __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// one leader lane of a converged warp (always the same lane for the full mask).  ptxas only emits back-to-back
+// UTCHMMA / UTMALDG when it can see that a single thread runs them: under `lane == 0` it wraps every such
+// instruction in an ELECT / BRA.U.ANY loop plus R2UR moves, measured at ~80 clk per MMA issued (the whole pass was
+// issue-bound: 36 MMAs x 80 clk = the 2900-clk tile period of profiles/r01_tc_pass_trace_before_elect.txt).
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ float tf32_rna(float x) {
     uint32_t r;
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
@@ -245,7 +254,8 @@ tc_pass_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_constan
 
     if (warp == 0) {
         // =============================== TMA producer ===============================
-        if (lane == 0) {
+        // The whole warp walks the loop (converged); one elected lane issues.
+        {
             auto prefetch_x = [&](int it) {
                 const int oth0 = int((t_begin + it) * OTH);
                 if (MODE == 0) {
@@ -256,43 +266,53 @@ tc_pass_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_constan
                     for (int b = 0; b < 4; b++) tma_prefetch_2d(&tm_x, int(own0) + 32 * b, oth0);
                 }
             };
-            for (int it = 0; it < PREFETCH_DIST && it < n_it; it++) prefetch_x(it);
             for (int it = 0; it < n_it; it++) {
                 const int s = it % NSTAGE;
                 const uint32_t ph = uint32_t(it / NSTAGE) & 1u;
-                if (it + PREFETCH_DIST < n_it) prefetch_x(it + PREFETCH_DIST);
                 mbar_wait(bar(EMPTY0 + s), ph ^ 1u);
-                TC_TRACE(TR_EMPTY_SEEN, it);
-                const uint32_t st = base + SmemLayout::stage0 + uint32_t(s) * SmemLayout::stage_bytes;
-                const int oth0 = int((t_begin + it) * OTH);
-                mbar_expect_tx(bar(FULL0 + s), (RESID ? 2u : 1u) * (NSPLIT == 3 ? 2 * Q_BYTES : Q_BYTES) + X_BYTES);
-                if (RESID) {
-                    tma_load_2d(st + SmemLayout::q_hi, &tm_q_hi, bar(FULL0 + s), 0, oth0);
-                    if (NSPLIT == 3) tma_load_2d(st + SmemLayout::q_lo, &tm_q_lo, bar(FULL0 + s), 0, oth0);
-                }
+                if (elect_one()) {
+                    TC_TRACE(TR_EMPTY_SEEN, it);
+                    const uint32_t st = base + SmemLayout::stage0 + uint32_t(s) * SmemLayout::stage_bytes;
+                    const int oth0 = int((t_begin + it) * OTH);
+                    mbar_expect_tx(bar(FULL0 + s), (RESID ? 2u : 1u) * (NSPLIT == 3 ? 2 * Q_BYTES : Q_BYTES) + X_BYTES);
+                    if (MODE == 0) {
+                        // X tile: own rows x 64 other columns, two 32-column boxes of 128 rows
+                        tma_load_2d(st + SmemLayout::x, &tm_x, bar(FULL0 + s), oth0, int(own0));
+                        tma_load_2d(st + SmemLayout::x + OWN * 128, &tm_x, bar(FULL0 + s), oth0 + 32, int(own0));
+                    } else {
+                        // X tile: 64 other rows x 128 own columns, four 32-column boxes of 64 rows
 #pragma unroll
-                for (int b = 0; b < 2; b++) {
-                    tma_load_2d(st + SmemLayout::qt_hi + uint32_t(b) * (KC * 128), &tm_qt_hi, bar(FULL0 + s), oth0 + 32 * b, 0);
-                    if (NSPLIT == 3)
-                        tma_load_2d(st + SmemLayout::qt_lo + uint32_t(b) * (KC * 128), &tm_qt_lo, bar(FULL0 + s), oth0 + 32 * b, 0);
-                }
-                if (MODE == 0) {
-                    // X tile: own rows x 64 other columns, two 32-column boxes of 128 rows
-                    tma_load_2d(st + SmemLayout::x, &tm_x, bar(FULL0 + s), oth0, int(own0));
-                    tma_load_2d(st + SmemLayout::x + OWN * 128, &tm_x, bar(FULL0 + s), oth0 + 32, int(own0));
-                } else {
-                    // X tile: 64 other rows x 128 own columns, four 32-column boxes of 64 rows
+                        for (int b = 0; b < 4; b++)
+                            tma_load_2d(st + SmemLayout::x + uint32_t(b) * OTH * 128, &tm_x, bar(FULL0 + s),
+                                        int(own0) + 32 * b, oth0);
+                    }
+                    if (RESID) {
+                        tma_load_2d(st + SmemLayout::q_hi, &tm_q_hi, bar(FULL0 + s), 0, oth0);
+                        if (NSPLIT == 3) tma_load_2d(st + SmemLayout::q_lo, &tm_q_lo, bar(FULL0 + s), 0, oth0);
+                    }
 #pragma unroll
-                    for (int b = 0; b < 4; b++)
-                        tma_load_2d(st + SmemLayout::x + uint32_t(b) * OTH * 128, &tm_x, bar(FULL0 + s),
-                                    int(own0) + 32 * b, oth0);
+                    for (int b = 0; b < 2; b++) {
+                        tma_load_2d(st + SmemLayout::qt_hi + uint32_t(b) * (KC * 128), &tm_qt_hi, bar(FULL0 + s), oth0 + 32 * b, 0);
+                        if (NSPLIT == 3)
+                            tma_load_2d(st + SmemLayout::qt_lo + uint32_t(b) * (KC * 128), &tm_qt_lo, bar(FULL0 + s), oth0 + 32 * b, 0);
+                    }
+                    TC_TRACE(TR_TMA_ISSUE, it);
+                    // L2 prefetch runs PREFETCH_DIST tiles ahead of the ring, but only once the ring's own loads are
+                    // queued: prefetching first put 8 tiles (256 KB per SM) in front of tile 0 (a 5500-clk pipeline fill)
+                    if (it >= NSTAGE - 1) {
+                        if (it == NSTAGE - 1)
+                            for (int a = NSTAGE; a < NSTAGE - 1 + PREFETCH_DIST && a < n_it; a++) prefetch_x(a);
+                        if (it + PREFETCH_DIST < n_it) prefetch_x(it + PREFETCH_DIST);
+                    }
                 }
-                TC_TRACE(TR_TMA_ISSUE, it);
+                __syncwarp();
             }
         }
     } else if (warp == 1) {
         // =============================== MMA issuer ================================
-        if (lane == 0) {
+        // The whole warp runs the event loop (converged, probes made warp-uniform); one elected lane issues the MMAs
+        // and the commits (tcgen05.commit tracks the MMAs of the issuing thread: elect.sync always picks the same lane).
+        {
             constexpr uint32_t idesc1 = make_idesc(OWN, OTH, 0, 0);   // S   = P (TMEM) x Q (K-major)
             constexpr uint32_t idesc2 = make_idesc(OWN, KC, 0, 0);    // OUT = R (TMEM) x Q^T tile (K-major)
             // B descriptors are built once per stage; inside a tile only the 14-bit start-address field changes,
@@ -356,22 +376,34 @@ tc_pass_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_constan
             // its operands have landed and its S buffer is free -- neither waits behind the other's barrier.
             int g1 = RESID ? 0 : n_it, g2 = 0;
             while (g2 < n_it) {
-                if (mbar_test(bar(RFULL0 + (g2 & 1)), uint32_t(g2 >> 1) & 1u) &&
-                    mbar_test(bar(FULL0 + g2 % NSTAGE), uint32_t(g2 / NSTAGE) & 1u)) {
+                // GEMM1 first: its S buffer frees at the moment R(t) is published, and the epilogue of tile t + 2 waits on it
+                bool go1 = g1 < n_it && mbar_test(bar(FULL0 + g1 % NSTAGE), uint32_t(g1 / NSTAGE) & 1u) &&
+                           mbar_test(bar(SEMPTY0 + (g1 & 1)), (uint32_t(g1 >> 1) & 1u) ^ 1u);
+                go1 = __all_sync(0xffffffffu, go1);
+                if (go1) {
                     tc_fence_after();
-                    TC_TRACE(TR_G2_ISSUE, g2);
-                    if (g2 == 0) issue_g2(0, true); else issue_g2(g2, false);
-                    g2++;
-                }
-                if (g1 < n_it && mbar_test(bar(FULL0 + g1 % NSTAGE), uint32_t(g1 / NSTAGE) & 1u) &&
-                    mbar_test(bar(SEMPTY0 + (g1 & 1)), (uint32_t(g1 >> 1) & 1u) ^ 1u)) {
-                    tc_fence_after();
-                    TC_TRACE(TR_G1_ISSUE, g1);
-                    issue_g1(g1);
+                    if (elect_one()) {
+                        TC_TRACE(TR_G1_ISSUE, g1);
+                        issue_g1(g1);
+                    }
+                    __syncwarp();
                     g1++;
                 }
+                bool go2 = mbar_test(bar(RFULL0 + (g2 & 1)), uint32_t(g2 >> 1) & 1u) &&
+                           mbar_test(bar(FULL0 + g2 % NSTAGE), uint32_t(g2 / NSTAGE) & 1u);
+                go2 = __all_sync(0xffffffffu, go2);
+                if (go2) {
+                    tc_fence_after();
+                    if (elect_one()) {
+                        TC_TRACE(TR_G2_ISSUE, g2);
+                        if (g2 == 0) issue_g2(0, true); else issue_g2(g2, false);
+                    }
+                    __syncwarp();
+                    g2++;
+                }
             }
-            umma_commit(bar(OUTFULL));
+            if (elect_one()) umma_commit(bar(OUTFULL));
+            __syncwarp();
         }
     } else if (warp >= 4) {
         // ================================ epilogue ================================
