@@ -244,10 +244,14 @@ class MUSolver(_IterativeCMFSolver):
             buf = be.mu_v_partial(st.X, st.U)                    # [X^T U ; U^T U] of this shard
             st.comm.all_reduce_sum(buf)
             be.mu_v_apply(st.V, buf, st.Y, st.Z, self.l1_reg, self.l2_reg)
+        # U and Z both read the new V and nothing of each other: the Z update runs on the auxiliary stream
+        side = be.fork() if (self.update_U and self.update_Z and hasattr(be, "fork")) else be
+        if self.update_Z:                                        # :261-263
+            side.mu_left(st.Z, st.V, st.Y, self.l1_reg, self.l2_reg, trans=True)
         if self.update_U:                                        # :257-259
             be.mu_left(st.U, st.V, st.X, self.l1_reg, self.l2_reg)
-        if self.update_Z:                                        # :261-263
-            be.mu_left(st.Z, st.V, st.Y, self.l1_reg, self.l2_reg, trans=True)
+        if side is not be:
+            be.join()
 
     def update_step(self, X, Y, U, V, Z, l1_reg, l2_reg, alpha):
         st = X if isinstance(X, FitState) else self.prepare(X, Y, U, V, Z)
@@ -346,12 +350,17 @@ class NewtonSolver(_IterativeCMFSolver):
         be = st.be
         m = self._masks(st) or {}
         alpha, l1, l2, pert = self.alpha, self.l1_reg, self.l2_reg, self.hessian_pertubation
+        # The U update reads (U, V, X) and the Z update (Z, V, Y): neither sees the other's result, so the order
+        # U, Z of the reference is kept by running Z on the auxiliary stream next to U (joined before V).
+        side = be.fork() if (self.update_U and self.update_Z and hasattr(be, "fork")) else be
+        if self.update_Z:                                        # :515-517 -> _newton_update_Z :488-508
+            side.newton_left(st.Z, st.V, st.Y, 1 - alpha, l1, l2, self.y_link, self.Z_non_negative, pert,
+                             l2_in_logit_hessian=True, idx=m.get("Z"), trans=True)
         if self.update_U:                                        # :511-513 -> _newton_update_U :394-430
             be.newton_left(st.U, st.V, st.X, alpha, l1, l2, self.x_link, self.U_non_negative, pert,
                            l2_in_logit_hessian=False, idx=m.get("U"))
-        if self.update_Z:                                        # :515-517 -> _newton_update_Z :488-508
-            be.newton_left(st.Z, st.V, st.Y, 1 - alpha, l1, l2, self.y_link, self.Z_non_negative, pert,
-                           l2_in_logit_hessian=True, idx=m.get("Z"), trans=True)
+        if side is not be:
+            be.join()
         if self.update_V:                                        # :519-522 -> _newton_update_V :432-486
             d, k = st.V.shape
             idx_x, idx_y = m.get("Vx"), m.get("Vy")

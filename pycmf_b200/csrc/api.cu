@@ -27,6 +27,35 @@ void* scratch(pycmf_ctx* ctx, int slot, size_t bytes) {
     return s.ptr;
 }
 
+pycmf_ctx* fork_side(pycmf_ctx* ctx) {
+    if (ctx->root != nullptr || !ctx->side_streams) return ctx;       // no nesting; option off: serial on the main stream
+    if (ctx->side == nullptr) {
+        pycmf_ctx* s = new pycmf_ctx();
+        s->device = ctx->device;
+        s->num_sms = ctx->num_sms;
+        s->max_smem_optin = ctx->max_smem_optin;
+        s->root = ctx;
+        PYCMF_CUDA(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+        PYCMF_CUDA(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+        PYCMF_CUDA(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
+        ctx->side = s;
+    }
+    pycmf_ctx* s = ctx->side;
+    s->chol_fastpath = ctx->chol_fastpath;
+    s->dense_path = ctx->dense_path;
+    s->tc_max_splits = ctx->tc_max_splits;
+    s->max_scratch = ctx->max_scratch;
+    PYCMF_CUDA(cudaEventRecord(ctx->ev_fork, ctx->stream));
+    PYCMF_CUDA(cudaStreamWaitEvent(s->stream, ctx->ev_fork, 0));
+    return s;
+}
+
+void join_side(pycmf_ctx* ctx) {
+    if (ctx->root != nullptr || !ctx->side_streams || ctx->side == nullptr) return;
+    PYCMF_CUDA(cudaEventRecord(ctx->ev_join, ctx->side->stream));
+    PYCMF_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
+}
+
 namespace {
 
 constexpr int SLOT_T0 = 4, SLOT_T1 = 5, SLOT_T2 = 6, SLOT_T3 = 7;
@@ -89,6 +118,9 @@ void sqerr_impl(pycmf_ctx* ctx, int64_t rows, int64_t m, int64_t k, const T* A, 
 template <typename T>
 void mu_v_partial_impl(pycmf_ctx* ctx, int64_t n, int64_t d, int64_t k, const T* X, int64_t ldx,
                        const int32_t* colptr, const int32_t* rowidx, const T* cvals, const T* U, T* out) {
+    // U^T U on the side stream, next to the pass over X
+    pycmf_ctx* sc = fork_side(ctx);
+    gemm<T>(sc, true, k, k, n, U, k, U, k, out + d * k, k, T(1), T(0));
     if (X != nullptr) {
         bool done = false;
         if constexpr (std::is_same<T, float>::value) {
@@ -102,7 +134,7 @@ void mu_v_partial_impl(pycmf_ctx* ctx, int64_t n, int64_t d, int64_t k, const T*
         PYCMF_CHECK(colptr && rowidx && cvals, "mu_v_partial: neither dense X nor CSC arrays given");
         spmm<T>(ctx, d, colptr, rowidx, cvals, U, k, k, out, k, T(1), T(0));
     }
-    gemm<T>(ctx, true, k, k, n, U, k, U, k, out + d * k, k, T(1), T(0));
+    join_side(ctx);
 }
 
 template <typename T>
@@ -123,8 +155,12 @@ template <typename T>
 void mu_left_impl(pycmf_ctx* ctx, int64_t rows, int64_t m, int64_t k, T* F, const T* B, const T* Tg, int64_t ldt,
                   bool trans_t, const int32_t* rowptr, const int32_t* colidx, const T* vals, double l1, double l2) {
     T* N = static_cast<T*>(scratch(ctx, SLOT_T0, sizeof(T) * size_t(rows) * k));
-    T* D = static_cast<T*>(scratch(ctx, SLOT_T1, sizeof(T) * size_t(rows) * k));
-    T* G = static_cast<T*>(scratch(ctx, SLOT_T2, sizeof(T) * size_t(k) * k));
+    // denominator F (B^T B) on the side stream, next to the pass over the target
+    pycmf_ctx* sc = fork_side(ctx);
+    T* D = static_cast<T*>(scratch(sc, SLOT_T1, sizeof(T) * size_t(rows) * k));
+    T* G = static_cast<T*>(scratch(sc, SLOT_T2, sizeof(T) * size_t(k) * k));
+    gemm<T>(sc, true, k, k, m, B, k, B, k, G, k, T(1), T(0));           // B^T B
+    gemm<T>(sc, false, rows, k, k, F, k, G, k, D, k, T(1), T(0));       // F (B^T B)
     if (Tg != nullptr) {
         bool done = false;
         if constexpr (std::is_same<T, float>::value) {
@@ -138,8 +174,7 @@ void mu_left_impl(pycmf_ctx* ctx, int64_t rows, int64_t m, int64_t k, T* F, cons
         PYCMF_CHECK(rowptr && colidx && vals, "mu_left: neither dense target nor CSR arrays given");
         spmm<T>(ctx, rows, rowptr, colidx, vals, B, k, k, N, k, T(1), T(0));
     }
-    gemm<T>(ctx, true, k, k, m, B, k, B, k, G, k, T(1), T(0));           // B^T B
-    gemm<T>(ctx, false, rows, k, k, F, k, G, k, D, k, T(1), T(0));       // F (B^T B)
+    join_side(ctx);
     mu_apply<T>(ctx, rows, k, F, N, D, l1, l2);
 }
 
@@ -164,6 +199,15 @@ void newton_left_impl(pycmf_ctx* ctx, int64_t rows, int64_t m, int64_t k, T* F, 
     T* g = static_cast<T*>(scratch(ctx, SLOT_T0, sizeof(T) * size_t(rows) * k));
 
     if (!sampled) {
+        // shared Hessian weight * B^T B + l2 I (cmf_solvers.py:407-410): Gram in float64 and its clamped inverse on the
+        // side stream, next to the gradient pass
+        const double* Hinv = nullptr;
+        if (link == PYCMF_LINEAR) {
+            pycmf_ctx* sc = fork_side(ctx);
+            double* G64 = static_cast<double*>(scratch(sc, SLOT_T1, sizeof(double) * size_t(k) * k));
+            gram_f64<T>(sc, m, k, B, G64);
+            Hinv = shared_inverse64(sc, k, G64, weight, l2_diag, pert);
+        }
         // data gradient for every row from the pre-update factor (cmf_solvers.py:399-400)
         if (!sparse) {
             resid_pass<T>(ctx, rows, m, k, F, B, Tg, ldt, trans_t, link, g, nullptr, nullptr);
@@ -180,10 +224,8 @@ void newton_left_impl(pycmf_ctx* ctx, int64_t rows, int64_t m, int64_t k, T* F, 
             spmm<T>(ctx, rows, rowptr, colidx, vals, B, k, k, g, k, T(-weight), T(1));
         }
         if (link == PYCMF_LINEAR) {
-            // shared Hessian weight * B^T B + l2 I (cmf_solvers.py:407-410), Gram accumulated in float64
-            double* G64 = static_cast<double*>(scratch(ctx, SLOT_T1, sizeof(double) * size_t(k) * k));
-            gram_f64<T>(ctx, m, k, B, G64);
-            newton_solve_shared64<T>(ctx, rows, k, F, g, G64, weight, l1, l2, l2_diag, pert, non_negative);
+            join_side(ctx);
+            apply_shared_inverse<T>(ctx, rows, k, F, g, Hinv, l1, l2, non_negative);
             return;
         }
     }
@@ -221,6 +263,11 @@ void newton_v_xpart_impl(pycmf_ctx* ctx, int64_t d_rows, int64_t n, int64_t k, c
                          n_sample, gx, Hx, false);
         return;
     }
+    if (x_link == PYCMF_LINEAR) {
+        // shared Hessian part alpha U^T U on the side stream, next to the gradient pass
+        pycmf_ctx* sc = fork_side(ctx);
+        gemm<T>(sc, true, k, k, n, U, k, U, k, Hx, k, T(alpha), T(0));
+    }
     if (!sparse) {
         resid_pass<T>(ctx, n, d_rows, k, U, V, Xc, ldx, false, x_link, nullptr, gx, nullptr);
         axpby<T>(ctx, d_rows * k, T(alpha), gx, T(0), nullptr, gx);
@@ -236,7 +283,7 @@ void newton_v_xpart_impl(pycmf_ctx* ctx, int64_t d_rows, int64_t n, int64_t k, c
         spmm<T>(ctx, d_rows, colptr, rowidx, cvals, U, k, k, gx, k, T(-alpha), T(1));
     }
     if (x_link == PYCMF_LINEAR) {
-        gemm<T>(ctx, true, k, k, n, U, k, U, k, Hx, k, T(alpha), T(0));
+        join_side(ctx);
     } else {
         row_grad_hess<T>(ctx, d_rows, n, k, V, U, nullptr, 0, false, nullptr, nullptr, nullptr, x_link, alpha,
                          nullptr, 0, nullptr, Hx, false);
@@ -345,6 +392,14 @@ int pycmf_destroy(pycmf_ctx* ctx) {
     clear_timers(ctx);
     for (auto& a : ctx->arena)
         if (a.ptr) cudaFree(a.ptr);
+    if (ctx->side != nullptr) {
+        for (auto& a : ctx->side->arena)
+            if (a.ptr) cudaFree(a.ptr);
+        cudaStreamDestroy(ctx->side->stream);
+        delete ctx->side;
+    }
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
     delete ctx;
     return 0;
 }
@@ -360,6 +415,7 @@ int pycmf_set_option(pycmf_ctx* ctx, const char* key, double value) {
         else if (k == "dense_path") ctx->dense_path = int(value);
         else if (k == "tc_max_splits") ctx->tc_max_splits = int(value);
         else if (k == "tc_trace") ctx->tc_trace = int(value);
+        else if (k == "side_streams") ctx->side_streams = value != 0.0;
         else if (k == "max_scratch_mb") ctx->max_scratch = size_t(std::max(16.0, value)) << 20;
         else throw pycmf::Error("unknown option: " + k);
     });

@@ -39,6 +39,12 @@ struct pycmf_ctx {
     // optional per-kernel-family timers (cudaEvent pairs recorded on the stream around each launch)
     int profile = 0;
     std::map<std::string, std::vector<std::pair<cudaEvent_t, cudaEvent_t>>> timers;
+    // Side context: a child with its own stream and arenas, used to run an independent branch of one phase next to the
+    // main branch (pycmf::fork_side / join_side).  Its launches and timers are booked on the root.
+    pycmf_ctx* root = nullptr;
+    pycmf_ctx* side = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    int side_streams = 1;    // option: 0 runs the side branches on the main stream (serial)
 };
 
 namespace pycmf {
@@ -64,7 +70,7 @@ struct Error : public std::runtime_error {
 
 #define PYCMF_LAUNCH_CHECK(ctx)                                                       \
     do {                                                                              \
-        (ctx)->launches++;                                                            \
+        ((ctx)->root ? (ctx)->root : (ctx))->launches++;                              \
         PYCMF_CUDA(cudaGetLastError());                                               \
     } while (0)
 
@@ -73,12 +79,13 @@ struct Timed {
     pycmf_ctx* ctx;
     cudaEvent_t stop = nullptr;
     Timed(pycmf_ctx* c, const char* name) : ctx(c) {
-        if (!c->profile) return;
+        pycmf_ctx* r = c->root ? c->root : c;
+        if (!r->profile) return;
         cudaEvent_t start;
         cudaEventCreate(&start);
         cudaEventCreate(&stop);
         cudaEventRecord(start, c->stream);
-        c->timers[name].emplace_back(start, stop);
+        r->timers[name].emplace_back(start, stop);
     }
     ~Timed() {
         if (stop) cudaEventRecord(stop, ctx->stream);
@@ -87,6 +94,13 @@ struct Timed {
 
 // scratch arena `slot`, at least `bytes` large (256-B aligned by cudaMalloc)
 void* scratch(pycmf_ctx* ctx, int slot, size_t bytes);
+
+// Returns the side context after making its stream wait for everything enqueued so far on ctx->stream; work enqueued
+// through the returned context runs concurrently with what the caller enqueues on ctx next.  join_side makes
+// ctx->stream wait for the side branch.  Both are plain event record / wait pairs, so they also work while the
+// stream is being captured into a CUDA graph (the side stream joins the capture and becomes a parallel branch).
+pycmf_ctx* fork_side(pycmf_ctx* ctx);
+void join_side(pycmf_ctx* ctx);
 
 static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
@@ -195,10 +209,12 @@ void row_grad_hess(pycmf_ctx* ctx, int64_t rows, int64_t m, int64_t k, const T* 
 template <typename T>
 void newton_solve_rows(pycmf_ctx* ctx, int64_t rows, int64_t k, T* F, const T* g, const T* H, int64_t h_stride,
                        double l1, double l2, double l2_diag, double pert, bool non_negative, bool known_pd = false);
-// shared Hessian given in float64 as h_scale * G (+ l2_diag I): invert once, apply to every row
+// shared Hessian given in float64 as h_scale * G (+ l2_diag I): the clamped inverse (k x k float64, arena 7 of ctx) ...
+double* shared_inverse64(pycmf_ctx* ctx, int64_t k, const double* G64, double h_scale, double l2_diag, double pert);
+// ... and its application to every row: F_i <- F_i - (g_i + l1 sign(F_i) + l2 F_i) Hinv ; clamp
 template <typename T>
-void newton_solve_shared64(pycmf_ctx* ctx, int64_t rows, int64_t k, T* F, const T* g, const double* G64, double h_scale,
-                           double l1, double l2, double l2_diag, double pert, bool non_negative);
+void apply_shared_inverse(pycmf_ctx* ctx, int64_t rows, int64_t k, T* F, const T* g, const double* Hinv, double l1,
+                          double l2, bool non_negative);
 // newton_small.cu : fused warp-per-row finish of the V update for k <= 32 and a small label factor; false = not eligible
 template <typename T>
 bool newton_finish_small(pycmf_ctx* ctx, int64_t rows, int64_t l, int64_t k, T* F, const T* Z, const T* Y, int64_t ldy,

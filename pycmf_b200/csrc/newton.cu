@@ -674,17 +674,25 @@ void newton_solve_rows(pycmf_ctx* ctx, int64_t rows, int64_t k, T* F, const T* g
     PYCMF_LAUNCH_CHECK(ctx);
 }
 
-template <typename T>
-void newton_solve_shared64(pycmf_ctx* ctx, int64_t rows, int64_t k, T* F, const T* g, const double* G64, double h_scale,
-                           double l1, double l2, double l2_diag, double pert, bool non_negative) {
-    if (rows <= 0) return;
-    double* buf = static_cast<double*>(scratch(ctx, 3, sizeof(double) * size_t(2) * k * k));
+// Hinv (k x k float64, in arena 7 of ctx) = S(h_scale * G64 + l2_diag I): k unit right-hand sides, one warp each.
+// Split from the application so that a caller can run it on a side stream next to the gradient pass.
+double* shared_inverse64(pycmf_ctx* ctx, int64_t k, const double* G64, double h_scale, double l2_diag, double pert) {
+    double* buf = static_cast<double*>(scratch(ctx, 7, sizeof(double) * size_t(2) * k * k));
     double *I64 = buf, *Hinv = buf + k * k;
     int64_t n = k * k;
     identity_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, ctx->stream>>>(int(k), I64);
     PYCMF_LAUNCH_CHECK(ctx);
+    // column c of Hinv = S(.) e_c ; S symmetric, so rows of the result are its columns
     launch_solve<double, 0>(ctx, k, k, G64, 0, I64, Hinv, 0.0, 0.0, l2_diag, pert, false, h_scale);
+    return Hinv;
+}
+
+template <typename T>
+void apply_shared_inverse(pycmf_ctx* ctx, int64_t rows, int64_t k, T* F, const T* g, const double* Hinv, double l1,
+                          double l2, bool non_negative) {
+    if (rows <= 0) return;
     size_t smem = sizeof(double) * size_t(8) * k;
+    Timed timer(ctx, "apply_shared_inverse");
     apply_shared_inverse_kernel<T><<<(unsigned)ceil_div(rows, 8), 256, smem, ctx->stream>>>(rows, int(k), F, g, Hinv, l1, l2,
                                                                                        non_negative);
     PYCMF_LAUNCH_CHECK(ctx);
@@ -706,8 +714,8 @@ void sample_indices(pycmf_ctx* ctx, int64_t rows, int64_t N, int64_t n_sample, u
                                    int64_t, T*, T*, bool);                                                      \
     template void newton_solve_rows<T>(pycmf_ctx*, int64_t, int64_t, T*, const T*, const T*, int64_t, double,   \
                                        double, double, double, bool, bool);                                        \
-    template void newton_solve_shared64<T>(pycmf_ctx*, int64_t, int64_t, T*, const T*, const double*, double,   \
-                                           double, double, double, double, bool);
+    template void apply_shared_inverse<T>(pycmf_ctx*, int64_t, int64_t, T*, const T*, const double*, double,    \
+                                          double, bool);
 INSTANTIATE(float)
 INSTANTIATE(double)
 

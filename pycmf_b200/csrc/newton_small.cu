@@ -1,12 +1,17 @@
-// Fused finish of the Newton V update for small n_components (k <= 32): one WARP per row of V does
+// Small-n_components (k <= 32) Newton kernels: one WARP per row / per matrix, register-resident Cholesky (warp_solve.cuh).
+//
+// newton_finish_small : fused finish of the V update.  One warp per row of V does
 //   g_j = gx_j + w (f2(v_j Z^T) - Y[j,:]) Z + l1 sign(v_j) + l2 v_j
 //   H_j = Hx(_j) + w Z^T diag(f2'(v_j Z^T)) Z + l2 I
 //   v_j <- v_j - S(H_j) g_j ; optional clamp                           (reference cmf_solvers.py:432-486)
-// entirely on chip: the row of H lives in registers (lane = Hessian row), the factorisation runs in a
-// per-warp shared-memory tile with warp-synchronous Cholesky (fast path, lambda_min(H) > pert) or a
-// warp-level one-sided Jacobi (eigenvalue clamp active).  Replaces five launches of the generic path
-// (small fused-residual pass, axpby, Hessian broadcast, per-row Hessian, batched solve) and the
-// d x k x k Hessian round trip through HBM.  All arithmetic in float64.
+// entirely on chip: the row of H is built in registers (lane = Hessian row) from 128-bit broadcast reads of Z,
+// factorised in float64 and applied.  Replaces five launches of the generic path (small fused-residual pass, axpby,
+// Hessian broadcast, per-row Hessian, batched solve) and the d x k x k Hessian round trip through HBM.
+//
+// safe_solve_small    : x_b = S(scale H_b + diag I) g_b (MODE 0) or the Newton row update (MODE 1), one warp per
+//                       right-hand side (a shared matrix is factorised redundantly by each warp: ~5 us of latency,
+//                       cheaper than any cross-warp hand-off at k <= 32).
+// Templates on KT = 8 / 16 / 32 (k padded with identity rows) so that all register arrays have compile-time indices.
 #include "warp_solve.cuh"
 
 namespace pycmf {
@@ -14,87 +19,118 @@ namespace {
 
 using wsolve::KS;
 using wsolve::WLD;
+using wsolve::TILE;
 using wsolve::shfl_d;
 constexpr int WARPS = 4;
 constexpr int LMAX = 128;         // max rows of the small factor (labels)
 
+// four consecutive elements of a shared-memory row (16-byte aligned for float, two 16-byte loads for double)
+__device__ __forceinline__ void load4(const float* p, float (&v)[4]) {
+    const float4 t = *reinterpret_cast<const float4*>(p);
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+}
+__device__ __forceinline__ void load4(const double* p, double (&v)[4]) {
+    const double2 t0 = *reinterpret_cast<const double2*>(p), t1 = *reinterpret_cast<const double2*>(p + 2);
+    v[0] = t0.x; v[1] = t0.y; v[2] = t1.x; v[3] = t1.y;
+}
+
 // pd_mode: 0 = test every row (Cholesky of H - pert I), 1 = read the shared verdict from *pd_flag, 2 = known PD
-template <typename T>
+template <typename T, int KT>
 __global__ void __launch_bounds__(WARPS * 32)
 newton_finish_small_kernel(int64_t rows, int l, int k, T* __restrict__ F, const T* __restrict__ Z,
                            const T* __restrict__ Y, int64_t ldy, int y_link, T wy,
                            const T* __restrict__ gx, const T* __restrict__ Hx, int64_t hx_stride,
                            double l1, double l2, double l2_diag, double pert, bool non_negative, bool chol_fastpath,
                            int pd_mode, const int* __restrict__ pd_flag) {
+    constexpr int ZLD = KT + 4;       // row stride of Z in shared memory: 16-byte aligned rows, conflict-free columns
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    double* Wall = reinterpret_cast<double*>(smem_raw);          // WARPS x KS x WLD solve tiles
-    T* Zs = reinterpret_cast<T*>(Wall + WARPS * KS * WLD);       // l x (k + 1)
-    T* Hs = Zs + size_t(l) * (k + 1);                            // k x k (shared Hessian part, if hx_stride == 0)
+    double* Wall = reinterpret_cast<double*>(smem_raw);          // WARPS solve tiles
+    T* Zs = reinterpret_cast<T*>(Wall + WARPS * TILE);           // l x ZLD (columns >= k zero)
+    T* Hs = Zs + size_t(l) * ZLD + 32;                           // KT x KT (shared Hessian part, if hx_stride == 0)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int kz = k + 1;
-    for (int e = threadIdx.x; e < l * k; e += blockDim.x) Zs[(e / k) * kz + (e % k)] = Z[e];
+    for (int e = threadIdx.x; e < l * ZLD + 32; e += blockDim.x) {
+        const int r = e / ZLD, c = e % ZLD;
+        Zs[e] = (r < l && c < k) ? Z[r * k + c] : T(0);
+    }
     if (hx_stride == 0)
-        for (int e = threadIdx.x; e < k * k; e += blockDim.x) {
-            int r = e / k, c = e % k;
-            Hs[e] = Hx[(r > c ? r : c) * k + (r > c ? c : r)];   // lower triangle, like eigh
+        for (int e = threadIdx.x; e < KT * KT; e += blockDim.x) {
+            const int r = e / KT, c = e % KT;
+            Hs[e] = (r < k && c < k) ? Hx[(r > c ? r : c) * k + (r > c ? c : r)] : T(0);   // lower triangle, like eigh
         }
     __syncthreads();
-    double* W = Wall + warp * (KS * WLD);
+    double* W = Wall + warp * TILE;
     const bool act = lane < k;
     const bool known_pd = pd_mode == 2 || (pd_mode == 1 && *pd_flag != 0);
     for (int64_t row = int64_t(blockIdx.x) * WARPS + warp; row < rows; row += int64_t(gridDim.x) * WARPS) {
         const T v = act ? F[row * k + lane] : T(0);
         T g = act ? gx[row * k + lane] : T(0);
-        // ---- estimates for the labels c2 = lane + 32 t
+        // ---- estimates for the labels c2 = lane + 32 t : d = v . z_c2
         T res[LMAX / 32], wgt[LMAX / 32];
 #pragma unroll
         for (int t = 0; t < LMAX / 32; t++) {
+            res[t] = T(0);
+            wgt[t] = T(0);
+            if (32 * t >= l) continue;
             const int c2 = lane + 32 * t;
-            if (32 * t >= l) { res[t] = T(0); wgt[t] = T(0); continue; }
+            const T* zr = Zs + (c2 < l ? c2 : 0) * ZLD;
             T d = T(0);
-            for (int a = 0; a < k; a++) d = fma(T(__shfl_sync(0xffffffffu, v, a)), (c2 < l) ? Zs[c2 * kz + a] : T(0), d);
+#pragma unroll
+            for (int a0 = 0; a0 < KT; a0 += 4) {
+                T z4[4];
+                load4(zr + a0, z4);
+#pragma unroll
+                for (int u = 0; u < 4; u++) d = fma(T(__shfl_sync(0xffffffffu, v, a0 + u)), z4[u], d);
+            }
             T est = d, fp = T(1);
             if (y_link == PYCMF_LOGIT) { est = sigmoid_<T>(d); fp = est * (T(1) - est); }
-            const T y = (c2 < l) ? Y[row * ldy + c2] : T(0);
-            res[t] = (c2 < l) ? wy * (est - y) : T(0);
-            wgt[t] = (c2 < l) ? wy * fp : T(0);
+            if (c2 < l) {
+                res[t] = wy * (est - Y[row * ldy + c2]);
+                wgt[t] = wy * fp;
+            }
         }
         // ---- row `lane` of the Hessian in registers (compute dtype)
-        T Wr[KS];
+        T Wr[KT];
+        if (hx_stride == 0) {
 #pragma unroll
-        for (int c = 0; c < KS; c++) {
-            T h = T(0);
-            if (act && c < k) {
-                if (hx_stride == 0) h = Hs[lane * k + c];
-                else {
-                    const int hi = lane > c ? lane : c, lo = lane > c ? c : lane;
-                    h = Hx[row * hx_stride + hi * k + lo];
-                }
+            for (int c = 0; c < KT; c += 4) {
+                T h4[4];
+                load4(Hs + (lane < KT ? lane : 0) * KT + c, h4);
+#pragma unroll
+                for (int u = 0; u < 4; u++) Wr[c + u] = h4[u];
             }
-            Wr[c] = h;
+        } else {
+#pragma unroll
+            for (int c = 0; c < KT; c++) {
+                const int hi = lane > c ? lane : c, lo = lane > c ? c : lane;
+                Wr[c] = (act && c < k) ? Hx[row * hx_stride + hi * k + lo] : T(0);
+            }
         }
 #pragma unroll
         for (int t = 0; t < LMAX / 32; t++) {
             const int lim = min(32, l - 32 * t);
             for (int cc = 0; cc < lim; cc++) {
-                const int c2 = 32 * t + cc;
+                const T* zr = Zs + (32 * t + cc) * ZLD;
                 const T r = __shfl_sync(0xffffffffu, res[t], cc), w = __shfl_sync(0xffffffffu, wgt[t], cc);
-                const T za = act ? Zs[c2 * kz + lane] : T(0);
+                const T za = zr[lane < KT ? lane : 0];
                 g = fma(r, za, g);
                 const T wza = w * za;
 #pragma unroll
-                for (int c = 0; c < KS; c++)
-                    if (c < k) Wr[c] = fma(wza, Zs[c2 * kz + c], Wr[c]);
+                for (int c = 0; c < KT; c += 4) {
+                    T z4[4];
+                    load4(zr + c, z4);
+#pragma unroll
+                    for (int u = 0; u < 4; u++) Wr[c + u] = fma(wza, z4[u], Wr[c + u]);
+                }
             }
         }
         const double vd = double(v);
         const double sgn = vd > 0.0 ? 1.0 : (vd < 0.0 ? -1.0 : 0.0);
         const double gfull = act ? double(g) + l1 * sgn + l2 * vd : 0.0;
-        // ---- l2 on the diagonal, then the clamped solve in float64
-        double Wd[KS];
-#pragma unroll
-        for (int c = 0; c < KS; c++) Wd[c] = double(Wr[c]) + ((c == lane) ? l2_diag : 0.0);
-        const double x = wsolve::safe_solve_warp(Wd, k, lane, gfull, pert, chol_fastpath, known_pd, W);
+        // ---- the clamped solve in float64 (l2 on the diagonal)
+        double a[KT];
+        const bool fac = wsolve::safe_factor_warp<KT, T>(Wr, l2_diag, k, lane, pert, chol_fastpath, known_pd, W, a);
+        const double x = wsolve::safe_apply_warp<KT>(fac, a, k, lane, gfull, pert, W);
+        __syncwarp();
         if (act) {
             double f = vd - x;
             if (non_negative && f < 0.0) f = 0.0;
@@ -103,146 +139,47 @@ newton_finish_small_kernel(int64_t rows, int l, int k, T* __restrict__ F, const 
     }
 }
 
-// ---- CTA-cooperative variants (32 x 32 threads, thread (r, c) owns one matrix element): used when there are only a
-// few matrices, where the one-warp-per-matrix kernels are pure latency (~30 us for a 32 x 32 factorisation).
-// LDL^T without square roots: step j updates W[r][c] -= W[r][j] W[c][j] / d_j for j < c <= r, then scales column j.
-// Returns false (uniformly) when a pivot is <= floor.  On success: unit-lower L below the diagonal, D on it.
-__device__ bool ldl_cta(double* W, int k, int r, int c, double floor) {
-    for (int j = 0; j < k; j++) {
-        __syncthreads();
-        const double piv = W[j * wsolve::WLD + j];
-        if (!(piv > floor)) return false;
-        if (r < k && c > j && c <= r) W[r * wsolve::WLD + c] -= W[r * wsolve::WLD + j] * W[c * wsolve::WLD + j] / piv;
-        __syncthreads();
-        if (c == j && r > j && r < k) W[r * wsolve::WLD + j] /= piv;
-    }
-    __syncthreads();
-    return true;
-}
-
-template <typename T>
-__device__ void load_tile_cta(double* W, const T* __restrict__ H, int k, int r, int c, double scale, double diag) {
-    if (r < k && c <= r) W[r * wsolve::WLD + c] = scale * double(H[r * k + c]) + (r == c ? diag : 0.0);
-}
-
-// *flag = 1 iff scale * H + (diag - pert) I is positive definite (H is k x k, lower triangle used)
-template <typename T>
-__global__ void __launch_bounds__(1024)
+// *flag = 1 iff scale * H + (diag - pert) I is positive definite (H is k x k, lower triangle used).  One warp.
+template <typename T, int KT>
+__global__ void __launch_bounds__(32)
 pd_flag_kernel(int k, const T* __restrict__ H, double scale, double diag, double pert, int* flag) {
-    __shared__ double W[KS * WLD];
-    __shared__ double red[32];
-    const int r = threadIdx.y, c = threadIdx.x;
-    load_tile_cta<T>(W, H, k, r, c, scale, diag - pert);
-    __syncthreads();
-    double tr = (r == 0 && c < k) ? fabs(W[c * WLD + c]) : 0.0;
-    tr = warp_sum(tr);
-    if (r == 0 && c == 0) red[0] = tr;
-    __syncthreads();
-    const bool ok = ldl_cta(W, k, r, c, 1e-13 * (red[0] + pert));
-    if (r == 0 && c == 0) *flag = ok ? 1 : 0;
-}
-
-// One CTA per matrix, nrhs right-hand sides per matrix (warp w takes rhs w, w + 32, ...).
-// MODE 0: X[b][q] = S(scale H_b + diag I) G[b][q].   MODE 1 (nrhs == 1): Newton row update of out[b].
-template <typename T, int MODE>
-__global__ void __launch_bounds__(1024)
-safe_solve_cta_kernel(int64_t batch, int k, const T* __restrict__ H, int64_t h_stride, const T* __restrict__ g,
-                      T* __restrict__ out, int nrhs, double l1, double l2, double l2_diag, double pert,
-                      bool non_negative, bool chol_fastpath, double h_scale, bool known_pd) {
-    __shared__ double W[KS * WLD];
-    __shared__ double red[32];
-    __shared__ int ok_s;
-    const int r = threadIdx.y, c = threadIdx.x, lane = c, warp = r;
+    __shared__ __align__(16) double W[TILE];
+    const int lane = threadIdx.x;
     const bool act = lane < k;
-    for (int64_t b = blockIdx.x; b < batch; b += gridDim.x) {
-        const T* Hb = H + b * h_stride;
-        bool ok = false;
-        __syncthreads();
-        if (chol_fastpath) {
-            ok = known_pd;
-            if (!ok) {
-                load_tile_cta<T>(W, Hb, k, r, c, h_scale, l2_diag - pert);
-                __syncthreads();
-                double tr = (r == 0 && c < k) ? fabs(W[c * WLD + c]) : 0.0;
-                tr = warp_sum(tr);
-                if (r == 0 && c == 0) red[0] = tr;
-                __syncthreads();
-                ok = ldl_cta(W, k, r, c, 1e-13 * (red[0] + pert));
-                __syncthreads();
-            }
-            if (ok) {
-                load_tile_cta<T>(W, Hb, k, r, c, h_scale, l2_diag);
-                ok = ldl_cta(W, k, r, c, 0.0);
-            }
-        }
-        if (!ok) {
-            // eigenvalue clamp active: symmetric tile, Jacobi sweeps by warp 0, then every warp applies it to its rhs
-            __syncthreads();
-            if (r < k && c < k) {
-                const int hi = r > c ? r : c, lo = r > c ? c : r;
-                W[r * WLD + c] = h_scale * double(Hb[hi * k + lo]) + (r == c ? l2_diag : 0.0);
-            }
-            __syncthreads();
-            if (warp == 0) wsolve::jacobi_sweeps_tile(W, k, lane, pert);
-            __syncthreads();
-        }
-        for (int q = warp; q < nrhs; q += 32) {
-            const int64_t gi = (b * nrhs + q) * k + lane;
-            double gr = act ? double(g[gi]) : 0.0, f = 0.0;
-            if (MODE == 1 && act) {
-                f = double(out[gi]);
-                gr += l1 * (f > 0.0 ? 1.0 : (f < 0.0 ? -1.0 : 0.0)) + l2 * f;
-            }
-            double x;
-            if (ok) {
-                double bv = gr;
-                for (int j = 0; j < k; j++) {                       // L y = b (unit lower)
-                    const double y = wsolve::shfl_d(bv, j);
-                    if (lane > j && act) bv = fma(-W[lane * WLD + j], y, bv);
-                }
-                if (act) bv /= W[lane * WLD + lane];                // D z = y
-                for (int j = k - 1; j >= 0; j--) {                  // L^T x = z
-                    const double xv = wsolve::shfl_d(bv, j);
-                    if (lane < j) bv = fma(-W[j * WLD + lane], xv, bv);
-                }
-                x = bv;
-            } else {
-                x = wsolve::jacobi_apply_tile(W, k, lane, gr, pert);
-            }
-            if (act) {
-                if (MODE == 0) out[gi] = T(x);
-                else {
-                    double fn = f - x;
-                    if (non_negative && fn < 0.0) fn = 0.0;
-                    out[gi] = T(fn);
-                }
-            }
-        }
+    double a[KT], tr = 0.0;
+#pragma unroll
+    for (int c = 0; c < KT; c++) {
+        a[c] = (act && c <= lane) ? scale * double(H[lane * k + c]) + (c == lane ? diag - pert : 0.0)
+                                  : (c == lane ? 1.0 : 0.0);
+        if (c == lane && act) tr = fabs(a[c]);
     }
+    tr = warp_sum(tr);
+    const bool ok = wsolve::chol_reg<KT>(a, lane, 1e-13 * (tr + pert), W);
+    if (lane == 0) *flag = ok ? 1 : 0;
 }
 
-// Warp-per-matrix clamped solve for k <= 32.  MODE 0: x_b = S(scale H_b + diag I) g_b.  MODE 1: Newton row update.
-template <typename T, int MODE>
+// Warp per right-hand side.  h_stride == 0: one shared matrix, rhs / outputs indexed by b.
+// MODE 0: x_b = S(scale H_b + diag I) g_b.  MODE 1: Newton row update of out[b].
+template <typename T, int MODE, int KT>
 __global__ void __launch_bounds__(WARPS * 32)
 safe_solve_small_kernel(int64_t batch, int k, const T* __restrict__ H, int64_t h_stride, const T* __restrict__ g,
                         T* __restrict__ out, double l1, double l2, double l2_diag, double pert, bool non_negative,
                         bool chol_fastpath, double h_scale, bool known_pd) {
-    __shared__ double Wall[WARPS * KS * WLD];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    double* W = Wall + warp * (KS * WLD);
+    __shared__ __align__(16) double Wall[WARPS * TILE];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;   // 1 or WARPS warps per CTA
+    double* W = Wall + warp * TILE;
     const bool act = lane < k;
-    for (int64_t b = int64_t(blockIdx.x) * WARPS + warp; b < batch; b += int64_t(gridDim.x) * WARPS) {
-        const T* Hb = H + b * h_stride;
-        double Hr[KS];
+    double a[KT];
+    bool fac = false, have = false;
+    for (int64_t b = int64_t(blockIdx.x) * nwarps + warp; b < batch; b += int64_t(gridDim.x) * nwarps) {
+        if (!have || h_stride != 0) {
+            const T* Hb = H + b * h_stride;
+            double Hr[KT];
 #pragma unroll
-        for (int c = 0; c < KS; c++) {
-            double h = 0.0;
-            if (act && c < k) {
-                const int hi = lane > c ? lane : c, lo = lane > c ? c : lane;
-                h = h_scale * double(Hb[hi * k + lo]);
-                if (c == lane) h += l2_diag;
-            }
-            Hr[c] = h;
+            for (int c = 0; c < KT; c++)
+                Hr[c] = (act && c <= lane) ? h_scale * double(Hb[lane * k + c]) : 0.0;
+            fac = wsolve::safe_factor_warp<KT, double>(Hr, l2_diag, k, lane, pert, chol_fastpath, known_pd, W, a);
+            have = true;
         }
         double gr = act ? double(g[b * k + lane]) : 0.0;
         double f = 0.0;
@@ -250,7 +187,8 @@ safe_solve_small_kernel(int64_t batch, int k, const T* __restrict__ H, int64_t h
             f = double(out[b * k + lane]);
             gr += l1 * (f > 0.0 ? 1.0 : (f < 0.0 ? -1.0 : 0.0)) + l2 * f;
         }
-        const double x = wsolve::safe_solve_warp(Hr, k, lane, gr, pert, chol_fastpath, known_pd, W);
+        const double x = wsolve::safe_apply_warp<KT>(fac, a, k, lane, gr, pert, W);
+        __syncwarp();
         if (act) {
             if (MODE == 0) {
                 out[b * k + lane] = T(x);
@@ -270,20 +208,18 @@ bool safe_solve_small(pycmf_ctx* ctx, int64_t batch, int64_t k, const T* H, int6
                       double l1, double l2, double l2_diag, double pert, bool non_negative, double h_scale, bool known_pd) {
     if (k > KS || batch < 1) return false;
     Timed timer(ctx, "safe_solve");
-    if (batch <= 2 * ctx->num_sms || (h_stride == 0 && MODE == 0)) {
-        // few matrices (or one matrix with many right-hand sides): CTA-cooperative factorisation
-        const bool shared = h_stride == 0 && MODE == 0;
-        const int64_t nb = shared ? 1 : batch;
-        const int nrhs = shared ? int(batch) : 1;
-        safe_solve_cta_kernel<T, MODE><<<(unsigned)nb, dim3(32, 32), 0, ctx->stream>>>(
-            nb, int(k), H, h_stride, g, out, nrhs, l1, l2, l2_diag, pert, non_negative, ctx->chol_fastpath != 0, h_scale,
-            known_pd);
-        PYCMF_LAUNCH_CHECK(ctx);
-        return true;
-    }
-    int64_t grid = std::min<int64_t>(ceil_div(batch, WARPS), int64_t(16) * ctx->num_sms);
-    safe_solve_small_kernel<T, MODE><<<(unsigned)grid, WARPS * 32, 0, ctx->stream>>>(
-        batch, int(k), H, h_stride, g, out, l1, l2, l2_diag, pert, non_negative, ctx->chol_fastpath != 0, h_scale, known_pd);
+    // few right-hand sides: one warp per CTA so that they spread over the SMs (pure latency otherwise)
+    const int warps = batch <= 2 * ctx->num_sms ? 1 : WARPS;
+    const int64_t grid = std::min<int64_t>(ceil_div(batch, warps), int64_t(16) * ctx->num_sms);
+    const bool fast = ctx->chol_fastpath != 0;
+#define LAUNCH(KT)                                                                                                      \
+    safe_solve_small_kernel<T, MODE, KT><<<(unsigned)grid, warps * 32, 0, ctx->stream>>>(                               \
+        batch, int(k), H, h_stride, g, out, l1, l2, l2_diag, pert, non_negative, fast, h_scale, known_pd)
+    const int kt = wsolve::pick_kt(int(k));
+    if (kt == 8) LAUNCH(8);
+    else if (kt == 16) LAUNCH(16);
+    else LAUNCH(32);
+#undef LAUNCH
     PYCMF_LAUNCH_CHECK(ctx);
     return true;
 }
@@ -293,7 +229,8 @@ bool newton_finish_small(pycmf_ctx* ctx, int64_t rows, int64_t l, int64_t k, T* 
                          int y_link, double wy, const T* gx, const T* Hx, bool hx_per_row, double l1, double l2,
                          double l2_diag, double pert, bool non_negative) {
     if (k > KS || l > LMAX || l < 1 || rows < 1) return false;
-    size_t smem = sizeof(double) * size_t(WARPS) * KS * WLD + sizeof(T) * (size_t(l) * (k + 1) + KS * KS);
+    const int kt = wsolve::pick_kt(int(k));
+    const size_t smem = sizeof(double) * size_t(WARPS) * TILE + sizeof(T) * (size_t(l) * (kt + 4) + 32 + size_t(kt) * kt);
     if (smem > size_t(ctx->max_smem_optin)) return false;
     // Definiteness shortcut: H_j = Hx(_j) + wy Z^T D Z + l2 I with the label term PSD when wy >= 0.
     //   l2 >= pert                      -> every H_j has lambda_min >= pert (pd_mode 2, if Hx is PSD: weights >= 0)
@@ -303,20 +240,31 @@ bool newton_finish_small(pycmf_ctx* ctx, int64_t rows, int64_t l, int64_t k, T* 
     if (wy >= 0.0 && ctx->chol_fastpath) {
         if (!hx_per_row) {
             flag = static_cast<int*>(scratch(ctx, 2, 256));
-            pd_flag_kernel<T><<<1, dim3(32, 32), 0, ctx->stream>>>(int(k), Hx, 1.0, l2_diag, pert, flag);
+            if (kt == 8) pd_flag_kernel<T, 8><<<1, 32, 0, ctx->stream>>>(int(k), Hx, 1.0, l2_diag, pert, flag);
+            else if (kt == 16) pd_flag_kernel<T, 16><<<1, 32, 0, ctx->stream>>>(int(k), Hx, 1.0, l2_diag, pert, flag);
+            else pd_flag_kernel<T, 32><<<1, 32, 0, ctx->stream>>>(int(k), Hx, 1.0, l2_diag, pert, flag);
             PYCMF_LAUNCH_CHECK(ctx);
             pd_mode = 1;
         } else if (l2_diag >= pert) {
             pd_mode = 2;
         }
     }
-    auto kern = newton_finish_small_kernel<T>;
-    PYCMF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-    int64_t grid = std::min<int64_t>(ceil_div(rows, WARPS), int64_t(16) * ctx->num_sms);
+    // two to three resident CTAs per SM (registers); every warp walks its rows with a grid stride, so the prologue
+    // (Z and the shared Hessian into shared memory) is paid once per CTA, not once per four rows
+    const int64_t grid = std::min<int64_t>(ceil_div(rows, WARPS), int64_t(3) * ctx->num_sms);
     Timed timer(ctx, "newton_finish_small");
-    kern<<<(unsigned)grid, WARPS * 32, smem, ctx->stream>>>(rows, int(l), int(k), F, Z, Y, ldy, y_link, T(wy), gx, Hx,
-                                                           hx_per_row ? k * k : 0, l1, l2, l2_diag, pert, non_negative,
-                                                           ctx->chol_fastpath != 0, pd_mode, flag);
+#define LAUNCH(KT)                                                                                                      \
+    do {                                                                                                                \
+        auto kern = newton_finish_small_kernel<T, KT>;                                                                  \
+        PYCMF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));                 \
+        kern<<<(unsigned)grid, WARPS * 32, smem, ctx->stream>>>(rows, int(l), int(k), F, Z, Y, ldy, y_link, T(wy), gx,  \
+                                                               Hx, hx_per_row ? k * k : 0, l1, l2, l2_diag, pert,      \
+                                                               non_negative, ctx->chol_fastpath != 0, pd_mode, flag);  \
+    } while (0)
+    if (kt == 8) LAUNCH(8);
+    else if (kt == 16) LAUNCH(16);
+    else LAUNCH(32);
+#undef LAUNCH
     PYCMF_LAUNCH_CHECK(ctx);
     return true;
 }

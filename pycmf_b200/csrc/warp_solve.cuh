@@ -1,10 +1,14 @@
 // Warp-level eigenvalue-clamped solve for small symmetric systems (k <= 32), float64.
 //   x = S(H) g,  S(H) = Q diag(1 / max(|lambda|, pert)) Q^T          (reference _safe_invert, cmf_solvers.py:346-356)
-// One warp per matrix; the matrix lives in a per-warp shared-memory tile (lane == row, leading dimension 33 so a
-// column access is bank-conflict free).  Fast path: Cholesky of H - pert I succeeds  <=>  lambda_min(H) > pert  <=>
-// the clamp is inactive and S(H) = H^-1, solved with a Cholesky of H.  When the caller can prove lambda_min >= pert
-// (Hessian = PSD term + l2 I with l2 >= pert, or a shared lower bound tested once) the test factorisation is skipped.
-// Otherwise: one-sided Jacobi in the same tile.  Runtime loops only (small code: the I-cache matters here).
+// One warp per matrix.  Fast path: Cholesky of H - pert I succeeds  <=>  lambda_min(H) > pert  <=>  the clamp is
+// inactive and S(H) = H^-1, solved with a Cholesky of H.  When the caller can prove lambda_min >= pert (Hessian =
+// PSD term + l2 I with l2 >= pert, or a shared lower bound tested once) the test factorisation is skipped.
+//
+// The factorisation is register-resident: lane r holds row r of the trailing matrix in KT registers (KT = 8 / 16 / 32,
+// compile-time indices), every step publishes one column of L to a per-warp shared-memory tile and the trailing
+// update reads it back as 128-bit broadcasts: ~1.9 k warp instructions for KT = 32 (the previous shared-memory
+// tile version with runtime loops and per-element predicates executed ~12 k, profiles/r01: 58 % of the V finish).
+// Fallback (eigenvalue clamp active): one-sided Jacobi in the same tile.
 #pragma once
 #include "common.cuh"
 
@@ -12,57 +16,58 @@ namespace pycmf {
 namespace wsolve {
 
 constexpr int KS = 32;
-constexpr int WLD = KS + 1;
+constexpr int WLD = KS + 2;     // even: a pair of doubles at an even column is 16-byte aligned
+constexpr int TILE = KS * WLD;  // doubles per warp
 
 __device__ __forceinline__ double shfl_d(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
 
-// In-place Cholesky of the lower triangle of the tile.  On success W[r][c] (c < r) = L[r][c] and the DIAGONAL holds
-// 1 / L[r][r].  Uniform return value (false: a pivot was <= floor).
-__device__ __forceinline__ bool chol_tile(double* W, int k, int lane, double floor) {
-    for (int j = 0; j < k; j++) {
-        const double piv = W[j * WLD + j];
+__host__ __device__ constexpr int pick_kt(int k) { return k <= 8 ? 8 : (k <= 16 ? 16 : 32); }
+
+// In-place Cholesky, rows in registers.  On entry a[c] = A[lane][c] for c <= lane (entries c > lane are ignored and
+// clobbered).  On success a[c] = L[lane][c] for c < lane, a[lane] = 1 / L[lane][lane], and Lc[j * WLD + r] = L[r][j]
+// (column j of L, diagonal included).  Uniform return value (false: a pivot was <= floor).
+template <int KT>
+__device__ __forceinline__ bool chol_reg(double (&a)[KT], int lane, double floor, double* __restrict__ Lc) {
+#pragma unroll
+    for (int j = 0; j < KT; j++) {
+        const double piv = shfl_d(a[j], j);
         if (!(piv > floor)) return false;
         const double inv = rsqrt(piv);
-        double lrj = 0.0;
-        if (lane > j && lane < k) {
-            lrj = W[lane * WLD + j] * inv;
-            W[lane * WLD + j] = lrj;
-        }
-        if (lane == j) W[j * WLD + j] = inv;
-        __syncwarp();
-        // trailing update of this lane's row: W[r][c] -= L[r][j] L[c][j] for j < c <= r (4 independent columns a time)
-        for (int c0 = j + 1; c0 < k; c0 += 4) {
-            double l4[4], w4[4];
-#pragma unroll
-            for (int u = 0; u < 4; u++) {
-                const int c = c0 + u;
-                const bool on = c < k && c <= lane && lane < k;
-                // L[c][j] for c == lane is lrj itself; for c < lane it is row c, column j (broadcast read)
-                l4[u] = on ? (c == lane ? lrj : W[c * WLD + j]) : 0.0;
-                w4[u] = on ? W[lane * WLD + c] : 0.0;
+        const double l = (lane >= j) ? a[j] * inv : 0.0;
+        a[j] = (lane == j) ? inv : l;
+        if (j + 1 < KT) {
+            Lc[j * WLD + lane] = l;
+            __syncwarp();
+            // trailing update of this lane's row: a[c] -= L[lane][j] L[c][j], c > j
+            int c = j + 1;
+            if (c & 1) {
+                a[c] = fma(-l, Lc[j * WLD + c], a[c]);
+                c++;
             }
 #pragma unroll
-            for (int u = 0; u < 4; u++) {
-                const int c = c0 + u;
-                if (c < k && c <= lane && lane < k) W[lane * WLD + c] = fma(-lrj, l4[u], w4[u]);
+            for (; c + 1 < KT; c += 2) {
+                const double2 p = *reinterpret_cast<const double2*>(Lc + j * WLD + c);
+                a[c] = fma(-l, p.x, a[c]);
+                a[c + 1] = fma(-l, p.y, a[c + 1]);
             }
         }
-        __syncwarp();
     }
     return true;
 }
 
-// Solve L L^T x = b with the factor left by chol_tile; lane r holds b_r on entry and x_r on return.
-__device__ __forceinline__ double chol_solve_tile(const double* W, int k, int lane, double b) {
-    for (int j = 0; j < k; j++) {
-        const double y = shfl_d(b, j) * W[j * WLD + j];
-        if (lane == j) b = y;
-        if (lane > j && lane < k) b = fma(-W[lane * WLD + j], y, b);
+// Solve L L^T x = b with the factor left by chol_reg; lane r holds b_r on entry and x_r on return.
+template <int KT>
+__device__ __forceinline__ double chol_solve_reg(const double (&a)[KT], int lane, double b, const double* __restrict__ Lc) {
+#pragma unroll
+    for (int j = 0; j < KT; j++) {                       // L y = b
+        const double y = shfl_d(b * a[j], j);            // lane j: a[j] = 1 / L[j][j]
+        b = (lane == j) ? y : ((lane > j) ? fma(-a[j], y, b) : b);
     }
-    for (int j = k - 1; j >= 0; j--) {
-        const double x = shfl_d(b, j) * W[j * WLD + j];
-        if (lane == j) b = x;
-        if (lane < j) b = fma(-W[j * WLD + lane], x, b);
+#pragma unroll
+    for (int j = KT - 1; j >= 0; j--) {                  // L^T x = y
+        const double x = shfl_d(b * a[j], j);
+        const double ljr = (lane < j) ? Lc[lane * WLD + j] : 0.0;   // L[j][lane]
+        b = (lane == j) ? x : fma(-ljr, x, b);
     }
     return b;
 }
@@ -108,59 +113,54 @@ __device__ __forceinline__ double jacobi_apply_tile(const double* W, int k, int 
     return x;
 }
 
-__device__ __forceinline__ double jacobi_solve_tile(double* W, int k, int lane, double g, double pert) {
-    jacobi_sweeps_tile(W, k, lane, pert);
-    return jacobi_apply_tile(W, k, lane, g, pert);
-}
-
-// Writes row `lane` (lower part c <= lane) of the matrix into the tile, shifting the diagonal by `shift`.
-template <typename R>
-__device__ __forceinline__ void store_row_lower(double* W, const R (&H_row)[KS], int k, int lane, double shift) {
-#pragma unroll
-    for (int c = 0; c < KS; c++)
-        if (c < k && c <= lane && lane < k) W[lane * WLD + c] = double(H_row[c]) + (c == lane ? shift : 0.0);
-}
-
-// The full clamped solve.  H_row: row `lane` of the symmetric matrix in registers (entries c <= lane are used, like
-// eigh(lower=True)); g: this lane's right-hand-side entry; W: per-warp tile of KS * WLD doubles.
-// known_pd: the caller guarantees lambda_min(H) >= pert (skips the test factorisation).
-template <typename R>
-__device__ __forceinline__ double safe_solve_warp(const R (&H_row)[KS], int k, int lane, double g, double pert,
-                                                  bool chol_fastpath, bool known_pd, double* W) {
+// Factorisation half of the clamped solve.  H_row: row `lane` of the symmetric matrix in registers (entries c <= lane
+// are used, like eigh(lower=True); rows / columns >= k are ignored); diag is added to the diagonal; W: per-warp tile of
+// TILE doubles.  known_pd: the caller guarantees lambda_min(H + diag I) >= pert.
+// Returns true when the Cholesky path ran (factor in `a` / W, apply with chol_solve_reg) and false when the eigenvalue
+// clamp is active (W then holds the Jacobi-orthogonalised tile, apply with jacobi_apply_tile).  Uniform.
+template <int KT, typename R>
+__device__ __forceinline__ bool safe_factor_warp(const R (&H_row)[KT], double diag, int k, int lane, double pert,
+                                                 bool chol_fastpath, bool known_pd, double* W, double (&a)[KT]) {
     const bool act = lane < k;
     if (chol_fastpath) {
-        bool ok = known_pd;
-        if (!ok) {
+        bool ok = true;
+        // pass 0: test factorisation of H - pert I (skipped when known_pd); pass 1: the factorisation that is used.
+        // One runtime loop so that the unrolled factorisation exists once in the instruction stream.
+        for (int pass = known_pd ? 1 : 0; pass < 2 && ok; pass++) {
+            const double shift = diag - (pass == 0 ? pert : 0.0);
             double tr = 0.0;
 #pragma unroll
-            for (int c = 0; c < KS; c++)
-                if (c == lane && act) tr = fabs(double(H_row[c]) - pert);
-            tr = warp_sum(tr);
-            store_row_lower(W, H_row, k, lane, -pert);
-            __syncwarp();
-            ok = chol_tile(W, k, lane, 1e-13 * (tr + pert));
-            __syncwarp();
-        }
-        if (ok) {
-            store_row_lower(W, H_row, k, lane, 0.0);
-            __syncwarp();
-            if (chol_tile(W, k, lane, 0.0)) {
-                const double x = chol_solve_tile(W, k, lane, act ? g : 0.0);
-                __syncwarp();
-                return x;
+            for (int c = 0; c < KT; c++) {
+                // rows / columns beyond k: identity padding
+                a[c] = (act && c < k) ? double(H_row[c]) + (c == lane ? shift : 0.0) : (c == lane ? 1.0 : 0.0);
+                if (c == lane && act) tr = fabs(a[c]);
             }
+            double floor = 0.0;
+            if (pass == 0) floor = 1e-13 * (warp_sum(tr) + pert);
+            ok = chol_reg<KT>(a, lane, floor, W);
             __syncwarp();
         }
+        if (ok) return true;
     }
     // eigenvalue clamp active (or fast path disabled): Jacobi on the symmetric tile built from the lower triangle
-    store_row_lower(W, H_row, k, lane, 0.0);
+#pragma unroll
+    for (int c = 0; c < KT; c++)
+        if (c < k && c <= lane && act) W[lane * WLD + c] = double(H_row[c]) + (c == lane ? diag : 0.0);
     __syncwarp();
     for (int c = lane + 1; c < k; c++)
         if (act) W[lane * WLD + c] = W[c * WLD + lane];
     __syncwarp();
-    const double x = jacobi_solve_tile(W, k, lane, act ? g : 0.0, pert);
-    __syncwarp();
-    return x;
+    jacobi_sweeps_tile(W, k, lane, pert);
+    return false;
+}
+
+// x = S(H) g for one right-hand side after safe_factor_warp (lane r holds g_r / returns x_r).
+template <int KT>
+__device__ __forceinline__ double safe_apply_warp(bool factored, const double (&a)[KT], int k, int lane, double g,
+                                                  double pert, const double* W) {
+    const double gr = lane < k ? g : 0.0;
+    if (factored) return chol_solve_reg<KT>(a, lane, gr, W);
+    return jacobi_apply_tile(W, k, lane, gr, pert);
 }
 
 }  // namespace wsolve

@@ -71,15 +71,45 @@ class CudaBackend:
         handle = C.c_void_p()
         _lib.check(self.lib.pycmf_create(self.device.index, C.byref(handle)))
         self.ctx = handle
+        self._aux = None
+        self._options = {}
         self.use_stream(torch.cuda.current_stream(self.device))
         for key, val in (options or {}).items():
             self.set_option(key, val)
 
     # ---- lifecycle ---------------------------------------------------------------------------
     def close(self):
+        if getattr(self, "_aux", None) is not None:
+            self._aux.close()
+            self._aux = None
         if getattr(self, "ctx", None) is not None:
             self.lib.pycmf_destroy(self.ctx)
             self.ctx = None
+
+    # ---- a second context on its own stream: phases that do not depend on each other (the U and Z updates of one
+    #      iteration: neither reads what the other writes) run side by side, in eager mode and under graph capture
+    def fork(self):
+        """The auxiliary backend, its stream waiting for everything enqueued so far on this one's."""
+        if self._options.get("side_streams", 1.0) == 0.0:
+            return self
+        if self._aux is None:
+            aux = CudaBackend.__new__(CudaBackend)
+            aux.torch, aux.lib, aux.device = self.torch, self.lib, self.device
+            aux.np_dtype, aux.code, aux.tdtype = self.np_dtype, self.code, self.tdtype
+            handle = C.c_void_p()
+            _lib.check(self.lib.pycmf_create(self.device.index, C.byref(handle)))
+            aux.ctx, aux._aux, aux._options = handle, None, {}
+            aux.use_stream(self.torch.cuda.Stream(device=self.device))
+            for key, val in self._options.items():
+                aux.set_option(key, val)
+            self._aux = aux
+        self._aux.stream.wait_stream(self.stream)
+        return self._aux
+
+    def join(self):
+        """This backend's stream waits for the auxiliary one."""
+        if self._aux is not None:
+            self.stream.wait_stream(self._aux.stream)
 
     def __del__(self):
         try:
@@ -93,24 +123,36 @@ class CudaBackend:
 
     def set_option(self, key, value):
         _lib.check(self.lib.pycmf_set_option(self.ctx, key.encode(), float(value)))
+        self._options[key] = float(value)
+        if self._aux is not None:
+            self._aux.set_option(key, value)
 
     def launch_count(self):
-        return int(self.lib.pycmf_launch_count(self.ctx))
+        n = int(self.lib.pycmf_launch_count(self.ctx))
+        return n + (self._aux.launch_count() if self._aux is not None else 0)
 
     def synchronize(self):
         self.torch.cuda.synchronize(self.device)
 
     def profile(self, on=True):
         _lib.check(self.lib.pycmf_profile_enable(self.ctx, int(bool(on))))
+        if self._aux is not None:
+            self._aux.profile(on)
 
     def profile_reset(self):
         _lib.check(self.lib.pycmf_profile_reset(self.ctx))
+        if self._aux is not None:
+            self._aux.profile_reset()
 
     def profile_query(self, family):
-        """(total milliseconds, launches) of one kernel family since the last reset."""
+        """(total milliseconds, launches) of one kernel family since the last reset (both contexts)."""
         ms, cnt = C.c_double(0.0), C.c_int64(0)
         _lib.check(self.lib.pycmf_profile_query(self.ctx, family.encode(), C.byref(ms), C.byref(cnt)))
-        return ms.value, cnt.value
+        tot, n = ms.value, cnt.value
+        if self._aux is not None:
+            t2, n2 = self._aux.profile_query(family)
+            tot, n = tot + t2, n + n2
+        return tot, n
 
     def capture_step(self, fn):
         """Runs fn() once under CUDA-graph capture (it executes on replay, not now) and returns the graph.
