@@ -42,6 +42,7 @@ def parse_args():
     ap.add_argument("--scale", type=float, default=None, help="row (and, if sparse, column) scale of the workload")
     ap.add_argument("--dtype", default="float32", choices=["float32", "float64"])
     ap.add_argument("--dense-path", type=int, default=None, help="0 generic FMA, 1 tcgen05 3xTF32, 2 tcgen05 1xTF32")
+    ap.add_argument("--opt", action="append", default=[], help="backend option key=value (repeatable)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=20.0)
@@ -188,6 +189,9 @@ def run_ours(args):
     opts = {}
     if args.dense_path is not None:
         opts["dense_path"] = args.dense_path
+    for kv in args.opt:
+        key, val = kv.split("=")
+        opts[key] = float(val)
     be = CudaBackend(device=local_rank, dtype=args.dtype, options=opts)
     scale = args.scale if args.scale is not None else default_scale(args.workload)
     cfg = W.describe(args.workload, scale)

@@ -44,7 +44,11 @@ pycmf_ctx* fork_side(pycmf_ctx* ctx) {
     s->chol_fastpath = ctx->chol_fastpath;
     s->dense_path = ctx->dense_path;
     s->tc_max_splits = ctx->tc_max_splits;
+    s->tc_ctas = ctx->tc_ctas;
+    s->tc_chain = ctx->tc_chain;
+    s->tc_prefetch = ctx->tc_prefetch;
     s->max_scratch = ctx->max_scratch;
+    s->finish_minblocks = ctx->finish_minblocks;
     PYCMF_CUDA(cudaEventRecord(ctx->ev_fork, ctx->stream));
     PYCMF_CUDA(cudaStreamWaitEvent(s->stream, ctx->ev_fork, 0));
     return s;
@@ -415,7 +419,11 @@ int pycmf_set_option(pycmf_ctx* ctx, const char* key, double value) {
         else if (k == "dense_path") ctx->dense_path = int(value);
         else if (k == "tc_max_splits") ctx->tc_max_splits = int(value);
         else if (k == "tc_trace") ctx->tc_trace = int(value);
+        else if (k == "tc_ctas") ctx->tc_ctas = int(value);
+        else if (k == "tc_chain") ctx->tc_chain = int(value);
+        else if (k == "tc_prefetch") ctx->tc_prefetch = int(value);
         else if (k == "side_streams") ctx->side_streams = value != 0.0;
+        else if (k == "finish_minblocks") ctx->finish_minblocks = int(value);
         else if (k == "max_scratch_mb") ctx->max_scratch = size_t(std::max(16.0, value)) << 20;
         else throw pycmf::Error("unknown option: " + k);
     });

@@ -32,7 +32,10 @@ struct pycmf_ctx {
     int chol_fastpath = 1;
     int dense_path = 1;
     int tc_trace = 0;        // diagnostics: record a pipeline trace of CTA (0,0) of every tcgen05 pass into arena 2
-    int tc_max_splits = 0;   // > 0: cap the split count of the tcgen05 passes (tests use 1 to get long tile loops)
+    int tc_max_splits = 0;   // > 0: at most this many CTAs per own tile in the tcgen05 passes (tests: 1 = one long chain)
+    int tc_ctas = 0;         // > 0: cap on the persistent CTA count of the tcgen05 passes (tests)
+    int tc_prefetch = 1;     // L2 prefetch of X in the tcgen05 passes: 0 none, 1 helper warp (prefetch.global.L2), 2 TMA
+    int tc_chain = 0;        // > 0: accumulation chain cap in tiles (default 16)
     size_t max_scratch = size_t(2) << 30;
     // scratch arenas (grown on demand; growth synchronises the stream)
     pycmf::Scratch arena[8];
@@ -44,6 +47,7 @@ struct pycmf_ctx {
     pycmf_ctx* root = nullptr;
     pycmf_ctx* side = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    int finish_minblocks = 4;   // option: resident CTAs per SM the V-finish kernel is compiled for (2: 255 registers, 4: 128)
     int side_streams = 1;    // option: 0 runs the side branches on the main stream (serial)
 };
 

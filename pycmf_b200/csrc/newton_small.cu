@@ -35,8 +35,8 @@ __device__ __forceinline__ void load4(const double* p, double (&v)[4]) {
 }
 
 // pd_mode: 0 = test every row (Cholesky of H - pert I), 1 = read the shared verdict from *pd_flag, 2 = known PD
-template <typename T, int KT>
-__global__ void __launch_bounds__(WARPS * 32)
+template <typename T, int KT, int MINB>
+__global__ void __launch_bounds__(WARPS * 32, MINB)
 newton_finish_small_kernel(int64_t rows, int l, int k, T* __restrict__ F, const T* __restrict__ Z,
                            const T* __restrict__ Y, int64_t ldy, int y_link, T wy,
                            const T* __restrict__ gx, const T* __restrict__ Hx, int64_t hx_stride,
@@ -251,11 +251,12 @@ bool newton_finish_small(pycmf_ctx* ctx, int64_t rows, int64_t l, int64_t k, T* 
     }
     // two to three resident CTAs per SM (registers); every warp walks its rows with a grid stride, so the prologue
     // (Z and the shared Hessian into shared memory) is paid once per CTA, not once per four rows
-    const int64_t grid = std::min<int64_t>(ceil_div(rows, WARPS), int64_t(3) * ctx->num_sms);
+    const int minb = ctx->finish_minblocks >= 4 ? 4 : 2;
+    const int64_t grid = std::min<int64_t>(ceil_div(rows, WARPS), int64_t(minb) * ctx->num_sms);
     Timed timer(ctx, "newton_finish_small");
 #define LAUNCH(KT)                                                                                                      \
     do {                                                                                                                \
-        auto kern = newton_finish_small_kernel<T, KT>;                                                                  \
+        auto kern = minb == 4 ? newton_finish_small_kernel<T, KT, 4> : newton_finish_small_kernel<T, KT, 2>;            \
         PYCMF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));                 \
         kern<<<(unsigned)grid, WARPS * 32, smem, ctx->stream>>>(rows, int(l), int(k), F, Z, Y, ldy, y_link, T(wy), gx,  \
                                                                Hx, hx_per_row ? k * k : 0, l1, l2, l2_diag, pert,      \

@@ -61,8 +61,8 @@ struct SmemLayout {
 };
 
 // barrier slots (8 bytes each) inside the `bars` region
-enum Bar { FULL0 = 0, EMPTY0 = FULL0 + NSTAGE, SFULL0 = EMPTY0 + NSTAGE, SEMPTY0 = SFULL0 + 2, RFULL0 = SEMPTY0 + 2,
-           REMPTY0 = RFULL0 + 2, PFULL = REMPTY0 + 2, OUTFULL, NBARS };
+enum Bar { FULL0 = 0, EMPTY0 = FULL0 + NSTAGE, SFULL0 = EMPTY0 + NSTAGE, RFULL0 = SFULL0 + 2,
+           REMPTY0 = RFULL0 + 2, PFULL = REMPTY0 + 2, OUTFULL, OUTEMPTY, NBARS };
 
 // ---- PTX wrappers ----------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return uint32_t(__cvta_generic_to_shared(p)); }
@@ -189,24 +189,44 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn_major, 
 
 struct Params {
     int64_t own_n, oth_n;       // extents of the own / other dimension
-    int64_t tiles_per_split;
+    int64_t n_oth_tiles;        // T: tiles of OTH along the other dimension
+    int64_t n_tiles;            // G: own tiles x T, linearised g = own_tile * T + t
+    int chain;                  // accumulation chain cap in tiles (TMEM accumulation is not round-to-nearest)
     int link;
     const float *p_hi, *p_lo;   // tf32 parts of the own-side factor (own_n x 32), RESID only
-    float* out;                 // (own_n x 32) or split partials
-    int64_t out_split_stride;
+    const float* x;             // X itself (rows x cols, row stride ldx) for the L2 prefetch warp
+    int64_t ldx, x_rows, x_cols;
+    int pf_mode;                // 0 none, 1 prefetch.global.L2 from a helper warp, 2 TMA L2 prefetch from the producer
+    float* part;                // partial outputs: [own tile][entry][OWN x 32]
+    int max_entries;            // entries per own tile in `part`
     double* sq_part;            // per-CTA partial of sum R^2 (may be null)
-    long long* trace;           // optional pipeline trace of CTA (0,0): [event][tile] clock64 stamps (diagnostics)
+    long long* trace;           // optional pipeline trace of CTA 0: [event][tile] clock64 stamps (diagnostics)
 };
 
+// Persistent tiling: CTA c of N walks the linearised tiles [c G / N, (c + 1) G / N).  first_cta(g) is the CTA that
+// owns tile g (inverse of the floor partition); the partial of own tile o written by CTA c goes to entry
+// c - first_cta(o T), and the reduction kernel sums entries 0 .. first_cta(o T + T - 1) - first_cta(o T).
+__host__ __device__ __forceinline__ int64_t tile_begin(int64_t c, int64_t G, int64_t N) { return (c * G) / N; }
+__host__ __device__ __forceinline__ int64_t first_cta(int64_t g, int64_t G, int64_t N) { return ((g + 1) * N - 1) / G; }
+
 constexpr int TRACE_TILES = 32;
-enum TraceEvent { TR_TMA_ISSUE = 0, TR_G1_ISSUE, TR_S_SEEN, TR_R_DONE, TR_G2_ISSUE, TR_EMPTY_SEEN, TR_FULL_SEEN_EPI, TR_NEVENTS };
+enum TraceEvent { TR_TMA_ISSUE = 0, TR_G1_ISSUE, TR_S_SEEN, TR_R_DONE, TR_G2_ISSUE, TR_EMPTY_SEEN, TR_FULL_SEEN_EPI,
+                  TR_W_S = 8,          // + epilogue warp index (0..15): S seen
+                  TR_W_LD = 24,        // S loaded from tensor memory
+                  TR_W_RE = 40,        // R buffer free (REMPTY seen)
+                  TR_W_R = 56,         // R published
+                  TR_NEVENTS = 72 };
 #define TC_TRACE(ev, it)                                                                        \
     do {                                                                                        \
-        if (prm.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && (it) < TRACE_TILES)   \
+        if (prm.trace != nullptr && blockIdx.x == 0 && (it) < TRACE_TILES)                      \
             prm.trace[(ev) * TRACE_TILES + (it)] = clock64();                                   \
     } while (0)
 
 // MODE 0 = LEFT (own = rows of X), 1 = RIGHT (own = columns of X).  RESID: R = f(S) - X, else R = X.
+// One persistent CTA per SM.  Tile i of the CTA is g = g0 + i -> (own tile o = g / T, other tile t = g % T).
+// A chain (one accumulation in OUT) starts at i == 0 or t % chain == 0 and ends at the CTA's last tile, at
+// (t + 1) % chain == 0 or at t == T - 1; the epilogue warps add the chains of one own tile in registers (fp32,
+// round to nearest) and write one partial per (CTA, own tile).
 template <int MODE, bool RESID, int NSPLIT>
 __global__ void __launch_bounds__(NTHREADS, 1)
 tc_pass_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_constant__ CUtensorMap tm_q_lo,
@@ -222,22 +242,24 @@ tc_pass_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_constan
     auto bar = [&](int i) { return bars + 8u * uint32_t(i); };
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int64_t own0 = int64_t(blockIdx.x) * OWN;
-    const int64_t n_tiles_total = (prm.oth_n + OTH - 1) / OTH;
-    const int64_t t_begin = int64_t(blockIdx.y) * prm.tiles_per_split;
-    const int64_t t_end = (t_begin + prm.tiles_per_split < n_tiles_total) ? t_begin + prm.tiles_per_split : n_tiles_total;
-    const int n_it = int(t_end - t_begin);
+    const int64_t T = prm.n_oth_tiles;
+    const int64_t g0 = tile_begin(blockIdx.x, prm.n_tiles, gridDim.x);
+    const int n_it = int(tile_begin(int64_t(blockIdx.x) + 1, prm.n_tiles, gridDim.x) - g0);
+    const int chain = prm.chain;
+    // schedule predicates, identical in every role
+    auto first_of_chain = [&](int it, int64_t t) { return it == 0 || (t % chain) == 0; };
+    auto last_of_chain = [&](int it, int64_t t) { return it == n_it - 1 || ((t + 1) % chain) == 0 || t == T - 1; };
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < NSTAGE; s++) { mbar_init(bar(FULL0 + s), 1); mbar_init(bar(EMPTY0 + s), 1); }
         for (int s = 0; s < 2; s++) {
             mbar_init(bar(SFULL0 + s), 1);
-            mbar_init(bar(SEMPTY0 + s), EPI_WARPS);
             mbar_init(bar(RFULL0 + s), EPI_WARPS);
             mbar_init(bar(REMPTY0 + s), 1);
         }
         mbar_init(bar(PFULL), EPI_WARPS);
         mbar_init(bar(OUTFULL), 1);
+        mbar_init(bar(OUTEMPTY), 2 * 4);          // the eight warps that read OUT
         *sq_slot = 0.0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         fence_async_smem();
@@ -255,132 +277,133 @@ tc_pass_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_constan
     if (warp == 0) {
         // =============================== TMA producer ===============================
         // The whole warp walks the loop (converged); one elected lane issues.
-        {
-            auto prefetch_x = [&](int it) {
-                const int oth0 = int((t_begin + it) * OTH);
-                if (MODE == 0) {
-                    tma_prefetch_2d(&tm_x, oth0, int(own0));
-                    tma_prefetch_2d(&tm_x, oth0 + 32, int(own0));
-                } else {
+        auto prefetch_x = [&](int it) {
+            const int64_t g = g0 + it;
+            const int own0 = int((g / T) * OWN), oth0 = int((g % T) * OTH);
+            if (MODE == 0) {
+                tma_prefetch_2d(&tm_x, oth0, own0);
+                tma_prefetch_2d(&tm_x, oth0 + 32, own0);
+            } else {
 #pragma unroll
-                    for (int b = 0; b < 4; b++) tma_prefetch_2d(&tm_x, int(own0) + 32 * b, oth0);
-                }
-            };
-            for (int it = 0; it < n_it; it++) {
-                const int s = it % NSTAGE;
-                const uint32_t ph = uint32_t(it / NSTAGE) & 1u;
-                mbar_wait(bar(EMPTY0 + s), ph ^ 1u);
-                if (elect_one()) {
-                    TC_TRACE(TR_EMPTY_SEEN, it);
-                    const uint32_t st = base + SmemLayout::stage0 + uint32_t(s) * SmemLayout::stage_bytes;
-                    const int oth0 = int((t_begin + it) * OTH);
-                    mbar_expect_tx(bar(FULL0 + s), (RESID ? 2u : 1u) * (NSPLIT == 3 ? 2 * Q_BYTES : Q_BYTES) + X_BYTES);
-                    if (MODE == 0) {
-                        // X tile: own rows x 64 other columns, two 32-column boxes of 128 rows
-                        tma_load_2d(st + SmemLayout::x, &tm_x, bar(FULL0 + s), oth0, int(own0));
-                        tma_load_2d(st + SmemLayout::x + OWN * 128, &tm_x, bar(FULL0 + s), oth0 + 32, int(own0));
-                    } else {
-                        // X tile: 64 other rows x 128 own columns, four 32-column boxes of 64 rows
-#pragma unroll
-                        for (int b = 0; b < 4; b++)
-                            tma_load_2d(st + SmemLayout::x + uint32_t(b) * OTH * 128, &tm_x, bar(FULL0 + s),
-                                        int(own0) + 32 * b, oth0);
-                    }
-                    if (RESID) {
-                        tma_load_2d(st + SmemLayout::q_hi, &tm_q_hi, bar(FULL0 + s), 0, oth0);
-                        if (NSPLIT == 3) tma_load_2d(st + SmemLayout::q_lo, &tm_q_lo, bar(FULL0 + s), 0, oth0);
-                    }
-#pragma unroll
-                    for (int b = 0; b < 2; b++) {
-                        tma_load_2d(st + SmemLayout::qt_hi + uint32_t(b) * (KC * 128), &tm_qt_hi, bar(FULL0 + s), oth0 + 32 * b, 0);
-                        if (NSPLIT == 3)
-                            tma_load_2d(st + SmemLayout::qt_lo + uint32_t(b) * (KC * 128), &tm_qt_lo, bar(FULL0 + s), oth0 + 32 * b, 0);
-                    }
-                    TC_TRACE(TR_TMA_ISSUE, it);
-                    // L2 prefetch runs PREFETCH_DIST tiles ahead of the ring, but only once the ring's own loads are
-                    // queued: prefetching first put 8 tiles (256 KB per SM) in front of tile 0 (a 5500-clk pipeline fill)
-                    if (it >= NSTAGE - 1) {
-                        if (it == NSTAGE - 1)
-                            for (int a = NSTAGE; a < NSTAGE - 1 + PREFETCH_DIST && a < n_it; a++) prefetch_x(a);
-                        if (it + PREFETCH_DIST < n_it) prefetch_x(it + PREFETCH_DIST);
-                    }
-                }
-                __syncwarp();
+                for (int b = 0; b < 4; b++) tma_prefetch_2d(&tm_x, own0 + 32 * b, oth0);
             }
+        };
+        for (int it = 0; it < n_it; it++) {
+            const int s = it % NSTAGE;
+            const uint32_t ph = uint32_t(it / NSTAGE) & 1u;
+            mbar_wait(bar(EMPTY0 + s), ph ^ 1u);
+            if (elect_one()) {
+                TC_TRACE(TR_EMPTY_SEEN, it);
+                const uint32_t st = base + SmemLayout::stage0 + uint32_t(s) * SmemLayout::stage_bytes;
+                const int64_t g = g0 + it;
+                const int own0 = int((g / T) * OWN), oth0 = int((g % T) * OTH);
+                mbar_expect_tx(bar(FULL0 + s), (RESID ? 2u : 1u) * (NSPLIT == 3 ? 2 * Q_BYTES : Q_BYTES) + X_BYTES);
+                if (MODE == 0) {
+                    // X tile: own rows x 64 other columns, two 32-column boxes of 128 rows
+                    tma_load_2d(st + SmemLayout::x, &tm_x, bar(FULL0 + s), oth0, own0);
+                    tma_load_2d(st + SmemLayout::x + OWN * 128, &tm_x, bar(FULL0 + s), oth0 + 32, own0);
+                } else {
+                    // X tile: 64 other rows x 128 own columns, four 32-column boxes of 64 rows
+#pragma unroll
+                    for (int b = 0; b < 4; b++)
+                        tma_load_2d(st + SmemLayout::x + uint32_t(b) * OTH * 128, &tm_x, bar(FULL0 + s), own0 + 32 * b, oth0);
+                }
+                if (RESID) {
+                    tma_load_2d(st + SmemLayout::q_hi, &tm_q_hi, bar(FULL0 + s), 0, oth0);
+                    if (NSPLIT == 3) tma_load_2d(st + SmemLayout::q_lo, &tm_q_lo, bar(FULL0 + s), 0, oth0);
+                }
+#pragma unroll
+                for (int b = 0; b < 2; b++) {
+                    tma_load_2d(st + SmemLayout::qt_hi + uint32_t(b) * (KC * 128), &tm_qt_hi, bar(FULL0 + s), oth0 + 32 * b, 0);
+                    if (NSPLIT == 3)
+                        tma_load_2d(st + SmemLayout::qt_lo + uint32_t(b) * (KC * 128), &tm_qt_lo, bar(FULL0 + s), oth0 + 32 * b, 0);
+                }
+                TC_TRACE(TR_TMA_ISSUE, it);
+                // L2 prefetch runs PREFETCH_DIST tiles ahead of the ring, but only once the ring's own loads are
+                // queued: prefetching first put 8 tiles (256 KB per SM) in front of tile 0 (a 5500-clk pipeline fill)
+                if (prm.pf_mode == 2 && it >= NSTAGE - 1) {
+                    if (it == NSTAGE - 1)
+                        for (int a = NSTAGE; a < NSTAGE - 1 + PREFETCH_DIST && a < n_it; a++) prefetch_x(a);
+                    if (it + PREFETCH_DIST < n_it) prefetch_x(it + PREFETCH_DIST);
+                }
+            }
+            __syncwarp();
         }
     } else if (warp == 1) {
         // =============================== MMA issuer ================================
         // The whole warp runs the event loop (converged, probes made warp-uniform); one elected lane issues the MMAs
         // and the commits (tcgen05.commit tracks the MMAs of the issuing thread: elect.sync always picks the same lane).
-        {
-            constexpr uint32_t idesc1 = make_idesc(OWN, OTH, 0, 0);   // S   = P (TMEM) x Q (K-major)
-            constexpr uint32_t idesc2 = make_idesc(OWN, KC, 0, 0);    // OUT = R (TMEM) x Q^T tile (K-major)
-            // B descriptors are built once per stage; inside a tile only the 14-bit start-address field changes,
-            // by small multiples of 16 bytes that cannot carry out of the field (all tiles live below 256 KB).
-            uint64_t dQ_hi[NSTAGE], dQ_lo[NSTAGE], dQt_hi[NSTAGE], dQt_lo[NSTAGE];
+        constexpr uint32_t idesc1 = make_idesc(OWN, OTH, 0, 0);   // S   = P (TMEM) x Q (K-major)
+        constexpr uint32_t idesc2 = make_idesc(OWN, KC, 0, 0);    // OUT = R (TMEM) x Q^T tile (K-major)
+        // B descriptors are built once per stage; inside a tile only the 14-bit start-address field changes,
+        // by small multiples of 16 bytes that cannot carry out of the field (all tiles live below 256 KB).
+        uint64_t dQ_hi[NSTAGE], dQ_lo[NSTAGE], dQt_hi[NSTAGE], dQt_lo[NSTAGE];
 #pragma unroll
-            for (int s = 0; s < NSTAGE; s++) {
-                const uint32_t st = base + SmemLayout::stage0 + uint32_t(s) * SmemLayout::stage_bytes;
-                dQ_hi[s] = make_desc(st + SmemLayout::q_hi, 16, 1024);
-                dQ_lo[s] = make_desc(st + SmemLayout::q_lo, 16, 1024);
-                dQt_hi[s] = make_desc(st + SmemLayout::qt_hi, 16, 1024);
-                dQt_lo[s] = make_desc(st + SmemLayout::qt_lo, 16, 1024);
-            }
-            auto pick = [&](const uint64_t (&d)[NSTAGE], int s) { return s == 0 ? d[0] : (s == 1 ? d[1] : d[2]); };
-            // Tensor-core accumulation into TMEM truncates (measured: ~2^-24 |acc| lost per MMA), so the order matters:
-            //  GEMM1: the small correction terms hi*lo, lo*hi first, the four hi*hi MMAs last;
-            //  GEMM2: corrections go to their own accumulator OUT2 (their rounding is relative to 2^-11 |OUT|), only the
-            //         eight hi*hi MMAs per tile extend the long chain in OUT; the epilogue adds OUT + OUT2.
-            auto issue_g1 = [&](int it) {
-                const int s = it % NSTAGE, sb = it & 1;
-                const uint32_t d = tmem + uint32_t(TM_S + sb * OTH);
-                const uint64_t qh = pick(dQ_hi, s), ql = pick(dQ_lo, s);
+        for (int s = 0; s < NSTAGE; s++) {
+            const uint32_t st = base + SmemLayout::stage0 + uint32_t(s) * SmemLayout::stage_bytes;
+            dQ_hi[s] = make_desc(st + SmemLayout::q_hi, 16, 1024);
+            dQ_lo[s] = make_desc(st + SmemLayout::q_lo, 16, 1024);
+            dQt_hi[s] = make_desc(st + SmemLayout::qt_hi, 16, 1024);
+            dQt_lo[s] = make_desc(st + SmemLayout::qt_lo, 16, 1024);
+        }
+        auto pick = [&](const uint64_t (&d)[NSTAGE], int s) { return s == 0 ? d[0] : (s == 1 ? d[1] : d[2]); };
+        // Tensor-core accumulation into TMEM truncates (measured: ~2^-24 |acc| lost per MMA), so the order matters:
+        //  GEMM1: the small correction terms hi*lo, lo*hi first, the four hi*hi MMAs last;
+        //  GEMM2: corrections go to their own accumulator OUT2 (their rounding is relative to 2^-11 |OUT|), only the
+        //         eight hi*hi MMAs per tile extend the long chain in OUT; the epilogue adds OUT + OUT2.
+        auto issue_g1 = [&](int it) {
+            const int s = it % NSTAGE, sb = it & 1;
+            const uint32_t d = tmem + uint32_t(TM_S + sb * OTH);
+            const uint64_t qh = pick(dQ_hi, s), ql = pick(dQ_lo, s);
 #pragma unroll
-                for (int t = 0; t < NSPLIT; t++) {
-                    const int term = NSPLIT == 3 ? (t == 0 ? 1 : (t == 1 ? 2 : 0)) : 0;   // hi*lo, lo*hi, hi*hi
-                    const uint32_t pa = tmem + uint32_t((term == 2) ? TM_P_LO : TM_P_HI);
-                    const uint64_t qa = (term == 1) ? ql : qh;
+            for (int t = 0; t < NSPLIT; t++) {
+                const int term = NSPLIT == 3 ? (t == 0 ? 1 : (t == 1 ? 2 : 0)) : 0;   // hi*lo, lo*hi, hi*hi
+                const uint32_t pa = tmem + uint32_t((term == 2) ? TM_P_LO : TM_P_HI);
+                const uint64_t qa = (term == 1) ? ql : qh;
 #pragma unroll
-                    for (int kk = 0; kk < KC / 8; kk++) {
-                        if (t == 0 && kk == 0) umma_tf32_ts<false>(d, pa, qa, idesc1);
-                        else umma_tf32_ts<true>(d, pa + uint32_t(kk * 8), qa + uint64_t(kk * 2), idesc1);
-                    }
+                for (int kk = 0; kk < KC / 8; kk++) {
+                    if (t == 0 && kk == 0) umma_tf32_ts<false>(d, pa, qa, idesc1);
+                    else umma_tf32_ts<true>(d, pa + uint32_t(kk * 8), qa + uint64_t(kk * 2), idesc1);
                 }
-                umma_commit(bar(SFULL0 + sb));
-            };
-            auto issue_g2 = [&](int it, bool first) {
-                const int s = it % NSTAGE, rb = it & 1;
-                const uint32_t r_hi = tmem + uint32_t(TM_R + rb * 2 * OTH), r_lo = r_hi + OTH;
-                const uint64_t qh = pick(dQt_hi, s), ql = pick(dQt_lo, s);
-#pragma unroll
-                for (int term = 0; term < NSPLIT; term++) {
-                    const uint32_t d = tmem + uint32_t(term == 0 ? TM_OUT : TM_OUT2);
-                    const uint32_t ra = (term == 2) ? r_lo : r_hi;
-                    const uint64_t qa = (term == 1) ? ql : qh;
-#pragma unroll
-                    for (int kk = 0; kk < OTH / 8; kk++) {
-                        // K-step kk: 8 TMEM columns of R; Q^T K-block kk / 4 (32 rows x 128 B = 256 x 16 B)
-                        const uint64_t bd = qa + uint64_t((kk / 4) * (KC * 128 / 16) + (kk % 4) * 2);
-                        if (term <= 1 && kk == 0 && first) umma_tf32_ts<false>(d, ra, bd, idesc2);
-                        else umma_tf32_ts<true>(d, ra + uint32_t(kk * 8), bd, idesc2);
-                    }
-                }
-                umma_commit(bar(REMPTY0 + rb));
-                umma_commit(bar(EMPTY0 + s));
-            };
-            if (RESID) {
-                mbar_wait(bar(PFULL), 0);      // epilogue warps have parked P in tensor memory
-                tc_fence_after();
             }
-            // Event-driven issue: GEMM2(t) goes out as soon as the epilogue has published R(t); GEMM1(t') as soon as
-            // its operands have landed and its S buffer is free -- neither waits behind the other's barrier.
-            int g1 = RESID ? 0 : n_it, g2 = 0;
-            while (g2 < n_it) {
-                // GEMM1 first: its S buffer frees at the moment R(t) is published, and the epilogue of tile t + 2 waits on it
-                bool go1 = g1 < n_it && mbar_test(bar(FULL0 + g1 % NSTAGE), uint32_t(g1 / NSTAGE) & 1u) &&
-                           mbar_test(bar(SEMPTY0 + (g1 & 1)), (uint32_t(g1 >> 1) & 1u) ^ 1u);
+            umma_commit(bar(SFULL0 + sb));
+        };
+        auto issue_g2 = [&](int it, bool first, bool last) {
+            const int s = it % NSTAGE, rb = it & 1;
+            const uint32_t r_hi = tmem + uint32_t(TM_R + rb * 2 * OTH), r_lo = r_hi + OTH;
+            const uint64_t qh = pick(dQt_hi, s), ql = pick(dQt_lo, s);
+#pragma unroll
+            for (int term = 0; term < NSPLIT; term++) {
+                const uint32_t d = tmem + uint32_t(term == 0 ? TM_OUT : TM_OUT2);
+                const uint32_t ra = (term == 2) ? r_lo : r_hi;
+                const uint64_t qa = (term == 1) ? ql : qh;
+#pragma unroll
+                for (int kk = 0; kk < OTH / 8; kk++) {
+                    // K-step kk: 8 TMEM columns of R; Q^T K-block kk / 4 (32 rows x 128 B = 256 x 16 B)
+                    const uint64_t bd = qa + uint64_t((kk / 4) * (KC * 128 / 16) + (kk % 4) * 2);
+                    if (term <= 1 && kk == 0 && first) umma_tf32_ts<false>(d, ra, bd, idesc2);
+                    else umma_tf32_ts<true>(d, ra + uint32_t(kk * 8), bd, idesc2);
+                }
+            }
+            umma_commit(bar(REMPTY0 + rb));
+            umma_commit(bar(EMPTY0 + s));
+            if (last) umma_commit(bar(OUTFULL));
+        };
+        // Event-driven issue.  GEMM1(i) needs its operands (FULL) and its S buffer: the epilogue of tile i - 2 has read
+        // it, which is implied by R(i - 2) having been published and GEMM2(i - 2) issued, i.e. g1 < g2 + 2.  At an own-tile
+        // change it also needs the new P in tensor memory (PFULL).  GEMM2(i) needs R(i) (the epilogue waited for FULL
+        // itself) and, at the start of a chain, the previous chain's OUT to have been read (OUTEMPTY).
+        int g1 = RESID ? 0 : n_it, g2 = 0;
+        int p_seen = 0;          // own-tile changes whose P has been seen (PFULL phases consumed)
+        int p_need = 1;          // PFULL phases GEMM1(g1) needs
+        int chains_done = 0;     // chains whose last GEMM2 has been issued
+        while (g2 < n_it) {
+            if (g1 < n_it && g1 < g2 + 2) {
+                bool go1 = mbar_test(bar(FULL0 + g1 % NSTAGE), uint32_t(g1 / NSTAGE) & 1u);
+                if (RESID && p_seen < p_need) go1 = go1 && mbar_test(bar(PFULL), uint32_t(p_seen) & 1u);
                 go1 = __all_sync(0xffffffffu, go1);
                 if (go1) {
+                    p_seen = p_need;
                     tc_fence_after();
                     if (elect_one()) {
                         TC_TRACE(TR_G1_ISSUE, g1);
@@ -388,37 +411,73 @@ tc_pass_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_constan
                     }
                     __syncwarp();
                     g1++;
+                    if (g1 < n_it && ((g0 + g1) % T) == 0) p_need++;      // next tile starts a new own tile
                 }
-                bool go2 = mbar_test(bar(RFULL0 + (g2 & 1)), uint32_t(g2 >> 1) & 1u) &&
-                           mbar_test(bar(FULL0 + g2 % NSTAGE), uint32_t(g2 / NSTAGE) & 1u);
+            }
+            {
+                const int64_t t2 = (g0 + g2) % T;
+                const bool first = first_of_chain(g2, t2), last = last_of_chain(g2, t2);
+                bool go2 = mbar_test(bar(RFULL0 + (g2 & 1)), uint32_t(g2 >> 1) & 1u);
+                if (first && chains_done > 0) go2 = go2 && mbar_test(bar(OUTEMPTY), uint32_t(chains_done - 1) & 1u);
                 go2 = __all_sync(0xffffffffu, go2);
                 if (go2) {
                     tc_fence_after();
                     if (elect_one()) {
                         TC_TRACE(TR_G2_ISSUE, g2);
-                        if (g2 == 0) issue_g2(0, true); else issue_g2(g2, false);
+                        if (first) issue_g2(g2, true, last); else issue_g2(g2, false, last);
                     }
                     __syncwarp();
                     g2++;
+                    if (last) chains_done++;
                 }
             }
-            if (elect_one()) umma_commit(bar(OUTFULL));
-            __syncwarp();
+        }
+    } else if (warp == 3) {
+        // =============================== L2 prefetch ===============================
+        // X is pulled into L2 PREFETCH_DIST tiles ahead of the shared-memory ring with plain prefetch.global.L2
+        // instructions (LSU path).  The TMA unit keeps a bounded number of requests in flight per SM (~256 lines by
+        // Little's law on profiles/r01 traces: 22 B/clk at the observed 5700-clk load latency), so its own requests
+        // must be L2 hits (~700 clk) for the ring to reach HBM speed; TMA-issued prefetches share that budget.
+        if (prm.pf_mode == 1) {
+            const char* xb = reinterpret_cast<const char*>(prm.x);
+            const int64_t pitch = prm.ldx * 4;
+            for (int it = 0; it < n_it; it++) {
+                if (it >= PREFETCH_DIST) {
+                    const int j = it - PREFETCH_DIST;
+                    mbar_wait(bar(FULL0 + j % NSTAGE), uint32_t(j / NSTAGE) & 1u);    // pace: stay PREFETCH_DIST ahead
+                }
+                const int64_t g = g0 + it;
+                const int64_t own0 = (g / T) * OWN, oth0 = (g % T) * OTH;
+                // tile rows in memory: MODE 0: OWN rows x OTH floats ; MODE 1: OTH rows x OWN floats
+                const int64_t r0 = MODE == 0 ? own0 : oth0, c0 = MODE == 0 ? oth0 : own0;
+                constexpr int TR = MODE == 0 ? OWN : OTH, TCB = (MODE == 0 ? OTH : OWN) * 4;   // rows, bytes per row
+                constexpr int LPR = TCB / 128 + 1;                                            // lines a row segment can touch
+                const int64_t cend = (c0 + TCB / 4 < prm.x_cols ? c0 + TCB / 4 : prm.x_cols) * 4;
+#pragma unroll 4
+                for (int idx = lane; idx < TR * LPR; idx += 32) {
+                    const int r = idx / LPR, kk = idx % LPR;
+                    const int64_t row = r0 + r;
+                    const int64_t seg0 = row * pitch + c0 * 4, seg1 = row * pitch + cend;
+                    const int64_t a = (seg0 & ~int64_t(127)) + kk * 128;
+                    if (row < prm.x_rows && a < seg1)
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(xb + a));
+                }
+            }
         }
     } else if (warp >= 4) {
         // ================================ epilogue ================================
         const int q = warp & 3;                   // TMEM lane quadrant (hardware: warp id % 4)
         const int cchunk = (warp - 4) >> 2;       // which 16-column chunk of the 64-wide tile this warp converts
         const int i = q * 32 + lane;              // own row inside the tile == TMEM lane
-        const int64_t own_idx = own0 + i;
-        const bool own_ok = own_idx < prm.own_n;
         const uint32_t lane_addr = tmem + (uint32_t(q * 32) << 16);
-        if (RESID) {
-            // park this thread's 8 + 8 columns of P (tf32 hi / lo of the own-side factor row) in tensor memory
+        const bool out_warp = cchunk < KC / 16;   // two warps per quadrant own the two 16-column halves of OUT
+        // this thread's 8 + 8 columns of P (tf32 hi / lo of the own-side factor row) -> tensor memory
+        auto park_p = [&](int64_t own_tile) {
+            const int64_t own_idx = own_tile * OWN + i;
             float ph[16];
 #pragma unroll
             for (int e = 0; e < 16; e++) ph[e] = 0.0f;
-            if (own_ok) {
+            if (own_idx < prm.own_n) {
                 const float4* src_h = reinterpret_cast<const float4*>(prm.p_hi + own_idx * KC + cchunk * 8);
                 const float4* src_l = reinterpret_cast<const float4*>(prm.p_lo + own_idx * KC + cchunk * 8);
                 const float4 a0 = src_h[0], a1 = src_h[1];
@@ -428,27 +487,33 @@ tc_pass_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_constan
                     ph[8] = b0.x; ph[9] = b0.y; ph[10] = b0.z; ph[11] = b0.w; ph[12] = b1.x; ph[13] = b1.y; ph[14] = b1.z; ph[15] = b1.w;
                 }
             }
-            {
-                asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
-                             ::"r"(lane_addr + uint32_t(TM_P_HI + cchunk * 8)), "r"(__float_as_uint(ph[0])),
-                               "r"(__float_as_uint(ph[1])), "r"(__float_as_uint(ph[2])), "r"(__float_as_uint(ph[3])),
-                               "r"(__float_as_uint(ph[4])), "r"(__float_as_uint(ph[5])), "r"(__float_as_uint(ph[6])),
-                               "r"(__float_as_uint(ph[7])) : "memory");
-                asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
-                             ::"r"(lane_addr + uint32_t(TM_P_LO + cchunk * 8)), "r"(__float_as_uint(ph[8])),
-                               "r"(__float_as_uint(ph[9])), "r"(__float_as_uint(ph[10])), "r"(__float_as_uint(ph[11])),
-                               "r"(__float_as_uint(ph[12])), "r"(__float_as_uint(ph[13])), "r"(__float_as_uint(ph[14])),
-                               "r"(__float_as_uint(ph[15])) : "memory");
-            }
+            asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                         ::"r"(lane_addr + uint32_t(TM_P_HI + cchunk * 8)), "r"(__float_as_uint(ph[0])),
+                           "r"(__float_as_uint(ph[1])), "r"(__float_as_uint(ph[2])), "r"(__float_as_uint(ph[3])),
+                           "r"(__float_as_uint(ph[4])), "r"(__float_as_uint(ph[5])), "r"(__float_as_uint(ph[6])),
+                           "r"(__float_as_uint(ph[7])) : "memory");
+            asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                         ::"r"(lane_addr + uint32_t(TM_P_LO + cchunk * 8)), "r"(__float_as_uint(ph[8])),
+                           "r"(__float_as_uint(ph[9])), "r"(__float_as_uint(ph[10])), "r"(__float_as_uint(ph[11])),
+                           "r"(__float_as_uint(ph[12])), "r"(__float_as_uint(ph[13])), "r"(__float_as_uint(ph[14])),
+                           "r"(__float_as_uint(ph[15])) : "memory");
             tmem_st_wait();
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(bar(PFULL));
-        }
+        };
+        if (RESID && n_it > 0) park_p(g0 / T);
         double sq = 0.0;
+        float acc[16];                            // sum of the chains of the current own tile (OUT + OUT2), out_warp only
+#pragma unroll
+        for (int e = 0; e < 16; e++) acc[e] = 0.0f;
+        int chains_seen = 0;
         for (int it = 0; it < n_it; it++) {
             const int s = it % NSTAGE, sb = it & 1;
-            const int64_t oth0 = (t_begin + it) * OTH;
+            const int64_t g = g0 + it;
+            const int64_t own_tile = g / T, t = g % T;
+            const int64_t own0 = own_tile * OWN, oth0 = t * OTH;
+            const bool own_ok = own0 + i < prm.own_n;
             mbar_wait(bar(FULL0 + s), uint32_t(it / NSTAGE) & 1u);
             if (warp == 4 && lane == 0) TC_TRACE(TR_FULL_SEEN_EPI, it);
             if (RESID) {
@@ -456,6 +521,7 @@ tc_pass_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_constan
                 tc_fence_after();
             }
             if (warp == 4 && lane == 0) TC_TRACE(TR_S_SEEN, it);
+            if (lane == 0) TC_TRACE(TR_W_S + (warp - 4), it);
             const unsigned char* xs = gen + SmemLayout::stage0 + s * SmemLayout::stage_bytes + SmemLayout::x;
             float sq_tile = 0.0f;
             // interior tiles need no bounds masks; the masked path only runs on the last row / column tiles
@@ -468,13 +534,14 @@ tc_pass_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_constan
                 if (RESID) {
                     tmem_ld16(lane_addr + uint32_t(TM_S + sb * OTH + c * 16), sv);
                 }
+                if (lane == 0) TC_TRACE(TR_W_LD + (warp - 4), it);
                 float rr[16];
 #pragma unroll
-                for (int g = 0; g < 4; g++) {
-                    // 4 consecutive other-indices j = 16c + 4g + e
+                for (int gq = 0; gq < 4; gq++) {
+                    // 4 consecutive other-indices j = 16c + 4gq + e
                     float xv[4];
                     if (MODE == 0) {
-                        const int j = c * 16 + g * 4;
+                        const int j = c * 16 + gq * 4;
                         const int blk = j >> 5, ch = (j & 31) >> 2;
                         const float4 t4 = *reinterpret_cast<const float4*>(xs + blk * (OWN * 128) + i * 128 +
                                                                            ((ch ^ (i & 7)) << 4));
@@ -483,7 +550,7 @@ tc_pass_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_constan
                         const int blk = i >> 5, ch = (i & 31) >> 2, w = i & 3;
 #pragma unroll
                         for (int e = 0; e < 4; e++) {
-                            const int j = c * 16 + g * 4 + e;
+                            const int j = c * 16 + gq * 4 + e;
                             xv[e] = *reinterpret_cast<const float*>(xs + blk * (OTH * 128) + j * 128 +
                                                                     ((ch ^ (j & 7)) << 4) + w * 4);
                         }
@@ -492,13 +559,13 @@ tc_pass_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_constan
                     for (int e = 0; e < 4; e++) {
                         float r;
                         if (RESID) {
-                            float est = sv[g * 4 + e];
+                            float est = sv[gq * 4 + e];
                             if (prm.link == PYCMF_LOGIT) est = 1.0f / (1.0f + __expf(-est));
                             r = est - xv[e];
                         } else {
                             r = xv[e];                         // TMA zero-fills out-of-range elements
                         }
-                        rr[g * 4 + e] = r;
+                        rr[gq * 4 + e] = r;
                     }
                 }
                 if (RESID && !interior) {
@@ -521,6 +588,7 @@ tc_pass_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_constan
                 // R buffer it & 1 in tensor memory: GEMM2 of tile it - 2 must have drained it
                 mbar_wait(bar(REMPTY0 + sb), (uint32_t(it >> 1) & 1u) ^ 1u);
                 tc_fence_after();
+                if (lane == 0) TC_TRACE(TR_W_RE + (warp - 4), it);
                 const uint32_t r_hi = lane_addr + uint32_t(TM_R + sb * 2 * OTH + c * 16);
                 tmem_st16(r_hi, hi);
                 if (NSPLIT == 3) tmem_st16(r_hi + OTH, lo);
@@ -530,34 +598,46 @@ tc_pass_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_constan
             tc_fence_before();
             __syncwarp();
             if (lane == 0) {
-                if (RESID) mbar_arrive(bar(SEMPTY0 + sb));
                 mbar_arrive(bar(RFULL0 + sb));
                 if (warp == 4) TC_TRACE(TR_R_DONE, it);
+                TC_TRACE(TR_W_R + (warp - 4), it);
             }
-        }
-        // ---- final: OUT (128 x 32) from TMEM to global
-        mbar_wait(bar(OUTFULL), 0);
-        tc_fence_after();
-        if (cchunk < KC / 16) {                   // two warps per quadrant write the two 16-column halves of OUT
-            float o[16];
-            if (n_it > 0) {
+            const bool last = last_of_chain(it, t);
+            const bool own_ends = (it == n_it - 1) || (t == T - 1);
+            // the next tile belongs to another own tile: its P may go to tensor memory now (every GEMM1 that read the
+            // old P has completed: this warp has just consumed the S of the last one)
+            if (RESID && own_ends && it + 1 < n_it) park_p(own_tile + 1);
+            if (last && out_warp) {
+                // ---- end of a chain: OUT (+ OUT2) from tensor memory into the register accumulators
+                mbar_wait(bar(OUTFULL), uint32_t(chains_seen) & 1u);
+                tc_fence_after();
+                float o[16];
                 tmem_ld16(lane_addr + uint32_t(TM_OUT + cchunk * 16), o);
+#pragma unroll
+                for (int e = 0; e < 16; e++) acc[e] += o[e];
                 if (NSPLIT == 3) {
-                    float o2[16];
-                    tmem_ld16(lane_addr + uint32_t(TM_OUT2 + cchunk * 16), o2);
+                    tmem_ld16(lane_addr + uint32_t(TM_OUT2 + cchunk * 16), o);
 #pragma unroll
-                    for (int e = 0; e < 16; e++) o[e] += o2[e];
+                    for (int e = 0; e < 16; e++) acc[e] += o[e];
                 }
-            } else {
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar(OUTEMPTY));
+                if (own_ends) {
+                    // ---- one partial per (CTA, own tile)
+                    const int64_t entry = int64_t(blockIdx.x) - first_cta(own_tile * T, prm.n_tiles, gridDim.x);
+                    if (own_ok) {
+                        float4* dst = reinterpret_cast<float4*>(
+                            prm.part + ((own_tile * prm.max_entries + entry) * OWN + i) * KC + cchunk * 16);
 #pragma unroll
-                for (int e = 0; e < 16; e++) o[e] = 0.0f;
-            }
-            if (own_ok) {
-                float4* dst = reinterpret_cast<float4*>(prm.out + int64_t(blockIdx.y) * prm.out_split_stride +
-                                                        own_idx * KC + cchunk * 16);
+                        for (int e = 0; e < 4; e++)
+                            dst[e] = make_float4(acc[4 * e], acc[4 * e + 1], acc[4 * e + 2], acc[4 * e + 3]);
+                    }
 #pragma unroll
-                for (int e = 0; e < 4; e++) dst[e] = make_float4(o[4 * e], o[4 * e + 1], o[4 * e + 2], o[4 * e + 3]);
+                    for (int e = 0; e < 16; e++) acc[e] = 0.0f;
+                }
             }
+            if (last) chains_seen++;
         }
         if (RESID && prm.sq_part != nullptr) {
             sq = warp_sum(sq);
@@ -566,12 +646,27 @@ tc_pass_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_constan
         tc_fence_before();
     }
     __syncthreads();
-    if (RESID && prm.sq_part != nullptr && threadIdx.x == 0)
-        prm.sq_part[blockIdx.y * gridDim.x + blockIdx.x] = *sq_slot;
+    if (RESID && prm.sq_part != nullptr && threadIdx.x == 0) prm.sq_part[blockIdx.x] = *sq_slot;
     if (warp == 2) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(uint32_t(TMEM_COLS)) : "memory");
     }
+}
+
+// out[r][:] = sum over the entries of own tile r / OWN of part[tile][entry][r % OWN][:]   (fixed order: deterministic)
+__global__ void tc_reduce_kernel(int64_t own_n, int64_t T, int64_t G, int64_t n_cta, int max_entries,
+                                 const float* __restrict__ part, float* __restrict__ out) {
+    const int64_t e4 = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;     // one float4 of the output per thread
+    if (e4 >= own_n * (KC / 4)) return;
+    const int64_t r = e4 / (KC / 4), c4 = e4 % (KC / 4);
+    const int64_t tile = r / OWN;
+    const int n = int(first_cta(tile * T + T - 1, G, n_cta) - first_cta(tile * T, G, n_cta)) + 1;
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int e = 0; e < n; e++) {
+        const float4 v = *reinterpret_cast<const float4*>(part + ((tile * max_entries + e) * OWN + (r % OWN)) * KC + c4 * 4);
+        s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    }
+    *reinterpret_cast<float4*>(out + r * KC + c4 * 4) = s;
 }
 
 // tf32 hi / lo parts of a factor F (rows x 32), in the original layout and transposed (32 x ldt)
@@ -646,17 +741,19 @@ CUtensorMap factor_t_map(const float* p, int64_t rows, int64_t ldt) { return mak
 template <int MODE, bool RESID, int NSPLIT>
 void launch_tc(pycmf_ctx* ctx, int64_t own_n, int64_t oth_n, const FactorParts& P, const FactorParts& Q,
                const float* X, int64_t x_rows, int64_t x_cols, int64_t ldx, int link, float* out, double* sq) {
-    const int64_t own_tiles = ceil_div(own_n, OWN), loop_tiles = ceil_div(oth_n, OTH);
-    int64_t splits = 1;
-    if (own_tiles < 4 * ctx->num_sms)
-        splits = std::max<int64_t>(1, std::min(loop_tiles, ceil_div(int64_t(4) * ctx->num_sms, own_tiles)));
+    const int64_t own_tiles = ceil_div(own_n, OWN), T = ceil_div(oth_n, OTH), G = own_tiles * T;
+    // one persistent CTA per SM; options for tests: tc_ctas caps the CTA count, tc_max_splits = s keeps the old meaning
+    // "at most s CTAs per own tile" (s == 1 also lifts the chain cap: one long accumulation chain per own tile)
+    int64_t n_cta = std::min<int64_t>(ctx->num_sms, G);
+    if (ctx->tc_ctas > 0) n_cta = std::min<int64_t>(n_cta, ctx->tc_ctas);
+    if (ctx->tc_max_splits > 0) n_cta = std::min<int64_t>(n_cta, own_tiles * ctx->tc_max_splits);
     // TMEM accumulation is fp32 without round-to-nearest: bound the chain length per accumulator (measured: 65 tiles
-    // of random-sign data -> 3e-5 relative, 8 tiles -> 7e-7): at most 16 tiles, the fp32 split reduction adds the partials
-    splits = std::max(splits, ceil_div(loop_tiles, int64_t(16)));
-    if (ctx->tc_max_splits > 0) splits = std::min<int64_t>(splits, ctx->tc_max_splits);
-    int64_t tiles_per_split = ceil_div(loop_tiles, splits);
-    splits = ceil_div(loop_tiles, tiles_per_split);
-    PYCMF_CHECK(splits <= 65535, "tc pass: too many splits");
+    // of random-sign data -> 3e-5 relative, 8 tiles -> 7e-7): at most 16 tiles, the chains are added in fp32 registers
+    int chain = ctx->tc_chain > 0 ? ctx->tc_chain : 16;
+    if (ctx->tc_max_splits == 1) chain = 1 << 30;
+    int max_entries = 1;
+    for (int64_t o = 0; o < own_tiles; o++)
+        max_entries = std::max<int>(max_entries, int(first_cta(o * T + T - 1, G, n_cta) - first_cta(o * T, G, n_cta)) + 1);
     CUtensorMap tm_q_hi = factor_map(Q.hi, Q.rows, OTH);
     CUtensorMap tm_q_lo = factor_map(Q.lo, Q.rows, OTH);
     CUtensorMap tm_qt_hi = factor_t_map(Q.hi_t, Q.rows, Q.ldt);
@@ -665,32 +762,35 @@ void launch_tc(pycmf_ctx* ctx, int64_t own_n, int64_t oth_n, const FactorParts& 
     Params prm;
     prm.own_n = own_n;
     prm.oth_n = oth_n;
-    prm.tiles_per_split = tiles_per_split;
+    prm.n_oth_tiles = T;
+    prm.n_tiles = G;
+    prm.chain = chain;
     prm.link = link;
     prm.p_hi = P.hi;
     prm.p_lo = P.lo;
-    prm.out = out;
-    prm.out_split_stride = 0;
-    if (splits > 1) {
-        prm.out = static_cast<float*>(scratch(ctx, 0, size_t(splits) * own_n * KC * sizeof(float)));
-        prm.out_split_stride = own_n * KC;
-    }
+    prm.x = X;
+    prm.ldx = ldx;
+    prm.x_rows = x_rows;
+    prm.x_cols = x_cols;
+    prm.pf_mode = ctx->tc_prefetch;
+    prm.part = static_cast<float*>(scratch(ctx, 0, size_t(own_tiles) * max_entries * OWN * KC * sizeof(float)));
+    prm.max_entries = max_entries;
     prm.sq_part = nullptr;
     prm.trace = ctx->tc_trace ? static_cast<long long*>(scratch(ctx, 2, sizeof(long long) * TR_NEVENTS * TRACE_TILES)) : nullptr;
-    const int64_t nparts = own_tiles * splits;
-    if (RESID && sq != nullptr) prm.sq_part = static_cast<double*>(scratch(ctx, 1, size_t(nparts) * sizeof(double)));
+    if (RESID && sq != nullptr) prm.sq_part = static_cast<double*>(scratch(ctx, 1, size_t(n_cta) * sizeof(double)));
     auto kern = tc_pass_kernel<MODE, RESID, NSPLIT>;
     const size_t smem = SmemLayout::total + 1024;
     PYCMF_CHECK(smem <= size_t(ctx->max_smem_optin), "tc pass: shared memory budget exceeded");
     PYCMF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-    dim3 grid((unsigned)own_tiles, (unsigned)splits);
     {
         Timed timer(ctx, RESID ? (MODE == 0 ? "tc_resid_left" : "tc_resid_right") : (MODE == 0 ? "tc_xv" : "tc_xtu"));
-        kern<<<grid, NTHREADS, smem, ctx->stream>>>(tm_q_hi, tm_q_lo, tm_qt_hi, tm_qt_lo, tm_x, prm);
+        kern<<<(unsigned)n_cta, NTHREADS, smem, ctx->stream>>>(tm_q_hi, tm_q_lo, tm_qt_hi, tm_qt_lo, tm_x, prm);
         PYCMF_LAUNCH_CHECK(ctx);
     }
-    if (splits > 1) reduce_parts<float>(ctx, own_n, KC, int(splits), prm.out, out, KC, 1.0f, 0.0f);
-    if (prm.sq_part != nullptr) final_sum(ctx, int(nparts), prm.sq_part, 1.0, sq, true);
+    tc_reduce_kernel<<<(unsigned)ceil_div(own_n * (KC / 4), 256), 256, 0, ctx->stream>>>(own_n, T, G, n_cta, max_entries,
+                                                                                       prm.part, out);
+    PYCMF_LAUNCH_CHECK(ctx);
+    if (prm.sq_part != nullptr) final_sum(ctx, int(n_cta), prm.sq_part, 1.0, sq, true);
 }
 
 size_t parts_floats(int64_t rows) { return size_t(2) * rows * KC + size_t(2) * KC * ((rows + 3) & ~int64_t(3)); }

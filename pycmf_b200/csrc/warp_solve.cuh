@@ -28,10 +28,15 @@ __host__ __device__ constexpr int pick_kt(int k) { return k <= 8 ? 8 : (k <= 16 
 // (column j of L, diagonal included).  Uniform return value (false: a pivot was <= floor).
 template <int KT>
 __device__ __forceinline__ bool chol_reg(double (&a)[KT], int lane, double floor, double* __restrict__ Lc) {
+    // No early exit: a failed pivot is replaced by 1 and only remembered, so that the whole factorisation is one
+    // basic block (the scheduler overlaps the tail of one trailing update with the next pivot's rsqrt chain).
+    bool ok = true;
 #pragma unroll
     for (int j = 0; j < KT; j++) {
-        const double piv = shfl_d(a[j], j);
-        if (!(piv > floor)) return false;
+        double piv = shfl_d(a[j], j);
+        const bool good = piv > floor;
+        ok = ok && good;
+        piv = good ? piv : 1.0;
         const double inv = rsqrt(piv);
         const double l = (lane >= j) ? a[j] * inv : 0.0;
         a[j] = (lane == j) ? inv : l;
@@ -52,7 +57,7 @@ __device__ __forceinline__ bool chol_reg(double (&a)[KT], int lane, double floor
             }
         }
     }
-    return true;
+    return ok;
 }
 
 // Solve L L^T x = b with the factor left by chol_reg; lane r holds b_r on entry and x_r on return.

@@ -19,14 +19,18 @@ Xd = DenseMatrix(X)
 U = torch.rand(n, 32, device=be.device); V = torch.rand(d, 32, device=be.device)
 names = ["tma_issue", "g1_issue", "s_seen", "r_done", "g2_issue", "empty_seen", "full_seen_epi"]
 def show(tag):
-    buf = np.zeros(7 * 32, dtype=np.int64)
+    buf = np.zeros(72 * 32, dtype=np.int64)
     _lib.check(be.lib.pycmf_debug_tc_trace(be.ctx, buf.ctypes.data_as(ctypes.c_void_p), buf.size))
-    t = buf.reshape(7, 32)
+    t = buf.reshape(72, 32)
     t0 = t[0, 0]
     print("==", tag)
     print("tile " + " ".join("%13s" % s for s in names))
     for it in range(20):
         print("%4d " % it + " ".join("%13d" % (t[e, it] - t0 if t[e, it] else -1) for e in range(7)))
+    for label, base in (("S seen", 8), ("S loaded", 24), ("R buffer free", 40), ("R published", 56)):
+        print("-- per epilogue warp (columns = warps 4..19), cycles after this tile's g1_issue: " + label)
+        for it in range(8, 14):
+            print("%4d " % it + " ".join("%6d" % (t[base + w, it] - t[1, it]) for w in range(16)))
 for rep in range(2):
     gx, Hx, pr = be.newton_v_xpart(V, U, Xd, 0, d, "linear", 1.0)
 show("resid RIGHT")

@@ -287,3 +287,33 @@ def test_tc_long_tile_loop_newton_step(path):
     assert (np.abs(hist - ref_hist) / np.abs(ref_hist)).max() < otol
     for got, ref in ((U, rU), (V, rV), (Z, rZ)):
         assert rel_fro(got, ref) < ftol
+
+
+@pytest.mark.parametrize("ctas", [1, 3, 7, 0])
+@pytest.mark.parametrize("chain", [0, 2, 5])
+@pytest.mark.parametrize("link", ["linear", "logit"])
+def test_tc_persistent_ranges_cross_own_tiles(ctas, chain, link):
+    """The persistent tcgen05 pass: few CTAs walk many tiles, crossing own-tile and chain boundaries inside one CTA
+    (P reloaded into tensor memory, partials per (CTA, own tile) summed by the reduce kernel).  Both directions
+    and the fused sum of squares against float64 NumPy; ragged edges in both dimensions."""
+    from pycmf_b200.device import CudaBackend
+    n, d = 1100, 709
+    rng = np.random.RandomState(ctas * 10 + chain)
+    U, V = 0.3 * rng.randn(n, 32), 0.3 * rng.randn(d, 32)
+    X = ((O.expit(U @ V.T) if link == "logit" else U @ V.T) + 0.05 * rng.randn(n, d)).astype(np.float32)
+    Xp = np.zeros((n, 712), dtype=np.float32)          # row stride a multiple of 4 floats (TMA), d itself ragged
+    Xp[:, :d] = X
+    opts = {"dense_path": 1}
+    if ctas:
+        opts["tc_ctas"] = ctas
+    if chain:
+        opts["tc_chain"] = chain
+    be = CudaBackend(dtype="float32", options=opts)
+    Xd = be.ingest(Xp)
+    from pycmf_b200.device import DenseMatrix
+    Xv = DenseMatrix(Xd.t[:, :d])
+    outL, outR, sq = be.resid_pass(be.to_device(U), be.to_device(V), Xv, link, want_sq=True)
+    R = O.inverse(U.astype(np.float32).astype(np.float64) @ V.astype(np.float32).astype(np.float64).T, link) - X
+    assert rel_fro(be.to_host(outL), R @ V) < 5e-5
+    assert rel_fro(be.to_host(outR), R.T @ U) < 5e-5
+    assert abs(float(be.to_host(sq)[0]) - (R ** 2).sum()) / (R ** 2).sum() < 1e-5
