@@ -34,7 +34,7 @@ struct pycmf_ctx {
     int tc_trace = 0;        // diagnostics: record a pipeline trace of CTA (0,0) of every tcgen05 pass into arena 2
     int tc_max_splits = 0;   // > 0: at most this many CTAs per own tile in the tcgen05 passes (tests: 1 = one long chain)
     int tc_ctas = 0;         // > 0: cap on the persistent CTA count of the tcgen05 passes (tests)
-    int tc_prefetch = 1;     // L2 prefetch of X in the tcgen05 passes: 0 none, 1 helper warp (prefetch.global.L2), 2 TMA
+    int tc_prefetch = 0;     // L2 prefetch of X in the tcgen05 passes: 0 none (measured: no gain), 2 TMA prefetch
     int tc_chain = 0;        // > 0: accumulation chain cap in tiles (default 16)
     size_t max_scratch = size_t(2) << 30;
     // scratch arenas (grown on demand; growth synchronises the stream)

@@ -6,23 +6,26 @@
 //   COPY,  LEFT  : out  = X   B                  MU numerator X V    (cmf_solvers.py:232)
 //   COPY,  RIGHT : out  = X^T A                  MU numerator X^T U  (cmf_solvers.py:244)
 //
-// A CTA owns 128 "own" rows (rows of X for LEFT, columns of X for RIGHT) and walks the other dimension in
-// tiles of 64.  Per tile:
-//   TMA        : X tile (128 x 64 fp32, SWIZZLE_128B) + the 64 x 32 factor tile Q and its transpose Q^T
-//                (tf32 hi / lo parts) into a 3-stage shared-memory ring; X is also prefetched into L2 8 tiles ahead
-//   tcgen05.mma: S[128 x 64]  = P Q^T     GEMM1, A operand P resident in TENSOR MEMORY for the whole CTA
+// A persistent CTA (one per SM) owns a range of 128 x 64 tiles of X (128 "own" rows: rows of X for LEFT, columns of X
+// for RIGHT; 64 "other" rows per tile).  Per tile:
+//   TMA        : X tile (128 x 64 fp32, SWIZZLE_128B) + the 64 x 32 factor tile Q (tf32 hi / lo parts) into a
+//                4-stage shared-memory ring (48 KB per stage)
+//   transposer : one warp turns the Q tile into the K-major Q^T tile GEMM2 needs (two-slot ring), on chip:
+//                loading Q^T through TMA as well doubled the factor traffic and cost the ring its fourth stage
+//   tcgen05.mma: S[128 x 64]  = P Q^T     GEMM1, A operand P resident in TENSOR MEMORY for the whole own tile
 //   epilogue   : tcgen05.ld S -> f() -> minus X -> R (tf32 hi / lo) -> tcgen05.st back into TENSOR MEMORY
 //   tcgen05.mma: OUT[128 x 32] += R Q     GEMM2, A operand R read from tensor memory, B = K-major Q^T tile
 // Neither U V^T nor the residual ever touches HBM -- or shared memory: with N = 32..64 the MMAs have too little
-// operand reuse for shared-memory A operands (a 128 x 8 tf32 A slice is 4 KB per instruction: at 128 B/clk the
-// SS form was measured shared-memory-bound at ~60 clk per MMA), so both A operands live in TMEM (TS form) and
-// shared memory only carries the TMA ring and the small B slices.  3xTF32: hi*hi + hi*lo + lo*hi.
-// GEMM1 of tile t+1 is issued before GEMM2 of tile t (two S buffers, two R buffers in TMEM); the MMA thread
-// issues whichever GEMM has its inputs ready (event-driven, non-blocking mbarrier probes).
+// operand reuse for shared-memory A operands (measured, profiles/r01_tcgen05_mma_rate.txt: SS form 32 + N/4 clk per
+// MMA, TS form N/2), so both A operands live in TMEM and shared memory only carries the rings.
+// 3xTF32: hi*hi + hi*lo + lo*hi.  Two S buffers and two R buffers in TMEM; GEMM1 and GEMM2 are issued by two different
+// warps (measured: one warp doing the waits, 36 MMAs and the commits of a tile needs ~2600 clk per tile and was the
+// bottleneck of the whole pass; the tensor pipe itself needs 768).
 //
-// Warp roles (640 threads): warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator,
-// warps 4-19 = epilogue: warp w works on TMEM lane quadrant w % 4 (own rows 32 (w % 4) ..) and on the
-// 16-column chunk (w - 4) / 4 of the 64-wide tile, so every SM sub-partition has four epilogue warps.
+// Warp roles (640 threads): warps 0-15 = epilogue (warp w works on TMEM lane quadrant w % 4 and on the 16-column chunk
+// w / 4 of the 64-wide tile, so every SM sub-partition has four epilogue warps); warp 16 = TMA producer, 17 = GEMM2
+// issuer, 18 = Q^T transposer + TMEM allocator, 19 = GEMM1 issuer.  The control warps have the highest warp ids on
+// purpose: the issue arbiter prefers high warp ids, and a late MMA issue stalls everything.
 #include <cuda.h>
 
 #include "common.cuh"
@@ -33,10 +36,13 @@ namespace {
 constexpr int OWN = 128;      // own rows per CTA  (UMMA M)
 constexpr int OTH = 64;       // other rows per tile (GEMM1 N, GEMM2 K)
 constexpr int KC = 32;        // n_components handled by this kernel (one 128-byte swizzle span)
-constexpr int NSTAGE = 3;
+constexpr int NSTAGE = 4;
+constexpr int NQT = 2;             // Q^T slots (produced on chip from the Q tile, consumed by GEMM2)
 constexpr int PREFETCH_DIST = 8;   // X tiles requested into L2 ahead of the shared-memory ring
 constexpr int EPI_WARPS = 16;
-constexpr int NTHREADS = 128 + 32 * EPI_WARPS;
+constexpr int NTHREADS = 32 * EPI_WARPS + 128;
+constexpr int W_TMA = EPI_WARPS, W_G2 = EPI_WARPS + 1, W_QT = EPI_WARPS + 2, W_G1 = EPI_WARPS + 3;
+static_assert(NQT == 2, "G2DONE doubles as the R-buffer and the Q^T-slot release: both rings must have two slots");
 
 // tensor-memory columns (512 x 128 lanes x 32 bit, all allocated: one CTA per SM)
 constexpr int TMEM_COLS = 512;
@@ -52,17 +58,22 @@ constexpr uint32_t X_BYTES = OWN * OTH * 4;      // 32 KB
 
 struct SmemLayout {
     // all tile buffers are 1024-byte aligned (SWIZZLE_128B atoms)
-    // offsets inside a stage: Q (64 x 32, K-major for GEMM1), Q^T (32 x 64 as two 32 x 32 K-blocks, GEMM2), X tile
-    static constexpr uint32_t q_hi = 0, q_lo = Q_BYTES, qt_hi = 2 * Q_BYTES, qt_lo = 3 * Q_BYTES, x = 4 * Q_BYTES;
-    static constexpr uint32_t stage_bytes = 4 * Q_BYTES + X_BYTES;
+    // stage: Q hi / lo (64 x 32, K-major for GEMM1; source of the transposer), X tile
+    static constexpr uint32_t q_hi = 0, q_lo = Q_BYTES, x = 2 * Q_BYTES;
+    static constexpr uint32_t stage_bytes = 2 * Q_BYTES + X_BYTES;
     static constexpr uint32_t stage0 = 0;
-    static constexpr uint32_t bars = stage0 + NSTAGE * stage_bytes;
+    // Q^T slot: hi / lo, each 32 x 64 as two 32 x 32 K-blocks (GEMM2's B operand)
+    static constexpr uint32_t qt0 = stage0 + NSTAGE * stage_bytes;
+    static constexpr uint32_t qt_hi = 0, qt_lo = Q_BYTES, qt_bytes = 2 * Q_BYTES;
+    static constexpr uint32_t bars = qt0 + NQT * qt_bytes;
     static constexpr uint32_t total = bars + 256;
 };
 
 // barrier slots (8 bytes each) inside the `bars` region
 enum Bar { FULL0 = 0, EMPTY0 = FULL0 + NSTAGE, SFULL0 = EMPTY0 + NSTAGE, RFULL0 = SFULL0 + 2,
-           REMPTY0 = RFULL0 + 2, PFULL = REMPTY0 + 2, OUTFULL, OUTEMPTY, NBARS };
+           G2DONE0 = RFULL0 + 2,      // GEMM2(t) complete: R buffer t & 1 and Q^T slot t & 1 are free again
+           QTFULL0 = G2DONE0 + 2, PFULL = QTFULL0 + NQT, OUTFULL, OUTEMPTY, NBARS };
+static_assert(NBARS * 8 + 32 <= 256, "barrier region too small");
 
 // ---- PTX wrappers ----------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return uint32_t(__cvta_generic_to_shared(p)); }
@@ -196,7 +207,7 @@ struct Params {
     const float *p_hi, *p_lo;   // tf32 parts of the own-side factor (own_n x 32), RESID only
     const float* x;             // X itself (rows x cols, row stride ldx) for the L2 prefetch warp
     int64_t ldx, x_rows, x_cols;
-    int pf_mode;                // 0 none, 1 prefetch.global.L2 from a helper warp, 2 TMA L2 prefetch from the producer
+    int pf_mode;                // 0 none, 2 TMA L2 prefetch of X from the producer
     float* part;                // partial outputs: [own tile][entry][OWN x 32]
     int max_entries;            // entries per own tile in `part`
     double* sq_part;            // per-CTA partial of sum R^2 (may be null)
@@ -227,7 +238,7 @@ enum TraceEvent { TR_TMA_ISSUE = 0, TR_G1_ISSUE, TR_S_SEEN, TR_R_DONE, TR_G2_ISS
 // A chain (one accumulation in OUT) starts at i == 0 or t % chain == 0 and ends at the CTA's last tile, at
 // (t + 1) % chain == 0 or at t == T - 1; the epilogue warps add the chains of one own tile in registers (fp32,
 // round to nearest) and write one partial per (CTA, own tile).
-template <int MODE, bool RESID, int NSPLIT>
+template <int MODE, bool RESID, int NSPLIT, bool LOGIT>
 __global__ void __launch_bounds__(NTHREADS, 1)
 tc_pass_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_constant__ CUtensorMap tm_q_lo,
                const __grid_constant__ CUtensorMap tm_qt_hi, const __grid_constant__ CUtensorMap tm_qt_lo,
@@ -246,16 +257,17 @@ tc_pass_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_constan
     const int64_t g0 = tile_begin(blockIdx.x, prm.n_tiles, gridDim.x);
     const int n_it = int(tile_begin(int64_t(blockIdx.x) + 1, prm.n_tiles, gridDim.x) - g0);
     const int chain = prm.chain;
-    // schedule predicates, identical in every role
-    auto first_of_chain = [&](int it, int64_t t) { return it == 0 || (t % chain) == 0; };
-    auto last_of_chain = [&](int it, int64_t t) { return it == n_it - 1 || ((t + 1) % chain) == 0 || t == T - 1; };
+    // schedule predicates, identical in every role; cpos = t % chain is carried incrementally (no divisions in the loops)
+    auto first_of_chain = [&](int it, int cpos) { return it == 0 || cpos == 0; };
+    auto last_of_chain = [&](int it, int t, int cpos) { return it == n_it - 1 || cpos == chain - 1 || t == T - 1; };
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < NSTAGE; s++) { mbar_init(bar(FULL0 + s), 1); mbar_init(bar(EMPTY0 + s), 1); }
         for (int s = 0; s < 2; s++) {
             mbar_init(bar(SFULL0 + s), 1);
             mbar_init(bar(RFULL0 + s), EPI_WARPS);
-            mbar_init(bar(REMPTY0 + s), 1);
+            mbar_init(bar(G2DONE0 + s), 1);
+            mbar_init(bar(QTFULL0 + s), 1);
         }
         mbar_init(bar(PFULL), EPI_WARPS);
         mbar_init(bar(OUTFULL), 1);
@@ -264,7 +276,7 @@ tc_pass_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_constan
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         fence_async_smem();
     }
-    if (warp == 2) {
+    if (warp == W_QT) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
                      "r"(uint32_t(TMEM_COLS)) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -273,21 +285,15 @@ tc_pass_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_constan
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
+    const int64_t o_first = g0 / T;
+    const int t_first = int(g0 % T);               // the only 64-bit divisions: every role walks (own tile, t) incrementally
+    const int c_first = t_first % chain;
 
-    if (warp == 0) {
+    if (warp == W_TMA) {
         // =============================== TMA producer ===============================
         // The whole warp walks the loop (converged); one elected lane issues.
-        auto prefetch_x = [&](int it) {
-            const int64_t g = g0 + it;
-            const int own0 = int((g / T) * OWN), oth0 = int((g % T) * OTH);
-            if (MODE == 0) {
-                tma_prefetch_2d(&tm_x, oth0, own0);
-                tma_prefetch_2d(&tm_x, oth0 + 32, own0);
-            } else {
-#pragma unroll
-                for (int b = 0; b < 4; b++) tma_prefetch_2d(&tm_x, own0 + 32 * b, oth0);
-            }
-        };
+        int64_t o = o_first;
+        int t = t_first;
         for (int it = 0; it < n_it; it++) {
             const int s = it % NSTAGE;
             const uint32_t ph = uint32_t(it / NSTAGE) & 1u;
@@ -295,9 +301,8 @@ tc_pass_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_constan
             if (elect_one()) {
                 TC_TRACE(TR_EMPTY_SEEN, it);
                 const uint32_t st = base + SmemLayout::stage0 + uint32_t(s) * SmemLayout::stage_bytes;
-                const int64_t g = g0 + it;
-                const int own0 = int((g / T) * OWN), oth0 = int((g % T) * OTH);
-                mbar_expect_tx(bar(FULL0 + s), (RESID ? 2u : 1u) * (NSPLIT == 3 ? 2 * Q_BYTES : Q_BYTES) + X_BYTES);
+                const int own0 = int(o * OWN), oth0 = t * OTH;
+                mbar_expect_tx(bar(FULL0 + s), (NSPLIT == 3 ? 2 * Q_BYTES : Q_BYTES) + X_BYTES);
                 if (MODE == 0) {
                     // X tile: own rows x 64 other columns, two 32-column boxes of 128 rows
                     tma_load_2d(st + SmemLayout::x, &tm_x, bar(FULL0 + s), oth0, own0);
@@ -308,166 +313,159 @@ tc_pass_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_constan
                     for (int b = 0; b < 4; b++)
                         tma_load_2d(st + SmemLayout::x + uint32_t(b) * OTH * 128, &tm_x, bar(FULL0 + s), own0 + 32 * b, oth0);
                 }
-                if (RESID) {
-                    tma_load_2d(st + SmemLayout::q_hi, &tm_q_hi, bar(FULL0 + s), 0, oth0);
-                    if (NSPLIT == 3) tma_load_2d(st + SmemLayout::q_lo, &tm_q_lo, bar(FULL0 + s), 0, oth0);
-                }
-#pragma unroll
-                for (int b = 0; b < 2; b++) {
-                    tma_load_2d(st + SmemLayout::qt_hi + uint32_t(b) * (KC * 128), &tm_qt_hi, bar(FULL0 + s), oth0 + 32 * b, 0);
-                    if (NSPLIT == 3)
-                        tma_load_2d(st + SmemLayout::qt_lo + uint32_t(b) * (KC * 128), &tm_qt_lo, bar(FULL0 + s), oth0 + 32 * b, 0);
-                }
+                tma_load_2d(st + SmemLayout::q_hi, &tm_q_hi, bar(FULL0 + s), 0, oth0);
+                if (NSPLIT == 3) tma_load_2d(st + SmemLayout::q_lo, &tm_q_lo, bar(FULL0 + s), 0, oth0);
                 TC_TRACE(TR_TMA_ISSUE, it);
-                // L2 prefetch runs PREFETCH_DIST tiles ahead of the ring, but only once the ring's own loads are
-                // queued: prefetching first put 8 tiles (256 KB per SM) in front of tile 0 (a 5500-clk pipeline fill)
-                if (prm.pf_mode == 2 && it >= NSTAGE - 1) {
-                    if (it == NSTAGE - 1)
-                        for (int a = NSTAGE; a < NSTAGE - 1 + PREFETCH_DIST && a < n_it; a++) prefetch_x(a);
-                    if (it + PREFETCH_DIST < n_it) prefetch_x(it + PREFETCH_DIST);
+                if (prm.pf_mode == 2) {
+                    // TMA L2 prefetch PREFETCH_DIST tiles ahead (same own tile only: the box is clipped at the edge)
+                    const int tp = t + PREFETCH_DIST;
+                    if (tp < T) {
+                        if (MODE == 0) {
+                            tma_prefetch_2d(&tm_x, tp * OTH, own0);
+                            tma_prefetch_2d(&tm_x, tp * OTH + 32, own0);
+                        } else {
+#pragma unroll
+                            for (int b = 0; b < 4; b++) tma_prefetch_2d(&tm_x, own0 + 32 * b, tp * OTH);
+                        }
+                    }
                 }
             }
             __syncwarp();
+            if (++t == T) { t = 0; o++; }
         }
-    } else if (warp == 1) {
-        // =============================== MMA issuer ================================
-        // The whole warp runs the event loop (converged, probes made warp-uniform); one elected lane issues the MMAs
-        // and the commits (tcgen05.commit tracks the MMAs of the issuing thread: elect.sync always picks the same lane).
+    } else if (warp == W_G1 || warp == W_G2) {
+        // =============================== MMA issuers ================================
+        // Each of the two warps walks its schedule converged, with blocking waits; one elected lane issues the MMAs and
+        // the commits (tcgen05.commit tracks the MMAs of the issuing thread: elect.sync always picks the same lane).
+        // Under `lane == 0` ptxas wraps every UTCHMMA in an ELECT / BRA.U.ANY loop (~80 clk per MMA issued).
         constexpr uint32_t idesc1 = make_idesc(OWN, OTH, 0, 0);   // S   = P (TMEM) x Q (K-major)
         constexpr uint32_t idesc2 = make_idesc(OWN, KC, 0, 0);    // OUT = R (TMEM) x Q^T tile (K-major)
-        // B descriptors are built once per stage; inside a tile only the 14-bit start-address field changes,
-        // by small multiples of 16 bytes that cannot carry out of the field (all tiles live below 256 KB).
-        uint64_t dQ_hi[NSTAGE], dQ_lo[NSTAGE], dQt_hi[NSTAGE], dQt_lo[NSTAGE];
-#pragma unroll
-        for (int s = 0; s < NSTAGE; s++) {
-            const uint32_t st = base + SmemLayout::stage0 + uint32_t(s) * SmemLayout::stage_bytes;
-            dQ_hi[s] = make_desc(st + SmemLayout::q_hi, 16, 1024);
-            dQ_lo[s] = make_desc(st + SmemLayout::q_lo, 16, 1024);
-            dQt_hi[s] = make_desc(st + SmemLayout::qt_hi, 16, 1024);
-            dQt_lo[s] = make_desc(st + SmemLayout::qt_lo, 16, 1024);
-        }
-        auto pick = [&](const uint64_t (&d)[NSTAGE], int s) { return s == 0 ? d[0] : (s == 1 ? d[1] : d[2]); };
-        // Tensor-core accumulation into TMEM truncates (measured: ~2^-24 |acc| lost per MMA), so the order matters:
-        //  GEMM1: the small correction terms hi*lo, lo*hi first, the four hi*hi MMAs last;
-        //  GEMM2: corrections go to their own accumulator OUT2 (their rounding is relative to 2^-11 |OUT|), only the
-        //         eight hi*hi MMAs per tile extend the long chain in OUT; the epilogue adds OUT + OUT2.
-        auto issue_g1 = [&](int it) {
-            const int s = it % NSTAGE, sb = it & 1;
-            const uint32_t d = tmem + uint32_t(TM_S + sb * OTH);
-            const uint64_t qh = pick(dQ_hi, s), ql = pick(dQ_lo, s);
-#pragma unroll
-            for (int t = 0; t < NSPLIT; t++) {
-                const int term = NSPLIT == 3 ? (t == 0 ? 1 : (t == 1 ? 2 : 0)) : 0;   // hi*lo, lo*hi, hi*hi
-                const uint32_t pa = tmem + uint32_t((term == 2) ? TM_P_LO : TM_P_HI);
-                const uint64_t qa = (term == 1) ? ql : qh;
-#pragma unroll
-                for (int kk = 0; kk < KC / 8; kk++) {
-                    if (t == 0 && kk == 0) umma_tf32_ts<false>(d, pa, qa, idesc1);
-                    else umma_tf32_ts<true>(d, pa + uint32_t(kk * 8), qa + uint64_t(kk * 2), idesc1);
-                }
-            }
-            umma_commit(bar(SFULL0 + sb));
-        };
-        auto issue_g2 = [&](int it, bool first, bool last) {
-            const int s = it % NSTAGE, rb = it & 1;
-            const uint32_t r_hi = tmem + uint32_t(TM_R + rb * 2 * OTH), r_lo = r_hi + OTH;
-            const uint64_t qh = pick(dQt_hi, s), ql = pick(dQt_lo, s);
-#pragma unroll
-            for (int term = 0; term < NSPLIT; term++) {
-                const uint32_t d = tmem + uint32_t(term == 0 ? TM_OUT : TM_OUT2);
-                const uint32_t ra = (term == 2) ? r_lo : r_hi;
-                const uint64_t qa = (term == 1) ? ql : qh;
-#pragma unroll
-                for (int kk = 0; kk < OTH / 8; kk++) {
-                    // K-step kk: 8 TMEM columns of R; Q^T K-block kk / 4 (32 rows x 128 B = 256 x 16 B)
-                    const uint64_t bd = qa + uint64_t((kk / 4) * (KC * 128 / 16) + (kk % 4) * 2);
-                    if (term <= 1 && kk == 0 && first) umma_tf32_ts<false>(d, ra, bd, idesc2);
-                    else umma_tf32_ts<true>(d, ra + uint32_t(kk * 8), bd, idesc2);
-                }
-            }
-            umma_commit(bar(REMPTY0 + rb));
-            umma_commit(bar(EMPTY0 + s));
-            if (last) umma_commit(bar(OUTFULL));
-        };
-        // Event-driven issue.  GEMM1(i) needs its operands (FULL) and its S buffer: the epilogue of tile i - 2 has read
-        // it, which is implied by R(i - 2) having been published and GEMM2(i - 2) issued, i.e. g1 < g2 + 2.  At an own-tile
-        // change it also needs the new P in tensor memory (PFULL).  GEMM2(i) needs R(i) (the epilogue waited for FULL
-        // itself) and, at the start of a chain, the previous chain's OUT to have been read (OUTEMPTY).
-        int g1 = RESID ? 0 : n_it, g2 = 0;
-        int p_seen = 0;          // own-tile changes whose P has been seen (PFULL phases consumed)
-        int p_need = 1;          // PFULL phases GEMM1(g1) needs
-        int chains_done = 0;     // chains whose last GEMM2 has been issued
-        while (g2 < n_it) {
-            if (g1 < n_it && g1 < g2 + 2) {
-                bool go1 = mbar_test(bar(FULL0 + g1 % NSTAGE), uint32_t(g1 / NSTAGE) & 1u);
-                if (RESID && p_seen < p_need) go1 = go1 && mbar_test(bar(PFULL), uint32_t(p_seen) & 1u);
-                go1 = __all_sync(0xffffffffu, go1);
-                if (go1) {
-                    p_seen = p_need;
+        // B descriptors: inside a tile only the 14-bit start-address field changes, by small multiples of 16 bytes that
+        // cannot carry out of the field (all tiles live below 256 KB).
+        if (warp == W_G1) {
+            if (RESID) {
+                // GEMM1(it) needs: Q(it) landed (FULL); S buffer it & 1 read by the epilogue of tile it - 2 (RFULL(it - 2):
+                // this warp only observes that barrier); at the first tile of an own tile, P in tensor memory (PFULL).
+                // Order inside a tile: the small correction terms hi*lo, lo*hi first, the four hi*hi MMAs last
+                // (tensor-core accumulation into TMEM truncates: ~2^-24 |acc| lost per MMA).
+                int t1 = t_first, p_phase = 0;
+                for (int it = 0; it < n_it; it++) {
+                    const int s = it % NSTAGE, sb = it & 1;
+                    mbar_wait(bar(FULL0 + s), uint32_t(it / NSTAGE) & 1u);
+                    if (it >= 2) mbar_wait(bar(RFULL0 + sb), uint32_t((it - 2) >> 1) & 1u);
+                    if (it == 0 || t1 == 0) {
+                        mbar_wait(bar(PFULL), uint32_t(p_phase) & 1u);
+                        p_phase++;
+                    }
                     tc_fence_after();
                     if (elect_one()) {
-                        TC_TRACE(TR_G1_ISSUE, g1);
-                        issue_g1(g1);
+                        TC_TRACE(TR_G1_ISSUE, it);
+                        const uint32_t st = base + SmemLayout::stage0 + uint32_t(s) * SmemLayout::stage_bytes;
+                        const uint64_t qh = make_desc(st + SmemLayout::q_hi, 16, 1024), ql = make_desc(st + SmemLayout::q_lo, 16, 1024);
+                        const uint32_t d = tmem + uint32_t(TM_S + sb * OTH);
+#pragma unroll
+                        for (int tt = 0; tt < NSPLIT; tt++) {
+                            const int term = NSPLIT == 3 ? (tt == 0 ? 1 : (tt == 1 ? 2 : 0)) : 0;   // hi*lo, lo*hi, hi*hi
+                            const uint32_t pa = tmem + uint32_t((term == 2) ? TM_P_LO : TM_P_HI);
+                            const uint64_t qa = (term == 1) ? ql : qh;
+#pragma unroll
+                            for (int kk = 0; kk < KC / 8; kk++) {
+                                if (tt == 0 && kk == 0) umma_tf32_ts<false>(d, pa, qa, idesc1);
+                                else umma_tf32_ts<true>(d, pa + uint32_t(kk * 8), qa + uint64_t(kk * 2), idesc1);
+                            }
+                        }
+                        umma_commit(bar(SFULL0 + sb));
                     }
                     __syncwarp();
-                    g1++;
-                    if (g1 < n_it && ((g0 + g1) % T) == 0) p_need++;      // next tile starts a new own tile
+                    if (++t1 == T) t1 = 0;
                 }
             }
-            {
-                const int64_t t2 = (g0 + g2) % T;
-                const bool first = first_of_chain(g2, t2), last = last_of_chain(g2, t2);
-                bool go2 = mbar_test(bar(RFULL0 + (g2 & 1)), uint32_t(g2 >> 1) & 1u);
-                if (first && chains_done > 0) go2 = go2 && mbar_test(bar(OUTEMPTY), uint32_t(chains_done - 1) & 1u);
-                go2 = __all_sync(0xffffffffu, go2);
-                if (go2) {
-                    tc_fence_after();
-                    if (elect_one()) {
-                        TC_TRACE(TR_G2_ISSUE, g2);
-                        if (first) issue_g2(g2, true, last); else issue_g2(g2, false, last);
+        } else {
+            // GEMM2(it) needs R(it) published (RFULL: X and S of the tile consumed), Q^T(it) written (QTFULL: Q consumed)
+            // and, at the start of a chain, the previous chain's OUT read (OUTEMPTY).  Corrections go to their own
+            // accumulator OUT2 (their rounding is relative to 2^-11 |OUT|), only the eight hi*hi MMAs per tile extend the
+            // long chain in OUT; the epilogue adds OUT + OUT2.
+            auto issue_g2 = [&](int it, bool first, bool last) {
+                const int rb = it & 1;
+                const uint32_t r_hi = tmem + uint32_t(TM_R + rb * 2 * OTH), r_lo = r_hi + OTH;
+                const uint32_t qt = base + SmemLayout::qt0 + uint32_t(rb) * SmemLayout::qt_bytes;
+                const uint64_t qh = make_desc(qt + SmemLayout::qt_hi, 16, 1024), ql = make_desc(qt + SmemLayout::qt_lo, 16, 1024);
+#pragma unroll
+                for (int term = 0; term < NSPLIT; term++) {
+                    const uint32_t d = tmem + uint32_t(term == 0 ? TM_OUT : TM_OUT2);
+                    const uint32_t ra = (term == 2) ? r_lo : r_hi;
+                    const uint64_t qa = (term == 1) ? ql : qh;
+#pragma unroll
+                    for (int kk = 0; kk < OTH / 8; kk++) {
+                        // K-step kk: 8 TMEM columns of R; Q^T K-block kk / 4 (32 rows x 128 B = 256 x 16 B)
+                        const uint64_t bd = qa + uint64_t((kk / 4) * (KC * 128 / 16) + (kk % 4) * 2);
+                        if (term <= 1 && kk == 0 && first) umma_tf32_ts<false>(d, ra, bd, idesc2);
+                        else umma_tf32_ts<true>(d, ra + uint32_t(kk * 8), bd, idesc2);
                     }
-                    __syncwarp();
-                    g2++;
-                    if (last) chains_done++;
                 }
-            }
-        }
-    } else if (warp == 3) {
-        // =============================== L2 prefetch ===============================
-        // X is pulled into L2 PREFETCH_DIST tiles ahead of the shared-memory ring with plain prefetch.global.L2
-        // instructions (LSU path).  The TMA unit keeps a bounded number of requests in flight per SM (~256 lines by
-        // Little's law on profiles/r01 traces: 22 B/clk at the observed 5700-clk load latency), so its own requests
-        // must be L2 hits (~700 clk) for the ring to reach HBM speed; TMA-issued prefetches share that budget.
-        if (prm.pf_mode == 1) {
-            const char* xb = reinterpret_cast<const char*>(prm.x);
-            const int64_t pitch = prm.ldx * 4;
+                umma_commit(bar(G2DONE0 + rb));
+                if (last) umma_commit(bar(OUTFULL));
+            };
+            int t2 = t_first, c2 = c_first, chains_done = 0;
             for (int it = 0; it < n_it; it++) {
-                if (it >= PREFETCH_DIST) {
-                    const int j = it - PREFETCH_DIST;
-                    mbar_wait(bar(FULL0 + j % NSTAGE), uint32_t(j / NSTAGE) & 1u);    // pace: stay PREFETCH_DIST ahead
+                const bool first = first_of_chain(it, c2), last = last_of_chain(it, t2, c2);
+                mbar_wait(bar(RFULL0 + (it & 1)), uint32_t(it >> 1) & 1u);
+                mbar_wait(bar(QTFULL0 + (it & 1)), uint32_t(it >> 1) & 1u);
+                if (first && chains_done > 0) mbar_wait(bar(OUTEMPTY), uint32_t(chains_done - 1) & 1u);
+                tc_fence_after();
+                if (elect_one()) {
+                    // X (epilogue), Q (GEMM1: complete before S was read; transposer) of this stage are no longer needed
+                    mbar_arrive(bar(EMPTY0 + it % NSTAGE));
+                    TC_TRACE(TR_G2_ISSUE, it);
+                    if (first) issue_g2(it, true, last); else issue_g2(it, false, last);
                 }
-                const int64_t g = g0 + it;
-                const int64_t own0 = (g / T) * OWN, oth0 = (g % T) * OTH;
-                // tile rows in memory: MODE 0: OWN rows x OTH floats ; MODE 1: OTH rows x OWN floats
-                const int64_t r0 = MODE == 0 ? own0 : oth0, c0 = MODE == 0 ? oth0 : own0;
-                constexpr int TR = MODE == 0 ? OWN : OTH, TCB = (MODE == 0 ? OTH : OWN) * 4;   // rows, bytes per row
-                constexpr int LPR = TCB / 128 + 1;                                            // lines a row segment can touch
-                const int64_t cend = (c0 + TCB / 4 < prm.x_cols ? c0 + TCB / 4 : prm.x_cols) * 4;
-#pragma unroll 4
-                for (int idx = lane; idx < TR * LPR; idx += 32) {
-                    const int r = idx / LPR, kk = idx % LPR;
-                    const int64_t row = r0 + r;
-                    const int64_t seg0 = row * pitch + c0 * 4, seg1 = row * pitch + cend;
-                    const int64_t a = (seg0 & ~int64_t(127)) + kk * 128;
-                    if (row < prm.x_rows && a < seg1)
-                        asm volatile("prefetch.global.L2 [%0];" ::"l"(xb + a));
-                }
+                __syncwarp();
+                if (last) chains_done++;
+                if (++t2 == T) { t2 = 0; c2 = 0; }
+                else if (++c2 == chain) c2 = 0;
             }
         }
-    } else if (warp >= 4) {
-        // ================================ epilogue ================================
+    } else if (warp == W_QT) {
+        // =============================== Q^T transposer ================================
+        // Q tile (64 other rows x 32 components, 128-byte rows, 16-byte chunk c of row j at position c ^ (j & 7)) ->
+        // Q^T as two K-blocks of 32 component rows x 32 other columns in the same swizzle.  Lane = other row inside the
+        // K-block: eight conflict-free 128-bit reads, thirty-two conflict-free 32-bit writes per block and part.
+        for (int it = 0; it < n_it; it++) {
+            const int s = it % NSTAGE, qs = it % NQT;
+            mbar_wait(bar(FULL0 + s), uint32_t(it / NSTAGE) & 1u);
+            mbar_wait(bar(G2DONE0 + qs), (uint32_t(it / NQT) & 1u) ^ 1u);
+            const unsigned char* src = gen + SmemLayout::stage0 + s * SmemLayout::stage_bytes;
+            unsigned char* dst = gen + SmemLayout::qt0 + qs * SmemLayout::qt_bytes;
+#pragma unroll
+            for (int part = 0; part < (NSPLIT == 3 ? 2 : 1); part++) {
+                const unsigned char* sp = src + (part == 0 ? SmemLayout::q_hi : SmemLayout::q_lo);
+                unsigned char* dp = dst + (part == 0 ? SmemLayout::qt_hi : SmemLayout::qt_lo);
+#pragma unroll
+                for (int b = 0; b < 2; b++) {
+                    float4 v[8];
+#pragma unroll
+                    for (int c = 0; c < 8; c++)
+                        v[c] = *reinterpret_cast<const float4*>(sp + (b * 32 + lane) * 128 + ((c ^ (lane & 7)) << 4));
+#pragma unroll
+                    for (int c = 0; c < 8; c++) {
+                        const float e4[4] = {v[c].x, v[c].y, v[c].z, v[c].w};
+#pragma unroll
+                        for (int e = 0; e < 4; e++) {
+                            const int kidx = 4 * c + e;
+                            *reinterpret_cast<float*>(dp + b * (KC * 128) + kidx * 128 + (((lane >> 2) ^ (kidx & 7)) << 4) +
+                                                      (lane & 3) * 4) = e4[e];
+                        }
+                    }
+                }
+            }
+            fence_async_smem();              // generic-proxy writes -> visible to the tensor core's async-proxy reads
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar(QTFULL0 + qs));
+        }
+    } else {
+        // ================================ epilogue (warps 0 .. 15) ================================
         const int q = warp & 3;                   // TMEM lane quadrant (hardware: warp id % 4)
-        const int cchunk = (warp - 4) >> 2;       // which 16-column chunk of the 64-wide tile this warp converts
+        const int cchunk = warp >> 2;             // which 16-column chunk of the 64-wide tile this warp converts
         const int i = q * 32 + lane;              // own row inside the tile == TMEM lane
         const uint32_t lane_addr = tmem + (uint32_t(q * 32) << 16);
         const bool out_warp = cchunk < KC / 16;   // two warps per quadrant own the two 16-column halves of OUT
@@ -502,107 +500,106 @@ tc_pass_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_constan
             __syncwarp();
             if (lane == 0) mbar_arrive(bar(PFULL));
         };
-        if (RESID && n_it > 0) park_p(g0 / T);
+        if (RESID && n_it > 0) park_p(o_first);
         double sq = 0.0;
         float acc[16];                            // sum of the chains of the current own tile (OUT + OUT2), out_warp only
 #pragma unroll
         for (int e = 0; e < 16; e++) acc[e] = 0.0f;
         int chains_seen = 0;
+        int64_t own_tile = o_first;
+        int t = t_first, cpos = c_first;
+        const int c = cchunk;
+        // loop-invariant byte offsets of this thread's 16 X elements inside a stage (swizzle XOR folded in)
+        uint32_t xoff[MODE == 0 ? 4 : 8];
+        if (MODE == 0) {
+#pragma unroll
+            for (int gq = 0; gq < 4; gq++) {
+                const int j = c * 16 + gq * 4;
+                const int blk = j >> 5, ch = (j & 31) >> 2;
+                xoff[gq] = uint32_t(SmemLayout::x + blk * (OWN * 128) + i * 128 + ((ch ^ (i & 7)) << 4));
+            }
+        } else {
+            const int blk = i >> 5, ch = (i & 31) >> 2, w = i & 3;
+#pragma unroll
+            for (int m = 0; m < 8; m++)       // m = j & 7 for the other index j = 16c + 4gq + e
+                xoff[m] = uint32_t(SmemLayout::x + blk * (OTH * 128) + c * 16 * 128 + ((ch ^ m) << 4) + w * 4);
+        }
         for (int it = 0; it < n_it; it++) {
             const int s = it % NSTAGE, sb = it & 1;
-            const int64_t g = g0 + it;
-            const int64_t own_tile = g / T, t = g % T;
-            const int64_t own0 = own_tile * OWN, oth0 = t * OTH;
+            const int64_t own0 = own_tile * OWN, oth0 = int64_t(t) * OTH;
             const bool own_ok = own0 + i < prm.own_n;
             mbar_wait(bar(FULL0 + s), uint32_t(it / NSTAGE) & 1u);
-            if (warp == 4 && lane == 0) TC_TRACE(TR_FULL_SEEN_EPI, it);
+            if (warp == 0 && lane == 0) TC_TRACE(TR_FULL_SEEN_EPI, it);
+            const unsigned char* xs = gen + SmemLayout::stage0 + s * SmemLayout::stage_bytes;
+            // this thread's 16 elements of the X tile (other indices j = 16c .. 16c + 15), read while GEMM1 still runs
+            float xv[16];
+            if (MODE == 0) {
+#pragma unroll
+                for (int gq = 0; gq < 4; gq++) {
+                    const float4 t4 = *reinterpret_cast<const float4*>(xs + xoff[gq]);
+                    xv[gq * 4] = t4.x; xv[gq * 4 + 1] = t4.y; xv[gq * 4 + 2] = t4.z; xv[gq * 4 + 3] = t4.w;
+                }
+            } else {
+#pragma unroll
+                for (int e = 0; e < 16; e++) xv[e] = *reinterpret_cast<const float*>(xs + xoff[e & 7] + e * 128);
+            }
+            float rr[16];
             if (RESID) {
                 mbar_wait(bar(SFULL0 + sb), uint32_t(it >> 1) & 1u);
                 tc_fence_after();
-            }
-            if (warp == 4 && lane == 0) TC_TRACE(TR_S_SEEN, it);
-            if (lane == 0) TC_TRACE(TR_W_S + (warp - 4), it);
-            const unsigned char* xs = gen + SmemLayout::stage0 + s * SmemLayout::stage_bytes + SmemLayout::x;
-            float sq_tile = 0.0f;
-            // interior tiles need no bounds masks; the masked path only runs on the last row / column tiles
-            const bool interior = (own0 + OWN <= prm.own_n) && (oth0 + OTH <= prm.oth_n);
-            const int64_t oth_rem = prm.oth_n - oth0;
-            const int oth_left = oth_rem < OTH ? int(oth_rem) : OTH;
-            {
-                const int c = cchunk;
+                if (warp == 0 && lane == 0) TC_TRACE(TR_S_SEEN, it);
                 float sv[16];
-                if (RESID) {
-                    tmem_ld16(lane_addr + uint32_t(TM_S + sb * OTH + c * 16), sv);
-                }
-                if (lane == 0) TC_TRACE(TR_W_LD + (warp - 4), it);
-                float rr[16];
+                tmem_ld16(lane_addr + uint32_t(TM_S + sb * OTH + c * 16), sv);
+                if (!LOGIT) {
+                    // Linear link: no bounds masks.  Out-of-range other rows of Q and out-of-range own rows of P are zero
+                    // (TMA zero fill / park_p), so S is exactly 0 there, and so is X (TMA zero fill): R = 0 - 0.
 #pragma unroll
-                for (int gq = 0; gq < 4; gq++) {
-                    // 4 consecutive other-indices j = 16c + 4gq + e
-                    float xv[4];
-                    if (MODE == 0) {
-                        const int j = c * 16 + gq * 4;
-                        const int blk = j >> 5, ch = (j & 31) >> 2;
-                        const float4 t4 = *reinterpret_cast<const float4*>(xs + blk * (OWN * 128) + i * 128 +
-                                                                           ((ch ^ (i & 7)) << 4));
-                        xv[0] = t4.x; xv[1] = t4.y; xv[2] = t4.z; xv[3] = t4.w;
-                    } else {
-                        const int blk = i >> 5, ch = (i & 31) >> 2, w = i & 3;
+                    for (int e = 0; e < 16; e++) rr[e] = sv[e] - xv[e];
+                } else {
 #pragma unroll
-                        for (int e = 0; e < 4; e++) {
-                            const int j = c * 16 + gq * 4 + e;
-                            xv[e] = *reinterpret_cast<const float*>(xs + blk * (OTH * 128) + j * 128 +
-                                                                    ((ch ^ (j & 7)) << 4) + w * 4);
-                        }
-                    }
+                    for (int e = 0; e < 16; e++) rr[e] = 1.0f / (1.0f + __expf(-sv[e])) - xv[e];
+                    // sigmoid(0) = 0.5 outside the matrix: the last row / column tiles are masked
+                    const bool interior = (own0 + OWN <= prm.own_n) && (oth0 + OTH <= prm.oth_n);
+                    if (!interior) {
+                        const int64_t oth_rem = prm.oth_n - oth0;
+                        const int oth_left = oth_rem < OTH ? int(oth_rem) : OTH;
 #pragma unroll
-                    for (int e = 0; e < 4; e++) {
-                        float r;
-                        if (RESID) {
-                            float est = sv[gq * 4 + e];
-                            if (prm.link == PYCMF_LOGIT) est = 1.0f / (1.0f + __expf(-est));
-                            r = est - xv[e];
-                        } else {
-                            r = xv[e];                         // TMA zero-fills out-of-range elements
-                        }
-                        rr[gq * 4 + e] = r;
+                        for (int e = 0; e < 16; e++)
+                            if (!own_ok || c * 16 + e >= oth_left) rr[e] = 0.0f;
                     }
                 }
-                if (RESID && !interior) {
-#pragma unroll
-                    for (int e = 0; e < 16; e++)
-                        if (!own_ok || c * 16 + e >= oth_left) rr[e] = 0.0f;
-                }
-                if (RESID) {
+                if (prm.sq_part != nullptr) {
+                    float sq_tile = 0.0f;
 #pragma unroll
                     for (int e = 0; e < 16; e++) sq_tile = fmaf(rr[e], rr[e], sq_tile);
+                    sq += double(sq_tile);
                 }
-                // tf32 split by truncation: hi = r with the 13 low mantissa bits cleared (exact tf32), lo = r - hi (exact
-                // in fp32; the tensor core reads its top 19 bits) -> hi*hi + hi*lo + lo*hi carries ~2^-20 relative error
-                float hi[16], lo[16];
+            } else {
 #pragma unroll
-                for (int e = 0; e < 16; e++) {
-                    hi[e] = NSPLIT == 3 ? __uint_as_float(__float_as_uint(rr[e]) & 0xffffe000u) : rr[e];
-                    lo[e] = rr[e] - hi[e];
-                }
-                // R buffer it & 1 in tensor memory: GEMM2 of tile it - 2 must have drained it
-                mbar_wait(bar(REMPTY0 + sb), (uint32_t(it >> 1) & 1u) ^ 1u);
-                tc_fence_after();
-                if (lane == 0) TC_TRACE(TR_W_RE + (warp - 4), it);
-                const uint32_t r_hi = lane_addr + uint32_t(TM_R + sb * 2 * OTH + c * 16);
-                tmem_st16(r_hi, hi);
-                if (NSPLIT == 3) tmem_st16(r_hi + OTH, lo);
-                tmem_st_wait();
+                for (int e = 0; e < 16; e++) rr[e] = xv[e];           // TMA zero-fills out-of-range elements
             }
-            sq += double(sq_tile);
+            // tf32 split by truncation: hi = r with the 13 low mantissa bits cleared (exact tf32), lo = r - hi (exact
+            // in fp32; the tensor core reads its top 19 bits) -> hi*hi + hi*lo + lo*hi carries ~2^-20 relative error
+            float hi[16], lo[16];
+#pragma unroll
+            for (int e = 0; e < 16; e++) {
+                hi[e] = NSPLIT == 3 ? __uint_as_float(__float_as_uint(rr[e]) & 0xffffe000u) : rr[e];
+                lo[e] = rr[e] - hi[e];
+            }
+            // R buffer it & 1 in tensor memory: GEMM2 of tile it - 2 must have drained it
+            mbar_wait(bar(G2DONE0 + sb), (uint32_t(it >> 1) & 1u) ^ 1u);
+            tc_fence_after();
+            const uint32_t r_hi = lane_addr + uint32_t(TM_R + sb * 2 * OTH + c * 16);
+            tmem_st16(r_hi, hi);
+            if (NSPLIT == 3) tmem_st16(r_hi + OTH, lo);
+            tmem_st_wait();
             tc_fence_before();
             __syncwarp();
             if (lane == 0) {
                 mbar_arrive(bar(RFULL0 + sb));
-                if (warp == 4) TC_TRACE(TR_R_DONE, it);
-                TC_TRACE(TR_W_R + (warp - 4), it);
+                if (warp == 0) TC_TRACE(TR_R_DONE, it);
             }
-            const bool last = last_of_chain(it, t);
+            const bool last = last_of_chain(it, t, cpos);
             const bool own_ends = (it == n_it - 1) || (t == T - 1);
             // the next tile belongs to another own tile: its P may go to tensor memory now (every GEMM1 that read the
             // old P has completed: this warp has just consumed the S of the last one)
@@ -638,6 +635,8 @@ tc_pass_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_constan
                 }
             }
             if (last) chains_seen++;
+            if (++t == T) { t = 0; cpos = 0; own_tile++; }
+            else if (++cpos == chain) cpos = 0;
         }
         if (RESID && prm.sq_part != nullptr) {
             sq = warp_sum(sq);
@@ -647,7 +646,7 @@ tc_pass_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_constan
     }
     __syncthreads();
     if (RESID && prm.sq_part != nullptr && threadIdx.x == 0) prm.sq_part[blockIdx.x] = *sq_slot;
-    if (warp == 2) {
+    if (warp == W_QT) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(uint32_t(TMEM_COLS)) : "memory");
     }
@@ -738,8 +737,8 @@ struct FactorParts {
 CUtensorMap factor_map(const float* p, int64_t rows, int box_rows) { return make_map(p, rows, KC, KC, box_rows); }
 CUtensorMap factor_t_map(const float* p, int64_t rows, int64_t ldt) { return make_map(p, KC, rows, ldt, KC); }
 
-template <int MODE, bool RESID, int NSPLIT>
-void launch_tc(pycmf_ctx* ctx, int64_t own_n, int64_t oth_n, const FactorParts& P, const FactorParts& Q,
+template <int MODE, bool RESID, int NSPLIT, bool LOGIT>
+void launch_tc_impl(pycmf_ctx* ctx, int64_t own_n, int64_t oth_n, const FactorParts& P, const FactorParts& Q,
                const float* X, int64_t x_rows, int64_t x_cols, int64_t ldx, int link, float* out, double* sq) {
     const int64_t own_tiles = ceil_div(own_n, OWN), T = ceil_div(oth_n, OTH), G = own_tiles * T;
     // one persistent CTA per SM; options for tests: tc_ctas caps the CTA count, tc_max_splits = s keeps the old meaning
@@ -778,7 +777,7 @@ void launch_tc(pycmf_ctx* ctx, int64_t own_n, int64_t oth_n, const FactorParts& 
     prm.sq_part = nullptr;
     prm.trace = ctx->tc_trace ? static_cast<long long*>(scratch(ctx, 2, sizeof(long long) * TR_NEVENTS * TRACE_TILES)) : nullptr;
     if (RESID && sq != nullptr) prm.sq_part = static_cast<double*>(scratch(ctx, 1, size_t(n_cta) * sizeof(double)));
-    auto kern = tc_pass_kernel<MODE, RESID, NSPLIT>;
+    auto kern = tc_pass_kernel<MODE, RESID, NSPLIT, LOGIT>;
     const size_t smem = SmemLayout::total + 1024;
     PYCMF_CHECK(smem <= size_t(ctx->max_smem_optin), "tc pass: shared memory budget exceeded");
     PYCMF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
@@ -791,6 +790,15 @@ void launch_tc(pycmf_ctx* ctx, int64_t own_n, int64_t oth_n, const FactorParts& 
                                                                                        prm.part, out);
     PYCMF_LAUNCH_CHECK(ctx);
     if (prm.sq_part != nullptr) final_sum(ctx, int(n_cta), prm.sq_part, 1.0, sq, true);
+}
+
+template <int MODE, bool RESID, int NSPLIT>
+void launch_tc(pycmf_ctx* ctx, int64_t own_n, int64_t oth_n, const FactorParts& P, const FactorParts& Q,
+               const float* X, int64_t x_rows, int64_t x_cols, int64_t ldx, int link, float* out, double* sq) {
+    if (RESID && link == PYCMF_LOGIT)
+        launch_tc_impl<MODE, RESID, NSPLIT, RESID>(ctx, own_n, oth_n, P, Q, X, x_rows, x_cols, ldx, link, out, sq);
+    else
+        launch_tc_impl<MODE, RESID, NSPLIT, false>(ctx, own_n, oth_n, P, Q, X, x_rows, x_cols, ldx, link, out, sq);
 }
 
 size_t parts_floats(int64_t rows) { return size_t(2) * rows * KC + size_t(2) * KC * ((rows + 3) & ~int64_t(3)); }

@@ -27,10 +27,6 @@ def show(tag):
     print("tile " + " ".join("%13s" % s for s in names))
     for it in range(20):
         print("%4d " % it + " ".join("%13d" % (t[e, it] - t0 if t[e, it] else -1) for e in range(7)))
-    for label, base in (("S seen", 8), ("S loaded", 24), ("R buffer free", 40), ("R published", 56)):
-        print("-- per epilogue warp (columns = warps 4..19), cycles after this tile's g1_issue: " + label)
-        for it in range(8, 14):
-            print("%4d " % it + " ".join("%6d" % (t[base + w, it] - t[1, it]) for w in range(16)))
 for rep in range(2):
     gx, Hx, pr = be.newton_v_xpart(V, U, Xd, 0, d, "linear", 1.0)
 show("resid RIGHT")
