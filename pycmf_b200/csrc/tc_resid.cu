@@ -10,8 +10,9 @@
 // for RIGHT; 64 "other" rows per tile).  Per tile:
 //   TMA        : X tile (128 x 64 fp32, SWIZZLE_128B) + the 64 x 32 factor tile Q (tf32 hi / lo parts) into a
 //                4-stage shared-memory ring (48 KB per stage)
-//   transposer : one warp turns the Q tile into the K-major Q^T tile GEMM2 needs (two-slot ring), on chip:
-//                loading Q^T through TMA as well doubled the factor traffic and cost the ring its fourth stage
+//   transpose  : the epilogue warps turn the Q tile into the K-major Q^T tile GEMM2 needs (two slots), on chip, each
+//                warp 1/16 of it next to its R stores: loading Q^T through TMA as well doubled the factor traffic and
+//                cost the ring its fourth stage; a single transposer warp needed 1700 clk per tile (measured)
 //   tcgen05.mma: S[128 x 64]  = P Q^T     GEMM1, A operand P resident in TENSOR MEMORY for the whole own tile
 //   epilogue   : tcgen05.ld S -> f() -> minus X -> R (tf32 hi / lo) -> tcgen05.st back into TENSOR MEMORY
 //   tcgen05.mma: OUT[128 x 32] += R Q     GEMM2, A operand R read from tensor memory, B = K-major Q^T tile
@@ -24,8 +25,9 @@
 //
 // Warp roles (640 threads): warps 0-15 = epilogue (warp w works on TMEM lane quadrant w % 4 and on the 16-column chunk
 // w / 4 of the 64-wide tile, so every SM sub-partition has four epilogue warps); warp 16 = TMA producer, 17 = GEMM2
-// issuer, 18 = Q^T transposer + TMEM allocator, 19 = GEMM1 issuer.  The control warps have the highest warp ids on
-// purpose: the issue arbiter prefers high warp ids, and a late MMA issue stalls everything.
+// issuer (hi*hi chain into OUT), 18 = GEMM2 issuer of the correction terms (into OUT2), 19 = GEMM1 issuer.  Several issuing warps because one thread cannot feed the tensor pipe with N = 32 MMAs
+// (profiles/r01_mma_issue_mix.txt: one warp 1035 clk per tile's worth of MMAs, two warps 614).  The control warps have
+// the highest warp ids on purpose: the issue arbiter prefers high warp ids, and a late MMA issue stalls everything.
 #include <cuda.h>
 
 #include "common.cuh"
@@ -41,7 +43,7 @@ constexpr int NQT = 2;             // Q^T slots (produced on chip from the Q til
 constexpr int PREFETCH_DIST = 8;   // X tiles requested into L2 ahead of the shared-memory ring
 constexpr int EPI_WARPS = 16;
 constexpr int NTHREADS = 32 * EPI_WARPS + 128;
-constexpr int W_TMA = EPI_WARPS, W_G2 = EPI_WARPS + 1, W_QT = EPI_WARPS + 2, W_G1 = EPI_WARPS + 3;
+constexpr int W_TMA = EPI_WARPS, W_G2 = EPI_WARPS + 1, W_G2B = EPI_WARPS + 2, W_G1 = EPI_WARPS + 3;
 static_assert(NQT == 2, "G2DONE doubles as the R-buffer and the Q^T-slot release: both rings must have two slots");
 
 // tensor-memory columns (512 x 128 lanes x 32 bit, all allocated: one CTA per SM)
@@ -71,8 +73,9 @@ struct SmemLayout {
 
 // barrier slots (8 bytes each) inside the `bars` region
 enum Bar { FULL0 = 0, EMPTY0 = FULL0 + NSTAGE, SFULL0 = EMPTY0 + NSTAGE, RFULL0 = SFULL0 + 2,
+           // RFULL(t & 1): R(t) and Q^T(t) published by the 16 epilogue warps
            G2DONE0 = RFULL0 + 2,      // GEMM2(t) complete: R buffer t & 1 and Q^T slot t & 1 are free again
-           QTFULL0 = G2DONE0 + 2, PFULL = QTFULL0 + NQT, OUTFULL, OUTEMPTY, NBARS };
+           PFULL = G2DONE0 + 2, OUTFULL, OUTEMPTY, NBARS };
 static_assert(NBARS * 8 + 32 <= 256, "barrier region too small");
 
 // ---- PTX wrappers ----------------------------------------------------------------------------
@@ -220,13 +223,10 @@ struct Params {
 __host__ __device__ __forceinline__ int64_t tile_begin(int64_t c, int64_t G, int64_t N) { return (c * G) / N; }
 __host__ __device__ __forceinline__ int64_t first_cta(int64_t g, int64_t G, int64_t N) { return ((g + 1) * N - 1) / G; }
 
-constexpr int TRACE_TILES = 32;
+constexpr int TRACE_TILES = 96;
 enum TraceEvent { TR_TMA_ISSUE = 0, TR_G1_ISSUE, TR_S_SEEN, TR_R_DONE, TR_G2_ISSUE, TR_EMPTY_SEEN, TR_FULL_SEEN_EPI,
-                  TR_W_S = 8,          // + epilogue warp index (0..15): S seen
-                  TR_W_LD = 24,        // S loaded from tensor memory
-                  TR_W_RE = 40,        // R buffer free (REMPTY seen)
-                  TR_W_R = 56,         // R published
-                  TR_NEVENTS = 72 };
+                  TR_CTA = 7,          // [0] kernel entry, [1] after the setup barrier, [2] CTA done
+                  TR_NEVENTS = 10 };
 #define TC_TRACE(ev, it)                                                                        \
     do {                                                                                        \
         if (prm.trace != nullptr && blockIdx.x == 0 && (it) < TRACE_TILES)                      \
@@ -253,6 +253,12 @@ tc_pass_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_constan
     auto bar = [&](int i) { return bars + 8u * uint32_t(i); };
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) TC_TRACE(TR_CTA, 0);
+    if (prm.trace != nullptr && threadIdx.x == 0) {
+        long long gt;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+        prm.trace[TR_NEVENTS * TRACE_TILES + 2 * blockIdx.x] = gt;
+    }
     const int64_t T = prm.n_oth_tiles;
     const int64_t g0 = tile_begin(blockIdx.x, prm.n_tiles, gridDim.x);
     const int n_it = int(tile_begin(int64_t(blockIdx.x) + 1, prm.n_tiles, gridDim.x) - g0);
@@ -266,17 +272,16 @@ tc_pass_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_constan
         for (int s = 0; s < 2; s++) {
             mbar_init(bar(SFULL0 + s), 1);
             mbar_init(bar(RFULL0 + s), EPI_WARPS);
-            mbar_init(bar(G2DONE0 + s), 1);
-            mbar_init(bar(QTFULL0 + s), 1);
+            mbar_init(bar(G2DONE0 + s), NSPLIT == 3 ? 2 : 1);     // both GEMM2 issuers commit
         }
         mbar_init(bar(PFULL), EPI_WARPS);
-        mbar_init(bar(OUTFULL), 1);
+        mbar_init(bar(OUTFULL), NSPLIT == 3 ? 2 : 1);
         mbar_init(bar(OUTEMPTY), 2 * 4);          // the eight warps that read OUT
         *sq_slot = 0.0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         fence_async_smem();
     }
-    if (warp == W_QT) {
+    if (warp == W_TMA) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
                      "r"(uint32_t(TMEM_COLS)) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -285,6 +290,7 @@ tc_pass_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_constan
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
+    if (threadIdx.x == 0) TC_TRACE(TR_CTA, 1);
     const int64_t o_first = g0 / T;
     const int t_first = int(g0 % T);               // the only 64-bit divisions: every role walks (own tile, t) incrementally
     const int c_first = t_first % chain;
@@ -333,7 +339,7 @@ tc_pass_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_constan
             __syncwarp();
             if (++t == T) { t = 0; o++; }
         }
-    } else if (warp == W_G1 || warp == W_G2) {
+    } else if (warp == W_G1 || warp == W_G2 || warp == W_G2B) {
         // =============================== MMA issuers ================================
         // Each of the two warps walks its schedule converged, with blocking waits; one elected lane issues the MMAs and
         // the commits (tcgen05.commit tracks the MMAs of the issuing thread: elect.sync always picks the same lane).
@@ -381,17 +387,26 @@ tc_pass_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_constan
                 }
             }
         } else {
-            // GEMM2(it) needs R(it) published (RFULL: X and S of the tile consumed), Q^T(it) written (QTFULL: Q consumed)
+            // GEMM2(it) needs R(it) and Q^T(it) published (RFULL: X, S and Q of the tile consumed)
             // and, at the start of a chain, the previous chain's OUT read (OUTEMPTY).  Corrections go to their own
             // accumulator OUT2 (their rounding is relative to 2^-11 |OUT|), only the eight hi*hi MMAs per tile extend the
             // long chain in OUT; the epilogue adds OUT + OUT2.
+            uint64_t dqt_hi[2], dqt_lo[2];
+#pragma unroll
+            for (int b = 0; b < 2; b++) {
+                const uint32_t qt = base + SmemLayout::qt0 + uint32_t(b) * SmemLayout::qt_bytes;
+                dqt_hi[b] = make_desc(qt + SmemLayout::qt_hi, 16, 1024);
+                dqt_lo[b] = make_desc(qt + SmemLayout::qt_lo, 16, 1024);
+            }
+            const bool main_issuer = warp == W_G2;       // hi*hi into OUT; the other warp: hi*lo + lo*hi into OUT2
+            const int n_g2 = (NSPLIT == 1 && !main_issuer) ? 0 : n_it;   // 1xTF32: no correction terms, no second issuer
             auto issue_g2 = [&](int it, bool first, bool last) {
                 const int rb = it & 1;
                 const uint32_t r_hi = tmem + uint32_t(TM_R + rb * 2 * OTH), r_lo = r_hi + OTH;
-                const uint32_t qt = base + SmemLayout::qt0 + uint32_t(rb) * SmemLayout::qt_bytes;
-                const uint64_t qh = make_desc(qt + SmemLayout::qt_hi, 16, 1024), ql = make_desc(qt + SmemLayout::qt_lo, 16, 1024);
+                const uint64_t qh = rb ? dqt_hi[1] : dqt_hi[0], ql = rb ? dqt_lo[1] : dqt_lo[0];
 #pragma unroll
                 for (int term = 0; term < NSPLIT; term++) {
+                    if ((term == 0) != main_issuer) continue;
                     const uint32_t d = tmem + uint32_t(term == 0 ? TM_OUT : TM_OUT2);
                     const uint32_t ra = (term == 2) ? r_lo : r_hi;
                     const uint64_t qa = (term == 1) ? ql : qh;
@@ -407,16 +422,17 @@ tc_pass_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_constan
                 if (last) umma_commit(bar(OUTFULL));
             };
             int t2 = t_first, c2 = c_first, chains_done = 0;
-            for (int it = 0; it < n_it; it++) {
+            for (int it = 0; it < n_g2; it++) {
                 const bool first = first_of_chain(it, c2), last = last_of_chain(it, t2, c2);
                 mbar_wait(bar(RFULL0 + (it & 1)), uint32_t(it >> 1) & 1u);
-                mbar_wait(bar(QTFULL0 + (it & 1)), uint32_t(it >> 1) & 1u);
                 if (first && chains_done > 0) mbar_wait(bar(OUTEMPTY), uint32_t(chains_done - 1) & 1u);
                 tc_fence_after();
                 if (elect_one()) {
                     // X (epilogue), Q (GEMM1: complete before S was read; transposer) of this stage are no longer needed
-                    mbar_arrive(bar(EMPTY0 + it % NSTAGE));
-                    TC_TRACE(TR_G2_ISSUE, it);
+                    if (main_issuer) {
+                        mbar_arrive(bar(EMPTY0 + it % NSTAGE));
+                        TC_TRACE(TR_G2_ISSUE, it);
+                    }
                     if (first) issue_g2(it, true, last); else issue_g2(it, false, last);
                 }
                 __syncwarp();
@@ -424,43 +440,6 @@ tc_pass_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_constan
                 if (++t2 == T) { t2 = 0; c2 = 0; }
                 else if (++c2 == chain) c2 = 0;
             }
-        }
-    } else if (warp == W_QT) {
-        // =============================== Q^T transposer ================================
-        // Q tile (64 other rows x 32 components, 128-byte rows, 16-byte chunk c of row j at position c ^ (j & 7)) ->
-        // Q^T as two K-blocks of 32 component rows x 32 other columns in the same swizzle.  Lane = other row inside the
-        // K-block: eight conflict-free 128-bit reads, thirty-two conflict-free 32-bit writes per block and part.
-        for (int it = 0; it < n_it; it++) {
-            const int s = it % NSTAGE, qs = it % NQT;
-            mbar_wait(bar(FULL0 + s), uint32_t(it / NSTAGE) & 1u);
-            mbar_wait(bar(G2DONE0 + qs), (uint32_t(it / NQT) & 1u) ^ 1u);
-            const unsigned char* src = gen + SmemLayout::stage0 + s * SmemLayout::stage_bytes;
-            unsigned char* dst = gen + SmemLayout::qt0 + qs * SmemLayout::qt_bytes;
-#pragma unroll
-            for (int part = 0; part < (NSPLIT == 3 ? 2 : 1); part++) {
-                const unsigned char* sp = src + (part == 0 ? SmemLayout::q_hi : SmemLayout::q_lo);
-                unsigned char* dp = dst + (part == 0 ? SmemLayout::qt_hi : SmemLayout::qt_lo);
-#pragma unroll
-                for (int b = 0; b < 2; b++) {
-                    float4 v[8];
-#pragma unroll
-                    for (int c = 0; c < 8; c++)
-                        v[c] = *reinterpret_cast<const float4*>(sp + (b * 32 + lane) * 128 + ((c ^ (lane & 7)) << 4));
-#pragma unroll
-                    for (int c = 0; c < 8; c++) {
-                        const float e4[4] = {v[c].x, v[c].y, v[c].z, v[c].w};
-#pragma unroll
-                        for (int e = 0; e < 4; e++) {
-                            const int kidx = 4 * c + e;
-                            *reinterpret_cast<float*>(dp + b * (KC * 128) + kidx * 128 + (((lane >> 2) ^ (kidx & 7)) << 4) +
-                                                      (lane & 3) * 4) = e4[e];
-                        }
-                    }
-                }
-            }
-            fence_async_smem();              // generic-proxy writes -> visible to the tensor core's async-proxy reads
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bar(QTFULL0 + qs));
         }
     } else {
         // ================================ epilogue (warps 0 .. 15) ================================
@@ -505,7 +484,9 @@ tc_pass_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_constan
         float acc[16];                            // sum of the chains of the current own tile (OUT + OUT2), out_warp only
 #pragma unroll
         for (int e = 0; e < 16; e++) acc[e] = 0.0f;
-        int chains_seen = 0;
+        int chains_seen = 0;                      // chains whose OUT this (out) warp has read
+        bool pend = false, pend_own_ends = false; // a finished chain whose OUT has not been read yet
+        int64_t pend_own_tile = 0;
         int64_t own_tile = o_first;
         int t = t_first, cpos = c_first;
         const int c = cchunk;
@@ -524,6 +505,18 @@ tc_pass_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_constan
             for (int m = 0; m < 8; m++)       // m = j & 7 for the other index j = 16c + 4gq + e
                 xoff[m] = uint32_t(SmemLayout::x + blk * (OTH * 128) + c * 16 * 128 + ((ch ^ m) << 4) + w * 4);
         }
+        // this warp's share of the transposition Q tile (64 other rows x 32 components, 128-byte rows, 16-byte chunk cc of
+        // row j at position cc ^ (j & 7)) -> Q^T as two K-blocks of 32 component rows x 32 other columns in the same
+        // swizzle: K-block qb, chunk qc of every row of the block (lane = other row inside the block): one conflict-free
+        // 128-bit read and four conflict-free 32-bit writes per part
+        const int qb = warp >> 3, qc = warp & 7;
+        const uint32_t qsrc = uint32_t((qb * 32 + lane) * 128 + ((qc ^ (lane & 7)) << 4));
+        uint32_t qdst[4];
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+            const int kidx = 4 * qc + e;
+            qdst[e] = uint32_t(SmemLayout::qt0 + qb * (KC * 128) + kidx * 128 + (((lane >> 2) ^ (kidx & 7)) << 4) + (lane & 3) * 4);
+        }
         for (int it = 0; it < n_it; it++) {
             const int s = it % NSTAGE, sb = it & 1;
             const int64_t own0 = own_tile * OWN, oth0 = int64_t(t) * OTH;
@@ -531,7 +524,11 @@ tc_pass_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_constan
             mbar_wait(bar(FULL0 + s), uint32_t(it / NSTAGE) & 1u);
             if (warp == 0 && lane == 0) TC_TRACE(TR_FULL_SEEN_EPI, it);
             const unsigned char* xs = gen + SmemLayout::stage0 + s * SmemLayout::stage_bytes;
-            // this thread's 16 elements of the X tile (other indices j = 16c .. 16c + 15), read while GEMM1 still runs
+            // this thread's 4 + 4 elements of the Q tile and 16 elements of the X tile (other indices j = 16c .. 16c + 15),
+            // read while GEMM1 still runs
+            const float4 qv_hi = *reinterpret_cast<const float4*>(xs + SmemLayout::q_hi + qsrc);
+            float4 qv_lo = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (NSPLIT == 3) qv_lo = *reinterpret_cast<const float4*>(xs + SmemLayout::q_lo + qsrc);
             float xv[16];
             if (MODE == 0) {
 #pragma unroll
@@ -592,6 +589,17 @@ tc_pass_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_constan
             const uint32_t r_hi = lane_addr + uint32_t(TM_R + sb * 2 * OTH + c * 16);
             tmem_st16(r_hi, hi);
             if (NSPLIT == 3) tmem_st16(r_hi + OTH, lo);
+            {
+                // Q^T slot it & 1 (free for the same reason as the R buffer)
+                unsigned char* qd = gen + sb * SmemLayout::qt_bytes;
+                const float h4[4] = {qv_hi.x, qv_hi.y, qv_hi.z, qv_hi.w}, l4[4] = {qv_lo.x, qv_lo.y, qv_lo.z, qv_lo.w};
+#pragma unroll
+                for (int e = 0; e < 4; e++) {
+                    *reinterpret_cast<float*>(qd + SmemLayout::qt_hi + qdst[e]) = h4[e];
+                    if (NSPLIT == 3) *reinterpret_cast<float*>(qd + SmemLayout::qt_lo + qdst[e]) = l4[e];
+                }
+                fence_async_smem();          // generic-proxy writes -> visible to the tensor core's async-proxy reads
+            }
             tmem_st_wait();
             tc_fence_before();
             __syncwarp();
@@ -604,8 +612,11 @@ tc_pass_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_constan
             // the next tile belongs to another own tile: its P may go to tensor memory now (every GEMM1 that read the
             // old P has completed: this warp has just consumed the S of the last one)
             if (RESID && own_ends && it + 1 < n_it) park_p(own_tile + 1);
-            if (last && out_warp) {
-                // ---- end of a chain: OUT (+ OUT2) from tensor memory into the register accumulators
+            // ---- end of a chain: OUT (+ OUT2) from tensor memory into the register accumulators.  Deferred by one tile:
+            // reading it right away would park half of the epilogue warps until the chain's last GEMM2 has drained
+            // (~2500 clk per chain, measured); one tile later OUTFULL has long completed and only GEMM2 of the new chain's
+            // first tile waits, for the few hundred cycles of the read itself.
+            auto flush_chain = [&](int64_t f_own_tile, bool f_own_ends) {
                 mbar_wait(bar(OUTFULL), uint32_t(chains_seen) & 1u);
                 tc_fence_after();
                 float o[16];
@@ -620,12 +631,13 @@ tc_pass_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_constan
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bar(OUTEMPTY));
-                if (own_ends) {
+                chains_seen++;
+                if (f_own_ends) {
                     // ---- one partial per (CTA, own tile)
-                    const int64_t entry = int64_t(blockIdx.x) - first_cta(own_tile * T, prm.n_tiles, gridDim.x);
-                    if (own_ok) {
+                    const int64_t entry = int64_t(blockIdx.x) - first_cta(f_own_tile * T, prm.n_tiles, gridDim.x);
+                    if (f_own_tile * OWN + i < prm.own_n) {
                         float4* dst = reinterpret_cast<float4*>(
-                            prm.part + ((own_tile * prm.max_entries + entry) * OWN + i) * KC + cchunk * 16);
+                            prm.part + ((f_own_tile * prm.max_entries + entry) * OWN + i) * KC + cchunk * 16);
 #pragma unroll
                         for (int e = 0; e < 4; e++)
                             dst[e] = make_float4(acc[4 * e], acc[4 * e + 1], acc[4 * e + 2], acc[4 * e + 3]);
@@ -633,8 +645,15 @@ tc_pass_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_constan
 #pragma unroll
                     for (int e = 0; e < 16; e++) acc[e] = 0.0f;
                 }
+            };
+            if (out_warp) {
+                if (pend) flush_chain(pend_own_tile, pend_own_ends);
+                pend = false;
+                if (last) {
+                    if (it == n_it - 1) flush_chain(own_tile, true);
+                    else { pend = true; pend_own_tile = own_tile; pend_own_ends = own_ends; }
+                }
             }
-            if (last) chains_seen++;
             if (++t == T) { t = 0; cpos = 0; own_tile++; }
             else if (++cpos == chain) cpos = 0;
         }
@@ -645,8 +664,14 @@ tc_pass_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_constan
         tc_fence_before();
     }
     __syncthreads();
+    if (threadIdx.x == 0) TC_TRACE(TR_CTA, 2);
+    if (prm.trace != nullptr && threadIdx.x == 0) {
+        long long gt;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+        prm.trace[TR_NEVENTS * TRACE_TILES + 2 * blockIdx.x + 1] = gt;
+    }
     if (RESID && prm.sq_part != nullptr && threadIdx.x == 0) prm.sq_part[blockIdx.x] = *sq_slot;
-    if (warp == W_QT) {
+    if (warp == W_TMA) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(uint32_t(TMEM_COLS)) : "memory");
     }
@@ -775,7 +800,7 @@ void launch_tc_impl(pycmf_ctx* ctx, int64_t own_n, int64_t oth_n, const FactorPa
     prm.part = static_cast<float*>(scratch(ctx, 0, size_t(own_tiles) * max_entries * OWN * KC * sizeof(float)));
     prm.max_entries = max_entries;
     prm.sq_part = nullptr;
-    prm.trace = ctx->tc_trace ? static_cast<long long*>(scratch(ctx, 2, sizeof(long long) * TR_NEVENTS * TRACE_TILES)) : nullptr;
+    prm.trace = ctx->tc_trace ? static_cast<long long*>(scratch(ctx, 2, sizeof(long long) * (TR_NEVENTS * TRACE_TILES + 2 * 160))) : nullptr;
     if (RESID && sq != nullptr) prm.sq_part = static_cast<double*>(scratch(ctx, 1, size_t(n_cta) * sizeof(double)));
     auto kern = tc_pass_kernel<MODE, RESID, NSPLIT, LOGIT>;
     const size_t smem = SmemLayout::total + 1024;
@@ -814,7 +839,7 @@ FactorParts split_factor(pycmf_ctx* ctx, int64_t rows, const float* F, float* bu
 
 }  // namespace
 
-int tc_trace_words() { return TR_NEVENTS * TRACE_TILES; }
+int tc_trace_words() { return TR_NEVENTS * TRACE_TILES + 2 * 160; }
 
 bool tc_dense_eligible(pycmf_ctx* ctx, int64_t ra, int64_t rb, int64_t k, const float* X, int64_t ldx, bool trans_t) {
     if (ctx->dense_path == 0 || trans_t || X == nullptr) return false;

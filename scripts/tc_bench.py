@@ -20,6 +20,19 @@ for combo in itertools.product(*grid) if grid else [()]:
         U = torch.rand(n, 32, device=be.device) * 0.1
         V = torch.rand(d, 32, device=be.device) * 0.1
     Xd = DenseMatrix(X)
+    if "copy" not in globals():
+        # box calibration: a plain device copy of X (read + write bytes) and the SM clock right after it
+        Y = torch.empty_like(X)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        for _ in range(3):
+            Y.copy_(X)
+        e0.record()
+        for _ in range(10):
+            Y.copy_(X)
+        e1.record(); torch.cuda.synchronize()
+        copy = 2 * n * d * 4 * 10 / (e0.elapsed_time(e1) * 1e-3) / 1e9
+        del Y
+        print("calibration: torch copy of X %.0f GB/s (read + write)" % copy, flush=True)
     res = {}
     for name, wl, wr in (("left", True, False), ("right", False, True)):
         for _ in range(3):
