@@ -167,7 +167,9 @@ class _IterativeCMFSolver:
 
     def _graphable(self, st):
         """One iteration can be replayed as a CUDA graph when it needs no host work: single rank, no sampling."""
-        if self.use_cuda_graph is False or st.comm.world > 1 or self.sg_sample_ratio < 1.:
+        if self.use_cuda_graph is False or self.sg_sample_ratio < 1.:
+            return False
+        if st.comm.world > 1 and not getattr(st.comm, "graph_capturable", False):
             return False
         return hasattr(st.be, "capture_step")
 
@@ -182,7 +184,12 @@ class _IterativeCMFSolver:
             if state["graph"] is not None:
                 state["graph"].replay()
             elif graphable and state["eager"] >= 2:
-                state["graph"] = st.be.capture_step(lambda: self._step(st))
+                try:
+                    state["graph"] = st.be.capture_step(lambda: self._step(st))
+                except RuntimeError as e:             # capture not possible (e.g. a collective that cannot be captured)
+                    warnings.warn("CUDA-graph capture of the iteration failed, running eagerly: %s" % (e,))
+                    state["eager"] = -(10 ** 9)
+                    self._step(st)
             else:
                 self._step(st)
                 state["eager"] += 1
@@ -365,6 +372,20 @@ class NewtonSolver(_IterativeCMFSolver):
             d, k = st.V.shape
             idx_x, idx_y = m.get("Vx"), m.get("Vy")
             per_row = be.newton_v_needs_per_row(self.x_link, idx_x is not None)
+            world = st.comm.world
+            if world > 1 and not per_row and idx_y is None and d % world == 0:
+                # Shared X-side Hessian: the gradient partial is reduce-scattered by rows of V, every rank finishes its
+                # d / G rows (the per-row solves are the expensive, replicated part otherwise) and the new rows are
+                # all-gathered: the two collectives together move what one all-reduce moves.
+                gx, Hx, pr = be.newton_v_xpart(st.V, st.U, st.X, 0, d, self.x_link, alpha)
+                st.comm.all_reduce_sum(Hx)
+                gx_loc = st.comm.reduce_scatter_rows(gx)
+                j0 = st.comm.rank * (d // world)
+                j1 = j0 + d // world
+                be.newton_v_finish(st.V, st.Z, st.Y, j0, j1, self.y_link, alpha, l1, l2, gx_loc, Hx, pr,
+                                   self.V_non_negative, pert)
+                st.comm.all_gather_into(st.V, st.V[j0:j1].clone())
+                return
             step = be.v_chunk_rows(d, k, per_row)
             for j0 in range(0, d, step):
                 j1 = min(d, j0 + step)

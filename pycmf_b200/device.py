@@ -162,10 +162,12 @@ class CudaBackend:
         g = torch.cuda.CUDAGraph()
         self.profile(False)
         torch.cuda.synchronize(self.device)
-        with torch.cuda.graph(g):
-            self.use_stream(torch.cuda.current_stream(self.device))
-            fn()
-        self.use_stream(prev_stream)
+        try:
+            with torch.cuda.graph(g):
+                self.use_stream(torch.cuda.current_stream(self.device))
+                fn()
+        finally:
+            self.use_stream(prev_stream)
         g.replay()          # the captured iteration has not run yet: run it now
         return g
 

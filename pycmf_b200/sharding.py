@@ -26,6 +26,16 @@ class Comm:
     def all_gather_rows(self, t, n_total):
         return t
 
+    def reduce_scatter_rows(self, t):
+        """Sum over ranks of a (rows x k) tensor whose rows split evenly; returns this rank's row block of the sum."""
+        return t
+
+    def all_gather_into(self, out, block):
+        """out (rows x k, rows split evenly over the ranks) <- concatenation of every rank's block."""
+        if out.data_ptr() != block.data_ptr():
+            out.copy_(block)
+        return out
+
     def barrier(self):
         pass
 
@@ -39,6 +49,10 @@ class TorchComm(Comm):
         self.group = group
         self.rank = dist.get_rank(group)
         self.world = dist.get_world_size(group)
+        # NCCL collectives can be captured into the CUDA graph of one solver iteration
+        import os
+        self.graph_capturable = (dist.get_backend(group) == "nccl" and
+                                 os.environ.get("PYCMF_B200_GRAPH_COLLECTIVES", "1") != "0")
 
     def all_reduce_sum(self, t):
         if self.world > 1:
@@ -58,6 +72,34 @@ class TorchComm(Comm):
         out = [torch.empty_like(pad) for _ in range(self.world)]
         self.dist.all_gather(out, pad, group=self.group)
         return torch.cat([o[:b - a] for o, (a, b) in zip(out, sizes)], 0)
+
+    def reduce_scatter_rows(self, t):
+        """Row block `rank` of the sum over ranks of t (rows x k, rows % world == 0).  NCCL: one reduce-scatter
+        (half the traffic of an all-reduce); other backends (gloo in the CPU tests): all-reduce + slice."""
+        if self.world == 1:
+            return t
+        import torch
+        rows = t.shape[0] // self.world
+        assert rows * self.world == t.shape[0]
+        if self.dist.get_backend(self.group) == "nccl":
+            out = torch.empty((rows,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+            self.dist.reduce_scatter_tensor(out, t.contiguous(), op=self.dist.ReduceOp.SUM, group=self.group)
+            return out
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM, group=self.group)
+        return t[self.rank * rows:(self.rank + 1) * rows]
+
+    def all_gather_into(self, out, block):
+        if self.world == 1:
+            return Comm.all_gather_into(self, out, block)
+        if self.dist.get_backend(self.group) == "nccl":
+            self.dist.all_gather_into_tensor(out, block.contiguous(), group=self.group)
+            return out
+        parts = [block.new_empty(block.shape) for _ in range(self.world)]
+        self.dist.all_gather(parts, block.contiguous(), group=self.group)
+        rows = block.shape[0]
+        for r, p in enumerate(parts):
+            out[r * rows:(r + 1) * rows] = p
+        return out
 
     def barrier(self):
         if self.world > 1:
