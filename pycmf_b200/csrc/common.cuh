@@ -47,7 +47,8 @@ struct pycmf_ctx {
     pycmf_ctx* root = nullptr;
     pycmf_ctx* side = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
-    int finish_minblocks = 4;   // option: resident CTAs per SM the V-finish kernel is compiled for (2: 255 registers, 4: 128)
+    int finish_minblocks = 2;   // option: resident CTAs per SM the V-finish kernel is compiled for (2: 255 registers, no
+                                // spills: 86 us on C2; 3: 168 registers: 91 us; 4: 128 registers, spills: 187 us)
     int side_streams = 1;    // option: 0 runs the side branches on the main stream (serial)
 };
 

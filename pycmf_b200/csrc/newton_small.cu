@@ -127,9 +127,9 @@ newton_finish_small_kernel(int64_t rows, int l, int k, T* __restrict__ F, const 
         const double sgn = vd > 0.0 ? 1.0 : (vd < 0.0 ? -1.0 : 0.0);
         const double gfull = act ? double(g) + l1 * sgn + l2 * vd : 0.0;
         // ---- the clamped solve in float64 (l2 on the diagonal)
-        double a[KT];
-        const bool fac = wsolve::safe_factor_warp<KT, T>(Wr, l2_diag, k, lane, pert, chol_fastpath, known_pd, W, a);
-        const double x = wsolve::safe_apply_warp<KT>(fac, a, k, lane, gfull, pert, W);
+        double a[KT], dinv;
+        const bool fac = wsolve::safe_factor_warp<KT, T>(Wr, l2_diag, k, lane, pert, chol_fastpath, known_pd, W, a, &dinv);
+        const double x = wsolve::safe_apply_warp<KT>(fac, a, dinv, k, lane, gfull, pert, W);
         __syncwarp();
         if (act) {
             double f = vd - x;
@@ -154,7 +154,8 @@ pd_flag_kernel(int k, const T* __restrict__ H, double scale, double diag, double
         if (c == lane && act) tr = fabs(a[c]);
     }
     tr = warp_sum(tr);
-    const bool ok = wsolve::chol_reg<KT>(a, lane, 1e-13 * (tr + pert), W);
+    double dinv;
+    const bool ok = wsolve::chol_reg<KT>(a, lane, 1e-13 * (tr + pert), W, &dinv);
     if (lane == 0) *flag = ok ? 1 : 0;
 }
 
@@ -169,7 +170,7 @@ safe_solve_small_kernel(int64_t batch, int k, const T* __restrict__ H, int64_t h
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;   // 1 or WARPS warps per CTA
     double* W = Wall + warp * TILE;
     const bool act = lane < k;
-    double a[KT];
+    double a[KT], dinv = 1.0;
     bool fac = false, have = false;
     for (int64_t b = int64_t(blockIdx.x) * nwarps + warp; b < batch; b += int64_t(gridDim.x) * nwarps) {
         if (!have || h_stride != 0) {
@@ -178,7 +179,7 @@ safe_solve_small_kernel(int64_t batch, int k, const T* __restrict__ H, int64_t h
 #pragma unroll
             for (int c = 0; c < KT; c++)
                 Hr[c] = (act && c <= lane) ? h_scale * double(Hb[lane * k + c]) : 0.0;
-            fac = wsolve::safe_factor_warp<KT, double>(Hr, l2_diag, k, lane, pert, chol_fastpath, known_pd, W, a);
+            fac = wsolve::safe_factor_warp<KT, double>(Hr, l2_diag, k, lane, pert, chol_fastpath, known_pd, W, a, &dinv);
             have = true;
         }
         double gr = act ? double(g[b * k + lane]) : 0.0;
@@ -187,7 +188,7 @@ safe_solve_small_kernel(int64_t batch, int k, const T* __restrict__ H, int64_t h
             f = double(out[b * k + lane]);
             gr += l1 * (f > 0.0 ? 1.0 : (f < 0.0 ? -1.0 : 0.0)) + l2 * f;
         }
-        const double x = wsolve::safe_apply_warp<KT>(fac, a, k, lane, gr, pert, W);
+        const double x = wsolve::safe_apply_warp<KT>(fac, a, dinv, k, lane, gr, pert, W);
         __syncwarp();
         if (act) {
             if (MODE == 0) {
@@ -251,12 +252,13 @@ bool newton_finish_small(pycmf_ctx* ctx, int64_t rows, int64_t l, int64_t k, T* 
     }
     // two to three resident CTAs per SM (registers); every warp walks its rows with a grid stride, so the prologue
     // (Z and the shared Hessian into shared memory) is paid once per CTA, not once per four rows
-    const int minb = ctx->finish_minblocks >= 4 ? 4 : 2;
+    const int minb = ctx->finish_minblocks >= 4 ? 4 : (ctx->finish_minblocks == 3 ? 3 : 2);
     const int64_t grid = std::min<int64_t>(ceil_div(rows, WARPS), int64_t(minb) * ctx->num_sms);
     Timed timer(ctx, "newton_finish_small");
 #define LAUNCH(KT)                                                                                                      \
     do {                                                                                                                \
-        auto kern = minb == 4 ? newton_finish_small_kernel<T, KT, 4> : newton_finish_small_kernel<T, KT, 2>;            \
+        auto kern = minb == 4 ? newton_finish_small_kernel<T, KT, 4>                                                    \
+                              : (minb == 3 ? newton_finish_small_kernel<T, KT, 3> : newton_finish_small_kernel<T, KT, 2>); \
         PYCMF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));                 \
         kern<<<(unsigned)grid, WARPS * 32, smem, ctx->stream>>>(rows, int(l), int(k), F, Z, Y, ldy, y_link, T(wy), gx,  \
                                                                Hx, hx_per_row ? k * k : 0, l1, l2, l2_diag, pert,      \

@@ -23,25 +23,38 @@ __device__ __forceinline__ double shfl_d(double v, int src) { return __shfl_sync
 
 __host__ __device__ constexpr int pick_kt(int k) { return k <= 8 ? 8 : (k <= 16 ? 16 : 32); }
 
+// 1 / sqrt(x) for x in [1e-30, 1e30]: single-precision seed (MUFU.RSQ) and two Newton steps in double: branch free,
+// ~10 instructions (the library rsqrt() carries a slow path for denormals / infinities).
+__device__ __forceinline__ double rsqrt_fast(double x) {
+    double y = double(rsqrtf(float(x)));
+    const double h = 0.5 * x;
+    y = fma(y, fma(-h * y, y, 0.5), y);
+    y = fma(y, fma(-h * y, y, 0.5), y);
+    return y;
+}
+
 // In-place Cholesky, rows in registers.  On entry a[c] = A[lane][c] for c <= lane (entries c > lane are ignored and
-// clobbered).  On success a[c] = L[lane][c] for c < lane, a[lane] = 1 / L[lane][lane], and Lc[j * WLD + r] = L[r][j]
-// (column j of L, diagonal included).  Uniform return value (false: a pivot was <= floor).
+// clobbered).  On success a[c] = L[lane][c] for c < lane and 0 for c >= lane, *dinv = 1 / L[lane][lane], and
+// Lc[j * WLD + r] = L[r][j] for r > j, 0 for r <= j (column j of L without its diagonal).  The zeros make the
+// triangular solves select-free.  Uniform return value (false: a pivot was <= floor or outside [1e-30, 1e30]).
 template <int KT>
-__device__ __forceinline__ bool chol_reg(double (&a)[KT], int lane, double floor, double* __restrict__ Lc) {
+__device__ __forceinline__ bool chol_reg(double (&a)[KT], int lane, double floor, double* __restrict__ Lc, double* dinv) {
     // No early exit: a failed pivot is replaced by 1 and only remembered, so that the whole factorisation is one
     // basic block (the scheduler overlaps the tail of one trailing update with the next pivot's rsqrt chain).
     bool ok = true;
+    double di = 1.0;
 #pragma unroll
     for (int j = 0; j < KT; j++) {
         double piv = shfl_d(a[j], j);
-        const bool good = piv > floor;
+        const bool good = piv > floor && piv > 1e-30 && piv < 1e30;
         ok = ok && good;
         piv = good ? piv : 1.0;
-        const double inv = rsqrt(piv);
-        const double l = (lane >= j) ? a[j] * inv : 0.0;
-        a[j] = (lane == j) ? inv : l;
+        const double inv = rsqrt_fast(piv);
+        const double l = (lane > j) ? a[j] * inv : 0.0;
+        di = (lane == j) ? inv : di;
+        a[j] = l;
+        Lc[j * WLD + lane] = l;
         if (j + 1 < KT) {
-            Lc[j * WLD + lane] = l;
             __syncwarp();
             // trailing update of this lane's row: a[c] -= L[lane][j] L[c][j], c > j
             int c = j + 1;
@@ -57,24 +70,27 @@ __device__ __forceinline__ bool chol_reg(double (&a)[KT], int lane, double floor
             }
         }
     }
+    __syncwarp();
+    *dinv = di;
     return ok;
 }
 
 // Solve L L^T x = b with the factor left by chol_reg; lane r holds b_r on entry and x_r on return.
 template <int KT>
-__device__ __forceinline__ double chol_solve_reg(const double (&a)[KT], int lane, double b, const double* __restrict__ Lc) {
+__device__ __forceinline__ double chol_solve_reg(const double (&a)[KT], double dinv, int lane, double b,
+                                                 const double* __restrict__ Lc) {
 #pragma unroll
-    for (int j = 0; j < KT; j++) {                       // L y = b
-        const double y = shfl_d(b * a[j], j);            // lane j: a[j] = 1 / L[j][j]
-        b = (lane == j) ? y : ((lane > j) ? fma(-a[j], y, b) : b);
+    for (int j = 0; j < KT; j++) {                       // L y = b : lanes > j subtract L[lane][j] y_j (a[j] = 0 elsewhere)
+        const double y = shfl_d(b * dinv, j);
+        b = fma(-a[j], y, b);
     }
+    b *= dinv;
 #pragma unroll
-    for (int j = KT - 1; j >= 0; j--) {                  // L^T x = y
-        const double x = shfl_d(b * a[j], j);
-        const double ljr = (lane < j) ? Lc[lane * WLD + j] : 0.0;   // L[j][lane]
-        b = (lane == j) ? x : fma(-ljr, x, b);
+    for (int j = KT - 1; j >= 0; j--) {                  // L^T x = y : lanes < j subtract L[j][lane] x_j (0 elsewhere)
+        const double x = shfl_d(b * dinv, j);
+        b = fma(-Lc[lane * WLD + j], x, b);
     }
-    return b;
+    return b * dinv;
 }
 
 // One-sided (Hestenes) Jacobi sweeps on the columns of the symmetric tile W (lane == row), executed by ONE warp.
@@ -121,11 +137,12 @@ __device__ __forceinline__ double jacobi_apply_tile(const double* W, int k, int 
 // Factorisation half of the clamped solve.  H_row: row `lane` of the symmetric matrix in registers (entries c <= lane
 // are used, like eigh(lower=True); rows / columns >= k are ignored); diag is added to the diagonal; W: per-warp tile of
 // TILE doubles.  known_pd: the caller guarantees lambda_min(H + diag I) >= pert.
-// Returns true when the Cholesky path ran (factor in `a` / W, apply with chol_solve_reg) and false when the eigenvalue
+// Returns true when the Cholesky path ran (factor in `a` / *dinv / W, apply with chol_solve_reg) and false when the eigenvalue
 // clamp is active (W then holds the Jacobi-orthogonalised tile, apply with jacobi_apply_tile).  Uniform.
 template <int KT, typename R>
 __device__ __forceinline__ bool safe_factor_warp(const R (&H_row)[KT], double diag, int k, int lane, double pert,
-                                                 bool chol_fastpath, bool known_pd, double* W, double (&a)[KT]) {
+                                                 bool chol_fastpath, bool known_pd, double* W, double (&a)[KT],
+                                                 double* dinv) {
     const bool act = lane < k;
     if (chol_fastpath) {
         bool ok = true;
@@ -142,8 +159,7 @@ __device__ __forceinline__ bool safe_factor_warp(const R (&H_row)[KT], double di
             }
             double floor = 0.0;
             if (pass == 0) floor = 1e-13 * (warp_sum(tr) + pert);
-            ok = chol_reg<KT>(a, lane, floor, W);
-            __syncwarp();
+            ok = chol_reg<KT>(a, lane, floor, W, dinv);
         }
         if (ok) return true;
     }
@@ -161,10 +177,10 @@ __device__ __forceinline__ bool safe_factor_warp(const R (&H_row)[KT], double di
 
 // x = S(H) g for one right-hand side after safe_factor_warp (lane r holds g_r / returns x_r).
 template <int KT>
-__device__ __forceinline__ double safe_apply_warp(bool factored, const double (&a)[KT], int k, int lane, double g,
-                                                  double pert, const double* W) {
+__device__ __forceinline__ double safe_apply_warp(bool factored, const double (&a)[KT], double dinv, int k, int lane,
+                                                  double g, double pert, const double* W) {
     const double gr = lane < k ? g : 0.0;
-    if (factored) return chol_solve_reg<KT>(a, lane, gr, W);
+    if (factored) return chol_solve_reg<KT>(a, dinv, lane, gr, W);
     return jacobi_apply_tile(W, k, lane, gr, pert);
 }
 
