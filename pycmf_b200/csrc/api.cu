@@ -46,6 +46,7 @@ pycmf_ctx* fork_side(pycmf_ctx* ctx) {
     s->tc_max_splits = ctx->tc_max_splits;
     s->tc_ctas = ctx->tc_ctas;
     s->tc_chain = ctx->tc_chain;
+    s->tc_x_promotion = ctx->tc_x_promotion;
     s->tc_prefetch = ctx->tc_prefetch;
     s->max_scratch = ctx->max_scratch;
     s->finish_minblocks = ctx->finish_minblocks;
@@ -421,6 +422,7 @@ int pycmf_set_option(pycmf_ctx* ctx, const char* key, double value) {
         else if (k == "tc_trace") ctx->tc_trace = int(value);
         else if (k == "tc_ctas") ctx->tc_ctas = int(value);
         else if (k == "tc_chain") ctx->tc_chain = int(value);
+        else if (k == "tc_x_promotion") ctx->tc_x_promotion = int(value);
         else if (k == "tc_prefetch") ctx->tc_prefetch = int(value);
         else if (k == "side_streams") ctx->side_streams = value != 0.0;
         else if (k == "finish_minblocks") ctx->finish_minblocks = int(value);

@@ -35,6 +35,7 @@ struct pycmf_ctx {
     int tc_max_splits = 0;   // > 0: at most this many CTAs per own tile in the tcgen05 passes (tests: 1 = one long chain)
     int tc_ctas = 0;         // > 0: cap on the persistent CTA count of the tcgen05 passes (tests)
     int tc_prefetch = 0;     // L2 prefetch of X in the tcgen05 passes: 0 none (measured: no gain), 2 TMA prefetch
+    int tc_x_promotion = 128; // L2 promotion (bytes) of the X tensor map of the tcgen05 passes: 0, 64, 128, 256
     int tc_chain = 0;        // > 0: accumulation chain cap in tiles (default 16)
     size_t max_scratch = size_t(2) << 30;
     // scratch arenas (grown on demand; growth synchronises the stream)

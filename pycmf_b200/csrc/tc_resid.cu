@@ -428,7 +428,9 @@ tc_pass_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_constan
                 if (first && chains_done > 0) mbar_wait(bar(OUTEMPTY), uint32_t(chains_done - 1) & 1u);
                 tc_fence_after();
                 if (elect_one()) {
-                    // X (epilogue), Q (GEMM1: complete before S was read; transposer) of this stage are no longer needed
+                    // X (epilogue), Q (GEMM1: complete before S was read; transposition) of this stage are no longer needed.
+                    // (Releasing the stage earlier -- from the epilogue warps when they publish R, or from the GEMM1 warp --
+                    //  was measured and gave nothing: the load phase grows, the GEMM1 latency grows by as much.)
                     if (main_issuer) {
                         mbar_arrive(bar(EMPTY0 + it % NSTAGE));
                         TC_TRACE(TR_G2_ISSUE, it);
@@ -739,15 +741,16 @@ EncodeTiledFn encode_fn() {
 }
 
 // 2-D fp32 row-major tensor (rows x cols, row stride ld elements); box = (32 columns, box_rows), SWIZZLE_128B
-CUtensorMap make_map(const float* ptr, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+CUtensorMap make_map(const float* ptr, int64_t rows, int64_t cols, int64_t ld, int box_rows,
+                     CUtensorMapL2promotion promo = CU_TENSOR_MAP_L2_PROMOTION_L2_256B) {
     CUtensorMap m;
     cuuint64_t dims[2] = {cuuint64_t(cols), cuuint64_t(rows)};
     cuuint64_t strides[1] = {cuuint64_t(ld) * sizeof(float)};
     cuuint32_t box[2] = {32u, cuuint32_t(box_rows)};
     cuuint32_t estr[2] = {1u, 1u};
     CUresult r = encode_fn()(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims, strides, box, estr,
-                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, promo,
+                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     PYCMF_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed");
     return m;
 }
@@ -782,7 +785,14 @@ void launch_tc_impl(pycmf_ctx* ctx, int64_t own_n, int64_t oth_n, const FactorPa
     CUtensorMap tm_q_lo = factor_map(Q.lo, Q.rows, OTH);
     CUtensorMap tm_qt_hi = factor_t_map(Q.hi_t, Q.rows, Q.ldt);
     CUtensorMap tm_qt_lo = factor_t_map(Q.lo_t, Q.rows, Q.ldt);
-    CUtensorMap tm_x = make_map(X, x_rows, x_cols, ldx, MODE == 0 ? OWN : OTH);
+    // X rows are in general not 256-byte aligned (row pitch 20000 B on C2): with 256-byte L2 promotion the RIGHT pass, whose
+    // neighbouring column blocks are read by other CTAs at other times, pulled 34 % more than X from HBM (ncu, r01)
+    const int promo = ctx->tc_x_promotion;
+    CUtensorMap tm_x = make_map(X, x_rows, x_cols, ldx, MODE == 0 ? OWN : OTH,
+                                promo == 256 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B
+                                             : (promo == 64 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
+                                                            : (promo == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE
+                                                                          : CU_TENSOR_MAP_L2_PROMOTION_L2_128B)));
     Params prm;
     prm.own_n = own_n;
     prm.oth_n = oth_n;
