@@ -248,7 +248,8 @@ def run_ours(args):
     launches = int(round((be.launch_count() - launches0) / n_prof * args.steps))
     fams = {}
     for fam in ("resid_left", "resid_right", "gemm", "spmm", "sddmm", "row_grad_hess", "safe_solve",
-                "apply_shared_inverse", "newton_finish_small", "tc_xv", "tc_xtu", "tc_resid_left", "tc_resid_right"):
+                "apply_shared_inverse", "newton_finish_small", "tc_xv", "tc_xtu", "tc_factor", "tc_ytv", "tc_resid_left",
+                "tc_resid_right"):
         tot, cnt = be.profile_query(fam)
         if cnt:
             fams[fam] = (tot, cnt)
@@ -276,7 +277,7 @@ def run_ours(args):
     if fams:
         # the roofline is reported for the kernel that carries the HBM traffic: the slowest of the passes over X
         # (every family's time is listed next to it)
-        streaming = [f for f in fams if f.startswith("tc_") or f.startswith("resid_") or f in ("spmm", "sddmm")]
+        streaming = [f for f in fams if (f.startswith("tc_") and f not in ("tc_factor", "tc_ytv")) or f.startswith("resid_") or f in ("spmm", "sddmm")]
         big = [f for f in streaming if not f.startswith("resid_")] or streaming
         dom = max(big or fams, key=lambda f: fams[f][0] / fams[f][1])
         tot, cnt = fams[dom]
@@ -296,15 +297,34 @@ def run_ours(args):
                 traffic = json.load(f).get("%s:%s:%s" % (args.workload, args.dtype, dom))
         except Exception:  # noqa: BLE001
             pass
-        roofline = {"bound": "hbm", "kernel": dom, "achieved": round(achieved, 1), "peak": hbm_peak,
-                    "peak_source": peak_src, "unit": "GB/s", "frac": round(achieved / hbm_peak, 4),
-                    "traffic": traffic, "algorithmic_bytes_per_launch": alg_bytes,
-                    "avg_launch_ms": round(per_launch_ms, 5), "launches_timed": cnt,
-                    "share_of_step": round(tot / ms_prof, 4),
-                    "timed_in": "region B: %d eager, serialised iterations with per-family CUDA-event timers "
-                                "(%.5f ms/step); value is region A (CUDA-graph replay, U / Z updates and shared-Hessian "
-                                "branches on side streams)" % (n_prof, ms_prof / n_prof),
-                    "families_ms_per_step": {f: round(v[0] / n_prof, 5) for f, v in fams.items()}}
+        common = {"traffic": traffic, "avg_launch_ms": round(per_launch_ms, 5), "launches_timed": cnt,
+                  "share_of_step": round(tot / ms_prof, 4),
+                  "timed_in": "region B: %d eager, serialised iterations with per-family CUDA-event timers "
+                              "(%.5f ms/step); value is region A (CUDA-graph replay, U / Z updates and shared-Hessian "
+                              "branches on side streams)" % (n_prof, ms_prof / n_prof),
+                  "families_ms_per_step": {f: round(v[0] / n_prof, 5) for f, v in fams.items()}}
+        if dom in ("tc_xv", "tc_xtu") and k >= 128 and args.dtype == "float32":
+            # wide factors: the dense MU contraction is tensor-core bound.  fp32 accuracy on TF32 tensor cores costs three
+            # MMAs per product (3xTF32: hi*hi + hi*lo + lo*hi), so the fp32-equivalent peak is a third of the TF32 peak;
+            # the TF32 peak is taken as half of the measured dense bf16 rate (same pipe, half the elements per clock).
+            alg_flops = 2.0 * n_loc * d * k
+            bf16_s, bf16_b = peaks.get("bf16_tflops_sustained"), peaks.get("bf16_tflops")
+            src = "measured (bf16 sustained / 2 / 3)"
+            if not bf16_s:
+                bf16_s, bf16_b, src = 1400.0, 1640.0, "fallback (bf16 1400 sustained / 2 / 3)"
+            ach = alg_flops / (per_launch_ms / 1e3) / 1e12
+            peak = bf16_s / 2.0 / 3.0
+            roofline = {"bound": "tensor", "kernel": dom, "achieved": round(ach, 1), "peak": round(peak, 1),
+                        "peak_source": src, "unit": "TFLOP/s", "frac": round(ach / peak, 4),
+                        "algorithmic_flops_per_launch": alg_flops, "executed_tf32_tflops": round(3 * ach, 1),
+                        "tf32_peak_sustained": round(bf16_s / 2.0, 1), "tf32_peak_burst": round((bf16_b or 0) / 2.0, 1),
+                        "frac_of_burst": round(3 * ach / (bf16_b / 2.0), 4) if bf16_b else None,
+                        "hbm_gbs_of_x": round(achieved, 1)}
+        else:
+            roofline = {"bound": "hbm", "kernel": dom, "achieved": round(achieved, 1), "peak": hbm_peak,
+                        "peak_source": peak_src, "unit": "GB/s", "frac": round(achieved / hbm_peak, 4),
+                        "algorithmic_bytes_per_launch": alg_bytes}
+        roofline.update(common)
 
     # ---- e2e through the solver seam with host buffers
     e2e = None

@@ -120,17 +120,34 @@ void sqerr_impl(pycmf_ctx* ctx, int64_t rows, int64_t m, int64_t k, const T* A, 
 }
 
 // ---- MU ------------------------------------------------------------------------------------------
+// out (contiguous, k columns) = X Q (trans == false) or X^T Q on the tensor cores when the shape qualifies (fp32, k = 32 uses
+// tc_resid.cu's pass, k = 64 .. 256 tc_mu.cu); false = caller runs the generic kernel.
+template <typename T>
+bool tc_try(pycmf_ctx* ctx, bool trans, int64_t rows, int64_t cols, int64_t k, const T* X, int64_t ldx, const T* Q, T* out) {
+    if constexpr (std::is_same<T, float>::value) {
+        if (tc_mu_eligible(ctx, rows, cols, k, X, ldx, false)) {
+            tc_mu_xmul(ctx, trans, rows, cols, k, X, ldx, Q, out, "tc_factor");
+            return true;
+        }
+    }
+    return false;
+}
+
 template <typename T>
 void mu_v_partial_impl(pycmf_ctx* ctx, int64_t n, int64_t d, int64_t k, const T* X, int64_t ldx,
                        const int32_t* colptr, const int32_t* rowidx, const T* cvals, const T* U, T* out) {
     // U^T U on the side stream, next to the pass over X
     pycmf_ctx* sc = fork_side(ctx);
-    gemm<T>(sc, true, k, k, n, U, k, U, k, out + d * k, k, T(1), T(0));
+    if (!tc_try<T>(sc, true, n, k, k, U, k, U, out + d * k))
+        gemm<T>(sc, true, k, k, n, U, k, U, k, out + d * k, k, T(1), T(0));
     if (X != nullptr) {
         bool done = false;
         if constexpr (std::is_same<T, float>::value) {
             if (tc_dense_eligible(ctx, n, d, k, X, ldx, false)) {
                 tc_xmul(ctx, true, n, d, X, ldx, U, out);
+                done = true;
+            } else if (tc_mu_eligible(ctx, n, d, k, X, ldx, false)) {
+                tc_mu_xmul(ctx, true, n, d, k, X, ldx, U, out);
                 done = true;
             }
         }
@@ -150,9 +167,13 @@ void mu_v_apply_impl(pycmf_ctx* ctx, int64_t d, int64_t l, int64_t k, T* V, cons
     T* G = static_cast<T*>(scratch(ctx, SLOT_T2, sizeof(T) * size_t(k) * k));
     copy_async<T>(ctx, N, xtu_utu, size_t(d) * k);
     copy_async<T>(ctx, G, xtu_utu + d * k, size_t(k) * k);
-    gemm<T>(ctx, false, d, k, l, Y, ldy, Z, k, N, k, T(1), T(1));        // + Y Z       (:244)
+    if (tc_try<T>(ctx, false, d, l, k, Y, ldy, Z, D))                   // + Y Z       (:244)
+        axpby<T>(ctx, d * k, T(1), N, T(1), D, N);
+    else
+        gemm<T>(ctx, false, d, k, l, Y, ldy, Z, k, N, k, T(1), T(1));
     gemm<T>(ctx, true, k, k, l, Z, k, Z, k, G, k, T(1), T(1));           // + Z^T Z     (:245)
-    gemm<T>(ctx, false, d, k, k, V, k, G, k, D, k, T(1), T(0));          // V (UtU+ZtZ) (:245)
+    if (!tc_try<T>(ctx, false, d, k, k, V, k, G, D))                    // V (UtU+ZtZ) (:245)
+        gemm<T>(ctx, false, d, k, k, V, k, G, k, D, k, T(1), T(0));
     mu_apply<T>(ctx, d, k, V, N, D, l1, l2);
 }
 
@@ -164,13 +185,21 @@ void mu_left_impl(pycmf_ctx* ctx, int64_t rows, int64_t m, int64_t k, T* F, cons
     pycmf_ctx* sc = fork_side(ctx);
     T* D = static_cast<T*>(scratch(sc, SLOT_T1, sizeof(T) * size_t(rows) * k));
     T* G = static_cast<T*>(scratch(sc, SLOT_T2, sizeof(T) * size_t(k) * k));
-    gemm<T>(sc, true, k, k, m, B, k, B, k, G, k, T(1), T(0));           // B^T B
-    gemm<T>(sc, false, rows, k, k, F, k, G, k, D, k, T(1), T(0));       // F (B^T B)
+    if (!tc_try<T>(sc, true, m, k, k, B, k, B, G))                      // B^T B
+        gemm<T>(sc, true, k, k, m, B, k, B, k, G, k, T(1), T(0));
+    if (!tc_try<T>(sc, false, rows, k, k, F, k, G, D))                  // F (B^T B)
+        gemm<T>(sc, false, rows, k, k, F, k, G, k, D, k, T(1), T(0));
     if (Tg != nullptr) {
         bool done = false;
         if constexpr (std::is_same<T, float>::value) {
             if (tc_dense_eligible(ctx, rows, m, k, Tg, ldt, trans_t)) {
                 tc_xmul(ctx, false, rows, m, Tg, ldt, B, N);
+                done = true;
+            } else if (!trans_t && tc_mu_eligible(ctx, rows, m, k, Tg, ldt, false)) {
+                tc_mu_xmul(ctx, false, rows, m, k, Tg, ldt, B, N);
+                done = true;
+            } else if (trans_t && tc_mu_eligible(ctx, m, rows, k, Tg, ldt, false)) {
+                tc_mu_xmul(ctx, true, m, rows, k, Tg, ldt, B, N, "tc_ytv");      // target stored transposed (m x rows): N = Tg^T B
                 done = true;
             }
         }

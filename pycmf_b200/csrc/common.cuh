@@ -201,6 +201,12 @@ void tc_resid_pass(pycmf_ctx* ctx, int64_t ra, int64_t rb, const float* A, const
 void tc_xmul(pycmf_ctx* ctx, bool trans, int64_t rows, int64_t cols, const float* X, int64_t ldx, const float* Q,
              float* out);
 
+// tc_mu.cu : tcgen05 MU numerators X Q / X^T Q for n_components in {64, 128, 192, 256} (fp32, 3xTF32)
+bool tc_mu_eligible(pycmf_ctx* ctx, int64_t rows, int64_t cols, int64_t k, const float* X, int64_t ldx, bool trans_t);
+// `family`: timer family the launch is booked under (default tc_xv / tc_xtu: the passes over X)
+void tc_mu_xmul(pycmf_ctx* ctx, bool trans, int64_t rows, int64_t cols, int64_t k, const float* X, int64_t ldx,
+                const float* Q, float* out, const char* family = nullptr);
+
 // newton.cu
 // Per-row gradient / Hessian accumulation for rows of A against (sampled) rows of B.
 //   g_i (+)= w * sum_{j in s_i} (f(a_i.b_j) - t_ij) b_j ;  H_i (+)= w * sum_{j in s_i} f'(a_i.b_j) b_j b_j^T

@@ -317,3 +317,71 @@ def test_tc_persistent_ranges_cross_own_tiles(ctas, chain, link):
     assert rel_fro(be.to_host(outL), R @ V) < 5e-5
     assert rel_fro(be.to_host(outR), R.T @ U) < 5e-5
     assert abs(float(be.to_host(sq)[0]) - (R ** 2).sum()) / (R ** 2).sum() < 1e-5
+
+
+# ---- tcgen05 MU contractions for n_components = 64 .. 256 (tc_mu.cu) ----------------------------------
+@pytest.mark.parametrize("k", [64, 128, 192, 256])
+@pytest.mark.parametrize("shape", [(1000, 520), (300, 2052), (4100, 260)])
+@pytest.mark.parametrize("signed", [True, False])
+def test_tc_mu_wide_products_match_numpy(k, shape, signed):
+    """X^T U and X V for wide factors on the tensor cores (3xTF32) vs float64 NumPy; ragged edges in both dimensions.
+    Non-negative data (the MU case) has no cancellation: tighter bound."""
+    n, d = shape
+    rng = np.random.RandomState(n + d + k)
+    X, U, V = rng.randn(n, d), rng.randn(n, k), rng.randn(d, k)
+    if not signed:
+        X, U, V = np.abs(X), np.abs(U), np.abs(V)
+    tol = 4e-5 if signed else 1.5e-5      # tensor-memory accumulation truncates (chains of 16 tiles, DESIGN 6)
+    be = _tc_backend(1)
+    Xd = be.ingest(X)
+    buf = be.to_host(be.mu_v_partial(Xd, be.to_device(U)))
+    assert rel_fro(buf[:d], X.T @ U) < tol
+    F = np.ones((n, k))
+    Fd = be.to_device(F)
+    be.mu_left(Fd, be.to_device(V), Xd, 0.0, 0.0)
+    got = be.to_host(Fd) * (F @ (V.T @ V))
+    assert rel_fro(got, X @ V) < max(tol, 1e-5)
+
+
+@pytest.mark.parametrize("ctas", [1, 3, 0])
+@pytest.mark.parametrize("chain", [0, 2, 5])
+def test_tc_mu_wide_persistent_ranges(ctas, chain):
+    """Few CTAs walk many tiles (own-tile and chain boundaries inside one CTA, several partials per own tile);
+    the same products from the generic FMA kernels must agree to fp32 accuracy."""
+    from pycmf_b200.device import CudaBackend, DenseMatrix
+    n, d, k = 1100, 709, 128
+    rng = np.random.RandomState(ctas * 10 + chain)
+    U, V = np.abs(rng.randn(n, k)), np.abs(rng.randn(d, k))
+    Xp = np.zeros((n, 712), dtype=np.float32)
+    Xp[:, :d] = np.abs(rng.randn(n, d))
+    X = Xp[:, :d].astype(np.float64)
+    opts = {"dense_path": 1}
+    if ctas:
+        opts["tc_ctas"] = ctas
+    if chain:
+        opts["tc_chain"] = chain
+    be = CudaBackend(dtype="float32", options=opts)
+    Xv = DenseMatrix(be.ingest(Xp).t[:, :d])
+    buf = be.to_host(be.mu_v_partial(Xv, be.to_device(U)))
+    assert rel_fro(buf[:d], X.T @ U) < 1.5e-5
+    F = np.ones((n, k))
+    Fd = be.to_device(F)
+    be.mu_left(Fd, be.to_device(V), Xv, 0.0, 0.0)
+    assert rel_fro(be.to_host(Fd) * (F @ (V.T @ V)), X @ V) < 1.5e-5
+
+
+def test_tc_mu_wide_fit_matches_oracle():
+    """30 MU iterations with k = 64 on a mid-size dense problem: tensor-core path vs the float64 oracle."""
+    from pycmf_b200.cmf_solvers import MUSolver
+    rng = np.random.RandomState(5)
+    n, d, l, k = 1500, 900, 40, 64
+    X = np.abs(rng.randn(n, 24) @ rng.randn(24, d)) + 0.1 * np.abs(rng.randn(n, d))
+    Y = np.abs(rng.randn(d, l))
+    U0, V0, Z0 = np.abs(rng.randn(n, k)) * 0.3, np.abs(rng.randn(d, k)) * 0.3, np.abs(rng.randn(l, k)) * 0.3
+    Uo, Vo, Zo = U0.copy(), V0.copy(), Z0.copy()
+    for _ in range(30):
+        O.mu_step(X, Y, Uo, Vo, Zo, 0.0, 0.0)
+    U, V, Z = U0.copy(), V0.copy(), Z0.copy()
+    s = MUSolver(tol=0, max_iter=30, dtype="float32", backend_options={"dense_path": 1})
+    s.fit_iterative_update(X, Y, U, V, Z)
+    assert rel_fro(U, Uo) < 1e-3 and rel_fro(V, Vo) < 1e-3 and rel_fro(Z, Zo) < 1e-3
