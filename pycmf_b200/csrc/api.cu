@@ -43,6 +43,7 @@ pycmf_ctx* fork_side(pycmf_ctx* ctx) {
     pycmf_ctx* s = ctx->side;
     s->chol_fastpath = ctx->chol_fastpath;
     s->dense_path = ctx->dense_path;
+    s->spmm_path = ctx->spmm_path;
     s->tc_max_splits = ctx->tc_max_splits;
     s->tc_ctas = ctx->tc_ctas;
     s->tc_chain = ctx->tc_chain;
@@ -448,6 +449,7 @@ int pycmf_set_option(pycmf_ctx* ctx, const char* key, double value) {
         if (k == "chol_fastpath") ctx->chol_fastpath = value != 0.0;
         else if (k == "dense_path") ctx->dense_path = int(value);
         else if (k == "tc_max_splits") ctx->tc_max_splits = int(value);
+        else if (k == "spmm_path") ctx->spmm_path = int(value);
         else if (k == "tc_trace") ctx->tc_trace = int(value);
         else if (k == "tc_ctas") ctx->tc_ctas = int(value);
         else if (k == "tc_chain") ctx->tc_chain = int(value);

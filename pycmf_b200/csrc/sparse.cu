@@ -96,6 +96,92 @@ spmm_kernel(int64_t rows, const int32_t* __restrict__ rowptr, const int32_t* __r
     }
 }
 
+
+// k = 32 * VEC: lane owns the VEC contiguous columns [lane * VEC, lane * VEC + VEC) of every factor row, so one
+// nonzero is one vector load per lane (a full 128 .. 1024-byte row of B per warp).  A warp walks a CONTIGUOUS range
+// of chunks (one binary search per warp instead of one per chunk: 18 dependent L2 round trips per ~100-nonzero row
+// were most of the old kernel's time) and keeps UNROLL independent row gathers in flight.
+template <typename T, int VEC> struct VecLoad;
+template <> struct VecLoad<float, 1> { static __device__ __forceinline__ void ld(const float* p, float (&o)[1]) { o[0] = __ldg(p); } };
+template <> struct VecLoad<float, 2> { static __device__ __forceinline__ void ld(const float* p, float (&o)[2]) {
+    const float2 v = __ldg(reinterpret_cast<const float2*>(p)); o[0] = v.x; o[1] = v.y; } };
+template <> struct VecLoad<float, 4> { static __device__ __forceinline__ void ld(const float* p, float (&o)[4]) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(p)); o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w; } };
+template <> struct VecLoad<float, 8> { static __device__ __forceinline__ void ld(const float* p, float (&o)[8]) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+    o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w; o[4] = b.x; o[5] = b.y; o[6] = b.z; o[7] = b.w; } };
+template <> struct VecLoad<double, 1> { static __device__ __forceinline__ void ld(const double* p, double (&o)[1]) { o[0] = __ldg(p); } };
+template <> struct VecLoad<double, 2> { static __device__ __forceinline__ void ld(const double* p, double (&o)[2]) {
+    const double2 v = __ldg(reinterpret_cast<const double2*>(p)); o[0] = v.x; o[1] = v.y; } };
+template <> struct VecLoad<double, 4> { static __device__ __forceinline__ void ld(const double* p, double (&o)[4]) {
+    const double2 a = __ldg(reinterpret_cast<const double2*>(p)), b = __ldg(reinterpret_cast<const double2*>(p) + 1);
+    o[0] = a.x; o[1] = a.y; o[2] = b.x; o[3] = b.y; } };
+template <> struct VecLoad<double, 8> { static __device__ __forceinline__ void ld(const double* p, double (&o)[8]) {
+#pragma unroll
+    for (int h = 0; h < 4; h++) { const double2 a = __ldg(reinterpret_cast<const double2*>(p) + h); o[2 * h] = a.x; o[2 * h + 1] = a.y; } } };
+
+template <typename T, int VEC>
+__global__ void __launch_bounds__(256)
+spmm_vec_kernel(int64_t rows, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx,
+                const T* __restrict__ vals, const T* __restrict__ B, int64_t ldb,
+                T* __restrict__ C, int64_t ldc, T alpha, T beta, const int* __restrict__ chunk_off) {
+    constexpr int UNROLL = 4;
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = (int64_t(gridDim.x) * blockDim.x) >> 5;
+    const int64_t total = chunk_off[rows];
+    const int64_t ch0 = (warp * total) / nwarps, ch1 = ((warp + 1) * total) / nwarps;
+    if (ch0 >= ch1) return;
+    // row of the first chunk: last r with chunk_off[r] <= ch0; chunk_off[r] >= r (every row has a chunk) and
+    // chunk_off[r] <= r + (total - rows), so r lies in [ch0 - (total - rows), ch0]
+    int64_t lo = max(int64_t(0), ch0 - (total - rows)), hi = min(rows, ch0 + 1);
+    while (hi - lo > 1) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (int64_t(chunk_off[mid]) <= ch0) lo = mid; else hi = mid;
+    }
+    int64_t row = lo;
+    int row_first = chunk_off[row], row_next = chunk_off[row + 1];
+    for (int64_t ch = ch0; ch < ch1; ch++) {
+        while (ch >= row_next) { row++; row_first = row_next; row_next = chunk_off[row + 1]; }
+        const int ci = int(ch - row_first);
+        const bool split = row_next - row_first > 1;
+        T acc[VEC];
+#pragma unroll
+        for (int t = 0; t < VEC; t++) acc[t] = T(0);
+        const int start = rowptr[row] + ci * CHUNK;
+        const int end = min(rowptr[row + 1], start + CHUNK);
+        for (int base = start; base < end; base += 32) {
+            const int cnt = min(32, end - base);
+            // lanes past the end carry a valid column (the chunk's first) and a zero value: no branches in the gather loop
+            int c = colidx[base + (lane < cnt ? lane : 0)];
+            T v = lane < cnt ? vals[base + lane] : T(0);
+            for (int j = 0; j < cnt; j += UNROLL) {
+                T bv[UNROLL][VEC], vj[UNROLL];
+#pragma unroll
+                for (int u = 0; u < UNROLL; u++) {
+                    const int cj = __shfl_sync(0xffffffffu, c, (j + u) & 31);
+                    vj[u] = __shfl_sync(0xffffffffu, v, (j + u) & 31);
+                    VecLoad<T, VEC>::ld(B + int64_t(cj) * ldb + lane * VEC, bv[u]);
+                }
+#pragma unroll
+                for (int u = 0; u < UNROLL; u++)
+#pragma unroll
+                    for (int t = 0; t < VEC; t++) acc[t] = fma(vj[u], bv[u][t], acc[t]);
+            }
+        }
+        T* crow = C + row * ldc + lane * VEC;
+#pragma unroll
+        for (int t = 0; t < VEC; t++) {
+            if (split) {
+                atomicAdd(&crow[t], alpha * acc[t]);                 // row pre-scaled by beta in the count pass
+            } else {
+                const T prev = beta != T(0) ? crow[t] : T(0);
+                crow[t] = alpha * acc[t] + beta * prev;
+            }
+        }
+    }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256)
 sddmm_reduce_kernel(int mode, int64_t rows, const int32_t* __restrict__ rowptr,
@@ -158,6 +244,20 @@ void spmm(pycmf_ctx* ctx, int64_t rows, const int32_t* rowptr, const int32_t* co
     PYCMF_CUDA(cub::DeviceScan::ExclusiveSum(cub_tmp, cub_bytes, counts, offsets, int(rows + 1), ctx->stream));
     ctx->launches++;
     const unsigned blocks = (unsigned)std::min<int64_t>(ceil_div(rows * 32, 256), int64_t(32) * ctx->num_sms);
+    // wide factors (k = 32, 64, 128, 256; 16-byte aligned rows): the vector kernel
+    const bool vec_ok = (k == 32 || k == 64 || k == 128 || k == 256) && (ldb * sizeof(T)) % 16 == 0 &&
+                        (reinterpret_cast<uintptr_t>(B) & 15) == 0 && ctx->spmm_path != 0;
+    if (vec_ok) {
+        const unsigned vb = (unsigned)std::min<int64_t>(ceil_div(rows * 32, 256 * 4), int64_t(16) * ctx->num_sms);
+#define LAUNCHV(V) spmm_vec_kernel<T, V><<<std::max(1u, vb), 256, 0, ctx->stream>>>(rows, rowptr, colidx, vals, B, ldb, C, ldc, alpha, beta, offsets)
+        if (k == 32) LAUNCHV(1);
+        else if (k == 64) LAUNCHV(2);
+        else if (k == 128) LAUNCHV(4);
+        else LAUNCHV(8);
+#undef LAUNCHV
+        PYCMF_LAUNCH_CHECK(ctx);
+        return;
+    }
 #define LAUNCH(G) spmm_kernel<T, G><<<blocks, 256, 0, ctx->stream>>>(rows, rowptr, colidx, vals, B, ldb, int(k), C, ldc, alpha, beta, offsets)
     if (k <= 1) LAUNCH(1);
     else if (k <= 2) LAUNCH(2);

@@ -169,16 +169,18 @@ def test_safe_solve_matches_eigh_clamp(k, chol):
     assert np.abs(got - ref).max() / np.abs(ref).max() < 1e-10
 
 
-def test_spmm_hot_rows_and_columns_are_split(be64):
-    """tf-idf-like skew: one row / one column holding thousands of nonzeros goes through the row-splitting path."""
+@pytest.mark.parametrize("k", [48, 32, 64, 128, 256])
+def test_spmm_hot_rows_and_columns_are_split(be64, k):
+    """tf-idf-like skew: one row / one column holding thousands of nonzeros goes through the row-splitting path
+    (k = 48: generic kernel; 32 .. 256: vector kernel, contiguous chunk ranges per warp)."""
     rng = np.random.RandomState(5)
     S = sp.random(3000, 2500, density=0.002, random_state=rng, format="lil")
     S[17, :] = rng.rand(2500)            # hot row: 2500 nonzeros = 5 chunks
     S[:, 33] = rng.rand(3000, 1)         # hot column: 3000 nonzeros in the CSC copy
     S = sp.csr_matrix(S)
     Sd = be64.ingest(S)
-    B, A = rng.randn(2500, 48), rng.randn(3000, 48)
-    C0 = rng.randn(3000, 48)
+    B, A = rng.randn(2500, k), rng.randn(3000, k)
+    C0 = rng.randn(3000, k)
     got = be64.to_host(be64.spmm(Sd, be64.to_device(B), alpha=0.5, beta=2.0, out=be64.to_device(C0)))
     assert np.allclose(got, 0.5 * (S @ B) + 2.0 * C0, atol=1e-10)
     assert np.allclose(be64.to_host(be64.spmm(Sd, be64.to_device(A), transposed=True)), S.T @ A, atol=1e-10)
