@@ -355,7 +355,8 @@ def run_ours(args):
         e2e = {"value": round(args.steps / dt, 3), "unit": UNIT,
                "h2d_bytes_per_step": int(h2d / args.steps), "d2h_bytes_per_step": int(d2h / args.steps),
                "call": "fit_iterative_update(X, Y, U, V, Z) with pinned float64 host arrays, max_iter=%d" % args.steps,
-               "seconds": round(dt, 4)}
+               "seconds": round(dt, 4),
+               "graph_capture_ms": round(getattr(s2, "capture_seconds_", 0.0) * 1e3, 2)}
 
     # ---- CPU baseline (rank 0, N = 1)
     cpu = None

@@ -185,7 +185,9 @@ class _IterativeCMFSolver:
                 state["graph"].replay()
             elif graphable and state["eager"] >= 2:
                 try:
+                    t0 = time.perf_counter()
                     state["graph"] = st.be.capture_step(lambda: self._step(st))
+                    self.capture_seconds_ = time.perf_counter() - t0      # host time of capture + instantiate
                 except RuntimeError as e:             # capture not possible (e.g. a collective that cannot be captured)
                     warnings.warn("CUDA-graph capture of the iteration failed, running eagerly: %s" % (e,))
                     state["eager"] = -(10 ** 9)
@@ -233,8 +235,12 @@ class _IterativeCMFSolver:
         n_iter = self.fit_device(st)
         be = st.be
         U_out = st.U if self.sharded_input else st.comm.all_gather_rows(st.U, st.n_total)
-        for host, dev in ((U, U_out), (V, st.V), (Z, st.Z)):
-            host[...] = be.to_host(dev)
+        if hasattr(be, "to_host_many"):
+            for host, got in zip((U, V, Z), be.to_host_many([U_out, st.V, st.Z])):
+                host[...] = got
+        else:
+            for host, dev in ((U, U_out), (V, st.V), (Z, st.Z)):
+                host[...] = be.to_host(dev)
         return U, V, Z, n_iter
 
 

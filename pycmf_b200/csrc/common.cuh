@@ -50,7 +50,7 @@ struct pycmf_ctx {
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     int finish_minblocks = 2;   // option: resident CTAs per SM the V-finish kernel is compiled for (2: 255 registers, no
                                 // spills: 86 us on C2; 3: 168 registers: 91 us; 4: 128 registers, spills: 187 us)
-    int spmm_path = 1;       // option: 0 = generic SpMM kernel only (tests), 1 = vector kernel for k = 32 / 64 / 128 / 256
+    int spmm_path = 1;       // option: 0 = generic SpMM kernel only (tests), 1 = vector kernels for k = 32 / 64 / 128 / 256, 2 = without the sub-warp grouping
     int side_streams = 1;    // option: 0 runs the side branches on the main stream (serial)
 };
 

@@ -6,6 +6,8 @@
 // sub-warp groups of G lanes walk different nonzeros when k < 32 so no lane idles.
 #include <cub/device/device_scan.cuh>
 
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace pycmf {
@@ -182,6 +184,81 @@ spmm_vec_kernel(int64_t rows, const int32_t* __restrict__ rowptr, const int32_t*
     }
 }
 
+// fp32, k = 32 / 64: a nonzero needs only LPN = k / 4 lanes for a 16-byte load each, so one load instruction gathers
+// 32 / LPN factor rows (ncu on the C3 slice: the one-row-per-instruction kernel was issue-bound at ~15 warp
+// instructions per nonzero, smsp issue active 52 - 64 %).  The sub-warp groups are summed by shuffles at the end of a chunk.
+template <int LPN>
+__global__ void __launch_bounds__(256)
+spmm_grp_kernel(int64_t rows, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx,
+                const float* __restrict__ vals, const float* __restrict__ B, int64_t ldb,
+                float* __restrict__ C, int64_t ldc, float alpha, float beta, const int* __restrict__ chunk_off) {
+    constexpr int NG = 32 / LPN;          // nonzeros per load instruction
+    constexpr int UNROLL = 4;
+    const int lane = threadIdx.x & 31;
+    const int gl = lane % LPN, gid = lane / LPN;
+    const int64_t warp = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = (int64_t(gridDim.x) * blockDim.x) >> 5;
+    const int64_t total = chunk_off[rows];
+    const int64_t ch0 = (warp * total) / nwarps, ch1 = ((warp + 1) * total) / nwarps;
+    if (ch0 >= ch1) return;
+    int64_t lo = max(int64_t(0), ch0 - (total - rows)), hi = min(rows, ch0 + 1);
+    while (hi - lo > 1) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (int64_t(chunk_off[mid]) <= ch0) lo = mid; else hi = mid;
+    }
+    int64_t row = lo;
+    int row_first = chunk_off[row], row_next = chunk_off[row + 1];
+    const float* Bl = B + gl * 4;
+    for (int64_t ch = ch0; ch < ch1; ch++) {
+        while (ch >= row_next) { row++; row_first = row_next; row_next = chunk_off[row + 1]; }
+        const int ci = int(ch - row_first);
+        const bool split = row_next - row_first > 1;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        const int start = rowptr[row] + ci * CHUNK;
+        const int end = min(rowptr[row + 1], start + CHUNK);
+        for (int base = start; base < end; base += 32) {
+            const int cnt = min(32, end - base);
+            // lanes past the end carry a valid column (the chunk's first) and a zero value: no branches in the gather loop
+            const int c = colidx[base + (lane < cnt ? lane : 0)];
+            const float v = lane < cnt ? vals[base + lane] : 0.0f;
+            for (int j = 0; j < cnt; j += NG * UNROLL) {
+                float4 bv[UNROLL];
+                float vj[UNROLL];
+#pragma unroll
+                for (int u = 0; u < UNROLL; u++) {
+                    const int src = (j + u * NG + gid) & 31;        // wraps only onto lanes already consumed ...
+                    const int cj = __shfl_sync(0xffffffffu, c, src);
+                    const float vv = __shfl_sync(0xffffffffu, v, src);
+                    vj[u] = (j + u * NG + gid) < 32 ? vv : 0.0f;     // ... whose value is masked here
+                    bv[u] = __ldg(reinterpret_cast<const float4*>(Bl + int64_t(cj) * ldb));
+                }
+#pragma unroll
+                for (int u = 0; u < UNROLL; u++) {
+                    acc.x = fmaf(vj[u], bv[u].x, acc.x); acc.y = fmaf(vj[u], bv[u].y, acc.y);
+                    acc.z = fmaf(vj[u], bv[u].z, acc.z); acc.w = fmaf(vj[u], bv[u].w, acc.w);
+                }
+            }
+        }
+#pragma unroll
+        for (int o = 16; o >= LPN; o >>= 1) {
+            acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o); acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
+            acc.z += __shfl_xor_sync(0xffffffffu, acc.z, o); acc.w += __shfl_xor_sync(0xffffffffu, acc.w, o);
+        }
+        if (gid == 0) {
+            float* crow = C + row * ldc + gl * 4;
+            if (split) {
+                atomicAdd(&crow[0], alpha * acc.x); atomicAdd(&crow[1], alpha * acc.y);
+                atomicAdd(&crow[2], alpha * acc.z); atomicAdd(&crow[3], alpha * acc.w);
+            } else {
+                float4 prev = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (beta != 0.0f) prev = *reinterpret_cast<const float4*>(crow);
+                *reinterpret_cast<float4*>(crow) = make_float4(alpha * acc.x + beta * prev.x, alpha * acc.y + beta * prev.y,
+                                                               alpha * acc.z + beta * prev.z, alpha * acc.w + beta * prev.w);
+            }
+        }
+    }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256)
 sddmm_reduce_kernel(int mode, int64_t rows, const int32_t* __restrict__ rowptr,
@@ -249,6 +326,14 @@ void spmm(pycmf_ctx* ctx, int64_t rows, const int32_t* rowptr, const int32_t* co
                         (reinterpret_cast<uintptr_t>(B) & 15) == 0 && ctx->spmm_path != 0;
     if (vec_ok) {
         const unsigned vb = (unsigned)std::min<int64_t>(ceil_div(rows * 32, 256 * 4), int64_t(16) * ctx->num_sms);
+        if constexpr (std::is_same<T, float>::value) {
+            if ((k == 32 || k == 64) && ctx->spmm_path == 1 && ldc % 4 == 0 && (reinterpret_cast<uintptr_t>(C) & 15) == 0) {
+                if (k == 32) spmm_grp_kernel<8><<<std::max(1u, vb), 256, 0, ctx->stream>>>(rows, rowptr, colidx, vals, B, ldb, C, ldc, alpha, beta, offsets);
+                else spmm_grp_kernel<16><<<std::max(1u, vb), 256, 0, ctx->stream>>>(rows, rowptr, colidx, vals, B, ldb, C, ldc, alpha, beta, offsets);
+                PYCMF_LAUNCH_CHECK(ctx);
+                return;
+            }
+        }
 #define LAUNCHV(V) spmm_vec_kernel<T, V><<<std::max(1u, vb), 256, 0, ctx->stream>>>(rows, rowptr, colidx, vals, B, ldb, C, ldc, alpha, beta, offsets)
         if (k == 32) LAUNCHV(1);
         else if (k == 64) LAUNCHV(2);

@@ -12,7 +12,7 @@
 //                   2 (k = 256) .. 4 slots -- L2 traffic, and the larger of the two: k = 256 moves 64 KB of Q^T per
 //                   16 KB of X, which is what bounds this kernel ("MU wide kernel")
 //   warps 0 .. 15 : X tile shared memory -> registers -> tf32 split (hi = truncation, lo = x - hi, both exact) ->
-//                   tcgen05.st into one of two R buffers in TENSOR MEMORY (for RIGHT this is also the transposition:
+//                   tcgen05.st into one of four R buffers in TENSOR MEMORY (for RIGHT this is also the transposition:
 //                   an MN-major tf32 A operand cannot be fed from shared memory)
 //   warp 18       : 12 tcgen05.mma (TS form: A = R from tensor memory, B = Q^T tile), M = 128, N = k, K = 8:
 //                   lo*hi, hi*lo first, hi*hi last, all into OUT[128 x k] in tensor memory
@@ -45,10 +45,12 @@ template <int KN> struct Cfg {
     static constexpr uint32_t QSLOT = 2u * QPART;
     static constexpr uint32_t x0 = 0, q0 = NX * X_BYTES, bars = q0 + NQ * QSLOT, total = bars + 256;
     static constexpr int CW = KN / 4;                               // OUT columns per converter warp
-    static constexpr int TM_OUT = 0, TM_R = KN;                      // R[2] : 2 x (32 hi + 32 lo) columns
+    static constexpr int NR = 4;                                    // R buffers in tensor memory
+    static constexpr int TM_OUT = 0, TM_R = KN;                      // R[NR] : NR x (32 hi + 32 lo) columns
+    static_assert(KN + NR * 2 * KS <= TMEM_COLS, "tensor memory budget");
     // barrier slots
     static constexpr int XFULL0 = 0, XEMPTY0 = XFULL0 + NX, QFULL0 = XEMPTY0 + NX, QEMPTY0 = QFULL0 + NQ,
-                         RFULL0 = QEMPTY0 + NQ, RFREE0 = RFULL0 + 2, OUTFULL = RFREE0 + 2, OUTEMPTY = OUTFULL + 1,
+                         RFULL0 = QEMPTY0 + NQ, RFREE0 = RFULL0 + NR, OUTFULL = RFREE0 + NR, OUTEMPTY = OUTFULL + 1,
                          NBARS = OUTEMPTY + 1;
     static_assert(NBARS * 8 + 16 <= 256, "barrier region too small");
 };
@@ -126,7 +128,7 @@ tc_mu_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ C
     if (threadIdx.x == 0) {
         for (int s = 0; s < NX; s++) { mbar_init(bar(C::XFULL0 + s), 1); mbar_init(bar(C::XEMPTY0 + s), CONV_WARPS); }
         for (int s = 0; s < C::NQ; s++) { mbar_init(bar(C::QFULL0 + s), 1); mbar_init(bar(C::QEMPTY0 + s), 1); }
-        for (int s = 0; s < 2; s++) { mbar_init(bar(C::RFULL0 + s), CONV_WARPS); mbar_init(bar(C::RFREE0 + s), 1); }
+        for (int s = 0; s < C::NR; s++) { mbar_init(bar(C::RFULL0 + s), CONV_WARPS); mbar_init(bar(C::RFREE0 + s), 1); }
         mbar_init(bar(C::OUTFULL), 1);
         mbar_init(bar(C::OUTEMPTY), CONV_WARPS);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -194,10 +196,10 @@ tc_mu_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ C
             const int t0 = ch * Tc, t1 = min(T, t0 + Tc);
             int cpos = 0;
             for (int t = t0; t < t1; t++, it++) {
-                const int qs = it % C::NQ, rb = it & 1;
+                const int qs = it % C::NQ, rb = it % C::NR;
                 const bool first = cpos == 0, last = cpos == chain - 1 || t == t1 - 1;
                 mbar_wait_wd(bar(C::QFULL0 + qs), uint32_t(it / C::NQ) & 1u);
-                mbar_wait_wd(bar(C::RFULL0 + rb), uint32_t(it >> 1) & 1u);
+                mbar_wait_wd(bar(C::RFULL0 + rb), uint32_t(it / C::NR) & 1u);
                 if (first && chains_done > 0) mbar_wait_wd(bar(C::OUTEMPTY), uint32_t(chains_done - 1) & 1u);
                 tc_fence_after();
                 if (elect_one()) {
@@ -283,7 +285,7 @@ tc_mu_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ C
             const bool last_unit = u + gridDim.x >= prm.n_units;
             int cpos = 0;
             for (int t = t0; t < t1; t++, it++) {
-                const int s = it % NX, rb = it & 1;
+                const int s = it % NX, rb = it % C::NR;
                 mbar_wait_wd(bar(C::XFULL0 + s), uint32_t(it / NX) & 1u);
                 const unsigned char* xs = gen + C::x0 + s * X_BYTES;
                 float xv[8];
@@ -306,8 +308,8 @@ tc_mu_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ C
                     hi[e] = __uint_as_float(__float_as_uint(xv[e]) & 0xffffe000u);
                     lo[e] = xv[e] - hi[e];
                 }
-                // R buffer it & 1: the MMAs of tile it - 2 must have read it
-                mbar_wait_wd(bar(C::RFREE0 + rb), (uint32_t(it >> 1) & 1u) ^ 1u);
+                // R buffer it % NR: the MMAs of tile it - NR must have read it
+                mbar_wait_wd(bar(C::RFREE0 + rb), (uint32_t(it / C::NR) & 1u) ^ 1u);
                 tc_fence_after();
                 const uint32_t r_hi = lane_addr + uint32_t(C::TM_R + rb * 2 * KS + c * 8);
                 tmem_st8(r_hi, hi);

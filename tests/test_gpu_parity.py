@@ -387,3 +387,24 @@ def test_tc_mu_wide_fit_matches_oracle():
     s = MUSolver(tol=0, max_iter=30, dtype="float32", backend_options={"dense_path": 1})
     s.fit_iterative_update(X, Y, U, V, Z)
     assert rel_fro(U, Uo) < 1e-3 and rel_fro(V, Vo) < 1e-3 and rel_fro(Z, Zo) < 1e-3
+
+
+@pytest.mark.parametrize("k", [32, 64, 128])
+@pytest.mark.parametrize("path", [0, 1, 2])
+def test_spmm_float32_kernels_agree(k, path):
+    """The three fp32 SpMM kernels (generic, vector, sub-warp grouped) on a skewed matrix with hot rows / columns,
+    alpha / beta handling included."""
+    from pycmf_b200.device import CudaBackend
+    rng = np.random.RandomState(11)
+    S = sp.random(3000, 2500, density=0.01, random_state=rng, format="lil")
+    S[17, :] = rng.rand(2500)
+    S[:, 33] = rng.rand(3000, 1)
+    S[5, :] = 0
+    S = sp.csr_matrix(S)
+    S.eliminate_zeros()
+    be = CudaBackend(dtype="float32", options={"spmm_path": path})
+    Sd = be.ingest(S)
+    B, A, C0 = rng.randn(2500, k), rng.randn(3000, k), rng.randn(3000, k)
+    got = be.to_host(be.spmm(Sd, be.to_device(B), alpha=0.5, beta=2.0, out=be.to_device(C0)))
+    assert rel_fro(got, 0.5 * (S @ B) + 2.0 * C0) < 2e-6
+    assert rel_fro(be.to_host(be.spmm(Sd, be.to_device(A), transposed=True)), S.T @ A) < 2e-6
