@@ -20,13 +20,13 @@ import zlib
 from pycmf_b200.cmf_solvers import MUSolver, NewtonSolver
 from pycmf_b200.sharding import TorchComm, Comm
 
-def run(case, dtype, comm, masks=None):
+def run(case, dtype, comm, masks=None, dense_path=0):
     p = dict(case["params"]); solver = p.pop("solver")
     cls = MUSolver if solver == "mu" else NewtonSolver
     # dense_path 0: both shard counts use the same (FMA) arithmetic, so only the summation order differs; the tcgen05
     # path switches on above a size threshold and would be compared against the FMA path on the smaller shards
     s = cls(max_iter=case["iters"], tol=0, random_state=case["rng_seed"], dtype=dtype, comm=comm,
-            backend_options={"dense_path": 0}, **p)
+            backend_options={"dense_path": dense_path}, **p)
     s.history = []; s.masks_per_iter = masks
     U, V, Z = case["U0"].copy(), case["V0"].copy(), case["Z0"].copy()
     s.fit_iterative_update(case["X"], case["Y"], U, V, Z)
@@ -48,6 +48,13 @@ for name in ["mu_dense_k32", "nt_signed_l1_lin_logit_k32", "mu_csr_k64"]:   # co
     assert np.abs(h2 - h1).max() / np.abs(h1).max() < 1e-5, (name, h1, h2)
     for a, b in ((U1, U2), (V1, V2), (Z1, Z2)):
         assert rel_fro(a, b) < 1e-4, name
+# tensor-core MU contractions (k = 64) on both shard counts: every shard is large enough for the tcgen05 path
+case = _mid_case("mu", 2000, 600, 10, 64, False, seed=7); case["iters"] = 4
+h2, U2, V2, Z2 = run(case, "float32", TorchComm(), dense_path=1)
+h1, U1, V1, Z1 = run(case, "float32", Comm(), dense_path=1)
+assert np.abs(h2 - h1).max() / np.abs(h1).max() < 1e-4, ("mu_tc_k64", h1, h2)
+for a, b in ((U1, U2), (V1, V2), (Z1, Z2)):
+    assert rel_fro(a, b) < 1e-3, "mu_tc_k64"
 dist.barrier(); dist.destroy_process_group()
 if rank == 0: print("MULTI_OK")
 '''
