@@ -349,7 +349,7 @@ def run_ours(args):
         if world > 1:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         dt = float(tt.item())
-        xbytes = (Xh.data.nbytes + Xh.indices.nbytes + Xh.indptr.nbytes) * 2 if cfg["sparse"] else Xh.nbytes
+        xbytes = (Xh.data.nbytes + Xh.indices.nbytes + Xh.indptr.nbytes) if cfg["sparse"] else Xh.nbytes   # CSC is built on the device
         h2d = xbytes + Yh.nbytes + Uh.nbytes + Vh.nbytes + Zh.nbytes
         d2h = (Uh.size + Vh.size + Zh.size) * sb
         e2e = {"value": round(args.steps / dt, 3), "unit": UNIT,

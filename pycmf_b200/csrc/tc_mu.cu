@@ -64,7 +64,16 @@ struct MuParams {
     int64_t n_units;            // own_tiles x n_chunks, unit u = chunk * own_tiles + own_tile (chunk-major)
     int chain;                  // accumulation chain cap in tiles
     float* part;                // [own tile][chunk][OWN x KN]
+    long long* trace;           // optional pipeline trace of CTA 0: [event][tile] clock64 stamps (diagnostics)
 };
+
+constexpr int TRACE_TILES = 96;
+enum MuTrace { TR_MMA_TOP = 0, TR_MMA_Q, TR_MMA_R, TR_MMA_ISSUED, TR_X_ISSUE, TR_Q_ISSUE, TR_CONV_X, TR_CONV_RFREE, TR_CONV_DONE };
+#define MU_TRACE(ev, it)                                                                        \
+    do {                                                                                        \
+        if (prm.trace != nullptr && blockIdx.x == 0 && (it) < TRACE_TILES)                      \
+            prm.trace[(ev) * TRACE_TILES + (it)] = clock64();                                   \
+    } while (0)
 
 // mbarrier wait with a watchdog: a protocol error traps (the launch fails) instead of hanging the device
 __device__ __forceinline__ void mbar_wait_wd(uint32_t bar, uint32_t parity) {
@@ -155,6 +164,7 @@ tc_mu_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ C
                 const int s = it % NX;
                 mbar_wait_wd(bar(C::XEMPTY0 + s), (uint32_t(it / NX) & 1u) ^ 1u);
                 if (elect_one()) {
+                    MU_TRACE(TR_X_ISSUE, it);
                     const uint32_t dst = base + C::x0 + uint32_t(s) * X_BYTES;
                     const int oth0 = t * KS;
                     mbar_expect_tx(bar(C::XFULL0 + s), X_BYTES);
@@ -179,6 +189,7 @@ tc_mu_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ C
                 const int s = it % C::NQ;
                 mbar_wait_wd(bar(C::QEMPTY0 + s), (uint32_t(it / C::NQ) & 1u) ^ 1u);
                 if (elect_one()) {
+                    MU_TRACE(TR_Q_ISSUE, it);
                     const uint32_t dst = base + C::q0 + uint32_t(s) * C::QSLOT;
                     mbar_expect_tx(bar(C::QFULL0 + s), C::QSLOT);
                     tma_load_2d(dst, &tm_qt_hi, bar(C::QFULL0 + s), t * KS, 0);
@@ -198,8 +209,11 @@ tc_mu_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ C
             for (int t = t0; t < t1; t++, it++) {
                 const int qs = it % C::NQ, rb = it % C::NR;
                 const bool first = cpos == 0, last = cpos == chain - 1 || t == t1 - 1;
+                if (lane == 0) MU_TRACE(TR_MMA_TOP, it);
                 mbar_wait_wd(bar(C::QFULL0 + qs), uint32_t(it / C::NQ) & 1u);
+                if (lane == 0) MU_TRACE(TR_MMA_Q, it);
                 mbar_wait_wd(bar(C::RFULL0 + rb), uint32_t(it / C::NR) & 1u);
+                if (lane == 0) MU_TRACE(TR_MMA_R, it);
                 if (first && chains_done > 0) mbar_wait_wd(bar(C::OUTEMPTY), uint32_t(chains_done - 1) & 1u);
                 tc_fence_after();
                 if (elect_one()) {
@@ -219,6 +233,7 @@ tc_mu_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ C
                     umma_commit(bar(C::QEMPTY0 + qs));      // Q^T slot read
                     umma_commit(bar(C::RFREE0 + rb));       // R buffer read
                     if (last) umma_commit(bar(C::OUTFULL));
+                    MU_TRACE(TR_MMA_ISSUED, it);
                 }
                 __syncwarp();
                 if (last) { chains_done++; cpos = 0; }
@@ -287,6 +302,7 @@ tc_mu_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ C
             for (int t = t0; t < t1; t++, it++) {
                 const int s = it % NX, rb = it % C::NR;
                 mbar_wait_wd(bar(C::XFULL0 + s), uint32_t(it / NX) & 1u);
+                if (threadIdx.x == 0) MU_TRACE(TR_CONV_X, it);
                 const unsigned char* xs = gen + C::x0 + s * X_BYTES;
                 float xv[8];
                 if (MODE == 0) {
@@ -310,6 +326,7 @@ tc_mu_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ C
                 }
                 // R buffer it % NR: the MMAs of tile it - NR must have read it
                 mbar_wait_wd(bar(C::RFREE0 + rb), (uint32_t(it / C::NR) & 1u) ^ 1u);
+                if (threadIdx.x == 0) MU_TRACE(TR_CONV_RFREE, it);
                 tc_fence_after();
                 const uint32_t r_hi = lane_addr + uint32_t(C::TM_R + rb * 2 * KS + c * 8);
                 tmem_st8(r_hi, hi);
@@ -318,6 +335,7 @@ tc_mu_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ C
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bar(C::RFULL0 + rb));
+                if (threadIdx.x == 0) MU_TRACE(TR_CONV_DONE, it);
                 const bool unit_ends = t == t1 - 1;
                 const bool last = cpos == chain - 1 || unit_ends;
                 // end of a chain: OUT -> registers, deferred by one tile (the chain's last MMAs have completed by then)
@@ -436,6 +454,11 @@ void launch_mu(pycmf_ctx* ctx, int64_t own_n, int64_t oth_n, const float* X, int
     prm.n_units = n_units;
     prm.chain = chain;
     prm.part = static_cast<float*>(scratch(ctx, 0, size_t(n_units) * OWN * KN * sizeof(float)));
+    prm.trace = nullptr;
+    if (ctx->tc_trace && family == nullptr) {      // the passes over X only
+        prm.trace = static_cast<long long*>(scratch(ctx, 2, sizeof(long long) * tc_trace_words()));
+        PYCMF_CUDA(cudaMemsetAsync(prm.trace, 0, sizeof(long long) * tc_trace_words(), ctx->stream));
+    }
     auto kern = tc_mu_kernel<MODE, KN>;
     const size_t smem = C::total + 1024;
     PYCMF_CHECK(smem <= size_t(ctx->max_smem_optin), "tc mu pass: shared memory budget exceeded");

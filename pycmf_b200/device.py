@@ -243,13 +243,14 @@ class CudaBackend:
             csr.sort_indices()
             if csr.nnz >= 2 ** 31 or max(csr.shape) >= 2 ** 31:
                 raise ValueError("sparse matrix too large for int32 indices")
-            csc = csr.T.tocsr()
-            csc.sort_indices()
-            i32 = self.torch.int32
-            return SparseMatrix(
-                csr.shape,
-                self.to_device(csr.indptr, np.int32), self.to_device(csr.indices, np.int32), self.to_device(csr.data),
-                self.to_device(csc.indptr, np.int32), self.to_device(csc.indices, np.int32), self.to_device(csc.data))
+            # only the CSR arrays cross PCIe; the CSC copy (the CSR of X^T: X^T U and the column access of the Newton V
+            # update) is built on the device by a stable sort on the column index -- rows stay ascending inside a column,
+            # i.e. exactly scipy's sorted csr.T.tocsr(), which on the host takes seconds at C3 scale (2e8 nonzeros)
+            rowptr = self.to_device(csr.indptr, np.int32)
+            colidx = self.to_device(csr.indices, np.int32)
+            vals = self.to_device(csr.data)
+            colptr, rowidx, cvals = self._csc_from_csr(rowptr, colidx, vals, csr.shape[0], csr.shape[1])
+            return SparseMatrix(csr.shape, rowptr, colidx, vals, colptr, rowidx, cvals)
         M = np.asarray(M)
         if M.ndim != 2:
             raise ValueError("Expected 2D array, got %dD array instead" % M.ndim)
@@ -264,15 +265,19 @@ class CudaBackend:
         lo, hi = int(rp[0]), int(rp[-1])
         rp -= lo
         colidx, vals = M.colidx[lo:hi].clone(), M.vals[lo:hi].clone()
-        # CSC of the slice, built on device by a stable sort on the column index
-        rows_of = torch.repeat_interleave(torch.arange(r1 - r0, device=self.device, dtype=torch.int32),
-                                          (rp[1:] - rp[:-1]).to(torch.int64))
-        order = torch.sort(colidx.to(torch.int64), stable=True).indices
-        counts = torch.bincount(colidx.to(torch.int64), minlength=M.shape[1])
-        colptr = torch.zeros(M.shape[1] + 1, dtype=torch.int32, device=self.device)
+        colptr, rowidx, cvals = self._csc_from_csr(rp, colidx, vals, r1 - r0, M.shape[1])
+        return SparseMatrix((r1 - r0, M.shape[1]), rp, colidx, vals, colptr, rowidx, cvals)
+
+    def _csc_from_csr(self, rowptr, colidx, vals, n_rows, n_cols):
+        """(colptr, rowidx, cvals) of the matrix whose CSR arrays are given: stable sort of the nonzeros on the column."""
+        torch = self.torch
+        counts_r = (rowptr[1:] - rowptr[:-1]).to(torch.int64)
+        rows_of = torch.repeat_interleave(torch.arange(n_rows, device=self.device, dtype=torch.int32), counts_r)
+        order = torch.sort(colidx, stable=True).indices
+        counts = torch.bincount(colidx, minlength=n_cols)
+        colptr = torch.zeros(n_cols + 1, dtype=torch.int32, device=self.device)
         colptr[1:] = torch.cumsum(counts, 0).to(torch.int32)
-        return SparseMatrix((r1 - r0, M.shape[1]), rp, colidx, vals, colptr, rows_of[order].contiguous(),
-                            vals[order].contiguous())
+        return colptr, rows_of[order].contiguous(), vals[order].contiguous()
 
     # ---- target argument packing ---------------------------------------------------------------
     def _target_args(self, T, trans=False, rows=None):

@@ -408,3 +408,27 @@ def test_spmm_float32_kernels_agree(k, path):
     got = be.to_host(be.spmm(Sd, be.to_device(B), alpha=0.5, beta=2.0, out=be.to_device(C0)))
     assert rel_fro(got, 0.5 * (S @ B) + 2.0 * C0) < 2e-6
     assert rel_fro(be.to_host(be.spmm(Sd, be.to_device(A), transposed=True)), S.T @ A) < 2e-6
+
+
+def test_ingest_builds_the_csc_copy_on_device(be64):
+    """Only the CSR arrays are uploaded; the CSC copy built on the device equals scipy's sorted transposition bit for bit
+    (same order inside a column => same summation order as the host-built copy), empty rows / columns included."""
+    rng = np.random.RandomState(3)
+    S = sp.random(700, 430, density=0.03, random_state=rng, format="lil")
+    S[11, :] = 0
+    S[:, 7] = 0
+    S[:, 20] = rng.rand(700, 1)
+    S = sp.csr_matrix(S)
+    S.eliminate_zeros()
+    Sd = be64.ingest(S)
+    ref = S.T.tocsr()
+    ref.sort_indices()
+    assert np.array_equal(be64.to_host(Sd.colptr), ref.indptr)
+    assert np.array_equal(be64.to_host(Sd.rowidx), ref.indices)
+    assert np.array_equal(be64.to_host(Sd.cvals), ref.data)
+    sub = be64.row_slice(Sd, 100, 613)
+    ref = S[100:613].T.tocsr()
+    ref.sort_indices()
+    assert np.array_equal(be64.to_host(sub.colptr), ref.indptr)
+    assert np.array_equal(be64.to_host(sub.rowidx), ref.indices)
+    assert np.array_equal(be64.to_host(sub.cvals), ref.data)
