@@ -294,7 +294,9 @@ def run_ours(args):
         traffic = None
         try:
             with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-                traffic = json.load(f).get("%s:%s:%s" % (args.workload, args.dtype, dom))
+                tj = json.load(f)
+                traffic = tj.get("%s@%s:%s:%s" % (args.workload, scale, args.dtype, dom),
+                                 tj.get("%s:%s:%s" % (args.workload, args.dtype, dom)) if scale == 1.0 else None)
         except Exception:  # noqa: BLE001
             pass
         common = {"traffic": traffic, "avg_launch_ms": round(per_launch_ms, 5), "launches_timed": cnt,

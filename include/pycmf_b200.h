@@ -48,21 +48,25 @@ int pycmf_destroy(pycmf_ctx* ctx);
 /* stream is a cudaStream_t (0 = legacy default stream) */
 int pycmf_set_stream(pycmf_ctx* ctx, void* stream);
 /* options: "chol_fastpath" (0/1, default 1), "dense_path" (0 = generic FMA kernels, 1 = tcgen05
- * 3xTF32, 2 = tcgen05 1xTF32; default 1 where available), "max_scratch_mb", "tc_max_splits" (tests) */
+ * 3xTF32 for n_components 32 / 64 / 128 / 192 / 256, 2 = tcgen05 1xTF32 (k = 32 only); default 1),
+ * "spmm_path" (0 = generic CSR kernel, 1 = vector / sub-warp-grouped kernels for k = 32 / 64 / 128 / 256,
+ * default 1), "max_scratch_mb", "side_streams" (0/1), and for tests and tuning: "tc_max_splits", "tc_ctas",
+ * "tc_chain", "tc_x_promotion", "tc_prefetch", "tc_trace", "finish_minblocks" */
 int pycmf_set_option(pycmf_ctx* ctx, const char* key, double value);
 /* number of kernels this context launched since creation (bench.py's gpu_launches) */
 int64_t pycmf_launch_count(pycmf_ctx* ctx);
 
 /* per-kernel-family device timers (bench.py's live roofline): enable, run, then query by family name
- * ("resid_left", "resid_right", "gemm", "spmm", "row_grad_hess", "safe_solve", "tc_xv", "tc_xtu", ...).
+ * ("resid_left", "resid_right", "gemm", "spmm", "row_grad_hess", "safe_solve", "tc_resid_left",
+ * "tc_resid_right", "tc_xv", "tc_xtu", "tc_ytv", "tc_factor", ...).
  * query synchronises the stream; total_ms / count cover everything since the last reset. */
 int pycmf_profile_enable(pycmf_ctx* ctx, int on);
 int pycmf_profile_query(pycmf_ctx* ctx, const char* family, double* total_ms, int64_t* count);
 int pycmf_profile_reset(pycmf_ctx* ctx);
 
-/* diagnostics: with option "tc_trace" = 1 every tcgen05 pass records clock64 stamps of its pipeline events
- * (TMA issue, GEMM1 issue, S seen, R published, GEMM2 issue, stage freed, operands landed) for the first 32
- * tiles of CTA (0,0); this copies the last trace (7 x 32 int64) to the host. */
+/* diagnostics: with option "tc_trace" = 1 every tcgen05 pass over X records clock64 stamps of its pipeline
+ * events for the first 96 tiles of CTA 0 ([event][tile] int64; events of the fused-residual pass: see
+ * scripts/tc_trace.py, of the MU pass: scripts/tc_mu_trace.py); this copies the last trace to the host. */
 int pycmf_debug_tc_trace(pycmf_ctx* ctx, int64_t* host, int64_t max_words);
 
 /* ---- primitives (used by the phases below; exported for tests and composition) ---------- */

@@ -302,10 +302,9 @@ __device__ void chol_solve(const double* W, int k, double* b) {
 // row-major == column-major).  On exit the columns are mutually orthogonal: W = Q diag(lambda) (up to
 // column order / sign), so x = S(H) g = g/p + sum_{sigma_i >= p} (1/sigma_i - 1/p) (w_i.g)/sigma_i^2 w_i.
 __device__ void jacobi_clamped_solve(double* W, int k, const double* g, double* x, double* xpart,
-                                     SolveShared* sh, double pert) {
+                                     SolveShared* sh, double pert, double tol) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     const int kk = (k + 1) & ~1;
-    const double tol = 1e-15;
     const double skip2 = (1e-3 * pert) * (1e-3 * pert);
     for (int sweep = 0; sweep < 60; sweep++) {
         __syncthreads();
@@ -324,7 +323,13 @@ __device__ void jacobi_clamped_solve(double* W, int k, const double* g, double* 
                     double a = wp[r], b = wq[r];
                     al = fma(a, a, al); be = fma(b, b, be); ga = fma(a, b, ga);
                 }
-                al = warp_sum(al); be = warp_sum(be); ga = warp_sum(ga);
+                // the three butterfly reductions interleaved: 5 dependent shuffle rounds instead of 15
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    const double a2 = __shfl_xor_sync(0xffffffffu, al, o), b2 = __shfl_xor_sync(0xffffffffu, be, o),
+                                 g2 = __shfl_xor_sync(0xffffffffu, ga, o);
+                    al += a2; be += b2; ga += g2;
+                }
                 if (ga == 0.0 || fmax(al, be) < skip2) continue;
                 if (fabs(ga) <= tol * sqrt(al * be)) continue;
                 double zeta = (be - al) / (2.0 * ga);
@@ -407,13 +412,15 @@ __device__ void safe_solve_one(double* W, const T* __restrict__ H, int k, double
     if (!done) {
         load_sym<T>(W, H, k, diag, scale);
         __syncthreads();
-        jacobi_clamped_solve(W, k, g, x, xpart, sh, pert);
+        // rotations stop at |w_p . w_q| <= tol |w_p| |w_q|: float64 inputs to working precision; float32 inputs carry 6e-8
+        // relative noise already, 1e-11 leaves the clamped solve exact to far below that and saves the last sweep
+        jacobi_clamped_solve(W, k, g, x, xpart, sh, pert, sizeof(T) == 4 ? 1e-11 : 1e-15);
     }
 }
 
 // MODE 0: x_b = S(H_b) g_b (all float64).  MODE 1: Newton row update on F.
 template <typename T, int MODE>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(1024)
 safe_solve_kernel(int64_t batch, int k, const T* __restrict__ H, int64_t h_stride, const T* __restrict__ g,
                   T* __restrict__ out, double l1, double l2, double l2_diag, double pert, bool non_negative,
                   bool chol_fastpath, double* __restrict__ Wglobal, double h_scale) {
@@ -548,7 +555,9 @@ void launch_solve(pycmf_ctx* ctx, int64_t batch, int64_t k, const T* H, int64_t 
     if (safe_solve_small<T, MODE>(ctx, batch, k, H, h_stride, g, out, l1, l2, l2_diag, pert, non_negative, h_scale,
                                   known_pd))
         return;
-    int nthreads = k <= 32 ? 64 : (k <= 64 ? 128 : 256);
+    // one warp per Jacobi pair: k / 2 pairs per step, so wide matrices get a full CTA (k = 128: 64 pairs on 32 warps are two
+    // rounds per step instead of eight on 8 warps)
+    int nthreads = k <= 32 ? 64 : (k <= 64 ? 128 : (k <= 96 ? 256 : 1024));
     bool w_in_smem = solve_smem_bytes(int(k), nthreads, true) <= size_t(ctx->max_smem_optin);
     size_t smem = solve_smem_bytes(int(k), nthreads, w_in_smem);
     auto kern = safe_solve_kernel<T, MODE>;
