@@ -121,8 +121,11 @@ class CudaBackend:
         self.stream = stream
         _lib.check(self.lib.pycmf_set_stream(self.ctx, C.c_void_p(stream.cuda_stream)))
 
+    HOST_OPTIONS = ("pad_pitch",)        # handled in this class, unknown to the C library
+
     def set_option(self, key, value):
-        _lib.check(self.lib.pycmf_set_option(self.ctx, key.encode(), float(value)))
+        if key not in self.HOST_OPTIONS:
+            _lib.check(self.lib.pycmf_set_option(self.ctx, key.encode(), float(value)))
         self._options[key] = float(value)
         if self._aux is not None:
             self._aux.set_option(key, value)
@@ -190,7 +193,7 @@ class CudaBackend:
     def zeros(self, *shape, dtype=None):
         return self.torch.zeros(*shape, dtype=dtype or self.tdtype, device=self.device)
 
-    def to_device(self, a, dtype=None):
+    def to_device(self, a, dtype=None, raw=False):
         """Host ndarray -> contiguous device tensor of the compute dtype (or `dtype`).
 
         The bytes are copied as they are (asynchronously when the array lives in pinned memory) and
@@ -207,9 +210,30 @@ class CudaBackend:
             a = a.copy()
         t = torch.from_numpy(a)
         d = t.to(self.device, non_blocking=t.is_pinned())
+        if raw:
+            return d
         tw = {np.dtype("float32"): torch.float32, np.dtype("float64"): torch.float64,
               np.dtype("int32"): torch.int32, np.dtype("int64"): torch.int64}[want]
         return d if d.dtype == tw else d.to(tw)
+
+    def dense(self, t):
+        """DenseMatrix of the compute dtype over the values of the device tensor `t` (rows x cols, any float dtype).
+
+        When a row is not a multiple of 128 bytes the matrix is stored with the row pitch padded up to one: the passes
+        that read column blocks of X (X^T U, the Newton V gradient) fetch 512-byte row segments, and at an unaligned
+        pitch every segment straddles one more 128-byte line (ncu, C2 with pitch 20000 B: 535 MB from HBM for a
+        404 MB X).  The cast of a float64 upload goes straight into the padded buffer: no extra pass."""
+        torch = self.torch
+        rows, cols = t.shape
+        es = torch.empty(0, dtype=self.tdtype).element_size()
+        pad = self._options.get("pad_pitch", 1.0) != 0.0 and rows * cols >= (1 << 16) and (cols * es) % 128 != 0
+        if not pad:
+            return DenseMatrix(t.contiguous() if t.dtype == self.tdtype else t.to(self.tdtype))
+        ld = (cols * es + 127) // 128 * 128 // es
+        buf = torch.empty(rows, ld, dtype=self.tdtype, device=self.device)
+        buf[:, cols:].zero_()
+        buf[:, :cols].copy_(t)
+        return DenseMatrix(buf[:, :cols])
 
     def to_host(self, t):
         return t.detach().to("cpu").numpy()
@@ -254,7 +278,7 @@ class CudaBackend:
         M = np.asarray(M)
         if M.ndim != 2:
             raise ValueError("Expected 2D array, got %dD array instead" % M.ndim)
-        return DenseMatrix(self.to_device(M))
+        return self.dense(self.to_device(M, raw=True))
 
     def row_slice(self, M, r0, r1):
         """Rows [r0, r1) of an ingested matrix (view for dense, re-based copy for sparse)."""

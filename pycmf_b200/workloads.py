@@ -129,7 +129,7 @@ def generate(be, name, r0, r1, scale=1.0, seed=1234):
         X = SparseMatrix((r1 - r0, d), rowptr, colidx, vals, colptr, row_ids[order].contiguous(),
                          vals[order].contiguous())
     else:
-        X = DenseMatrix(torch.cat(blocks_x, 0).contiguous())
+        X = be.dense(torch.cat(blocks_x, 0))
     return dict(X=X, Y=DenseMatrix(Y.contiguous()), U_raw=torch.cat(blocks_u, 0), V_raw=(V0a, V0b), Z_raw=Z0,
                 x_sum=x_sum, y_sum=float(Y.sum(dtype=torch.float64)), shape=(n, d, l, k), config=c)
 

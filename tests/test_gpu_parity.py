@@ -432,3 +432,26 @@ def test_ingest_builds_the_csc_copy_on_device(be64):
     assert np.array_equal(be64.to_host(sub.colptr), ref.indptr)
     assert np.array_equal(be64.to_host(sub.rowidx), ref.indices)
     assert np.array_equal(be64.to_host(sub.cvals), ref.data)
+
+
+def test_dense_ingest_pads_the_row_pitch_to_128_bytes():
+    """Unaligned row pitch (here 1300 x 4 B) is padded at ingest; every kernel family takes the leading dimension, so
+    products and the objective must not change (compared with the unpadded layout, and against NumPy)."""
+    from pycmf_b200.device import CudaBackend
+    rng = np.random.RandomState(2)
+    n, d, k = 700, 1300, 32
+    X, U, V = rng.rand(n, d), rng.rand(n, k), rng.rand(d, k)
+    outs = []
+    for pad in (1, 0):
+        be = CudaBackend(dtype="float32", options={"pad_pitch": pad})
+        Xd = be.ingest(X)
+        assert (Xd.t.stride(0) * 4) % 128 == (0 if pad else 1300 * 4 % 128) and Xd.shape == (n, d)
+        buf = be.to_host(be.mu_v_partial(Xd, be.to_device(U)))
+        sq = float(be.to_host(be.sqerr(be.to_device(U), be.to_device(V), Xd, "linear"))[0])
+        outL, outR, _ = be.resid_pass(be.to_device(U), be.to_device(V), Xd, "linear")
+        outs.append((buf, sq, be.to_host(outL), be.to_host(outR)))
+    R = U @ V.T - X
+    assert rel_fro(outs[0][0][:d], X.T @ U) < 2e-5 and rel_fro(outs[0][2], R @ V) < 5e-5 and rel_fro(outs[0][3], R.T @ U) < 5e-5
+    assert abs(outs[0][1] - (R ** 2).sum()) / (R ** 2).sum() < 1e-5
+    for a, b in zip(outs[0], outs[1]):
+        assert rel_fro(np.asarray(a), np.asarray(b)) < 1e-5
