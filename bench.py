@@ -300,7 +300,9 @@ def run_ours(args):
         except Exception:  # noqa: BLE001
             pass
         common = {"traffic": traffic, "avg_launch_ms": round(per_launch_ms, 5), "launches_timed": cnt,
-                  "share_of_step": round(tot / ms_prof, 4),
+                  # device time of this family / device time of all timed families of the step (serialised, like the
+                  # ncu launch list it is to be compared with; the host-side gaps of the eager region are excluded)
+                  "share_of_step": round(tot / sum(v[0] for v in fams.values()), 4),
                   "timed_in": "region B: %d eager, serialised iterations with per-family CUDA-event timers "
                               "(%.5f ms/step); value is region A (CUDA-graph replay, U / Z updates and shared-Hessian "
                               "branches on side streams)" % (n_prof, ms_prof / n_prof),
