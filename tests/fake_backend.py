@@ -34,6 +34,9 @@ class FakeBackend:
     def ingest(self, A):
         return A if isinstance(A, M) else M(A)
 
+    def row_slice(self, T, r0, r1):
+        return M(T.a[r0:r1])
+
     def synchronize(self):
         pass
 

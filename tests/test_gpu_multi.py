@@ -18,6 +18,7 @@ from helpers import load_golden, draw_masks_for_case, rel_fro
 from test_gpu_parity import _mid_case, MID, NT
 import zlib
 from pycmf_b200.cmf_solvers import MUSolver, NewtonSolver
+MUSolver.SHARD_V_MIN = 0          # exercise the row-sharded V update on the small test shapes
 from pycmf_b200.sharding import TorchComm, Comm
 
 def run(case, dtype, comm, masks=None, dense_path=0):

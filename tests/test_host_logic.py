@@ -50,6 +50,7 @@ def test_product_never_imports_the_oracle():
 
 def _run_fake(case, masks=None, comm=None):
     from pycmf_b200.cmf_solvers import MUSolver, NewtonSolver
+    MUSolver.SHARD_V_MIN = 0          # exercise the row-sharded V update on the small test shapes
     p = dict(case["params"])
     solver = p.pop("solver")
     cls = MUSolver if solver == "mu" else NewtonSolver
