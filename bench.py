@@ -40,6 +40,7 @@ def parse_args():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=["c1", "c2", "c3", "c4", "c5"])
     ap.add_argument("--scale", type=float, default=None, help="row (and, if sparse, column) scale of the workload")
+    ap.add_argument("--col-scale", type=float, default=1.0, help="column scale (toy slices of the sparse workloads)")
     ap.add_argument("--dtype", default="float32", choices=["float32", "float64"])
     ap.add_argument("--dense-path", type=int, default=None, help="0 generic FMA, 1 tcgen05 3xTF32, 2 tcgen05 1xTF32")
     ap.add_argument("--opt", action="append", default=[], help="backend option key=value (repeatable)")
@@ -194,11 +195,11 @@ def run_ours(args):
         opts[key] = float(val)
     be = CudaBackend(device=local_rank, dtype=args.dtype, options=opts)
     scale = args.scale if args.scale is not None else default_scale(args.workload)
-    cfg = W.describe(args.workload, scale)
+    cfg = W.describe(args.workload, scale, args.col_scale)
     params = W.SOLVER_PARAMS[args.workload]
     n = cfg["n"]
     r0, r1 = row_range(n, rank, world)
-    data = W.generate(be, args.workload, r0, r1, scale)
+    data = W.generate(be, args.workload, r0, r1, scale, col_scale=args.col_scale)
     xs = torch.tensor([data["x_sum"]], dtype=torch.float64, device=be.device)
     comm.all_reduce_sum(xs)
     U, V, Z = W.finish_init(be, data, float(xs.item()))
@@ -411,14 +412,14 @@ def run_reference(args):
         return
     from pycmf_b200 import workloads as W
     scale = args.scale if args.scale is not None else default_scale(args.workload)
-    cfg = W.describe(args.workload, scale)
+    cfg = W.describe(args.workload, scale, args.col_scale)
     params = W.SOLVER_PARAMS[args.workload]
     n, d, l, k = cfg["n"], cfg["d"], cfg["l"], cfg["k"]
     try:
         import torch
         from pycmf_b200.device import CudaBackend
         be = CudaBackend(device=int(os.environ.get("LOCAL_RANK", "0")), dtype=args.dtype)
-        data = W.generate(be, args.workload, 0, n, scale)
+        data = W.generate(be, args.workload, 0, n, scale, col_scale=args.col_scale)
         U, V, Z = W.finish_init(be, data, data["x_sum"])
         host = host_problem_from_device(be, data, U, V, Z)
         del data, be

@@ -235,6 +235,18 @@ class CudaBackend:
         buf[:, :cols].copy_(t)
         return DenseMatrix(buf[:, :cols])
 
+    def dense_empty(self, rows, cols):
+        """Uninitialised DenseMatrix (rows x cols) with the padded row pitch of dense(): filled in place by the caller
+        (a 40 GB X is generated / uploaded block by block without a second full-size buffer)."""
+        torch = self.torch
+        es = torch.empty(0, dtype=self.tdtype).element_size()
+        pad = self._options.get("pad_pitch", 1.0) != 0.0 and rows * cols >= (1 << 16) and (cols * es) % 128 != 0
+        ld = (cols * es + 127) // 128 * 128 // es if pad else cols
+        buf = torch.empty(rows, ld, dtype=self.tdtype, device=self.device)
+        if ld != cols:
+            buf[:, cols:].zero_()
+        return DenseMatrix(buf[:, :cols])
+
     def to_host(self, t):
         return t.detach().to("cpu").numpy()
 

@@ -1,13 +1,14 @@
-"""Synthetic workloads of BASELINE.json (`configs`), generated on the device in fixed row blocks so that
-the data are identical for every shard count.  Used by bench.py and the full-size tests.
+"""Synthetic workloads of BASELINE.json (`configs`), generated with plain torch in fixed row blocks so that the data
+are identical for every shard count and for every row sample.  Used by bench.py and the full-size tests.
+
+This module imports nothing of the package at module level: `generate_raw` needs only torch and a device, so the
+reference arm of bench.py builds its inputs without loading libpycmf_b200.so.
 """
 import math
 
-import numpy as np
-
 ROW_BLOCK = 1000
 
-# name -> shape / solver description (BASELINE.json configs[0..4]; c3 / c4 / c5 can be row-scaled)
+# name -> shape / solver description (BASELINE.json configs[0..4])
 CONFIGS = {
     "c1": dict(n=1000, d=500, l=20, k=10, solver="mu", sparse=False, x_link="linear", y_link="linear"),
     "c2": dict(n=20000, d=5000, l=50, k=32, solver="newton", sparse=False, x_link="linear", y_link="logit"),
@@ -31,13 +32,22 @@ SOLVER_PARAMS = {
 }
 
 
-def describe(name, scale=1.0):
+def describe(name, scale=1.0, col_scale=1.0):
+    """Shape / solver description; `scale` shrinks the rows of X (a row shard of the full problem keeps every
+    column: V stays full size), `col_scale` additionally shrinks d (toy slices only)."""
     c = dict(CONFIGS[name])
     if scale != 1.0:
-        c["n"] = max(ROW_BLOCK, int(c["n"] * scale) // ROW_BLOCK * ROW_BLOCK)
-        if c["sparse"]:
-            c["d"] = max(1000, int(c["d"] * scale))
+        c["n"] = max(ROW_BLOCK, int(round(c["n"] * scale)) // ROW_BLOCK * ROW_BLOCK)
+    if col_scale != 1.0:
+        c["d"] = max(1000, int(c["d"] * col_scale))
     return c
+
+
+def label(name, c):
+    """The workload string both bench arms print in `config.workload`."""
+    return "%s: %s X %dx%d + Y %dx%d, k=%d, solver=%s, x_link=%s, y_link=%s%s" % (
+        name, "CSR" if c["sparse"] else "dense", c["n"], c["d"], c["d"], c["l"], c["k"], c["solver"], c["x_link"],
+        c["y_link"], (", sg=%.2f" % c["sg_sample_ratio"]) if "sg_sample_ratio" in c else "")
 
 
 def _gen(torch, device, seed):
@@ -46,15 +56,17 @@ def _gen(torch, device, seed):
     return g
 
 
-def generate(be, name, r0, r1, scale=1.0, seed=1234):
-    """Rows [r0, r1) of workload `name` on be.device.  Returns dict(X, Y, U, V, Z, sums) where X is a
-    DenseMatrix / SparseMatrix of the compute dtype, factors are the non-negative random init of the
-    reference (cmf.py:110-117 scaling, (V+V_)/2 merge) and `sums` = (sum X over these rows, sum Y)."""
-    from .device import DenseMatrix, SparseMatrix
-    torch = be.torch
-    c = describe(name, scale)
+def generate_raw(torch, device, name, r0, r1, scale=1.0, col_scale=1.0, seed=1234, dtype=None, x_out=None):
+    """Rows [r0, r1) of workload `name` as plain torch tensors on `device`.
+
+    Returns dict(X = dense (rows x d) tensor | None, csr = (rowptr int32, colidx int32, vals) | None, Y, U_raw, V_raw,
+    Z_raw, x_sum, y_sum, shape, config).  Factors are the raw |N(0,1)| draws of the reference's random init
+    (`finish_init` applies the cmf.py:110-117 scaling and the (V+V_)/2 merge).  `x_out`, if given, is a preallocated
+    (rows x d) tensor (any row pitch) the dense X is written into block by block."""
+    c = describe(name, scale, col_scale)
     n, d, l, k = c["n"], c["d"], c["l"], c["k"]
-    dev, dt = be.device, be.tdtype
+    dev = device
+    dt = dtype or torch.float32
     g0 = _gen(torch, dev, seed)
     Vt = 0.5 * torch.randn(d, k, generator=g0, device=dev, dtype=torch.float32).abs()
     Zt = 0.5 * torch.randn(l, k, generator=g0, device=dev, dtype=torch.float32)
@@ -75,7 +87,10 @@ def generate(be, name, r0, r1, scale=1.0, seed=1234):
         w = (torch.arange(d, device=dev, dtype=torch.float64) + 10.0) ** -0.9
         perm = torch.randperm(d, generator=g0, device=dev)
         col_cdf = torch.cumsum(w / w.sum(), 0)
-    blocks_x, blocks_u, x_sum = [], [], 0.0
+    blocks_u, x_sum = [], 0.0
+    Xd = None
+    if not c["sparse"]:
+        Xd = x_out if x_out is not None else torch.empty(r1 - r0, d, dtype=dt, device=dev)
     rp_parts, ci_parts, vl_parts, nnz_off = [], [], [], 0
     for b0 in range((r0 // ROW_BLOCK) * ROW_BLOCK, r1, ROW_BLOCK):
         g = _gen(torch, dev, seed + 1 + b0 // ROW_BLOCK)
@@ -116,37 +131,52 @@ def generate(be, name, r0, r1, scale=1.0, seed=1234):
                 Xb = torch.randn(rows, d, generator=g, device=dev, dtype=torch.float32).abs()
             Xb = Xb[lo:hi]
             x_sum += float(Xb.sum(dtype=torch.float64))
-            blocks_x.append(Xb.to(dt))
+            Xd[b0 + lo - r0:b0 + hi - r0].copy_(Xb)
         blocks_u.append(U0[lo:hi])
+    csr = None
     if c["sparse"]:
         rowptr = torch.cat([torch.zeros(1, device=dev, dtype=torch.int64)] + rp_parts).to(torch.int32)
-        colidx, vals = torch.cat(ci_parts), torch.cat(vl_parts)
-        order = torch.sort(colidx.to(torch.int64), stable=True).indices
-        row_ids = torch.repeat_interleave(torch.arange(r1 - r0, device=dev, dtype=torch.int32),
-                                          (rowptr[1:] - rowptr[:-1]).to(torch.int64))
-        colptr = torch.zeros(d + 1, device=dev, dtype=torch.int32)
-        colptr[1:] = torch.cumsum(torch.bincount(colidx.to(torch.int64), minlength=d), 0).to(torch.int32)
-        X = SparseMatrix((r1 - r0, d), rowptr, colidx, vals, colptr, row_ids[order].contiguous(),
-                         vals[order].contiguous())
-    else:
-        X = be.dense(torch.cat(blocks_x, 0))
-    return dict(X=X, Y=DenseMatrix(Y.contiguous()), U_raw=torch.cat(blocks_u, 0), V_raw=(V0a, V0b), Z_raw=Z0,
-                x_sum=x_sum, y_sum=float(Y.sum(dtype=torch.float64)), shape=(n, d, l, k), config=c)
+        csr = (rowptr, torch.cat(ci_parts), torch.cat(vl_parts))
+    return dict(X=Xd, csr=csr, Y=Y.contiguous(), U_raw=torch.cat(blocks_u, 0), V_raw=(V0a, V0b), Z_raw=Z0,
+                x_sum=x_sum, y_sum=float(Y.sum(dtype=torch.float64)), shape=(n, d, l, k), config=c,
+                rows=(r0, r1))
 
 
-def finish_init(be, data, x_sum_total):
-    """Scale the raw N(0,1) draws like the reference's random init: sqrt(mean / k) (cmf.py:111)."""
-    n, d, l, k = data["shape"]
-    sx = math.sqrt(abs(x_sum_total / (float(n) * d)) / k)
-    sy = math.sqrt(abs(data["y_sum"] / (float(d) * l)) / k)
-    dt = be.tdtype
+def generate(be, name, r0, r1, scale=1.0, seed=1234, col_scale=1.0):
+    """`generate_raw` on the backend's device with X / Y wrapped as the backend's DenseMatrix / SparseMatrix (padded
+    row pitch, CSC copy built on the device)."""
+    from .device import DenseMatrix, SparseMatrix
+    torch = be.torch
+    c = describe(name, scale, col_scale)
+    Xm = None if c["sparse"] else be.dense_empty(r1 - r0, c["d"])     # filled block by block (C5: 40 GB, one copy)
+    raw = generate_raw(torch, be.device, name, r0, r1, scale, col_scale, seed, dtype=be.tdtype,
+                       x_out=None if Xm is None else Xm.t)
+    if c["sparse"]:
+        rowptr, colidx, vals = raw["csr"]
+        colptr, rowidx, cvals = be._csc_from_csr(rowptr, colidx, vals, r1 - r0, c["d"])
+        Xm = SparseMatrix((r1 - r0, c["d"]), rowptr, colidx, vals, colptr, rowidx, cvals)
+    raw["X"] = Xm
+    raw["Y"] = DenseMatrix(raw["Y"])
+    return raw
+
+
+def init_scales(shape, x_sum_total, y_sum):
+    """sqrt(mean / k) of the reference's random init (cmf.py:111) for X and for Y."""
+    n, d, l, k = shape
+    return (math.sqrt(abs(x_sum_total / (float(n) * d)) / k), math.sqrt(abs(y_sum / (float(d) * l)) / k))
+
+
+def finish_init(be_or_dtype, data, x_sum_total):
+    """Scale the raw |N(0,1)| draws like the reference's random init and merge V = (V + V_) / 2 (cmf.py:425-430)."""
+    sx, sy = init_scales(data["shape"], x_sum_total, data["y_sum"])
+    dt = getattr(be_or_dtype, "tdtype", be_or_dtype)
     U = (sx * data["U_raw"]).to(dt).contiguous()
     V = ((sx * data["V_raw"][0] + sy * data["V_raw"][1]) / 2).to(dt).contiguous()
     Z = (sy * data["Z_raw"]).to(dt).contiguous()
     return U, V, Z
 
 
-def algorithmic_work(name, c, dtype_bytes=4):
+def algorithmic_work(c, dtype_bytes=4, nnz=None):
     """Per-iteration algorithmic flops / bytes (SURVEY 8d formulas)."""
     n, d, l, k = c["n"], c["d"], c["l"], c["k"]
     s = dtype_bytes
@@ -154,7 +184,7 @@ def algorithmic_work(name, c, dtype_bytes=4):
         flops = 4 * n * d * k + 4 * d * l * k + 4 * n * k * k + 4 * d * k * k + 4 * l * k * k
         byts = 2 * n * d * s + 2 * d * l * s + 3 * (n + d + l) * k * s
     elif c["solver"] == "mu":
-        nnz = n * c["nnz_per_row"]
+        nnz = n * c["nnz_per_row"] if nnz is None else nnz
         flops = 4 * nnz * k + 4 * n * k * k + 4 * d * k * k + 4 * d * l * k
         byts = 2 * nnz * (s + 4) + 2 * (n + 1) * 4 + 3 * n * k * s + 6 * d * k * s
     else:
