@@ -142,8 +142,9 @@ int pycmf_newton_left(pycmf_ctx* ctx, int dtype, int64_t rows, int64_t m, int64_
                       const int32_t* sample_idx, int64_t n_sample);
 /* Shard-local X part of the V update for V rows [0, d_rows) of the given slice (:432-486):
  *   gx_j = alpha sum_{i in s} (f1(u_i . v_j) - X[i, j]) u_i                     -> gx (d_rows x k)
- *   Hx   = alpha U^T U (k x k, shared) if x_link is linear and no sampling, else
- *   Hx_j = alpha sum_{i in s} f1'(u_i . v_j) u_i u_i^T                          -> (d_rows x k x k)
+ *   Hx   = alpha U^T U (k x k, shared, ALWAYS FLOAT64 whatever `dtype`: rounded to float32 it costs 6e-8 x cond(H)
+ *          on the Newton step) if x_link is linear and no sampling, else
+ *   Hx_j = alpha sum_{i in s} f1'(u_i . v_j) u_i u_i^T                          -> (d_rows x k x k, compute dtype)
  * X is dense (n x d_total, ldx; the slice's first column is X + col0) or CSC arrays already
  * offset to the slice.  *hx_per_row tells the caller which Hx layout was written.
  * With row-sharded X/U the caller all-reduces gx and Hx before pycmf_newton_v_finish. */
@@ -173,6 +174,17 @@ int pycmf_safe_solve(pycmf_ctx* ctx, int64_t batch, int64_t k, const double* H, 
  * keyed by (seed, stream_id, row) through a cycle-walking Feistel permutation. */
 int pycmf_sample_indices(pycmf_ctx* ctx, int64_t rows, int64_t N, int64_t n_sample,
                          uint64_t seed, uint64_t stream_id, int32_t* idx);
+/* Topic-term extraction (reference analysis.py:1-16, `topic.argsort()[-10:]` per column of the term-topic matrix):
+ * out (k x topn int32) <- for every column c of F (rows x k, row pitch ld) the row indices of its topn largest entries
+ * in ascending weight order, ties by ascending index; -1 where the column has fewer than topn rows. */
+int pycmf_topk_columns(pycmf_ctx* ctx, int dtype, int64_t rows, int64_t k, const void* F, int64_t ld,
+                       int64_t topn, int32_t* out);
+/* The same sampler for a row-sharded fit: this rank draws the sets of global rows [row0, row0 + rows) (the key uses the
+ * global row, so every shard count sees the same sets), and, when hi > lo, keeps only the indices inside the window
+ * [lo, hi) re-based to lo -- the others become -1 and are skipped by the kernels (the rows of U a rank does not hold,
+ * cmf_solvers.py:455). */
+int pycmf_sample_indices_sharded(pycmf_ctx* ctx, int64_t rows, int64_t row0, int64_t N, int64_t n_sample,
+                                 uint64_t seed, uint64_t stream_id, int64_t lo, int64_t hi, int32_t* idx);
 
 #ifdef __cplusplus
 }

@@ -43,6 +43,8 @@ SIGNATURES = {
                                      _i32p, _i64, _vp, _vp, _int, _int, _dbl]),
     "pycmf_safe_solve": (_int, [_vp, _i64, _i64, _vp, _i64, _vp, _vp, _dbl]),
     "pycmf_sample_indices": (_int, [_vp, _i64, _i64, _i64, C.c_uint64, C.c_uint64, _i32p]),
+    "pycmf_topk_columns": (_int, [_vp, _int, _i64, _i64, _vp, _i64, _i64, _i32p]),
+    "pycmf_sample_indices_sharded": (_int, [_vp, _i64, _i64, _i64, _i64, C.c_uint64, C.c_uint64, _i64, _i64, _i32p]),
 }
 
 _lib = None

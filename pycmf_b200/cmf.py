@@ -223,8 +223,20 @@ class CMF(BaseEstimator, TransformerMixin):
         names = vectorizer.get_feature_names_out() if hasattr(vectorizer, "get_feature_names_out") \
             else vectorizer.get_feature_names()
         idx_to_word = np.array(names)
+        device = self._topk_device()
         if importances:
             _print_topic_terms_with_importances_from_matrices(
-                self.x_weights, self.y_weights, idx_to_word, topn_words=topn_words)
+                self.x_weights, self.y_weights, idx_to_word, topn_words=topn_words, device=device)
         else:
-            _print_topic_terms_from_matrix(self.x_weights, idx_to_word, topn_words=topn_words)
+            _print_topic_terms_from_matrix(self.x_weights, idx_to_word, topn_words=topn_words, device=device)
+
+    def _topk_device(self):
+        """The GPU the estimator fits on, for the per-topic top-k (None = host argsort when no GPU is visible: printing a
+        fitted model must work wherever the pickled estimator is loaded)."""
+        try:
+            import torch
+            if torch.cuda.is_available():
+                return True if self.device is None else self.device
+        except Exception:  # noqa: BLE001
+            pass
+        return None

@@ -20,6 +20,7 @@ import scipy.sparse as sp
 from .sharding import Comm, default_comm, localize_indices, row_range
 
 EPSILON = np.finfo(np.float32).eps
+MAX_COMPONENTS = 256
 INTEGER_TYPES = (numbers.Integral, np.integer)
 
 
@@ -106,6 +107,11 @@ class _IterativeCMFSolver:
 
     def prepare(self, X, Y, U, V, Z):
         """Host inputs -> FitState in HBM (row shard of X / U for this rank)."""
+        k = np.shape(V)[1]
+        if k > MAX_COMPONENTS:
+            raise ValueError("n_components = %d: the B200 backend keeps a factor row in registers / tensor memory and "
+                             "supports n_components <= %d (with n_components=None the reference's default is "
+                             "max(X.shape[1], Y.shape[1]): pass n_components explicitly)" % (k, MAX_COMPONENTS))
         be = self._get_backend()
         comm = self.comm if self.comm is not None else default_comm()
         n_local = X.shape[0] if X is not None else np.shape(U)[0]
@@ -350,6 +356,7 @@ class NewtonSolver(_IterativeCMFSolver):
                                   "equivalent to, but not the same stream as, the reference's np.random draws)")
             if mode == "device":
                 return self._masks_device(st)
+            self._sync_numpy_rng(st)
             host = _draw_masks_numpy(n, d, l, ratio, self.update_U, self.update_Z, self.update_V)
         dev = {}
         for key, val in host.items():
@@ -361,22 +368,39 @@ class NewtonSolver(_IterativeCMFSolver):
             dev[key] = be.to_device(val, np.int32)
         return dev
 
+    def _sync_numpy_rng(self, st):
+        """More than one rank drawing from NumPy's global RNG: every rank must see the same stream, or the replicated
+        V / Z silently diverge.  An integer / array random_state already seeded every rank alike (constructor); otherwise
+        rank 0 draws one seed from its stream and every rank re-seeds with it (once per solver)."""
+        if st.comm.world == 1 or getattr(self, "_rng_synced", False):
+            return
+        self._rng_synced = True
+        if self.random_state is not None and isinstance(self.random_state, INTEGER_TYPES + (np.ndarray, list)):
+            return
+        be = st.be
+        seed = be.zeros(1, dtype=be.torch.int64)
+        if st.comm.rank == 0:
+            seed[0] = int(np.random.randint(0, 2 ** 31 - 1))
+        st.comm.all_reduce_sum(seed)
+        np.random.seed(int(be.to_host(seed)[0]))
+
     def _masks_device(self, st):
         n, d, l, _ = st.shapes
         be, ratio = st.be, self.sg_sample_ratio
-        if st.comm.world > 1:
-            raise NotImplementedError("device sampler with row-sharded X: pass masks or use sampler='numpy'")
         seed = 0 if self.random_state is None or not isinstance(self.random_state, INTEGER_TYPES) \
             else int(self.random_state)
         it = st.iteration
         s_d, s_n, s_l = int(d * ratio), int(n * ratio), int(l * ratio)
         out = {}
+        # keyed by (seed, stream, GLOBAL row): a rank draws the sets of the rows of U it owns, and of the V update's
+        # samples of U rows it keeps the ones inside its row block -- the sets do not depend on the shard count
         if self.update_U:
-            out["U"] = be.sample_indices(n, d, s_d, seed, 4 * it + 0)
+            out["U"] = be.sample_indices(st.r1 - st.r0, d, s_d, seed, 4 * it + 0, row0=st.r0)
         if self.update_Z:
             out["Z"] = be.sample_indices(l, d, s_d, seed, 4 * it + 1)
         if self.update_V:
-            out["Vx"] = be.sample_indices(d, n, s_n, seed, 4 * it + 2)
+            out["Vx"] = be.sample_indices(d, n, s_n, seed, 4 * it + 2,
+                                          window=(st.r0, st.r1) if st.comm.world > 1 else None)
             out["Vy"] = be.sample_indices(d, l, s_l, seed, 4 * it + 3)
         return out
 

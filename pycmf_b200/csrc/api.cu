@@ -15,8 +15,14 @@ void* scratch(pycmf_ctx* ctx, int slot, size_t bytes) {
     Scratch& s = ctx->arena[slot];
     if (bytes == 0) bytes = 256;
     if (s.bytes < bytes) {
+        // growing an arena frees memory: never under stream capture (it would invalidate the capture, and a graph captured
+        // earlier has the old address baked in -- callers run two eager iterations first so that arenas have their size)
+        cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+        PYCMF_CUDA(cudaStreamIsCapturing(ctx->stream, &cap));
+        PYCMF_CHECK(cap == cudaStreamCaptureStatusNone,
+                    "scratch arena would have to grow during CUDA-graph capture: run the same step eagerly first");
         PYCMF_CUDA(cudaStreamSynchronize(ctx->stream));
-        if (s.ptr) PYCMF_CUDA(cudaFree(s.ptr));
+        if (s.ptr) ctx->retired.push_back(s.ptr);      // not freed: a graph captured earlier may replay with this address
         s.ptr = nullptr;
         s.bytes = 0;
         size_t want = std::max(bytes, size_t(1) << 20);
@@ -44,6 +50,8 @@ pycmf_ctx* fork_side(pycmf_ctx* ctx) {
     s->chol_fastpath = ctx->chol_fastpath;
     s->dense_path = ctx->dense_path;
     s->spmm_path = ctx->spmm_path;
+    s->spmm_blocks_per_sm = ctx->spmm_blocks_per_sm;
+    s->spmm_unroll = ctx->spmm_unroll;
     s->tc_max_splits = ctx->tc_max_splits;
     s->tc_ctas = ctx->tc_ctas;
     s->tc_chain = ctx->tc_chain;
@@ -283,8 +291,11 @@ void newton_left_impl(pycmf_ctx* ctx, int64_t rows, int64_t m, int64_t k, T* F, 
 template <typename T>
 void newton_v_xpart_impl(pycmf_ctx* ctx, int64_t d_rows, int64_t n, int64_t k, const T* V, const T* U,
                          const T* Xc, int64_t ldx, const int32_t* colptr, const int32_t* rowidx, const T* cvals,
-                         int x_link, double alpha, const int32_t* idx, int64_t n_sample, T* gx, T* Hx,
+                         int x_link, double alpha, const int32_t* idx, int64_t n_sample, T* gx, void* Hx_any,
                          int* hx_per_row) {
+    // Hx: per-row Hessians (d_rows x k x k, compute dtype) or ONE shared k x k matrix in FLOAT64 (linear link, no
+    // sampling): alpha U^T U rounded to fp32 costs 6e-8 x cond(H) on the Newton step -- 8e-3 on V in C2's first iteration
+    T* Hx = static_cast<T*>(Hx_any);
     const bool sampled = idx != nullptr;
     const bool sparse = Xc == nullptr;
     if (sparse && !(sampled && n_sample == 0))
@@ -301,7 +312,9 @@ void newton_v_xpart_impl(pycmf_ctx* ctx, int64_t d_rows, int64_t n, int64_t k, c
     if (x_link == PYCMF_LINEAR) {
         // shared Hessian part alpha U^T U on the side stream, next to the gradient pass
         pycmf_ctx* sc = fork_side(ctx);
-        gemm<T>(sc, true, k, k, n, U, k, U, k, Hx, k, T(alpha), T(0));
+        double* Hx64 = static_cast<double*>(Hx_any);
+        gram_f64<T>(sc, n, k, U, Hx64);
+        axpby<double>(sc, k * k, alpha, Hx64, 0.0, nullptr, Hx64);
     }
     if (!sparse) {
         resid_pass<T>(ctx, n, d_rows, k, U, V, Xc, ldx, false, x_link, nullptr, gx, nullptr);
@@ -328,23 +341,34 @@ void newton_v_xpart_impl(pycmf_ctx* ctx, int64_t d_rows, int64_t n, int64_t k, c
 template <typename T>
 void newton_v_finish_impl(pycmf_ctx* ctx, int64_t d_rows, int64_t l, int64_t k, T* V, const T* Z, const T* Yr,
                           int64_t ldy, int y_link, double alpha, double l1, double l2, const int32_t* idx,
-                          int64_t n_sample, const T* gx, const T* Hx, bool hx_per_row, bool non_negative,
+                          int64_t n_sample, const T* gx, const void* Hx_any, bool hx_per_row, bool non_negative,
                           double pert) {
     if (d_rows <= 0) return;
     const bool sampled = idx != nullptr;
     const double wy = 1.0 - alpha;
-    if (!sampled && newton_finish_small<T>(ctx, d_rows, l, k, V, Z, Yr, ldy, y_link, wy, gx, Hx, hx_per_row, l1, l2, l2,
-                                           pert, non_negative))
+    if (!sampled && newton_finish_small<T>(ctx, d_rows, l, k, V, Z, Yr, ldy, y_link, wy, gx, Hx_any, hx_per_row, l1, l2,
+                                           l2, pert, non_negative))
         return;
     const bool per_row = hx_per_row || sampled || y_link == PYCMF_LOGIT;
+    // a shared X-side Hessian arrives in float64 and stays there: it is added to the per-row label parts inside the
+    // solve (Hbase), or, with a shared label part as well, the whole shared Hessian is inverted once in float64
+    const T* Hx = hx_per_row ? static_cast<const T*>(Hx_any) : nullptr;
+    const double* Hx64 = hx_per_row ? nullptr : static_cast<const double*>(Hx_any);
     T* g = static_cast<T*>(scratch(ctx, SLOT_T0, sizeof(T) * size_t(d_rows) * k));
-    T* H = static_cast<T*>(scratch(ctx, SLOT_T1, sizeof(T) * size_t(per_row ? d_rows : 1) * k * k));
-    if (per_row) {
-        if (hx_per_row) copy_async<T>(ctx, H, Hx, size_t(d_rows) * k * k);
-        else broadcast_add<T>(ctx, d_rows, k * k, H, Hx, T(1), true);
-    } else {
-        copy_async<T>(ctx, H, Hx, size_t(k) * k);
+    if (!per_row) {
+        T* gy = static_cast<T*>(scratch(ctx, SLOT_T2, sizeof(T) * size_t(d_rows) * k));
+        resid_pass<T>(ctx, d_rows, l, k, V, Z, Yr, ldy, false, y_link, gy, nullptr, nullptr);
+        axpby<T>(ctx, d_rows * k, T(wy), gy, T(1), gx, g);
+        double* H64 = static_cast<double*>(scratch(ctx, SLOT_T1, sizeof(double) * size_t(k) * k));   // (arena 7 = the inverse)
+        gram_f64<T>(ctx, l, k, Z, H64);                                           // Z^T Z
+        axpby<double>(ctx, k * k, wy, H64, 1.0, Hx64, H64);                       // (1 - alpha) Z^T Z + alpha U^T U
+        const double* Hinv = shared_inverse64(ctx, k, H64, 1.0, l2, pert);
+        apply_shared_inverse<T>(ctx, d_rows, k, V, g, Hinv, l1, l2, non_negative);
+        return;
     }
+    T* H = static_cast<T*>(scratch(ctx, SLOT_T1, sizeof(T) * size_t(d_rows) * k * k));
+    if (hx_per_row) copy_async<T>(ctx, H, Hx, size_t(d_rows) * k * k);
+    else PYCMF_CUDA(cudaMemsetAsync(H, 0, sizeof(T) * size_t(d_rows) * k * k, ctx->stream));
     if (sampled) {
         copy_async<T>(ctx, g, gx, size_t(d_rows) * k);
         row_grad_hess<T>(ctx, d_rows, l, k, V, Z, Yr, ldy, false, nullptr, nullptr, nullptr, y_link, wy, idx,
@@ -359,11 +383,10 @@ void newton_v_finish_impl(pycmf_ctx* ctx, int64_t d_rows, int64_t l, int64_t k, 
         } else {
             T* Gz = static_cast<T*>(scratch(ctx, SLOT_T3, sizeof(T) * size_t(k) * k));
             gemm<T>(ctx, true, k, k, l, Z, k, Z, k, Gz, k, T(wy), T(0));
-            if (per_row) broadcast_add<T>(ctx, d_rows, k * k, H, Gz, T(1), false);
-            else axpby<T>(ctx, k * k, T(1), H, T(1), Gz, H);
+            broadcast_add<T>(ctx, d_rows, k * k, H, Gz, T(1), false);
         }
     }
-    newton_solve_rows<T>(ctx, d_rows, k, V, g, H, per_row ? k * k : 0, l1, l2, l2, pert, non_negative);
+    newton_solve_rows<T>(ctx, d_rows, k, V, g, H, k * k, l1, l2, l2, pert, non_negative, false, Hx64);
 }
 
 }  // namespace
@@ -427,9 +450,11 @@ int pycmf_destroy(pycmf_ctx* ctx) {
     clear_timers(ctx);
     for (auto& a : ctx->arena)
         if (a.ptr) cudaFree(a.ptr);
+    for (void* p : ctx->retired) cudaFree(p);
     if (ctx->side != nullptr) {
         for (auto& a : ctx->side->arena)
             if (a.ptr) cudaFree(a.ptr);
+        for (void* p : ctx->side->retired) cudaFree(p);
         cudaStreamDestroy(ctx->side->stream);
         delete ctx->side;
     }
@@ -450,6 +475,8 @@ int pycmf_set_option(pycmf_ctx* ctx, const char* key, double value) {
         else if (k == "dense_path") ctx->dense_path = int(value);
         else if (k == "tc_max_splits") ctx->tc_max_splits = int(value);
         else if (k == "spmm_path") ctx->spmm_path = int(value);
+        else if (k == "spmm_blocks_per_sm") ctx->spmm_blocks_per_sm = int(value);
+        else if (k == "spmm_unroll") ctx->spmm_unroll = int(value);
         else if (k == "tc_trace") ctx->tc_trace = int(value);
         else if (k == "tc_ctas") ctx->tc_ctas = int(value);
         else if (k == "tc_chain") ctx->tc_chain = int(value);
@@ -615,11 +642,11 @@ int pycmf_newton_v_xpart(pycmf_ctx* ctx, int dtype, int64_t d_rows, int64_t n, i
         DISPATCH(dtype,
                  newton_v_xpart_impl<float>(ctx, d_rows, n, k, (const float*)V, (const float*)U, (const float*)Xcols,
                                             ldx, csc_colptr, csc_rowidx, (const float*)csc_vals, x_link, alpha,
-                                            sample_idx_x, n_sample_x, (float*)gx, (float*)Hx, hx_per_row),
+                                            sample_idx_x, n_sample_x, (float*)gx, Hx, hx_per_row),
                  newton_v_xpart_impl<double>(ctx, d_rows, n, k, (const double*)V, (const double*)U,
                                              (const double*)Xcols, ldx, csc_colptr, csc_rowidx,
                                              (const double*)csc_vals, x_link, alpha, sample_idx_x, n_sample_x,
-                                             (double*)gx, (double*)Hx, hx_per_row));
+                                             (double*)gx, Hx, hx_per_row));
     });
 }
 
@@ -632,11 +659,11 @@ int pycmf_newton_v_finish(pycmf_ctx* ctx, int dtype, int64_t d_rows, int64_t l, 
         DISPATCH(dtype,
                  newton_v_finish_impl<float>(ctx, d_rows, l, k, (float*)V, (const float*)Z, (const float*)Yrows, ldy,
                                              y_link, alpha, l1_reg, l2_reg, sample_idx_y, n_sample_y,
-                                             (const float*)gx, (const float*)Hx, hx_per_row != 0, non_negative != 0,
+                                             (const float*)gx, Hx, hx_per_row != 0, non_negative != 0,
                                              hessian_pertubation),
                  newton_v_finish_impl<double>(ctx, d_rows, l, k, (double*)V, (const double*)Z, (const double*)Yrows,
                                               ldy, y_link, alpha, l1_reg, l2_reg, sample_idx_y, n_sample_y,
-                                              (const double*)gx, (const double*)Hx, hx_per_row != 0,
+                                              (const double*)gx, Hx, hx_per_row != 0,
                                               non_negative != 0, hessian_pertubation));
     });
 }
@@ -648,7 +675,20 @@ int pycmf_safe_solve(pycmf_ctx* ctx, int64_t batch, int64_t k, const double* H, 
 
 int pycmf_sample_indices(pycmf_ctx* ctx, int64_t rows, int64_t N, int64_t n_sample, uint64_t seed,
                          uint64_t stream_id, int32_t* idx) {
-    return guarded(ctx, [&] { sample_indices(ctx, rows, N, n_sample, seed, stream_id, idx); });
+    return guarded(ctx, [&] { sample_indices(ctx, rows, 0, N, n_sample, seed, stream_id, 0, 0, idx); });
+}
+
+int pycmf_topk_columns(pycmf_ctx* ctx, int dtype, int64_t rows, int64_t k, const void* F, int64_t ld, int64_t topn,
+                       int32_t* out) {
+    return guarded(ctx, [&] {
+        DISPATCH(dtype, topk_columns<float>(ctx, rows, k, (const float*)F, ld, int(topn), out),
+                 topk_columns<double>(ctx, rows, k, (const double*)F, ld, int(topn), out));
+    });
+}
+
+int pycmf_sample_indices_sharded(pycmf_ctx* ctx, int64_t rows, int64_t row0, int64_t N, int64_t n_sample, uint64_t seed,
+                                 uint64_t stream_id, int64_t lo, int64_t hi, int32_t* idx) {
+    return guarded(ctx, [&] { sample_indices(ctx, rows, row0, N, n_sample, seed, stream_id, lo, hi, idx); });
 }
 
 }  // extern "C"

@@ -40,6 +40,7 @@ struct pycmf_ctx {
     size_t max_scratch = size_t(2) << 30;
     // scratch arenas (grown on demand; growth synchronises the stream)
     pycmf::Scratch arena[8];
+    std::vector<void*> retired;   // outgrown arenas: kept until destroy (a CUDA graph captured earlier may still point at them)
     // optional per-kernel-family timers (cudaEvent pairs recorded on the stream around each launch)
     int profile = 0;
     std::map<std::string, std::vector<std::pair<cudaEvent_t, cudaEvent_t>>> timers;
@@ -51,6 +52,8 @@ struct pycmf_ctx {
     int finish_minblocks = 2;   // option: resident CTAs per SM the V-finish kernel is compiled for (2: 255 registers, no
                                 // spills: 86 us on C2; 3: 168 registers: 91 us; 4: 128 registers, spills: 187 us)
     int spmm_path = 1;       // option: 0 = generic SpMM kernel only (tests), 1 = vector kernels for k = 32 / 64 / 128 / 256, 2 = without the sub-warp grouping
+    int spmm_blocks_per_sm = 0;  // option: resident 256-thread CTAs per SM of the nonzero-balanced SpMM (0 = default 4)
+    int spmm_unroll = 4;     // option: independent factor-row gathers per lane in flight (4 or 8)
     int side_streams = 1;    // option: 0 runs the side branches on the main stream (serial)
 };
 
@@ -169,6 +172,10 @@ void dot_f64(pycmf_ctx* ctx, int64_t n, const T* a, const T* b, double scale, do
 
 template <typename T>
 void broadcast_add(pycmf_ctx* ctx, int64_t rows, int64_t kk, T* H, const T* Hs, T scale, bool overwrite);
+// out (k x topn int32): for every column c of F (rows x k, ld) the row indices of its topn largest entries in ASCENDING
+// weight order (ties by ascending index) == np.argsort(F[:, c], kind="stable")[-topn:]   (reference analysis.py:6)
+template <typename T>
+void topk_columns(pycmf_ctx* ctx, int64_t rows, int64_t k, const T* F, int64_t ld, int topn, int32_t* out);
 // G (k x k float64) = A^T A accumulated in float64
 template <typename T>
 void gram_f64(pycmf_ctx* ctx, int64_t rows, int64_t k, const T* A, double* G);
@@ -221,7 +228,8 @@ void row_grad_hess(pycmf_ctx* ctx, int64_t rows, int64_t m, int64_t k, const T* 
 // F_i <- F_i - (g_i + l1 sign(F_i) + l2 F_i) S(H_i + l2_diag I); clamp. H: (rows x k x k) or shared (h_stride 0)
 template <typename T>
 void newton_solve_rows(pycmf_ctx* ctx, int64_t rows, int64_t k, T* F, const T* g, const T* H, int64_t h_stride,
-                       double l1, double l2, double l2_diag, double pert, bool non_negative, bool known_pd = false);
+                       double l1, double l2, double l2_diag, double pert, bool non_negative, bool known_pd = false,
+                       const double* Hbase = nullptr);   // Hbase: shared k x k float64 part added to every H_i in double
 // shared Hessian given in float64 as h_scale * G (+ l2_diag I): the clamped inverse (k x k float64, arena 7 of ctx) ...
 double* shared_inverse64(pycmf_ctx* ctx, int64_t k, const double* G64, double h_scale, double l2_diag, double pert);
 // ... and its application to every row: F_i <- F_i - (g_i + l1 sign(F_i) + l2 F_i) Hinv ; clamp
@@ -231,15 +239,15 @@ void apply_shared_inverse(pycmf_ctx* ctx, int64_t rows, int64_t k, T* F, const T
 // newton_small.cu : fused warp-per-row finish of the V update for k <= 32 and a small label factor; false = not eligible
 template <typename T>
 bool newton_finish_small(pycmf_ctx* ctx, int64_t rows, int64_t l, int64_t k, T* F, const T* Z, const T* Y, int64_t ldy,
-                         int y_link, double wy, const T* gx, const T* Hx, bool hx_per_row, double l1, double l2,
-                         double l2_diag, double pert, bool non_negative);
+                         int y_link, double wy, const T* gx, const void* Hx, bool hx_per_row, double l1, double l2,
+                         double l2_diag, double pert, bool non_negative);   // Hx: per row (T) or shared (k x k FLOAT64)
 // warp-per-matrix clamped solve for k <= 32 (false = not eligible). MODE 0: x = S(.) g ; MODE 1: Newton row update
 template <typename T, int MODE>
 bool safe_solve_small(pycmf_ctx* ctx, int64_t batch, int64_t k, const T* H, int64_t h_stride, const T* g, T* out,
                       double l1, double l2, double l2_diag, double pert, bool non_negative, double h_scale, bool known_pd);
 void safe_solve_f64(pycmf_ctx* ctx, int64_t batch, int64_t k, const double* H, int64_t h_stride,
                     const double* g, double* x, double pert);
-void sample_indices(pycmf_ctx* ctx, int64_t rows, int64_t N, int64_t n_sample, uint64_t seed,
-                    uint64_t stream_id, int32_t* idx);
+void sample_indices(pycmf_ctx* ctx, int64_t rows, int64_t row0, int64_t N, int64_t n_sample, uint64_t seed,
+                    uint64_t stream_id, int64_t lo, int64_t hi, int32_t* idx);
 
 }  // namespace pycmf

@@ -350,6 +350,64 @@ void gram_f64(pycmf_ctx* ctx, int64_t rows, int64_t k, const T* A, double* G) {
     reduce_parts<double>(ctx, k, k, blocks, part, G, k, 1.0, 0.0);
 }
 
+// ---- top-k per column (topic-term extraction, reference analysis.py:1-16) -----------------------------------------------
+// One CTA per column, topn selection rounds: round r finds the largest (value, index) pair below the pair picked in round
+// r - 1 (pairs ordered by value, then index), i.e. a selection sort on the top end only -- topn x rows / 256 comparisons per
+// thread, no scratch.  The pick of round r lands at position topn - 1 - r: ascending weight, ties by ascending index.
+template <typename T>
+__global__ void __launch_bounds__(256)
+topk_columns_kernel(int64_t rows, int k, const T* __restrict__ F, int64_t ld, int topn, int32_t* __restrict__ out) {
+    __shared__ T sv[256];
+    __shared__ int64_t si[256];
+    const int c = blockIdx.x;
+    T pv = T(0);
+    int64_t pi = -1;                      // previous pick; -1 = none yet
+    bool exhausted = false;               // fewer than topn (non-NaN) rows: the remaining slots get -1
+    for (int r = 0; r < topn; r++) {
+        if (exhausted) {
+            if (threadIdx.x == 0) out[int64_t(c) * topn + (topn - 1 - r)] = -1;
+            continue;
+        }
+        T bv = T(0);
+        int64_t bi = -1;
+        for (int64_t i = threadIdx.x; i < rows; i += blockDim.x) {
+            const T v = F[i * ld + c];
+            if (v != v) continue;                                             // NaN never ranks
+            const bool below = pi < 0 || v < pv || (v == pv && i < pi);
+            if (below && (bi < 0 || v > bv || (v == bv && i > bi))) { bv = v; bi = i; }
+        }
+        sv[threadIdx.x] = bv;
+        si[threadIdx.x] = bi;
+        __syncthreads();
+        for (int s = 128; s > 0; s >>= 1) {
+            if (threadIdx.x < s) {
+                const T ov = sv[threadIdx.x + s];
+                const int64_t oi = si[threadIdx.x + s];
+                const int64_t mi = si[threadIdx.x];
+                if (oi >= 0 && (mi < 0 || ov > sv[threadIdx.x] || (ov == sv[threadIdx.x] && oi > mi))) {
+                    sv[threadIdx.x] = ov;
+                    si[threadIdx.x] = oi;
+                }
+            }
+            __syncthreads();
+        }
+        pv = sv[0];
+        pi = si[0];
+        if (threadIdx.x == 0) out[int64_t(c) * topn + (topn - 1 - r)] = int32_t(pi);    // -1 when fewer than topn rows
+        __syncthreads();
+        exhausted = pi < 0;
+    }
+}
+
+template <typename T>
+void topk_columns(pycmf_ctx* ctx, int64_t rows, int64_t k, const T* F, int64_t ld, int topn, int32_t* out) {
+    if (k <= 0 || topn <= 0) return;
+    PYCMF_CHECK(rows < (int64_t(1) << 31), "topk_columns: too many rows for int32 indices");
+    PYCMF_CHECK(topn <= 1024, "topk_columns: topn too large");
+    topk_columns_kernel<T><<<(unsigned)k, 256, 0, ctx->stream>>>(rows, int(k), F, ld, topn, out);
+    PYCMF_LAUNCH_CHECK(ctx);
+}
+
 #define INSTANTIATE(T)                                                                                   \
     template void gemm<T>(pycmf_ctx*, bool, int64_t, int64_t, int64_t, const T*, int64_t, const T*,     \
                           int64_t, T*, int64_t, T, T);                                                   \
@@ -363,4 +421,9 @@ void gram_f64(pycmf_ctx* ctx, int64_t rows, int64_t k, const T* A, double* G) {
 INSTANTIATE(float)
 INSTANTIATE(double)
 
+}  // namespace pycmf
+
+namespace pycmf {
+template void topk_columns<float>(pycmf_ctx*, int64_t, int64_t, const float*, int64_t, int, int32_t*);
+template void topk_columns<double>(pycmf_ctx*, int64_t, int64_t, const double*, int64_t, int, int32_t*);
 }  // namespace pycmf

@@ -247,11 +247,13 @@ struct SolveShared {
 // Load the LOWER triangle of H (row-major, like scipy.linalg.eigh(lower=True)) into W (column-major
 // == row-major for a symmetric matrix), adding `diag` on the diagonal.
 template <typename T>
-__device__ __forceinline__ void load_sym(double* W, const T* __restrict__ H, int k, double diag, double scale) {
+__device__ __forceinline__ void load_sym(double* W, const T* __restrict__ H, int k, double diag, double scale,
+                                         const double* __restrict__ base = nullptr) {
     for (int e = threadIdx.x; e < k * k; e += blockDim.x) {
         int r = e / k, c = e % k;
         int hi = r > c ? r : c, lo = r > c ? c : r;
         double v = scale * double(H[hi * k + lo]);
+        if (base != nullptr) v += base[hi * k + lo];      // shared float64 part of the Hessian (never rounded to T)
         if (r == c) v += diag;
         W[e] = v;
     }
@@ -386,18 +388,18 @@ __device__ void jacobi_clamped_solve(double* W, int k, const double* g, double* 
 template <typename T>
 __device__ void safe_solve_one(double* W, const T* __restrict__ H, int k, double diag, const double* g,
                                double* x, double* xpart, SolveShared* sh, double pert, bool chol_fastpath,
-                               double scale) {
+                               double scale, const double* __restrict__ base = nullptr) {
     bool done = false;
     if (chol_fastpath) {
         // lambda_min(H) > pert  <=>  H - pert I is positive definite  <=>  its Cholesky succeeds
-        load_sym<T>(W, H, k, diag - pert, scale);
+        load_sym<T>(W, H, k, diag - pert, scale, base);
         __syncthreads();
         double tr = 0.0;
         for (int r = 0; r < k; r++) tr += fabs(W[r * k + r]);   // every thread, same value (k <= 256)
         bool ok = cholesky_inplace(W, k, sh, 1e-13 * (tr + pert));
         __syncthreads();
         if (ok) {
-            load_sym<T>(W, H, k, diag, scale);
+            load_sym<T>(W, H, k, diag, scale, base);
             __syncthreads();
             ok = cholesky_inplace(W, k, sh, 0.0);
             if (ok) {
@@ -410,7 +412,7 @@ __device__ void safe_solve_one(double* W, const T* __restrict__ H, int k, double
         __syncthreads();
     }
     if (!done) {
-        load_sym<T>(W, H, k, diag, scale);
+        load_sym<T>(W, H, k, diag, scale, base);
         __syncthreads();
         // rotations stop at |w_p . w_q| <= tol |w_p| |w_q|: float64 inputs to working precision; float32 inputs carry 6e-8
         // relative noise already, 1e-11 leaves the clamped solve exact to far below that and saves the last sweep
@@ -423,7 +425,8 @@ template <typename T, int MODE>
 __global__ void __launch_bounds__(1024)
 safe_solve_kernel(int64_t batch, int k, const T* __restrict__ H, int64_t h_stride, const T* __restrict__ g,
                   T* __restrict__ out, double l1, double l2, double l2_diag, double pert, bool non_negative,
-                  bool chol_fastpath, double* __restrict__ Wglobal, double h_scale) {
+                  bool chol_fastpath, double* __restrict__ Wglobal, double h_scale,
+                  const double* __restrict__ Hbase) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int nwarps = blockDim.x >> 5;
     double* gv = reinterpret_cast<double*>(smem_raw);   // k
@@ -444,7 +447,7 @@ safe_solve_kernel(int64_t batch, int k, const T* __restrict__ H, int64_t h_strid
             gv[r] = gr;
         }
         __syncthreads();
-        safe_solve_one<T>(W, H + b * h_stride, k, l2_diag, gv, xv, xpart, sh, pert, chol_fastpath, h_scale);
+        safe_solve_one<T>(W, H + b * h_stride, k, l2_diag, gv, xv, xpart, sh, pert, chol_fastpath, h_scale, Hbase);
         __syncthreads();
         for (int r = threadIdx.x; r < k; r += blockDim.x) {
             if (MODE == 0) {
@@ -510,11 +513,11 @@ __device__ __forceinline__ uint32_t mix32(uint32_t x) {
     return x;
 }
 
-__global__ void sample_indices_kernel(int64_t rows, int64_t N, int64_t n_sample, uint64_t seed,
-                                      uint64_t stream_id, int32_t* __restrict__ idx) {
+__global__ void sample_indices_kernel(int64_t rows, int64_t row0, int64_t N, int64_t n_sample, uint64_t seed,
+                                      uint64_t stream_id, int64_t lo, int64_t hi, int32_t* __restrict__ idx) {
     int64_t e = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
     if (e >= rows * n_sample) return;
-    int64_t row = e / n_sample;
+    int64_t row = row0 + e / n_sample;          // the key uses the GLOBAL row: every shard count draws the same sets
     uint32_t t = uint32_t(e % n_sample);
     int bits = 2;
     while ((int64_t(1) << bits) < N) bits += 2;   // even number of bits
@@ -534,7 +537,8 @@ __global__ void sample_indices_kernel(int64_t rows, int64_t N, int64_t n_sample,
         }
         v = (L << half) | R;
     } while (int64_t(v) >= N);
-    idx[e] = int32_t(v);
+    // window [lo, hi) = the part of the population this rank holds (rows of U in the V update): others become -1
+    idx[e] = hi > lo ? ((int64_t(v) >= lo && int64_t(v) < hi) ? int32_t(int64_t(v) - lo) : -1) : int32_t(v);
 }
 
 size_t solve_smem_bytes(int k, int nthreads, bool w_in_smem) {
@@ -548,11 +552,12 @@ size_t solve_smem_bytes(int k, int nthreads, bool w_in_smem) {
 template <typename T, int MODE>
 void launch_solve(pycmf_ctx* ctx, int64_t batch, int64_t k, const T* H, int64_t h_stride, const T* g, T* out,
                   double l1, double l2, double l2_diag, double pert, bool non_negative, double h_scale = 1.0,
-                  bool known_pd = false) {
+                  bool known_pd = false, const double* Hbase = nullptr) {
     if (batch <= 0) return;
     PYCMF_CHECK(k >= 1 && k <= 256, "n_components must be in [1, 256] for the Newton solve");
     PYCMF_CHECK(pert > 0.0, "hessian_pertubation must be > 0");
-    if (safe_solve_small<T, MODE>(ctx, batch, k, H, h_stride, g, out, l1, l2, l2_diag, pert, non_negative, h_scale,
+    if (Hbase == nullptr &&
+        safe_solve_small<T, MODE>(ctx, batch, k, H, h_stride, g, out, l1, l2, l2_diag, pert, non_negative, h_scale,
                                   known_pd))
         return;
     // one warp per Jacobi pair: k / 2 pairs per step, so wide matrices get a full CTA (k = 128: 64 pairs on 32 warps are two
@@ -572,7 +577,7 @@ void launch_solve(pycmf_ctx* ctx, int64_t batch, int64_t k, const T* H, int64_t 
     }
     Timed timer(ctx, "safe_solve");
     kern<<<(unsigned)grid, nthreads, smem, ctx->stream>>>(batch, int(k), H, h_stride, g, out, l1, l2, l2_diag,
-                                                         pert, non_negative, ctx->chol_fastpath != 0, Wg, h_scale);
+                                                         pert, non_negative, ctx->chol_fastpath != 0, Wg, h_scale, Hbase);
     PYCMF_LAUNCH_CHECK(ctx);
 }
 
@@ -661,12 +666,14 @@ void safe_solve_f64(pycmf_ctx* ctx, int64_t batch, int64_t k, const double* H, i
 
 template <typename T>
 void newton_solve_rows(pycmf_ctx* ctx, int64_t rows, int64_t k, T* F, const T* g, const T* H, int64_t h_stride,
-                       double l1, double l2, double l2_diag, double pert, bool non_negative, bool known_pd) {
+                       double l1, double l2, double l2_diag, double pert, bool non_negative, bool known_pd,
+                       const double* Hbase) {
     if (rows <= 0) return;
     if (h_stride != 0) {
-        launch_solve<T, 1>(ctx, rows, k, H, h_stride, g, F, l1, l2, l2_diag, pert, non_negative, 1.0, known_pd);
+        launch_solve<T, 1>(ctx, rows, k, H, h_stride, g, F, l1, l2, l2_diag, pert, non_negative, 1.0, known_pd, Hbase);
         return;
     }
+    PYCMF_CHECK(Hbase == nullptr, "newton_solve_rows: a float64 base goes with per-row Hessians only");
     // shared Hessian: invert once (k unit right-hand sides), then one small GEMM-like pass over the rows
     double* buf = static_cast<double*>(scratch(ctx, 3, sizeof(double) * size_t(3) * k * k));
     double *H64 = buf, *I64 = buf + k * k, *Hinv = buf + 2 * k * k;
@@ -707,13 +714,13 @@ void apply_shared_inverse(pycmf_ctx* ctx, int64_t rows, int64_t k, T* F, const T
     PYCMF_LAUNCH_CHECK(ctx);
 }
 
-void sample_indices(pycmf_ctx* ctx, int64_t rows, int64_t N, int64_t n_sample, uint64_t seed,
-                    uint64_t stream_id, int32_t* idx) {
+void sample_indices(pycmf_ctx* ctx, int64_t rows, int64_t row0, int64_t N, int64_t n_sample, uint64_t seed,
+                    uint64_t stream_id, int64_t lo, int64_t hi, int32_t* idx) {
     int64_t n = rows * n_sample;
     if (n <= 0) return;
     PYCMF_CHECK(n_sample <= N, "cannot sample more indices than the population");
     PYCMF_CHECK(N < (int64_t(1) << 31), "population too large for int32 indices");
-    sample_indices_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, ctx->stream>>>(rows, N, n_sample, seed, stream_id, idx);
+    sample_indices_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, ctx->stream>>>(rows, row0, N, n_sample, seed, stream_id, lo, hi, idx);
     PYCMF_LAUNCH_CHECK(ctx);
 }
 
@@ -722,7 +729,7 @@ void sample_indices(pycmf_ctx* ctx, int64_t rows, int64_t N, int64_t n_sample, u
                                    bool, const int32_t*, const int32_t*, const T*, int, double, const int32_t*, \
                                    int64_t, T*, T*, bool);                                                      \
     template void newton_solve_rows<T>(pycmf_ctx*, int64_t, int64_t, T*, const T*, const T*, int64_t, double,   \
-                                       double, double, double, bool, bool);                                        \
+                                       double, double, double, bool, bool, const double*);                         \
     template void apply_shared_inverse<T>(pycmf_ctx*, int64_t, int64_t, T*, const T*, const double*, double,    \
                                           double, bool);
 INSTANTIATE(float)

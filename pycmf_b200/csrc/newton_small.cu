@@ -39,14 +39,15 @@ template <typename T, int KT, int MINB>
 __global__ void __launch_bounds__(WARPS * 32, MINB)
 newton_finish_small_kernel(int64_t rows, int l, int k, T* __restrict__ F, const T* __restrict__ Z,
                            const T* __restrict__ Y, int64_t ldy, int y_link, T wy,
-                           const T* __restrict__ gx, const T* __restrict__ Hx, int64_t hx_stride,
+                           const T* __restrict__ gx, const T* __restrict__ Hx, const double* __restrict__ Hx64,
+                           int64_t hx_stride,
                            double l1, double l2, double l2_diag, double pert, bool non_negative, bool chol_fastpath,
                            int pd_mode, const int* __restrict__ pd_flag) {
     constexpr int ZLD = KT + 4;       // row stride of Z in shared memory: 16-byte aligned rows, conflict-free columns
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double* Wall = reinterpret_cast<double*>(smem_raw);          // WARPS solve tiles
-    T* Zs = reinterpret_cast<T*>(Wall + WARPS * TILE);           // l x ZLD (columns >= k zero)
-    T* Hs = Zs + size_t(l) * ZLD + 32;                           // KT x KT (shared Hessian part, if hx_stride == 0)
+    double* Hs = Wall + WARPS * TILE;                            // KT x KT float64 (shared Hessian part, if hx_stride == 0)
+    T* Zs = reinterpret_cast<T*>(Hs + KT * KT);                  // l x ZLD (columns >= k zero)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     for (int e = threadIdx.x; e < l * ZLD + 32; e += blockDim.x) {
         const int r = e / ZLD, c = e % ZLD;
@@ -55,7 +56,7 @@ newton_finish_small_kernel(int64_t rows, int l, int k, T* __restrict__ F, const 
     if (hx_stride == 0)
         for (int e = threadIdx.x; e < KT * KT; e += blockDim.x) {
             const int r = e / KT, c = e % KT;
-            Hs[e] = (r < k && c < k) ? Hx[(r > c ? r : c) * k + (r > c ? c : r)] : T(0);   // lower triangle, like eigh
+            Hs[e] = (r < k && c < k) ? Hx64[(r > c ? r : c) * k + (r > c ? c : r)] : 0.0;   // lower triangle, like eigh
         }
     __syncthreads();
     double* W = Wall + warp * TILE;
@@ -91,13 +92,10 @@ newton_finish_small_kernel(int64_t rows, int l, int k, T* __restrict__ F, const 
         // ---- row `lane` of the Hessian in registers (compute dtype)
         T Wr[KT];
         if (hx_stride == 0) {
+            // the shared part stays in float64 shared memory and is added inside the factorisation: rounding alpha U^T U
+            // to fp32 cost 8e-3 on V in C2's first iteration (6e-8 x cond(H)); only the label part is built in T
 #pragma unroll
-            for (int c = 0; c < KT; c += 4) {
-                T h4[4];
-                load4(Hs + (lane < KT ? lane : 0) * KT + c, h4);
-#pragma unroll
-                for (int u = 0; u < 4; u++) Wr[c + u] = h4[u];
-            }
+            for (int c = 0; c < KT; c++) Wr[c] = T(0);
         } else {
 #pragma unroll
             for (int c = 0; c < KT; c++) {
@@ -128,7 +126,8 @@ newton_finish_small_kernel(int64_t rows, int l, int k, T* __restrict__ F, const 
         const double gfull = act ? double(g) + l1 * sgn + l2 * vd : 0.0;
         // ---- the clamped solve in float64 (l2 on the diagonal)
         double a[KT], dinv;
-        const bool fac = wsolve::safe_factor_warp<KT, T>(Wr, l2_diag, k, lane, pert, chol_fastpath, known_pd, W, a, &dinv);
+        const bool fac = wsolve::safe_factor_warp<KT, T>(Wr, l2_diag, k, lane, pert, chol_fastpath, known_pd, W, a, &dinv,
+                                                         hx_stride == 0 ? Hs + (lane < KT ? lane : 0) * KT : nullptr);
         const double x = wsolve::safe_apply_warp<KT>(fac, a, dinv, k, lane, gfull, pert, W);
         __syncwarp();
         if (act) {
@@ -227,11 +226,13 @@ bool safe_solve_small(pycmf_ctx* ctx, int64_t batch, int64_t k, const T* H, int6
 
 template <typename T>
 bool newton_finish_small(pycmf_ctx* ctx, int64_t rows, int64_t l, int64_t k, T* F, const T* Z, const T* Y, int64_t ldy,
-                         int y_link, double wy, const T* gx, const T* Hx, bool hx_per_row, double l1, double l2,
+                         int y_link, double wy, const T* gx, const void* Hx_any, bool hx_per_row, double l1, double l2,
                          double l2_diag, double pert, bool non_negative) {
     if (k > KS || l > LMAX || l < 1 || rows < 1) return false;
+    const T* Hx = hx_per_row ? static_cast<const T*>(Hx_any) : nullptr;                 // per-row Hessians: compute dtype
+    const double* Hx64 = hx_per_row ? nullptr : static_cast<const double*>(Hx_any);     // shared Hessian: float64
     const int kt = wsolve::pick_kt(int(k));
-    const size_t smem = sizeof(double) * size_t(WARPS) * TILE + sizeof(T) * (size_t(l) * (kt + 4) + 32 + size_t(kt) * kt);
+    const size_t smem = sizeof(double) * (size_t(WARPS) * TILE + size_t(kt) * kt) + sizeof(T) * (size_t(l) * (kt + 4) + 32);
     if (smem > size_t(ctx->max_smem_optin)) return false;
     // Definiteness shortcut: H_j = Hx(_j) + wy Z^T D Z + l2 I with the label term PSD when wy >= 0.
     //   l2 >= pert                      -> every H_j has lambda_min >= pert (pd_mode 2, if Hx is PSD: weights >= 0)
@@ -241,9 +242,9 @@ bool newton_finish_small(pycmf_ctx* ctx, int64_t rows, int64_t l, int64_t k, T* 
     if (wy >= 0.0 && ctx->chol_fastpath) {
         if (!hx_per_row) {
             flag = static_cast<int*>(scratch(ctx, 2, 256));
-            if (kt == 8) pd_flag_kernel<T, 8><<<1, 32, 0, ctx->stream>>>(int(k), Hx, 1.0, l2_diag, pert, flag);
-            else if (kt == 16) pd_flag_kernel<T, 16><<<1, 32, 0, ctx->stream>>>(int(k), Hx, 1.0, l2_diag, pert, flag);
-            else pd_flag_kernel<T, 32><<<1, 32, 0, ctx->stream>>>(int(k), Hx, 1.0, l2_diag, pert, flag);
+            if (kt == 8) pd_flag_kernel<double, 8><<<1, 32, 0, ctx->stream>>>(int(k), Hx64, 1.0, l2_diag, pert, flag);
+            else if (kt == 16) pd_flag_kernel<double, 16><<<1, 32, 0, ctx->stream>>>(int(k), Hx64, 1.0, l2_diag, pert, flag);
+            else pd_flag_kernel<double, 32><<<1, 32, 0, ctx->stream>>>(int(k), Hx64, 1.0, l2_diag, pert, flag);
             PYCMF_LAUNCH_CHECK(ctx);
             pd_mode = 1;
         } else if (l2_diag >= pert) {
@@ -261,7 +262,7 @@ bool newton_finish_small(pycmf_ctx* ctx, int64_t rows, int64_t l, int64_t k, T* 
                               : (minb == 3 ? newton_finish_small_kernel<T, KT, 3> : newton_finish_small_kernel<T, KT, 2>); \
         PYCMF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));                 \
         kern<<<(unsigned)grid, WARPS * 32, smem, ctx->stream>>>(rows, int(l), int(k), F, Z, Y, ldy, y_link, T(wy), gx,  \
-                                                               Hx, hx_per_row ? k * k : 0, l1, l2, l2_diag, pert,      \
+                                                               Hx, Hx64, hx_per_row ? k * k : 0, l1, l2, l2_diag, pert, \
                                                                non_negative, ctx->chol_fastpath != 0, pd_mode, flag);  \
     } while (0)
     if (kt == 8) LAUNCH(8);
@@ -279,10 +280,10 @@ template bool safe_solve_small<double, 0>(pycmf_ctx*, int64_t, int64_t, const do
 template bool safe_solve_small<double, 1>(pycmf_ctx*, int64_t, int64_t, const double*, int64_t, const double*, double*,
                                           double, double, double, double, bool, double, bool);
 template bool newton_finish_small<float>(pycmf_ctx*, int64_t, int64_t, int64_t, float*, const float*, const float*,
-                                         int64_t, int, double, const float*, const float*, bool, double, double, double,
+                                         int64_t, int, double, const float*, const void*, bool, double, double, double,
                                          double, bool);
 template bool newton_finish_small<double>(pycmf_ctx*, int64_t, int64_t, int64_t, double*, const double*, const double*,
-                                          int64_t, int, double, const double*, const double*, bool, double, double,
+                                          int64_t, int, double, const double*, const void*, bool, double, double,
                                           double, double, bool);
 
 }  // namespace pycmf

@@ -259,6 +259,128 @@ spmm_grp_kernel(int64_t rows, const int32_t* __restrict__ rowptr, const int32_t*
     }
 }
 
+
+// ---- nonzero-balanced SpMM (fp32, k = 32 / 64 / 128) ------------------------------------------------------------------
+// Every warp owns an EQUAL share of the nonzeros, [w * nnz / W, (w + 1) * nnz / W), found by one binary search in rowptr
+// (merge-path style) -- no per-call chunk count / scan, and no tail: with chunk-count shares a warp that drew 512-nonzero
+// chunks of a hot tf-idf column ran 50x longer than one that drew tail columns (ncu: 29 % achieved occupancy).
+// The warp streams its share in flat 32-nonzero blocks (coalesced colidx / vals, the next block prefetched while the
+// current one is gathered) and walks the row boundaries inside; a row that lies completely inside the share is stored
+// (C = alpha * acc + beta * C), a row cut by a share boundary is combined by atomics -- such rows, and empty rows, are
+// pre-scaled by beta in the prologue kernel, which finds them in O(1) per row from the same partition formula.
+// What bounds the kernel is the L2 -> SM gather of one k * 4-byte factor row per nonzero (UNROLL independent 16-byte loads
+// per lane in flight): see DESIGN section 4.
+__device__ __forceinline__ int64_t nzb_share_begin(int64_t w, int64_t total, int64_t nwarps) {
+    return (w * total) / nwarps;
+}
+
+__global__ void spmm_nzb_prologue_kernel(int64_t rows, const int32_t* __restrict__ rowptr, int64_t nwarps,
+                                         float* __restrict__ C, int64_t ldc, int k, float beta) {
+    const int64_t r = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (r >= rows) return;
+    const int64_t total = rowptr[rows];
+    const int64_t a = rowptr[r], b = rowptr[r + 1];
+    bool touch = a == b;                                   // empty row: nobody else writes it
+    if (!touch && total > 0) {
+        // is there a share boundary strictly inside (a, b)?  smallest w with begin(w) > a
+        int64_t w = (a * nwarps) / total;
+        while (w <= nwarps && nzb_share_begin(w, total, nwarps) <= a) w++;
+        touch = w < nwarps && nzb_share_begin(w, total, nwarps) < b;
+    }
+    if (touch)
+        for (int c = 0; c < k; c++) C[r * ldc + c] = beta != 0.0f ? beta * C[r * ldc + c] : 0.0f;
+}
+
+template <int LPN, int UNROLL, int MINB>
+__global__ void __launch_bounds__(256, MINB)
+spmm_nzb_kernel(int64_t rows, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx,
+                const float* __restrict__ vals, const float* __restrict__ B, int64_t ldb,
+                float* __restrict__ C, int64_t ldc, float alpha, float beta) {
+    constexpr int NG = 32 / LPN;          // nonzeros per load instruction
+    constexpr int BATCH = NG * UNROLL;    // nonzeros per round trip
+    const int lane = threadIdx.x & 31;
+    const int gl = lane % LPN, gid = lane / LPN;
+    const int64_t warp = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = (int64_t(gridDim.x) * blockDim.x) >> 5;
+    const int total = rowptr[rows];                       // nnz < 2^31 (int32 CSR): 32-bit positions keep registers down
+    const int e0 = int(nzb_share_begin(warp, total, nwarps)), e1 = int(nzb_share_begin(warp + 1, total, nwarps));
+    if (e0 >= e1) return;
+    // row holding nonzero e0: last r with rowptr[r] <= e0
+    int lo = 0, hi = int(rows);
+    while (hi - lo > 1) {
+        const int mid = int((unsigned(lo) + unsigned(hi)) >> 1);
+        if (rowptr[mid] <= e0) lo = mid; else hi = mid;
+    }
+    int row = lo;
+    int row_begin = rowptr[row], row_end = rowptr[row + 1];
+    const float* Bl = B + gl * 4;
+    const int last = total - 1;
+    // current block [pos, pos + 32) of the flat nonzero stream; lanes past the share end read a valid address, value 0
+    int pos = e0;
+    int c = colidx[min(pos + lane, last)];
+    float v = pos + lane < e1 ? vals[pos + lane] : 0.0f;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    while (pos < e1) {
+        const int npos = pos + 32;
+        int cn = 0; float vn = 0.0f;
+        if (npos < e1) {                                     // prefetch the next block
+            cn = colidx[min(npos + lane, last)];
+            vn = npos + lane < e1 ? vals[npos + lane] : 0.0f;
+        }
+        const int bend = min(32, e1 - pos);    // nonzeros of this block inside the share
+        int j0 = 0;
+        while (j0 < bend) {
+            const int j1 = min(bend, row_end - pos);      // this row's part of the block: [j0, j1)
+            for (int j = j0; j < j1; j += BATCH) {
+                float4 bv[UNROLL];
+                float vj[UNROLL];
+#pragma unroll
+                for (int u = 0; u < UNROLL; u++) {
+                    const int src = j + u * NG + gid;
+                    const int s2 = src < j1 ? src : j0;          // past the row's part: a valid column, value masked
+                    const int cj = __shfl_sync(0xffffffffu, c, s2);
+                    const float vv = __shfl_sync(0xffffffffu, v, s2);
+                    vj[u] = src < j1 ? vv : 0.0f;
+                    bv[u] = __ldg(reinterpret_cast<const float4*>(Bl + int64_t(cj) * ldb));
+                }
+#pragma unroll
+                for (int u = 0; u < UNROLL; u++) {
+                    acc.x = fmaf(vj[u], bv[u].x, acc.x); acc.y = fmaf(vj[u], bv[u].y, acc.y);
+                    acc.z = fmaf(vj[u], bv[u].z, acc.z); acc.w = fmaf(vj[u], bv[u].w, acc.w);
+                }
+            }
+            j0 = j1;
+            if (pos + j1 == row_end || pos + j1 == e1) {
+                // the row (or the share) ends here: combine the sub-warp groups and write
+#pragma unroll
+                for (int o = 16; o >= LPN; o >>= 1) {
+                    acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o); acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
+                    acc.z += __shfl_xor_sync(0xffffffffu, acc.z, o); acc.w += __shfl_xor_sync(0xffffffffu, acc.w, o);
+                }
+                const bool whole = row_begin >= e0 && row_end <= e1;
+                if (gid == 0) {
+                    float* crow = C + int64_t(row) * ldc + gl * 4;
+                    if (!whole) {
+                        atomicAdd(&crow[0], alpha * acc.x); atomicAdd(&crow[1], alpha * acc.y);
+                        atomicAdd(&crow[2], alpha * acc.z); atomicAdd(&crow[3], alpha * acc.w);
+                    } else {
+                        float4 prev = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (beta != 0.0f) prev = *reinterpret_cast<const float4*>(crow);
+                        *reinterpret_cast<float4*>(crow) = make_float4(alpha * acc.x + beta * prev.x, alpha * acc.y + beta * prev.y,
+                                                                       alpha * acc.z + beta * prev.z, alpha * acc.w + beta * prev.w);
+                    }
+                }
+                acc = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (pos + j1 == row_end && pos + j1 < e1) {
+                    // next non-empty row (empty rows were written by the prologue)
+                    do { row++; row_begin = row_end; row_end = rowptr[row + 1]; } while (row_end == row_begin);
+                }
+            }
+        }
+        pos = npos; c = cn; v = vn;
+    }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256)
 sddmm_reduce_kernel(int mode, int64_t rows, const int32_t* __restrict__ rowptr,
@@ -308,6 +430,26 @@ void spmm(pycmf_ctx* ctx, int64_t rows, const int32_t* rowptr, const int32_t* co
     PYCMF_CHECK(k <= 32 * MAXT, "spmm: n_components > 256 is not supported");
     PYCMF_CHECK(rows < (int64_t(1) << 31) - 1, "spmm: too many rows");
     Timed timer(ctx, "spmm");
+    if constexpr (std::is_same<T, float>::value) {
+        // fp32, k = 32 / 64 / 128, 16-byte aligned rows: the nonzero-balanced kernel (no chunk count / scan per call)
+        if ((k == 32 || k == 64 || k == 128) && ctx->spmm_path == 1 && (ldb % 4) == 0 && (ldc % 4) == 0 &&
+            (reinterpret_cast<uintptr_t>(B) & 15) == 0 && (reinterpret_cast<uintptr_t>(C) & 15) == 0) {
+            const bool deep = ctx->spmm_unroll != 4;
+            // one resident wave: 3 CTAs per SM at 80 registers (8 gathers in flight per lane), 4 at 56 (4 in flight)
+            const int per_sm = ctx->spmm_blocks_per_sm > 0 ? ctx->spmm_blocks_per_sm : (deep ? 3 : 4);
+            const unsigned nb = (unsigned)std::max<int64_t>(1, std::min<int64_t>(ceil_div(rows * 4, 8), int64_t(per_sm) * ctx->num_sms));
+            const int64_t nwarps = int64_t(nb) * 8;
+            spmm_nzb_prologue_kernel<<<(unsigned)ceil_div(rows, 256), 256, 0, ctx->stream>>>(rows, rowptr, nwarps, C, ldc, int(k), beta);
+            PYCMF_LAUNCH_CHECK(ctx);
+#define LAUNCHN(L, U, M) spmm_nzb_kernel<L, U, M><<<nb, 256, 0, ctx->stream>>>(rows, rowptr, colidx, vals, B, ldb, C, ldc, alpha, beta)
+            if (k == 32) { if (deep) LAUNCHN(8, 8, 3); else LAUNCHN(8, 4, 4); }
+            else if (k == 64) { if (deep) LAUNCHN(16, 8, 3); else LAUNCHN(16, 4, 4); }
+            else { if (deep) LAUNCHN(32, 8, 3); else LAUNCHN(32, 4, 4); }
+#undef LAUNCHN
+            PYCMF_LAUNCH_CHECK(ctx);
+            return;
+        }
+    }
     // chunk counts -> exclusive scan -> chunk offsets (rows + 1 ints), all on the stream
     size_t cub_bytes = 0;
     cub::DeviceScan::ExclusiveSum(nullptr, cub_bytes, (int*)nullptr, (int*)nullptr, int(rows + 1), ctx->stream);
@@ -327,7 +469,7 @@ void spmm(pycmf_ctx* ctx, int64_t rows, const int32_t* rowptr, const int32_t* co
     if (vec_ok) {
         const unsigned vb = (unsigned)std::min<int64_t>(ceil_div(rows * 32, 256 * 4), int64_t(16) * ctx->num_sms);
         if constexpr (std::is_same<T, float>::value) {
-            if ((k == 32 || k == 64) && ctx->spmm_path == 1 && ldc % 4 == 0 && (reinterpret_cast<uintptr_t>(C) & 15) == 0) {
+            if ((k == 32 || k == 64) && ctx->spmm_path == 3 && ldc % 4 == 0 && (reinterpret_cast<uintptr_t>(C) & 15) == 0) {
                 if (k == 32) spmm_grp_kernel<8><<<std::max(1u, vb), 256, 0, ctx->stream>>>(rows, rowptr, colidx, vals, B, ldb, C, ldc, alpha, beta, offsets);
                 else spmm_grp_kernel<16><<<std::max(1u, vb), 256, 0, ctx->stream>>>(rows, rowptr, colidx, vals, B, ldb, C, ldc, alpha, beta, offsets);
                 PYCMF_LAUNCH_CHECK(ctx);

@@ -142,7 +142,8 @@ __device__ __forceinline__ double jacobi_apply_tile(const double* W, int k, int 
 template <int KT, typename R>
 __device__ __forceinline__ bool safe_factor_warp(const R (&H_row)[KT], double diag, int k, int lane, double pert,
                                                  bool chol_fastpath, bool known_pd, double* W, double (&a)[KT],
-                                                 double* dinv) {
+                                                 double* dinv, const double* base_row = nullptr) {
+    // base_row: row `lane` (KT doubles) of a float64 matrix added to H in double (the shared part of the Hessian)
     const bool act = lane < k;
     if (chol_fastpath) {
         bool ok = true;
@@ -154,7 +155,8 @@ __device__ __forceinline__ bool safe_factor_warp(const R (&H_row)[KT], double di
 #pragma unroll
             for (int c = 0; c < KT; c++) {
                 // rows / columns beyond k: identity padding
-                a[c] = (act && c < k) ? double(H_row[c]) + (c == lane ? shift : 0.0) : (c == lane ? 1.0 : 0.0);
+                a[c] = (act && c < k) ? double(H_row[c]) + (base_row != nullptr ? base_row[c] : 0.0) + (c == lane ? shift : 0.0)
+                                      : (c == lane ? 1.0 : 0.0);
                 if (c == lane && act) tr = fabs(a[c]);
             }
             double floor = 0.0;
@@ -166,7 +168,8 @@ __device__ __forceinline__ bool safe_factor_warp(const R (&H_row)[KT], double di
     // eigenvalue clamp active (or fast path disabled): Jacobi on the symmetric tile built from the lower triangle
 #pragma unroll
     for (int c = 0; c < KT; c++)
-        if (c < k && c <= lane && act) W[lane * WLD + c] = double(H_row[c]) + (c == lane ? diag : 0.0);
+        if (c < k && c <= lane && act)
+            W[lane * WLD + c] = double(H_row[c]) + (base_row != nullptr ? base_row[c] : 0.0) + (c == lane ? diag : 0.0);
     __syncwarp();
     for (int c = lane + 1; c < k; c++)
         if (act) W[lane * WLD + c] = W[c * WLD + lane];

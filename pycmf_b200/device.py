@@ -138,6 +138,7 @@ class CudaBackend:
         self.torch.cuda.synchronize(self.device)
 
     def profile(self, on=True):
+        self._profiling = bool(on)
         _lib.check(self.lib.pycmf_profile_enable(self.ctx, int(bool(on))))
         if self._aux is not None:
             self._aux.profile(on)
@@ -167,6 +168,7 @@ class CudaBackend:
         torch = self.torch
         prev_stream = self.stream
         g = torch.cuda.CUDAGraph()
+        was_profiling = bool(getattr(self, "_profiling", False))
         self.profile(False)
         if getattr(self, "_cap_stream", None) is None:
             self._cap_stream = torch.cuda.Stream(device=self.device)
@@ -182,6 +184,8 @@ class CudaBackend:
                     g.capture_end()
         finally:
             self.use_stream(prev_stream)
+            if was_profiling:
+                self.profile(True)
         torch.cuda.current_stream(self.device).wait_stream(cap)
         g.replay()          # the captured iteration has not run yet: run it now
         return g
@@ -290,7 +294,45 @@ class CudaBackend:
         M = np.asarray(M)
         if M.ndim != 2:
             raise ValueError("Expected 2D array, got %dD array instead" % M.ndim)
+        if M.nbytes > self.INGEST_CHUNK_BYTES and M.dtype in (np.float32, np.float64) and M.flags.c_contiguous:
+            return self._ingest_dense_chunked(M)
         return self.dense(self.to_device(M, raw=True))
+
+    INGEST_CHUNK_BYTES = 1 << 28
+
+    def _ingest_dense_chunked(self, M):
+        """Large dense host matrix -> padded-pitch DenseMatrix through two staging buffers of INGEST_CHUNK_BYTES: the raw
+        bytes of a row block cross PCIe while the previous block is cast / pitched into place, and HBM never holds a
+        second full-size copy (C5: 40 GB of X next to 40 GB of staging would not leave room for anything else)."""
+        torch = self.torch
+        rows, cols = M.shape
+        out = self.dense_empty(rows, cols)
+        step = max(1, self.INGEST_CHUNK_BYTES // max(1, M.strides[0]))
+        host = torch.from_numpy(M if M.flags.writeable else M.copy())
+        pinned = host.is_pinned()
+        stages = [torch.empty(step, cols, dtype=host.dtype, device=self.device) for _ in range(2)]
+        copy_stream = getattr(self, "_ingest_stream", None)
+        if copy_stream is None:
+            copy_stream = self._ingest_stream = torch.cuda.Stream(device=self.device)
+        main = torch.cuda.current_stream(self.device)
+        copy_stream.wait_stream(main)
+        done = [None, None]          # event: the cast out of stage i has finished
+        for i, r0 in enumerate(range(0, rows, step)):
+            r1 = min(rows, r0 + step)
+            stg = stages[i & 1][:r1 - r0]
+            with torch.cuda.stream(copy_stream):
+                if done[i & 1] is not None:
+                    copy_stream.wait_event(done[i & 1])
+                stg.copy_(host[r0:r1], non_blocking=pinned)
+                arrived = torch.cuda.Event()
+                arrived.record(copy_stream)
+            main.wait_event(arrived)
+            out.t[r0:r1].copy_(stg)
+            done[i & 1] = torch.cuda.Event()
+            done[i & 1].record(main)
+        for s in stages:
+            s.record_stream(copy_stream)
+        return out
 
     def row_slice(self, M, r0, r1):
         """Rows [r0, r1) of an ingested matrix (view for dense, re-based copy for sparse)."""
@@ -409,7 +451,8 @@ class CudaBackend:
         rows = j1 - j0
         per_row = self.newton_v_needs_per_row(x_link, idx is not None)
         gx = self.empty(rows, k)
-        Hx = self.empty(rows if per_row else 1, k, k)
+        # per-row Hessians in the compute dtype; the shared one (alpha U^T U) always in float64
+        Hx = self.empty(rows, k, k) if per_row else self.empty(1, k, k, dtype=self.torch.float64)
         if X.is_sparse:
             xargs = (0, 0, X.colptr[j0:].data_ptr(), _ptr(X.rowidx), _ptr(X.cvals))
         else:
@@ -445,11 +488,25 @@ class CudaBackend:
         _lib.check(self.lib.pycmf_safe_solve(self.ctx, batch, k, _ptr(H), stride, _ptr(g), _ptr(x), float(pert)))
         return x
 
-    def sample_indices(self, rows, N, n_sample, seed, stream_id):
+    def sample_indices(self, rows, N, n_sample, seed, stream_id, row0=0, window=None):
+        """idx (rows x n_sample): the sample sets of global rows [row0, row0 + rows); `window` = (lo, hi) keeps only the
+        indices a rank holds (re-based to lo, the others -1)."""
         idx = self.empty(rows, n_sample, dtype=self.torch.int32)
-        _lib.check(self.lib.pycmf_sample_indices(self.ctx, rows, N, n_sample, int(seed) & (2 ** 64 - 1),
-                                                 int(stream_id), _ptr(idx)))
+        lo, hi = window if window is not None else (0, 0)
+        _lib.check(self.lib.pycmf_sample_indices_sharded(self.ctx, rows, int(row0), N, n_sample,
+                                                         int(seed) & (2 ** 64 - 1), int(stream_id), int(lo), int(hi),
+                                                         _ptr(idx)))
         return idx
+
+    def topk_per_column(self, F, topn):
+        """(columns x topn) int32: row indices of the topn largest entries of every column of F (rows x k), ascending
+        weight == np.argsort(F[:, c], kind="stable")[-topn:] (reference analysis.py:6)."""
+        rows, k = F.shape
+        topn = int(min(topn, rows))
+        out = self.empty(k, topn, dtype=self.torch.int32)
+        assert F.stride(1) == 1
+        _lib.check(self.lib.pycmf_topk_columns(self.ctx, self.code, rows, k, _ptr(F), F.stride(0), topn, _ptr(out)))
+        return out
 
     def gemm(self, A, B, trans_a=False, alpha=1.0, beta=0.0, out=None):
         m = A.shape[1] if trans_a else A.shape[0]

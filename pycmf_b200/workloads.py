@@ -32,6 +32,28 @@ SOLVER_PARAMS = {
 }
 
 
+# where a workload's solver parameters leave SURVEY 8d, and why (printed in bench.py's `config`)
+DEVIATIONS = {
+    "c2": "U / V / Z_non_negative=False, l2_reg=0.1 (SURVEY 8d: U, V non-negative): with the projection the reference's "
+          "own full Newton steps diverge on this data (oracle objective 1.6e4 -> 1e17 in 6 iterations)",
+    "c4": "toy slice (rows x 0.02, columns x 0.02): the per-row 128 x 128 Hessian builds / clamped solves do not run at "
+          "width yet",
+}
+
+
+def bench_config(name, scale, col_scale, world):
+    """The `config` object of a bench line: identical in our arm and in the reference arm."""
+    c = describe(name, scale, col_scale)
+    n_loc = -(-c["n"] // world)
+    x_mb = (n_loc * c.get("nnz_per_row", 0) * 8 * 2 if c["sparse"] else n_loc * c["d"] * 4) / 1e6
+    l2 = ("inputs larger than L2 (X shard ~%.0f MB per rank, re-read from HBM every iteration)" % x_mb) if x_mb > 126 else \
+        ("X shard %.1f MB is L2-resident (launch-bound workload); no flush: the fit loop itself re-reads X every "
+         "iteration" % x_mb)
+    return {"workload": label(name, c), "scale": scale, "col_scale": col_scale, "n_ranks": world,
+            "sharding": "rows of X / U over the ranks, V / Z / Y replicated", "l2_policy": l2,
+            "solver_params": SOLVER_PARAMS[name], "deviation_from_SURVEY_8d": DEVIATIONS.get(name)}
+
+
 def describe(name, scale=1.0, col_scale=1.0):
     """Shape / solver description; `scale` shrinks the rows of X (a row shard of the full problem keeps every
     column: V stays full size), `col_scale` additionally shrinks d (toy slices only)."""

@@ -390,10 +390,36 @@ def test_tc_mu_wide_fit_matches_oracle():
 
 
 @pytest.mark.parametrize("k", [32, 64, 128])
-@pytest.mark.parametrize("path", [0, 1, 2])
+@pytest.mark.parametrize("unroll", [4, 8])
+@pytest.mark.parametrize("shape", [(3000, 2500, 0.01), (40, 70, 0.2), (5000, 300, 0.002), (257, 4000, 0.05)])
+def test_spmm_nonzero_balanced_kernel(k, unroll, shape):
+    """The nonzero-balanced fp32 SpMM: shares that cut rows (atomics), whole rows (stores), empty rows (prologue), more
+    warps than nonzeros, hot rows / columns, alpha / beta -- against scipy in float64."""
+    from pycmf_b200.device import CudaBackend
+    n, d, dens = shape
+    rng = np.random.RandomState(5)
+    S = sp.random(n, d, density=dens, random_state=rng, format="lil")
+    S[min(17, n - 1), :] = rng.rand(d)
+    S[:, min(33, d - 1)] = rng.rand(n, 1)
+    S[5, :] = 0
+    S[n - 1, :] = 0                     # trailing empty row
+    S = sp.csr_matrix(S)
+    S.eliminate_zeros()
+    be = CudaBackend(dtype="float32", options={"spmm_path": 1, "spmm_unroll": unroll})
+    Sd = be.ingest(S)
+    B, A, C0 = rng.randn(d, k), rng.randn(n, k), rng.randn(n, k)
+    got = be.to_host(be.spmm(Sd, be.to_device(B), alpha=0.5, beta=2.0, out=be.to_device(C0)))
+    assert rel_fro(got, 0.5 * (S @ B) + 2.0 * C0) < 2e-6
+    got0 = be.to_host(be.spmm(Sd, be.to_device(B), out=be.to_device(np.full((n, k), np.nan))))   # beta = 0 ignores C
+    assert rel_fro(got0, S @ B) < 2e-6
+    assert rel_fro(be.to_host(be.spmm(Sd, be.to_device(A), transposed=True)), S.T @ A) < 2e-6
+
+
+@pytest.mark.parametrize("k", [32, 64, 128])
+@pytest.mark.parametrize("path", [0, 1, 2, 3])
 def test_spmm_float32_kernels_agree(k, path):
-    """The three fp32 SpMM kernels (generic, vector, sub-warp grouped) on a skewed matrix with hot rows / columns,
-    alpha / beta handling included."""
+    """The fp32 SpMM kernels (generic, nonzero-balanced, vector, sub-warp grouped) on a skewed matrix with hot rows /
+    columns, alpha / beta handling included."""
     from pycmf_b200.device import CudaBackend
     rng = np.random.RandomState(11)
     S = sp.random(3000, 2500, density=0.01, random_state=rng, format="lil")
