@@ -13,7 +13,7 @@ from sklearn.utils import check_array
 
 from .analysis import _print_topic_terms_from_matrix, _print_topic_terms_with_importances_from_matrices
 from .cmf_solvers import MUSolver, NewtonSolver
-from .init import _init_custom, _initialize_mf
+from .init import _init_custom
 
 
 def _validated(M):
@@ -45,7 +45,7 @@ def collective_matrix_factorization(X, Y, U=None, V=None, Z=None,
                                     x_link="linear", y_link="linear",
                                     hessian_pertubation=0.2, sg_sample_ratio=1.,
                                     dtype="float32", device=None, sampler="auto", comm=None,
-                                    backend_options=None):
+                                    backend_options=None, init_on_device=False):
     """Compute Collective Matrix Factorization: X ~= f1(U V^T), Y ~= f2(V Z^T).
 
     Same contract as the reference function (cmf.py:215-456): returns (U, V, Z, n_iter); custom
@@ -66,6 +66,20 @@ def collective_matrix_factorization(X, Y, U=None, V=None, Z=None,
         raise ValueError("No such link %s for y_link" % y_link)
 
     # ---- initial factors (cmf.py:401-430)
+    backend = None
+    if init_on_device and x_init != 'custom' and y_init != 'custom':
+        # the same algorithms on the ingested, device-resident matrices (init_device.py); the fit then reuses them
+        from .device import CudaBackend
+        from .init_device import initialize_mf_device
+        backend = CudaBackend(device=device, dtype=dtype, options=backend_options)
+        X = backend.ingest(X) if X is not None else None
+        Y = backend.ingest(Y.toarray() if hasattr(Y, "toarray") else Y) if Y is not None else None
+
+        def _initialize_mf(M, k, init=None, random_state=None, non_negative=False):       # noqa: F811 (shadows the host one)
+            A, B = initialize_mf_device(backend, M, k, init=init, random_state=random_state, non_negative=non_negative)
+            return backend.to_host(A).astype(np.float64), backend.to_host(B).astype(np.float64)
+    else:
+        from .init import _initialize_mf
     if x_init == 'custom':
         if X is not None:
             U = _init_custom(U, X, n_components, 0, non_negative=U_non_negative, random_state=random_state)
@@ -88,7 +102,8 @@ def collective_matrix_factorization(X, Y, U=None, V=None, Z=None,
     elif Z_non_negative:
         V = V_
 
-    backend_kw = dict(dtype=dtype, device=device, sampler=sampler, comm=comm, backend_options=backend_options)
+    backend_kw = dict(dtype=dtype, device=device, sampler=sampler, comm=comm, backend_options=backend_options,
+                      backend=backend)
     if solver == "mu":
         if x_link != "linear" or y_link != "linear":
             warnings.warn("mu solver does not accept link functions other than linear, link arguments will be ignored")
@@ -130,7 +145,7 @@ class CMF(BaseEstimator, TransformerMixin):
                  random_state=None, l1_reg=0., l2_reg=0., verbose=0,
                  U_non_negative=True, V_non_negative=True, Z_non_negative=True,
                  x_link="linear", y_link="linear", hessian_pertubation=0.2, sg_sample_ratio=1.,
-                 dtype="float32", device=None, sampler="auto", backend_options=None):
+                 dtype="float32", device=None, sampler="auto", backend_options=None, init_on_device=False):
         self.n_components = n_components
         self.x_init = x_init
         self.y_init = y_init
@@ -154,10 +169,11 @@ class CMF(BaseEstimator, TransformerMixin):
         self.device = device
         self.sampler = sampler
         self.backend_options = backend_options
+        self.init_on_device = init_on_device
 
     def _backend_kw(self):
         return dict(dtype=self.dtype, device=self.device, sampler=self.sampler,
-                    backend_options=self.backend_options)
+                    backend_options=self.backend_options, init_on_device=self.init_on_device)
 
     def fit_transform(self, X, Y, U=None, V=None, Z=None):
         """Learn a CMF model for X and Y and return (U, V, Z) (reference cmf.py:645-706)."""

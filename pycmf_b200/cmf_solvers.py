@@ -129,13 +129,15 @@ class _IterativeCMFSolver:
             take = slice(r0, r1)
         Xd = None
         if X is not None:
-            if sp.issparse(X):
-                Xd = be.ingest(sp.csr_matrix(X)[take])
+            if getattr(X, "is_sparse", None) is not None:        # already ingested (device initialisation, bench)
+                Xd = X if (r0, r1) == (0, X.shape[0]) or take == slice(None) else be.row_slice(X, r0, r1)
+            elif sp.issparse(X):
+                Xd = be.ingest(X if take == slice(None) or (r0, r1) == (0, X.shape[0]) else sp.csr_matrix(X)[take])
             else:
                 Xd = be.ingest(np.asarray(X)[take])
         Yd = None
         if Y is not None:
-            Yd = be.ingest(Y.toarray() if sp.issparse(Y) else Y)
+            Yd = Y if getattr(Y, "is_sparse", None) is not None else be.ingest(Y.toarray() if sp.issparse(Y) else Y)
         Ud = be.to_device(np.asarray(U)[take])
         Vd = be.to_device(np.asarray(V))
         Zd = be.to_device(np.asarray(Z))
@@ -240,12 +242,20 @@ class _IterativeCMFSolver:
         st = self.prepare(X, Y, U, V, Z)
         n_iter = self.fit_device(st)
         be = st.be
-        U_out = st.U if self.sharded_input else st.comm.all_gather_rows(st.U, st.n_total)
-        if hasattr(be, "to_host_many"):
-            for host, got in zip((U, V, Z), be.to_host_many([U_out, st.V, st.Z])):
+        # only the factors that were updated come back: a factor held fixed (update_V=False in transform(), cmf.py:741)
+        # stays bit-identical on the host, as in the reference (tests/test_cmf.py:408) -- a float32 round trip would not
+        pairs = []
+        if self.update_U:
+            pairs.append((U, st.U if self.sharded_input else st.comm.all_gather_rows(st.U, st.n_total)))
+        if self.update_V:
+            pairs.append((V, st.V))
+        if self.update_Z:
+            pairs.append((Z, st.Z))
+        if pairs and hasattr(be, "to_host_many"):
+            for (host, _), got in zip(pairs, be.to_host_many([dev for _, dev in pairs])):
                 host[...] = got
         else:
-            for host, dev in ((U, U_out), (V, st.V), (Z, st.Z)):
+            for host, dev in pairs:
                 host[...] = be.to_host(dev)
         return U, V, Z, n_iter
 
@@ -262,9 +272,82 @@ class MUSolver(_IterativeCMFSolver):
     def _error_links(self):
         return "linear", "linear"
 
+    # Slab counts tried by the overlapped V update (first one that divides).  OFF by default (PYCMF_B200_V_SLABS unset):
+    # measured on 2 B200s (profiles/r02_overlap_n2.txt) the four slab passes cost more than the hidden collectives save --
+    # C5: X^T U 12.3 -> 16.4 ms for ~0.3 ms of exchange; C3: SpMM 0.96 -> 1.82 ms -- see DESIGN section 5.
+    V_SLABS = ()
+
+    def _v_slabs(self, st):
+        """Number of column slabs of X for the overlapped V update (1 = one pass, no overlap)."""
+        import os
+        d, k = st.V.shape
+        world = st.comm.world
+        want = getattr(self, "v_slabs", None) or int(os.environ.get("PYCMF_B200_V_SLABS", "0")) or "auto"
+        if world == 1 or d * k < self.SHARD_V_MIN or not getattr(st.comm, "overlap_capable", False) or want == 1:
+            return 1
+        for s in ((want,) if want != "auto" else self.V_SLABS):
+            # every rank gets d / (s * world) rows of every slab; dense slabs must start on a 16-byte boundary (TMA)
+            if d % (s * world) == 0 and (d // s) % 4 == 0:
+                return s
+        return 1
+
+    def _step_v_overlapped(self, st, slabs):
+        """The V update (:242-246, :252-255) on several ranks with the exchange hidden behind the pass over X.
+
+        X^T U is computed in `slabs` column slabs of X; while slab i + 1 is in the tensor cores, slab i's partial is
+        reduce-scattered by rows of V on a communication stream (NCCL over NVLink).  Every rank then applies the update
+        to its d / (slabs * G) rows of each slab (Y Z, V (U^T U + Z^T Z) and the elementwise step shrink by G instead of
+        being replicated), and slab i's new rows are all-gathered while slab i + 1 is updated.  What stays exposed is the
+        last slab's reduce-scatter and all-gather."""
+        be, comm = st.be, st.comm
+        torch = be.torch
+        d, k = st.V.shape
+        world, rank = comm.world, comm.rank
+        rows_s = d // slabs
+        piece = rows_s // world
+        ws = getattr(st, "_v_overlap", None)
+        if ws is None or ws["slabs"] != slabs:
+            ws = st._v_overlap = dict(
+                slabs=slabs, stream=torch.cuda.Stream(device=be.device),
+                part=[be.empty(rows_s + k, k) for _ in range(slabs)],
+                num=[be.empty(piece + k, k) for _ in range(slabs)],      # [reduced numerator rows ; U^T U]
+                send=[be.empty(piece, k) for _ in range(slabs)])
+        cs = ws["stream"]
+        main = be.stream
+        cs.wait_stream(main)
+        reduced = []
+        for s in range(slabs):
+            be.mu_v_partial(be.col_slice(st.X, s * rows_s, (s + 1) * rows_s), st.U, out=ws["part"][s])
+            ev = torch.cuda.Event()
+            ev.record(main)
+            with torch.cuda.stream(cs):
+                cs.wait_event(ev)
+                if s == 0:
+                    comm.all_reduce_sum(ws["part"][0][rows_s:])                       # U^T U, k x k
+                comm.reduce_scatter_rows(ws["part"][s][:rows_s], out=ws["num"][s][:piece])
+                done = torch.cuda.Event()
+                done.record(cs)
+            reduced.append(done)
+        for s in range(slabs):
+            main.wait_event(reduced[s])
+            ws["num"][s][piece:].copy_(ws["part"][0][rows_s:])
+            j0 = s * rows_s + rank * piece
+            v_loc = st.V[j0:j0 + piece]
+            be.mu_v_apply(v_loc, ws["num"][s], be.row_slice(st.Y, j0, j0 + piece), st.Z, self.l1_reg, self.l2_reg)
+            ws["send"][s].copy_(v_loc)
+            ev = torch.cuda.Event()
+            ev.record(main)
+            with torch.cuda.stream(cs):
+                cs.wait_event(ev)
+                comm.all_gather_into(st.V[s * rows_s:(s + 1) * rows_s], ws["send"][s])
+        main.wait_stream(cs)
+
     def _step(self, st):
         be = st.be
-        if self.update_V:                                        # :252-255
+        slabs = self._v_slabs(st) if self.update_V else 1
+        if self.update_V and slabs > 1:
+            self._step_v_overlapped(st, slabs)
+        elif self.update_V:                                      # :252-255
             buf = be.mu_v_partial(st.X, st.U)                    # [X^T U ; U^T U] of this shard
             d, k = st.V.shape
             world = st.comm.world
@@ -306,9 +389,12 @@ class MUSolver(_IterativeCMFSolver):
 
     def _write_back(self, st, U, V, Z):
         be = st.be
-        U[...] = be.to_host(st.comm.all_gather_rows(st.U, st.n_total))
-        V[...] = be.to_host(st.V)
-        Z[...] = be.to_host(st.Z)
+        if self.update_U:
+            U[...] = be.to_host(st.comm.all_gather_rows(st.U, st.n_total))
+        if self.update_V:
+            V[...] = be.to_host(st.V)
+        if self.update_Z:
+            Z[...] = be.to_host(st.Z)
 
 
 def _draw_masks_numpy(n, d, l, ratio, update_U, update_Z, update_V):

@@ -52,6 +52,7 @@ pycmf_ctx* fork_side(pycmf_ctx* ctx) {
     s->spmm_path = ctx->spmm_path;
     s->spmm_blocks_per_sm = ctx->spmm_blocks_per_sm;
     s->spmm_unroll = ctx->spmm_unroll;
+    s->mu_fused = ctx->mu_fused;
     s->tc_max_splits = ctx->tc_max_splits;
     s->tc_ctas = ctx->tc_ctas;
     s->tc_chain = ctx->tc_chain;
@@ -181,6 +182,7 @@ void mu_v_apply_impl(pycmf_ctx* ctx, int64_t d, int64_t l, int64_t k, T* V, cons
     else
         gemm<T>(ctx, false, d, k, l, Y, ldy, Z, k, N, k, T(1), T(1));
     gemm<T>(ctx, true, k, k, l, Z, k, Z, k, G, k, T(1), T(1));           // + Z^T Z     (:245)
+    if (mu_fused_apply<T>(ctx, d, k, V, N, G, l1, l2)) return;          // V (UtU+ZtZ) and the ratio in one kernel
     if (!tc_try<T>(ctx, false, d, k, k, V, k, G, D))                    // V (UtU+ZtZ) (:245)
         gemm<T>(ctx, false, d, k, k, V, k, G, k, D, k, T(1), T(0));
     mu_apply<T>(ctx, d, k, V, N, D, l1, l2);
@@ -196,7 +198,8 @@ void mu_left_impl(pycmf_ctx* ctx, int64_t rows, int64_t m, int64_t k, T* F, cons
     T* G = static_cast<T*>(scratch(sc, SLOT_T2, sizeof(T) * size_t(k) * k));
     if (!tc_try<T>(sc, true, m, k, k, B, k, B, G))                      // B^T B
         gemm<T>(sc, true, k, k, m, B, k, B, k, G, k, T(1), T(0));
-    if (!tc_try<T>(sc, false, rows, k, k, F, k, G, D))                  // F (B^T B)
+    const bool fused = k <= 128 && ctx->mu_fused != 0;                  // F (B^T B) inside the ratio kernel below
+    if (!fused && !tc_try<T>(sc, false, rows, k, k, F, k, G, D))        // F (B^T B)
         gemm<T>(sc, false, rows, k, k, F, k, G, k, D, k, T(1), T(0));
     if (Tg != nullptr) {
         bool done = false;
@@ -218,6 +221,11 @@ void mu_left_impl(pycmf_ctx* ctx, int64_t rows, int64_t m, int64_t k, T* F, cons
         spmm<T>(ctx, rows, rowptr, colidx, vals, B, k, k, N, k, T(1), T(0));
     }
     join_side(ctx);
+    if (fused && mu_fused_apply<T>(ctx, rows, k, F, N, G, l1, l2)) return;
+    if (fused) {                                                        // not eligible after all (shared memory): unfused
+        if (!tc_try<T>(ctx, false, rows, k, k, F, k, G, D))
+            gemm<T>(ctx, false, rows, k, k, F, k, G, k, D, k, T(1), T(0));
+    }
     mu_apply<T>(ctx, rows, k, F, N, D, l1, l2);
 }
 
@@ -477,6 +485,7 @@ int pycmf_set_option(pycmf_ctx* ctx, const char* key, double value) {
         else if (k == "spmm_path") ctx->spmm_path = int(value);
         else if (k == "spmm_blocks_per_sm") ctx->spmm_blocks_per_sm = int(value);
         else if (k == "spmm_unroll") ctx->spmm_unroll = int(value);
+        else if (k == "mu_fused") ctx->mu_fused = int(value);
         else if (k == "tc_trace") ctx->tc_trace = int(value);
         else if (k == "tc_ctas") ctx->tc_ctas = int(value);
         else if (k == "tc_chain") ctx->tc_chain = int(value);

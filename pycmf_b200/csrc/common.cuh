@@ -53,6 +53,7 @@ struct pycmf_ctx {
                                 // spills: 86 us on C2; 3: 168 registers: 91 us; 4: 128 registers, spills: 187 us)
     int spmm_path = 1;       // option: 0 = generic SpMM kernel only (tests), 1 = vector kernels for k = 32 / 64 / 128 / 256, 2 = without the sub-warp grouping
     int spmm_blocks_per_sm = 0;  // option: resident 256-thread CTAs per SM of the nonzero-balanced SpMM (0 = default 4)
+    int mu_fused = 1;        // option: 0 = separate F G GEMM + elementwise ratio launches (tests)
     int spmm_unroll = 4;     // option: independent factor-row gathers per lane in flight (4 or 8)
     int side_streams = 1;    // option: 0 runs the side branches on the main stream (serial)
 };
@@ -161,6 +162,9 @@ void reduce_parts(pycmf_ctx* ctx, int64_t m, int64_t q, int splits, const T* par
 // F *= N / (D + l1 + l2 F) with zero guard (cmf_solvers.py:212-228); all (rows x k) contiguous, ld given
 template <typename T>
 void mu_apply(pycmf_ctx* ctx, int64_t rows, int64_t k, T* F, const T* N, const T* D, double l1, double l2);
+// the same update with the denominator D = F G (G: k x k) formed inside the kernel (k <= 128); false = not eligible
+template <typename T>
+bool mu_fused_apply(pycmf_ctx* ctx, int64_t rows, int64_t k, T* F, const T* N, const T* G, double l1, double l2);
 template <typename T>
 void transpose(pycmf_ctx* ctx, int64_t rows, int64_t cols, const T* A, int64_t lda, T* At, int64_t ldat);
 // out[i] = alpha*a[i] + beta*b[i]
@@ -172,6 +176,12 @@ void dot_f64(pycmf_ctx* ctx, int64_t n, const T* a, const T* b, double scale, do
 
 template <typename T>
 void broadcast_add(pycmf_ctx* ctx, int64_t rows, int64_t kk, T* H, const T* Hs, T scale, bool overwrite);
+// dmma.cu : the same product for float64 operands on the fp64 tensor-core pipe (mma.sync.m8n8k4.f64); gemm<double> routes
+// to it when eligible (16-byte aligned operands, even pitches, not a launch-bound size, dense_path != 0)
+bool dmma_gemm_eligible(pycmf_ctx* ctx, int64_t m, int64_t q, int64_t p, const double* A, int64_t lda, const double* B,
+                        int64_t ldb);
+void dmma_gemm(pycmf_ctx* ctx, bool trans_a, int64_t m, int64_t q, int64_t p, const double* A, int64_t lda,
+               const double* B, int64_t ldb, double* C, int64_t ldc, double alpha, double beta);
 // out (k x topn int32): for every column c of F (rows x k, ld) the row indices of its topn largest entries in ASCENDING
 // weight order (ties by ascending index) == np.argsort(F[:, c], kind="stable")[-topn:]   (reference analysis.py:6)
 template <typename T>

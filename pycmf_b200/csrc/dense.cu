@@ -1,6 +1,8 @@
 // Generic dense kernels (fp32 / fp64 FMA pipes): tiled GEMM with split-K, MU ratio epilogue,
 // transpose, axpby, dot.  These are the exact-precision path; the tcgen05 TF32 kernels in
 // tc_dense.cu take over the large fp32 contractions when ctx->dense_path != 0.
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace pycmf {
@@ -238,6 +240,12 @@ template <typename T>
 void gemm(pycmf_ctx* ctx, bool trans_a, int64_t m, int64_t q, int64_t p, const T* A, int64_t lda,
           const T* B, int64_t ldb, T* C, int64_t ldc, T alpha, T beta) {
     if (m <= 0 || q <= 0) return;
+    if constexpr (std::is_same<T, double>::value) {
+        if (p > 0 && dmma_gemm_eligible(ctx, m, q, p, A, lda, B, ldb)) {
+            dmma_gemm(ctx, trans_a, m, q, p, A, lda, B, ldb, C, ldc, alpha, beta);
+            return;
+        }
+    }
     Timed timer(ctx, "gemm");
     int64_t tiles = ceil_div(m, BM) * ceil_div(q, BN);
     int splits = 1;
@@ -350,6 +358,69 @@ void gram_f64(pycmf_ctx* ctx, int64_t rows, int64_t k, const T* A, double* G) {
     reduce_parts<double>(ctx, k, k, blocks, part, G, k, 1.0, 0.0);
 }
 
+// ---- fused MU factor update ----------------------------------------------------------------------------------------------
+//     F <- F * N / (F G + l1 + l2 F),  zero denominators -> float32 eps          (cmf_solvers.py:212-228, :233, :239, :245)
+// with the denominator product F G (G = k x k Gram sum, k <= 128) formed inside the kernel: a CTA stages G and a block of
+// MUF_ROWS rows of F in shared memory, every thread builds four entries of its rows of F G in registers and applies the ratio
+// and the zero guard before anything is written.  Replaces a (rows x k x k) GEMM launch, the rows x k denominator round trip
+// through HBM (write + read) and the separate elementwise launch: the update reads F and N once and writes F once.
+constexpr int MUF_ROWS = 32;
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+mu_fused_kernel(int64_t rows, int k, T* __restrict__ F, const T* __restrict__ N, const T* __restrict__ G, T l1, T l2,
+                T eps) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int ldg = k + 1;                                   // odd pitch: column reads of G are conflict-free
+    T* Gs = reinterpret_cast<T*>(smem_raw);                  // k x ldg
+    T* Fs = Gs + size_t(k) * ldg;                            // MUF_ROWS x k
+    for (int e = threadIdx.x; e < k * k; e += blockDim.x) Gs[(e / k) * ldg + e % k] = G[e];
+    const int cgroups = (k + 3) / 4;                         // column groups of 4
+    for (int64_t r0 = int64_t(blockIdx.x) * MUF_ROWS; r0 < rows; r0 += int64_t(gridDim.x) * MUF_ROWS) {
+        __syncthreads();
+        const int nr = int(min(int64_t(MUF_ROWS), rows - r0));
+        for (int e = threadIdx.x; e < nr * k; e += blockDim.x) Fs[e] = F[r0 * k + e];
+        __syncthreads();
+        for (int item = threadIdx.x; item < nr * cgroups; item += blockDim.x) {
+            const int r = item / cgroups, c0 = (item % cgroups) * 4;
+            T d0 = T(0), d1 = T(0), d2 = T(0), d3 = T(0);
+            const T* fr = Fs + r * k;
+            const int c1 = min(c0 + 1, k - 1), c2 = min(c0 + 2, k - 1), c3 = min(c0 + 3, k - 1);
+            for (int j = 0; j < k; j++) {
+                const T f = fr[j];
+                const T* g = Gs + j * ldg;
+                d0 = fma(f, g[c0], d0); d1 = fma(f, g[c1], d1); d2 = fma(f, g[c2], d2); d3 = fma(f, g[c3], d3);
+            }
+            const T den[4] = {d0, d1, d2, d3};
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int c = c0 + u;
+                if (c >= k) break;
+                const T f = fr[c];
+                T dd = den[u];
+                if (l1 > T(0)) dd += l1;
+                if (l2 > T(0)) dd = dd + l2 * f;
+                if (dd == T(0)) dd = eps;
+                F[(r0 + r) * k + c] = f * (N[(r0 + r) * k + c] / dd);
+            }
+        }
+    }
+}
+
+template <typename T>
+bool mu_fused_apply(pycmf_ctx* ctx, int64_t rows, int64_t k, T* F, const T* N, const T* G, double l1, double l2) {
+    if (k > 128 || rows <= 0 || ctx->mu_fused == 0) return false;
+    const size_t smem = sizeof(T) * (size_t(k) * (k + 1) + size_t(MUF_ROWS) * k);
+    if (smem > size_t(ctx->max_smem_optin)) return false;
+    auto kern = mu_fused_kernel<T>;
+    PYCMF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    const int64_t grid = std::min<int64_t>(ceil_div(rows, MUF_ROWS), int64_t(4) * ctx->num_sms);
+    Timed timer(ctx, "mu_fused");
+    kern<<<(unsigned)grid, 256, smem, ctx->stream>>>(rows, int(k), F, N, G, T(l1), T(l2), T(kEpsF32));
+    PYCMF_LAUNCH_CHECK(ctx);
+    return true;
+}
+
 // ---- top-k per column (topic-term extraction, reference analysis.py:1-16) -----------------------------------------------
 // One CTA per column, topn selection rounds: round r finds the largest (value, index) pair below the pair picked in round
 // r - 1 (pairs ordered by value, then index), i.e. a selection sort on the top end only -- topn x rows / 256 comparisons per
@@ -424,6 +495,8 @@ INSTANTIATE(double)
 }  // namespace pycmf
 
 namespace pycmf {
+template bool mu_fused_apply<float>(pycmf_ctx*, int64_t, int64_t, float*, const float*, const float*, double, double);
+template bool mu_fused_apply<double>(pycmf_ctx*, int64_t, int64_t, double*, const double*, const double*, double, double);
 template void topk_columns<float>(pycmf_ctx*, int64_t, int64_t, const float*, int64_t, int, int32_t*);
 template void topk_columns<double>(pycmf_ctx*, int64_t, int64_t, const double*, int64_t, int, int32_t*);
 }  // namespace pycmf

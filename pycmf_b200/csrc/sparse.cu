@@ -278,8 +278,9 @@ __global__ void spmm_nzb_prologue_kernel(int64_t rows, const int32_t* __restrict
                                          float* __restrict__ C, int64_t ldc, int k, float beta) {
     const int64_t r = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
     if (r >= rows) return;
-    const int64_t total = rowptr[rows];
-    const int64_t a = rowptr[r], b = rowptr[r + 1];
+    const int64_t base = rowptr[0];                        // a slice of a larger CSR keeps absolute offsets
+    const int64_t total = rowptr[rows] - base;
+    const int64_t a = rowptr[r] - base, b = rowptr[r + 1] - base;
     bool touch = a == b;                                   // empty row: nobody else writes it
     if (!touch && total > 0) {
         // is there a share boundary strictly inside (a, b)?  smallest w with begin(w) > a
@@ -302,8 +303,9 @@ spmm_nzb_kernel(int64_t rows, const int32_t* __restrict__ rowptr, const int32_t*
     const int gl = lane % LPN, gid = lane / LPN;
     const int64_t warp = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = (int64_t(gridDim.x) * blockDim.x) >> 5;
-    const int total = rowptr[rows];                       // nnz < 2^31 (int32 CSR): 32-bit positions keep registers down
-    const int e0 = int(nzb_share_begin(warp, total, nwarps)), e1 = int(nzb_share_begin(warp + 1, total, nwarps));
+    const int base = rowptr[0];                           // a slice of a larger CSR keeps absolute offsets
+    const int total = rowptr[rows] - base;                // nnz < 2^31 (int32 CSR): 32-bit positions keep registers down
+    const int e0 = base + int(nzb_share_begin(warp, total, nwarps)), e1 = base + int(nzb_share_begin(warp + 1, total, nwarps));
     if (e0 >= e1) return;
     // row holding nonzero e0: last r with rowptr[r] <= e0
     int lo = 0, hi = int(rows);
@@ -314,7 +316,7 @@ spmm_nzb_kernel(int64_t rows, const int32_t* __restrict__ rowptr, const int32_t*
     int row = lo;
     int row_begin = rowptr[row], row_end = rowptr[row + 1];
     const float* Bl = B + gl * 4;
-    const int last = total - 1;
+    const int last = base + total - 1;
     // current block [pos, pos + 32) of the flat nonzero stream; lanes past the share end read a valid address, value 0
     int pos = e0;
     int c = colidx[min(pos + lane, last)];

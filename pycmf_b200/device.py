@@ -278,9 +278,14 @@ class CudaBackend:
         if isinstance(M, (DenseMatrix, SparseMatrix)):
             return M
         if sp.issparse(M):
-            csr = sp.csr_matrix(M, dtype=self.np_dtype)
-            csr.sum_duplicates()
-            csr.sort_indices()
+            # no host-side passes over the nonzeros that are not needed: a canonical CSR (sorted, no duplicates -- what
+            # TfidfVectorizer / check_array hand over) is uploaded as it is and cast on the GPU; at C3 scale every avoided
+            # host copy of the 2.5e7-nonzero shard is ~100 ms of a 0.4 s fit
+            csr = M if sp.isspmatrix_csr(M) else sp.csr_matrix(M)
+            if not csr.has_canonical_format:
+                csr = csr.copy() if csr is M else csr
+                csr.sum_duplicates()
+                csr.sort_indices()
             if csr.nnz >= 2 ** 31 or max(csr.shape) >= 2 ** 31:
                 raise ValueError("sparse matrix too large for int32 indices")
             # only the CSR arrays cross PCIe; the CSC copy (the CSR of X^T: X^T U and the column access of the Newton V
@@ -345,6 +350,18 @@ class CudaBackend:
         colidx, vals = M.colidx[lo:hi].clone(), M.vals[lo:hi].clone()
         colptr, rowidx, cvals = self._csc_from_csr(rp, colidx, vals, r1 - r0, M.shape[1])
         return SparseMatrix((r1 - r0, M.shape[1]), rp, colidx, vals, colptr, rowidx, cvals)
+
+    def col_slice(self, M, c0, c1):
+        """Columns [c0, c1) of an ingested matrix as the operand of a V-side pass (X^T U over a column slab): a strided
+        view for dense X, the CSC arrays with the column pointer sliced (offsets stay absolute) for sparse X."""
+        if not M.is_sparse:
+            return DenseMatrix(M.t[:, c0:c1])
+        S = SparseMatrix.__new__(SparseMatrix)
+        S.shape = (M.shape[0], c1 - c0)
+        S.rowptr = S.colidx = S.vals = None                      # row access is not defined on a column slab
+        S.colptr, S.rowidx, S.cvals = M.colptr[c0:c1 + 1], M.rowidx, M.cvals
+        S.nnz = None
+        return S
 
     def _csc_from_csr(self, rowptr, colidx, vals, n_rows, n_cols):
         """(colptr, rowidx, cvals) of the matrix whose CSR arrays are given: stable sort of the nonzeros on the column."""

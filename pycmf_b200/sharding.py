@@ -26,8 +26,12 @@ class Comm:
     def all_gather_rows(self, t, n_total):
         return t
 
-    def reduce_scatter_rows(self, t):
-        """Sum over ranks of a (rows x k) tensor whose rows split evenly; returns this rank's row block of the sum."""
+    def reduce_scatter_rows(self, t, out=None):
+        """Sum over ranks of a (rows x k) tensor whose rows split evenly; returns this rank's row block of the sum
+        (written into `out` when given)."""
+        if out is not None:
+            out.copy_(t)
+            return out
         return t
 
     def all_gather_into(self, out, block):
@@ -53,6 +57,9 @@ class TorchComm(Comm):
         import os
         self.graph_capturable = (dist.get_backend(group) == "nccl" and
                                  os.environ.get("PYCMF_B200_GRAPH_COLLECTIVES", "1") != "0")
+        # collectives can run on a communication stream next to the compute stream (MUSolver._step_v_overlapped)
+        self.overlap_capable = (dist.get_backend(group) == "nccl" and
+                                os.environ.get("PYCMF_B200_OVERLAP", "1") != "0")
 
     def all_reduce_sum(self, t):
         if self.world > 1:
@@ -73,20 +80,26 @@ class TorchComm(Comm):
         self.dist.all_gather(out, pad, group=self.group)
         return torch.cat([o[:b - a] for o, (a, b) in zip(out, sizes)], 0)
 
-    def reduce_scatter_rows(self, t):
-        """Row block `rank` of the sum over ranks of t (rows x k, rows % world == 0).  NCCL: one reduce-scatter
-        (half the traffic of an all-reduce); other backends (gloo in the CPU tests): all-reduce + slice."""
+    def reduce_scatter_rows(self, t, out=None):
+        """Row block `rank` of the sum over ranks of t (rows x k, rows % world == 0), written into `out` when given.
+        NCCL: one reduce-scatter (half the traffic of an all-reduce); other backends (gloo in the CPU tests):
+        all-reduce + slice."""
         if self.world == 1:
-            return t
+            return Comm.reduce_scatter_rows(self, t, out)
         import torch
         rows = t.shape[0] // self.world
         assert rows * self.world == t.shape[0]
         if self.dist.get_backend(self.group) == "nccl":
-            out = torch.empty((rows,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+            if out is None:
+                out = torch.empty((rows,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
             self.dist.reduce_scatter_tensor(out, t.contiguous(), op=self.dist.ReduceOp.SUM, group=self.group)
             return out
         self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM, group=self.group)
-        return t[self.rank * rows:(self.rank + 1) * rows]
+        mine = t[self.rank * rows:(self.rank + 1) * rows]
+        if out is not None:
+            out.copy_(mine)
+            return out
+        return mine
 
     def all_gather_into(self, out, block):
         if self.world == 1:

@@ -89,3 +89,38 @@ def test_print_topic_terms_uses_the_device_topk_and_matches_the_reference_format
             ref.analysis._print_topic_terms_with_importances_from_matrices(U, Z, words)
         assert ours == buf.getvalue()
     assert ours.count("Topic") == 5
+
+
+@pytest.mark.parametrize("init", ["random", "svd", "nndsvd", "nndsvda", "nndsvdar"])
+@pytest.mark.parametrize("sparse", [False, True])
+def test_device_initialisation_matches_the_host_path(init, sparse):
+    """`_initialize_mf` on the GPU (init_device.py: the library's GEMM / SpMM for every product with M) against the host
+    restatement of reference cmf.py:41-202 (init.py, itself checked against the live reference on the CPU): same NumPy
+    random draws on both sides, so the factors agree to rounding."""
+    from pycmf_b200.device import CudaBackend
+    from pycmf_b200.init import _initialize_mf
+    from pycmf_b200.init_device import initialize_mf_device
+    rng = np.random.RandomState(8)
+    n, d, k = 500, 180, 7
+    M = np.abs(rng.randn(n, 12)) @ np.abs(rng.randn(12, d)) * (1.0 + np.arange(d) / d)[None, :] + 0.01 * np.abs(rng.randn(n, d))
+    if sparse:
+        M = sp.csr_matrix(M * (rng.rand(n, d) < 0.3))
+    nn = init != "svd"
+    A, B = _initialize_mf(M, k, init=init, random_state=11, non_negative=nn)
+    be = CudaBackend(dtype="float64")
+    Ad, Bd = initialize_mf_device(be, be.ingest(M), k, init=init, random_state=11, non_negative=nn)
+    assert rel_fro(be.to_host(Ad), A) < 1e-7 and rel_fro(be.to_host(Bd), B) < 1e-7
+    for rows, cols in ((60, 300),):                       # rows < cols: the transposed branch of the range finder
+        M2 = np.abs(rng.randn(rows, 9)) @ np.abs(rng.randn(9, cols)) + 0.01 * np.abs(rng.randn(rows, cols))
+        A2, B2 = _initialize_mf(M2, 5, init=init, random_state=2, non_negative=nn)
+        A2d, B2d = initialize_mf_device(be, be.ingest(M2), 5, init=init, random_state=2, non_negative=nn)
+        assert rel_fro(be.to_host(A2d), A2) < 1e-7 and rel_fro(be.to_host(B2d), B2) < 1e-7
+
+
+def test_fit_with_device_initialisation_matches_host_initialisation():
+    from pycmf_b200 import CMF
+    X, Y = _data(6, n=400, d=150, l=6, k=5)
+    kw = dict(n_components=5, solver="mu", max_iter=20, tol=0, random_state=1, dtype="float64")
+    Uh, Vh, Zh = CMF(**kw).fit_transform(X, Y)
+    Ud, Vd, Zd = CMF(init_on_device=True, **kw).fit_transform(X, Y)
+    assert max(rel_fro(Ud, Uh), rel_fro(Vd, Vh), rel_fro(Zd, Zh)) < 1e-6

@@ -19,19 +19,21 @@ from test_gpu_parity import _mid_case, MID, NT
 import zlib
 from pycmf_b200.cmf_solvers import MUSolver, NewtonSolver
 MUSolver.SHARD_V_MIN = 0          # exercise the row-sharded V update on the small test shapes
+MUSolver.V_SLABS = (4, 5, 3, 2)   # and its slab-overlapped variant (opt-in in the product)
 from pycmf_b200.sharding import TorchComm, Comm
 
-def run(case, dtype, comm, masks=None, dense_path=0):
+def run(case, dtype, comm, masks=None, dense_path=0, history=True, **extra):
     p = dict(case["params"]); solver = p.pop("solver")
+    p.update(extra)
     cls = MUSolver if solver == "mu" else NewtonSolver
     # dense_path 0: both shard counts use the same (FMA) arithmetic, so only the summation order differs; the tcgen05
     # path switches on above a size threshold and would be compared against the FMA path on the smaller shards
     s = cls(max_iter=case["iters"], tol=0, random_state=case["rng_seed"], dtype=dtype, comm=comm,
             backend_options={"dense_path": dense_path}, **p)
-    s.history = []; s.masks_per_iter = masks
+    s.history = [] if history else None; s.masks_per_iter = masks
     U, V, Z = case["U0"].copy(), case["V0"].copy(), case["Z0"].copy()
     s.fit_iterative_update(case["X"], case["Y"], U, V, Z)
-    return np.asarray(s.history), U, V, Z
+    return np.asarray(s.history if history else []), U, V, Z
 
 names = ["mu_dense", "mu_csr_reg", "nt_lin_logit", "nt_logit_logit", "nt_csr_lin_logit", "nt_sg_logit_logit"]
 for name in names:
@@ -56,6 +58,28 @@ h1, U1, V1, Z1 = run(case, "float32", Comm(), dense_path=1)
 assert np.abs(h2 - h1).max() / np.abs(h1).max() < 1e-4, ("mu_tc_k64", h1, h2)
 for a, b in ((U1, U2), (V1, V2), (Z1, Z2)):
     assert rel_fro(a, b) < 1e-3, "mu_tc_k64"
+# the same fit through the default stepper: two eager iterations, then CUDA-graph replay with the NCCL collectives (and the
+# communication-stream overlap of the V update) captured inside the graph -- must equal the eager, per-iteration run
+case["iters"] = 7
+_, Ug, Vg, Zg = run(case, "float32", TorchComm(), dense_path=1, history=False)
+_, Ue, Ve, Ze = run(case, "float32", TorchComm(), dense_path=1)
+for a, b in ((Ug, Ue), (Vg, Ve), (Zg, Ze)):
+    assert rel_fro(a, b) < 1e-6, "graph replay vs eager on 2 ranks"
+# one slab (no overlap) and four slabs give the same V update up to summation order
+MUSolver.V_SLABS = (1,)
+_, U1s, V1s, Z1s = run(case, "float32", TorchComm(), dense_path=1)
+MUSolver.V_SLABS = (4, 5, 3, 2)
+for a, b in ((U1s, Ue), (V1s, Ve), (Z1s, Ze)):
+    assert rel_fro(a, b) < 1e-5, "slab-overlapped V update vs single pass"
+# on-device sampler: the sample sets are keyed by the GLOBAL row, so 2 ranks draw what 1 rank draws
+solver, n, d, l, k, sparse, params = MID["nt_signed_l1_lin_logit_k32"]
+case = _mid_case(solver, 600, 200, 6, 16, False, seed=3, **params); case["iters"] = 3
+case["params"]["sg_sample_ratio"] = 0.5
+h2, U2, V2, Z2 = run(case, "float64", TorchComm(), sampler="device")
+h1, U1, V1, Z1 = run(case, "float64", Comm(), sampler="device")
+assert np.abs(h2 - h1).max() / np.abs(h1).max() < 1e-9, ("device sampler, 2 ranks vs 1", h1, h2)
+for a, b in ((U1, U2), (V1, V2), (Z1, Z2)):
+    assert rel_fro(a, b) < 1e-9, "device sampler, 2 ranks vs 1"
 dist.barrier(); dist.destroy_process_group()
 if rank == 0: print("MULTI_OK")
 '''

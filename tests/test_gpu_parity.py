@@ -135,6 +135,35 @@ def test_gemm(be64, shape, trans):
     assert np.allclose(got, ref, rtol=1e-11, atol=1e-11)
 
 
+@pytest.mark.parametrize("shape", [(1000, 32, 700), (300, 50, 4000), (129, 256, 65), (5000, 32, 20000), (64, 8, 64),
+                                   (777, 10, 333), (2000, 130, 1500)])
+@pytest.mark.parametrize("trans", [False, True])
+def test_dmma_gemm_matches_numpy(be64, shape, trans):
+    """float64 tensor-core GEMM (mma.sync.m8n8k4.f64, dmma.cu): ragged tiles, split-K, alpha / beta, both operand
+    layouts -- against NumPy and against the FMA kernel it replaces."""
+    from pycmf_b200.device import CudaBackend
+    m, q, p = shape
+    rng = np.random.RandomState(1)
+    A = rng.randn(p, m) if trans else rng.randn(m, p)
+    if A.shape[1] % 2:                                   # odd pitch: not eligible (16-byte chunks); pad the pitch instead
+        A = np.ascontiguousarray(np.pad(A, ((0, 0), (0, 1))))[:, :-1]
+    B, C0 = rng.randn(p, q + q % 2)[:, :q], rng.randn(m, q)
+    ref = 0.7 * ((A.T if trans else A) @ B) - 1.3 * C0
+    Ad = be64.to_device(np.ascontiguousarray(np.pad(A, ((0, 0), (0, A.shape[1] % 2)))))[:, :A.shape[1]]
+    Bd = be64.to_device(np.ascontiguousarray(np.pad(B, ((0, 0), (0, q % 2)))))[:, :q]
+    launches = be64.launch_count()
+    be64.profile(True); be64.profile_reset()
+    got = be64.to_host(be64.gemm(Ad, Bd, trans_a=trans, alpha=0.7, beta=-1.3, out=be64.to_device(C0)))
+    _, cnt = be64.profile_query("dmma_gemm")
+    be64.profile(False)
+    assert cnt == 1, "the DMMA kernel did not run"
+    assert np.abs(got - ref).max() <= 1e-12 * np.abs(ref).max() * max(1, p // 100)
+    fma = CudaBackend(dtype="float64", options={"dense_path": 0})
+    got0 = fma.to_host(fma.gemm(fma.to_device(np.ascontiguousarray(A)), fma.to_device(np.ascontiguousarray(B)),
+                                trans_a=trans, alpha=0.7, beta=-1.3, out=fma.to_device(C0)))
+    assert np.abs(got - got0).max() <= 1e-12 * np.abs(ref).max() * max(1, p // 100)
+
+
 @pytest.mark.parametrize("k", [1, 3, 10, 32, 64, 100, 256])
 def test_spmm_and_transpose(be64, k):
     rng = np.random.RandomState(k)
@@ -481,3 +510,25 @@ def test_dense_ingest_pads_the_row_pitch_to_128_bytes():
     assert abs(outs[0][1] - (R ** 2).sum()) / (R ** 2).sum() < 1e-5
     for a, b in zip(outs[0], outs[1]):
         assert rel_fro(np.asarray(a), np.asarray(b)) < 1e-5
+
+
+@pytest.mark.parametrize("dtype,tol", [("float64", 1e-12), ("float32", 2e-6)])
+@pytest.mark.parametrize("shape", [(1000, 64), (77, 10), (300, 128), (5000, 33)])
+def test_mu_fused_update_matches_the_unfused_path(dtype, tol, shape):
+    """F <- F * N / (F G + l1 + l2 F) with the denominator product inside the kernel (mu_fused_kernel) against the
+    separate GEMM + elementwise launches, through the MU left update (zero denominators included)."""
+    from pycmf_b200.device import CudaBackend
+    rows, k = shape
+    rng = np.random.RandomState(12)
+    F0, B, T = np.abs(rng.randn(rows, k)), np.abs(rng.randn(90, k)), np.abs(rng.randn(rows, 90))
+    F0[3] = 0.0                                             # a zero row: denominator 0 -> float32 eps (cmf_solvers.py:219)
+    outs = []
+    for fused in (1, 0):
+        be = CudaBackend(dtype=dtype, options={"mu_fused": fused, "dense_path": 0})
+        F = be.to_device(F0)
+        be.profile(True); be.profile_reset()
+        be.mu_left(F, be.to_device(B), be.ingest(T), 0.01, 0.02)
+        assert be.profile_query("mu_fused")[1] == fused
+        outs.append(be.to_host(F))
+    ref = F0 * ((T @ B) / np.where((d := F0 @ (B.T @ B) + 0.01 + 0.02 * F0) == 0, np.finfo(np.float32).eps, d))
+    assert rel_fro(outs[0], outs[1]) < tol and rel_fro(outs[0], ref) < max(tol, 1e-6 if dtype == "float32" else 1e-12)
