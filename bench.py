@@ -520,6 +520,7 @@ def build_roofline(env, name, cfg, fams, n_prof, ms_prof, n_loc, nnz_loc, sb, sc
     d, l, k = cfg["d"], cfg["l"], cfg["k"]
     # the roofline is reported for the kernel that carries the traffic / flops: the slowest of the passes over X
     streaming = [f for f in fams if (f.startswith("tc_") and f not in ("tc_factor", "tc_ytv")) or f.startswith("resid_")
+                 or f.startswith("dmma_resid")
                  or f in ("spmm", "sddmm", "dmma_gemm")]
     big = [f for f in streaming if not f.startswith("resid_")] or streaming
     dom = max(big or fams, key=lambda f: fams[f][0] / fams[f][1])
@@ -620,7 +621,7 @@ def run_ours(args):
     env.be = CudaBackend(device=local_rank, dtype=args.dtype, options=opts)
     env.families = ("resid_left", "resid_right", "gemm", "spmm", "sddmm", "row_grad_hess", "safe_solve",
                     "apply_shared_inverse", "newton_finish_small", "tc_xv", "tc_xtu", "tc_factor", "tc_ytv",
-                    "tc_resid_left", "tc_resid_right", "dmma_gemm", "mu_fused")
+                    "tc_resid_left", "tc_resid_right", "dmma_gemm", "dmma_resid_left", "dmma_resid_right", "mu_fused")
     env.peaks = load_measured_peaks()
     env.run_peaks = None
     if not args.no_peaks:

@@ -182,6 +182,10 @@ bool dmma_gemm_eligible(pycmf_ctx* ctx, int64_t m, int64_t q, int64_t p, const d
                         int64_t ldb);
 void dmma_gemm(pycmf_ctx* ctx, bool trans_a, int64_t m, int64_t q, int64_t p, const double* A, int64_t lda,
                const double* B, int64_t ldb, double* C, int64_t ldc, double alpha, double beta);
+// ... and the fused residual pass (R = f(A B^T) - Tgt in shared memory, out = R B or R^T A, sum R^2) for k <= 128
+bool dmma_resid_eligible(pycmf_ctx* ctx, int64_t ra, int64_t rb, int64_t k);
+void dmma_resid(pycmf_ctx* ctx, int mode, int64_t ra, int64_t rb, int64_t k, const double* A, const double* B,
+                const double* Tgt, int64_t ldt, bool trans_t, int link, double* out, double* sq);
 // out (k x topn int32): for every column c of F (rows x k, ld) the row indices of its topn largest entries in ASCENDING
 // weight order (ties by ascending index) == np.argsort(F[:, c], kind="stable")[-topn:]   (reference analysis.py:6)
 template <typename T>

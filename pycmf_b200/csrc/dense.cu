@@ -364,44 +364,97 @@ void gram_f64(pycmf_ctx* ctx, int64_t rows, int64_t k, const T* A, double* G) {
 // MUF_ROWS rows of F in shared memory, every thread builds four entries of its rows of F G in registers and applies the ratio
 // and the zero guard before anything is written.  Replaces a (rows x k x k) GEMM launch, the rows x k denominator round trip
 // through HBM (write + read) and the separate elementwise launch: the update reads F and N once and writes F once.
-constexpr int MUF_ROWS = 32;
+constexpr int MUF_ROWS = 64;
 
-template <typename T>
+template <typename T> struct Vec4 { T v[4]; };
+template <typename T> __device__ __forceinline__ Vec4<T> ld4s(const T* p) {      // 4 consecutive elements, 16-byte aligned for float
+    Vec4<T> o;
+    load4<T>(p, o.v);
+    return o;
+}
+
+// VEC4: k % 4 == 0 -- a thread owns a 4 x 4 block of F G (4 rows, 4 columns) and walks the contraction four steps at a
+// time with 128-bit shared-memory reads of both operands (16 FMAs per 2 loads); otherwise the scalar form (k = 10 on C1).
+template <typename T, bool VEC4>
 __global__ void __launch_bounds__(256)
 mu_fused_kernel(int64_t rows, int k, T* __restrict__ F, const T* __restrict__ N, const T* __restrict__ G, T l1, T l2,
                 T eps) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int ldg = k + 1;                                   // odd pitch: column reads of G are conflict-free
+    const int ldg = VEC4 ? k + 4 : k + 1;                    // pitch of G: 16-byte aligned rows / odd (conflict-free columns)
+    const int ldf = VEC4 ? k + 4 : k;
     T* Gs = reinterpret_cast<T*>(smem_raw);                  // k x ldg
-    T* Fs = Gs + size_t(k) * ldg;                            // MUF_ROWS x k
+    T* Fs = Gs + size_t(k) * ldg;                            // MUF_ROWS x ldf
     for (int e = threadIdx.x; e < k * k; e += blockDim.x) Gs[(e / k) * ldg + e % k] = G[e];
     const int cgroups = (k + 3) / 4;                         // column groups of 4
     for (int64_t r0 = int64_t(blockIdx.x) * MUF_ROWS; r0 < rows; r0 += int64_t(gridDim.x) * MUF_ROWS) {
         __syncthreads();
         const int nr = int(min(int64_t(MUF_ROWS), rows - r0));
-        for (int e = threadIdx.x; e < nr * k; e += blockDim.x) Fs[e] = F[r0 * k + e];
+        for (int e = threadIdx.x; e < MUF_ROWS * k; e += blockDim.x) {
+            const int r = e / k, c = e % k;
+            Fs[r * ldf + c] = r < nr ? F[(r0 + r) * k + c] : T(0);
+        }
         __syncthreads();
-        for (int item = threadIdx.x; item < nr * cgroups; item += blockDim.x) {
-            const int r = item / cgroups, c0 = (item % cgroups) * 4;
-            T d0 = T(0), d1 = T(0), d2 = T(0), d3 = T(0);
-            const T* fr = Fs + r * k;
-            const int c1 = min(c0 + 1, k - 1), c2 = min(c0 + 2, k - 1), c3 = min(c0 + 3, k - 1);
-            for (int j = 0; j < k; j++) {
-                const T f = fr[j];
-                const T* g = Gs + j * ldg;
-                d0 = fma(f, g[c0], d0); d1 = fma(f, g[c1], d1); d2 = fma(f, g[c2], d2); d3 = fma(f, g[c3], d3);
-            }
-            const T den[4] = {d0, d1, d2, d3};
+        if (VEC4) {
+            for (int item = threadIdx.x; item < (MUF_ROWS / 4) * cgroups; item += blockDim.x) {
+                const int rg = item / cgroups, c0 = (item % cgroups) * 4;
+                T d[4][4];
 #pragma unroll
-            for (int u = 0; u < 4; u++) {
-                const int c = c0 + u;
-                if (c >= k) break;
-                const T f = fr[c];
-                T dd = den[u];
-                if (l1 > T(0)) dd += l1;
-                if (l2 > T(0)) dd = dd + l2 * f;
-                if (dd == T(0)) dd = eps;
-                F[(r0 + r) * k + c] = f * (N[(r0 + r) * k + c] / dd);
+                for (int u = 0; u < 4; u++)
+#pragma unroll
+                    for (int w = 0; w < 4; w++) d[u][w] = T(0);
+                const T* f0 = Fs + (rg * 4) * ldf;
+                for (int j = 0; j < k; j += 4) {
+                    Vec4<T> f[4], g[4];
+#pragma unroll
+                    for (int u = 0; u < 4; u++) f[u] = ld4s<T>(f0 + u * ldf + j);
+#pragma unroll
+                    for (int jj = 0; jj < 4; jj++) g[jj] = ld4s<T>(Gs + (j + jj) * ldg + c0);
+#pragma unroll
+                    for (int jj = 0; jj < 4; jj++)
+#pragma unroll
+                        for (int u = 0; u < 4; u++)
+#pragma unroll
+                            for (int w = 0; w < 4; w++) d[u][w] = fma(f[u].v[jj], g[jj].v[w], d[u][w]);
+                }
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const int r = rg * 4 + u;
+                    if (r >= nr) break;
+#pragma unroll
+                    for (int w = 0; w < 4; w++) {
+                        const int c = c0 + w;
+                        const T fv = f0[u * ldf + c];
+                        T dd = d[u][w];
+                        if (l1 > T(0)) dd += l1;
+                        if (l2 > T(0)) dd = dd + l2 * fv;
+                        if (dd == T(0)) dd = eps;
+                        F[(r0 + r) * k + c] = fv * (N[(r0 + r) * k + c] / dd);
+                    }
+                }
+            }
+        } else {
+            for (int item = threadIdx.x; item < nr * cgroups; item += blockDim.x) {
+                const int r = item / cgroups, c0 = (item % cgroups) * 4;
+                T d0 = T(0), d1 = T(0), d2 = T(0), d3 = T(0);
+                const T* fr = Fs + r * ldf;
+                const int c1 = min(c0 + 1, k - 1), c2 = min(c0 + 2, k - 1), c3 = min(c0 + 3, k - 1);
+                for (int j = 0; j < k; j++) {
+                    const T f = fr[j];
+                    const T* g = Gs + j * ldg;
+                    d0 = fma(f, g[c0], d0); d1 = fma(f, g[c1], d1); d2 = fma(f, g[c2], d2); d3 = fma(f, g[c3], d3);
+                }
+                const T den[4] = {d0, d1, d2, d3};
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const int c = c0 + u;
+                    if (c >= k) break;
+                    const T f = fr[c];
+                    T dd = den[u];
+                    if (l1 > T(0)) dd += l1;
+                    if (l2 > T(0)) dd = dd + l2 * f;
+                    if (dd == T(0)) dd = eps;
+                    F[(r0 + r) * k + c] = f * (N[(r0 + r) * k + c] / dd);
+                }
             }
         }
     }
@@ -410,9 +463,10 @@ mu_fused_kernel(int64_t rows, int k, T* __restrict__ F, const T* __restrict__ N,
 template <typename T>
 bool mu_fused_apply(pycmf_ctx* ctx, int64_t rows, int64_t k, T* F, const T* N, const T* G, double l1, double l2) {
     if (k > 128 || rows <= 0 || ctx->mu_fused == 0) return false;
-    const size_t smem = sizeof(T) * (size_t(k) * (k + 1) + size_t(MUF_ROWS) * k);
+    const bool vec = k % 4 == 0;
+    const size_t smem = sizeof(T) * (size_t(k) * (k + 4) + size_t(MUF_ROWS) * (k + 4));
     if (smem > size_t(ctx->max_smem_optin)) return false;
-    auto kern = mu_fused_kernel<T>;
+    auto kern = vec ? mu_fused_kernel<T, true> : mu_fused_kernel<T, false>;
     PYCMF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
     const int64_t grid = std::min<int64_t>(ceil_div(rows, MUF_ROWS), int64_t(4) * ctx->num_sms);
     Timed timer(ctx, "mu_fused");

@@ -162,6 +162,197 @@ void launch_dmma(pycmf_ctx* ctx, dim3 grid, int64_t m, int64_t q, int64_t p, int
     PYCMF_LAUNCH_CHECK(ctx);
 }
 
+
+// ---- fused residual pass on the fp64 tensor cores ---------------------------------------------------------------------
+//     R = f(Own Oth^T) - target tile  (never written to HBM),   out (own x k) += R Oth,   sq += sum R^2
+// = the float64 form of reference cmf_solvers.py:399-400 (own = rows of U: out = R V) and :436-440 (own = rows of V,
+// target read transposed: out = R^T U) and of the dense objective (:36-42).  A CTA owns 64 "own" rows (their factor rows
+// stay in shared memory for the whole kernel) and walks the other factor in 32-row tiles (cp.async, double-buffered):
+// GEMM 1 (64 x 32 x k DMMAs) -> link, minus target (loaded into the accumulator layout before the tile arrives) -> R tile
+// in shared memory -> GEMM 2 (64 x k x 32 DMMAs) into register accumulators.  k <= 128.
+constexpr int ROWN = 64, ROT = 32;
+
+template <int NB2>          // n-blocks of GEMM 2 per warp: the padded factor width is 16 * NB2
+__global__ void __launch_bounds__(256)
+dmma_resid_kernel(int64_t own_n, int64_t oth_n, int k, const double* __restrict__ Own, const double* __restrict__ Oth,
+                  const double* __restrict__ Tgt, int64_t ldt, bool t_own_major, int link,
+                  double* __restrict__ out, int64_t out_split_stride, int64_t tiles_per_split,
+                  double* __restrict__ sq_part, bool want_out) {
+    constexpr int KPAD = 16 * NB2;
+    constexpr int LD = KPAD + 4;                   // = 4 mod 16: conflict-free 64-bit fragment reads
+    constexpr int LDR = ROT + 4;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double* red = reinterpret_cast<double*>(smem_raw);              // 32
+    double* own_s = red + 32;                                       // ROWN x LD
+    double* oth_s = own_s + ROWN * LD;                              // 2 x ROT x LD
+    double* R_s = oth_s + 2 * ROT * LD;                             // ROWN x LDR
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int wm = warp & 3, wn = warp >> 2;
+    const int fr = lane >> 2, fk = lane & 3;
+    const int64_t own0 = int64_t(blockIdx.x) * ROWN;
+    const int64_t t_begin = int64_t(blockIdx.y) * tiles_per_split;
+    const int64_t t_end = min(t_begin + tiles_per_split, (oth_n + ROT - 1) / ROT);
+
+    // factor rows -> shared memory, zero-padded to KPAD columns / missing rows (plain loads: k need not be even)
+    for (int e = tid; e < ROWN * KPAD; e += 256) {
+        const int r = e / KPAD, c = e % KPAD;
+        own_s[r * LD + c] = (own0 + r < own_n && c < k) ? Own[(own0 + r) * k + c] : 0.0;
+    }
+    auto load_oth = [&](int buf, int64_t t) {
+        double* dst = oth_s + buf * ROT * LD;
+        const int64_t o0 = t * ROT;
+        if ((k & 1) == 0) {
+            for (int e = tid; e < ROT * (KPAD / 2); e += 256) {
+                const int r = e / (KPAD / 2), c = 2 * (e % (KPAD / 2));
+                const bool ok = o0 + r < oth_n && c < k;
+                cp_async16(dst + r * LD + c, ok ? Oth + (o0 + r) * k + c : Oth, ok ? 16 : 0);
+            }
+        } else {
+            for (int e = tid; e < ROT * KPAD; e += 256) {
+                const int r = e / KPAD, c = e % KPAD;
+                dst[r * LD + c] = (o0 + r < oth_n && c < k) ? Oth[(o0 + r) * k + c] : 0.0;
+            }
+        }
+    };
+
+    double acc2[2][NB2][2];
+#pragma unroll
+    for (int i = 0; i < 2; i++)
+#pragma unroll
+        for (int j = 0; j < NB2; j++) acc2[i][j][0] = acc2[i][j][1] = 0.0;
+    double sq_local = 0.0;
+
+    if (t_begin < t_end) load_oth(0, t_begin);
+    cp_async_commit();
+    for (int64_t t = t_begin; t < t_end; t++) {
+        const int buf = int((t - t_begin) & 1);
+        const int64_t oth0 = t * ROT;
+        // target values of this thread's S elements, requested before the tile is waited for
+        double tg[2][2][2];
+#pragma unroll
+        for (int i = 0; i < 2; i++)
+#pragma unroll
+            for (int j = 0; j < 2; j++)
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    const int64_t ro = own0 + wm * 16 + i * 8 + fr, co = oth0 + wn * 16 + j * 8 + 2 * fk + h;
+                    double v = 0.0;
+                    if (Tgt != nullptr && ro < own_n && co < oth_n) v = t_own_major ? __ldg(Tgt + ro * ldt + co) : __ldg(Tgt + co * ldt + ro);
+                    tg[i][j][h] = v;
+                }
+        if (t + 1 < t_end) load_oth(buf ^ 1, t + 1);      // the other buffer was released by the barrier that ended tile t - 1
+        cp_async_commit();
+        cp_async_wait<1>();
+        __syncthreads();
+        const double* os = oth_s + buf * ROT * LD;
+        // ---- GEMM 1: S (64 x 32) = Own (64 x KPAD) Oth^T
+        double s1[2][2][2];
+#pragma unroll
+        for (int i = 0; i < 2; i++)
+#pragma unroll
+            for (int j = 0; j < 2; j++) s1[i][j][0] = s1[i][j][1] = 0.0;
+#pragma unroll 4
+        for (int kk = 0; kk < KPAD; kk += 4) {
+            double a[2], b[2];
+#pragma unroll
+            for (int i = 0; i < 2; i++) a[i] = own_s[(wm * 16 + i * 8 + fr) * LD + kk + fk];
+#pragma unroll
+            for (int j = 0; j < 2; j++) b[j] = os[(wn * 16 + j * 8 + fr) * LD + kk + fk];
+#pragma unroll
+            for (int i = 0; i < 2; i++)
+#pragma unroll
+                for (int j = 0; j < 2; j++) dmma884(s1[i][j], a[i], b[j]);
+        }
+        // ---- link, minus target, R tile to shared memory
+#pragma unroll
+        for (int i = 0; i < 2; i++)
+#pragma unroll
+            for (int j = 0; j < 2; j++)
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    const int rl = wm * 16 + i * 8 + fr, cl = wn * 16 + j * 8 + 2 * fk + h;
+                    double r = 0.0;
+                    if (own0 + rl < own_n && oth0 + cl < oth_n) {
+                        const double est = link == PYCMF_LOGIT ? sigmoid_<double>(s1[i][j][h]) : s1[i][j][h];
+                        r = est - tg[i][j][h];
+                        sq_local = fma(r, r, sq_local);
+                    }
+                    R_s[rl * LDR + cl] = r;
+                }
+        __syncthreads();
+        // ---- GEMM 2: out (64 x KPAD) += R (64 x 32) Oth (32 x KPAD)
+        if (want_out) {
+#pragma unroll
+            for (int kk = 0; kk < ROT; kk += 4) {
+                double a[2], b[NB2];
+#pragma unroll
+                for (int i = 0; i < 2; i++) a[i] = R_s[(wm * 16 + i * 8 + fr) * LDR + kk + fk];
+#pragma unroll
+                for (int j = 0; j < NB2; j++) b[j] = os[(kk + fk) * LD + wn * (KPAD / 2) + j * 8 + fr];
+#pragma unroll
+                for (int i = 0; i < 2; i++)
+#pragma unroll
+                    for (int j = 0; j < NB2; j++) dmma884(acc2[i][j], a[i], b[j]);
+            }
+        }
+        __syncthreads();          // R_s and this tile's buffer are free again
+    }
+    cp_async_wait<0>();
+    if (want_out) {
+        double* o = out + int64_t(blockIdx.y) * out_split_stride;
+#pragma unroll
+        for (int i = 0; i < 2; i++) {
+            const int64_t gr = own0 + wm * 16 + i * 8 + fr;
+            if (gr >= own_n) continue;
+#pragma unroll
+            for (int j = 0; j < NB2; j++)
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    const int c = wn * (KPAD / 2) + j * 8 + 2 * fk + h;
+                    if (c < k) o[gr * k + c] = acc2[i][j][h];
+                }
+        }
+    }
+    if (sq_part != nullptr) {
+        const double v = block_sum(sq_local, red);
+        if (tid == 0) sq_part[blockIdx.y * gridDim.x + blockIdx.x] = v;
+    }
+}
+
+template <int NB2>
+void launch_dmma_resid(pycmf_ctx* ctx, const char* family, int64_t own_n, int64_t oth_n, int64_t k, const double* Own,
+                       const double* Oth, const double* Tgt, int64_t ldt, bool t_own_major, int link, double* out,
+                       double* sq) {
+    constexpr int KPAD = 16 * NB2, LD = KPAD + 4;
+    const int64_t own_blocks = ceil_div(own_n, ROWN), loop_tiles = ceil_div(oth_n, ROT);
+    int64_t splits = 1;
+    // two resident CTAs per SM (registers): aim at ~4 waves of CTAs so that the last wave's tail stays small
+    if (own_blocks < 8 * ctx->num_sms)
+        splits = std::max<int64_t>(1, std::min(ceil_div(loop_tiles, 8), ceil_div(int64_t(8) * ctx->num_sms, own_blocks)));
+    int64_t tiles_per_split = ceil_div(loop_tiles, splits);
+    splits = ceil_div(loop_tiles, tiles_per_split);
+    PYCMF_CHECK(splits <= 65535, "resid_pass: too many splits");
+    const size_t smem = sizeof(double) * (32 + size_t(ROWN) * LD + size_t(2) * ROT * LD + size_t(ROWN) * (ROT + 4));
+    auto kern = dmma_resid_kernel<NB2>;
+    PYCMF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    double* target = out;
+    int64_t stride = 0;
+    if (out != nullptr && splits > 1) {
+        target = static_cast<double*>(scratch(ctx, 0, size_t(splits) * own_n * k * sizeof(double)));
+        stride = own_n * k;
+    }
+    double* sq_part = nullptr;
+    const int64_t nparts = own_blocks * splits;
+    if (sq != nullptr) sq_part = static_cast<double*>(scratch(ctx, 1, size_t(nparts) * sizeof(double)));
+    dim3 grid((unsigned)own_blocks, (unsigned)splits);
+    Timed timer(ctx, family);
+    kern<<<grid, 256, smem, ctx->stream>>>(own_n, oth_n, int(k), Own, Oth, Tgt, ldt, t_own_major, link, target, stride,
+                                           tiles_per_split, sq_part, out != nullptr);
+    PYCMF_LAUNCH_CHECK(ctx);
+    if (out != nullptr && splits > 1) reduce_parts<double>(ctx, own_n, k, int(splits), target, out, k, 1.0, 0.0);
+    if (sq != nullptr) final_sum(ctx, int(nparts), sq_part, 1.0, sq, true);
+}
+
 }  // namespace
 
 bool dmma_gemm_eligible(pycmf_ctx* ctx, int64_t m, int64_t q, int64_t p, const double* A, int64_t lda, const double* B,
@@ -203,6 +394,25 @@ void dmma_gemm(pycmf_ctx* ctx, bool trans_a, int64_t m, int64_t q, int64_t p, co
     else { if (bn == 32) GO(false, 32); else GO(false, 64); }
 #undef GO
     if (splits > 1) reduce_parts<double>(ctx, m, q, splits, out, C, ldc, alpha, beta);
+}
+
+bool dmma_resid_eligible(pycmf_ctx* ctx, int64_t ra, int64_t rb, int64_t k) {
+    return ctx->dense_path != 0 && k <= 128 && ra >= 64 && rb >= 64;
+}
+
+// mode 0: own = rows of A, out = R B (ra x k); mode 1: own = rows of B, out = R^T A (rb x k).  R = f(A B^T) - Tgt.
+void dmma_resid(pycmf_ctx* ctx, int mode, int64_t ra, int64_t rb, int64_t k, const double* A, const double* B,
+                const double* Tgt, int64_t ldt, bool trans_t, int link, double* out, double* sq) {
+    const double* own = mode == 0 ? A : B;
+    const double* oth = mode == 0 ? B : A;
+    const int64_t own_n = mode == 0 ? ra : rb, oth_n = mode == 0 ? rb : ra;
+    // target element of (own i, other j): Tgt[a, b] stored row-major (or transposed when trans_t)
+    const bool t_own_major = (mode == 0) != trans_t;
+    const char* fam = mode == 0 ? "dmma_resid_left" : "dmma_resid_right";
+    if (k <= 16) launch_dmma_resid<1>(ctx, fam, own_n, oth_n, k, own, oth, Tgt, ldt, t_own_major, link, out, sq);
+    else if (k <= 32) launch_dmma_resid<2>(ctx, fam, own_n, oth_n, k, own, oth, Tgt, ldt, t_own_major, link, out, sq);
+    else if (k <= 64) launch_dmma_resid<4>(ctx, fam, own_n, oth_n, k, own, oth, Tgt, ldt, t_own_major, link, out, sq);
+    else launch_dmma_resid<8>(ctx, fam, own_n, oth_n, k, own, oth, Tgt, ldt, t_own_major, link, out, sq);
 }
 
 }  // namespace pycmf

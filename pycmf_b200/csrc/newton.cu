@@ -313,36 +313,51 @@ __device__ void jacobi_clamped_solve(double* W, int k, const double* g, double* 
         if (threadIdx.x == 0) sh->flag = 0;
         __syncthreads();
         for (int step = 0; step < kk - 1; step++) {
-            for (int mth = warp; mth < kk / 2; mth += nwarps) {
-                int p, q;
-                if (mth == 0) { p = step; q = kk - 1; }
-                else { p = (step + mth) % (kk - 1); q = (step - mth + (kk - 1)) % (kk - 1); }
-                if (p >= k || q >= k) continue;
+            // TWO pairs per warp at a time, one per half-warp: the rotation scalars (three float64 rsqrt sequences) are
+            // the expensive part of a pair -- they issue for the whole warp whatever the active lanes -- so packing two pairs
+            // into one pass halves that cost, and the rsqrt-only formulation replaces two IEEE divisions and two square roots.
+            const int half = lane >> 4, hl = lane & 15;
+            for (int base = warp * 2; base < kk / 2; base += nwarps * 2) {
+                const int mth = base + half;
+                int p = 0, q = 0;
+                bool valid = mth < kk / 2;
+                if (valid) {
+                    if (mth == 0) { p = step; q = kk - 1; }
+                    else { p = (step + mth) % (kk - 1); q = (step - mth + (kk - 1)) % (kk - 1); }
+                    valid = p < k && q < k;
+                }
                 double* wp = W + p * k;
                 double* wq = W + q * k;
                 double al = 0.0, be = 0.0, ga = 0.0;
-                for (int r = lane; r < k; r += 32) {
-                    double a = wp[r], b = wq[r];
-                    al = fma(a, a, al); be = fma(b, b, be); ga = fma(a, b, ga);
-                }
-                // the three butterfly reductions interleaved: 5 dependent shuffle rounds instead of 15
+                if (valid)
+                    for (int r = hl; r < k; r += 16) {
+                        double a = wp[r], b = wq[r];
+                        al = fma(a, a, al); be = fma(b, b, be); ga = fma(a, b, ga);
+                    }
+                // the three butterfly reductions interleaved, inside each half-warp (offsets < 16 stay in the half)
 #pragma unroll
-                for (int o = 16; o > 0; o >>= 1) {
+                for (int o = 8; o > 0; o >>= 1) {
                     const double a2 = __shfl_xor_sync(0xffffffffu, al, o), b2 = __shfl_xor_sync(0xffffffffu, be, o),
                                  g2 = __shfl_xor_sync(0xffffffffu, ga, o);
                     al += a2; be += b2; ga += g2;
                 }
-                if (ga == 0.0 || fmax(al, be) < skip2) continue;
-                if (fabs(ga) <= tol * sqrt(al * be)) continue;
-                double zeta = (be - al) / (2.0 * ga);
-                double t = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
-                double c = 1.0 / sqrt(1.0 + t * t), s = c * t;
-                for (int r = lane; r < k; r += 32) {
-                    double a = wp[r], b = wq[r];
-                    wp[r] = c * a - s * b;
-                    wq[r] = s * a + c * b;
+                const bool rot = valid && ga != 0.0 && fmax(al, be) >= skip2 && ga * ga > (tol * tol) * (al * be);
+                if (rot) {
+                    // t = tan(theta) = sign(zeta) / (|zeta| + sqrt(1 + zeta^2)), zeta = (be - al) / (2 ga), written without
+                    // divisions: t = 2 ga sgn / (|delta| + sqrt(delta^2 + 4 ga^2)); c = rsqrt(1 + t^2), s = c t
+                    const double delta = be - al, g2 = 2.0 * ga;
+                    const double h = fma(delta, delta, g2 * g2);
+                    const double den = fabs(delta) + h * rsqrt(h);
+                    const double rd = rsqrt(den);
+                    const double t = ((delta >= 0.0) == (ga > 0.0) ? fabs(g2) : -fabs(g2)) * (rd * rd);
+                    const double c = rsqrt(fma(t, t, 1.0)), s = c * t;
+                    for (int r = hl; r < k; r += 16) {
+                        double a = wp[r], b = wq[r];
+                        wp[r] = c * a - s * b;
+                        wq[r] = s * a + c * b;
+                    }
+                    if (hl == 0) sh->flag = 1;
                 }
-                if (lane == 0) sh->flag = 1;
             }
             __syncthreads();
         }
@@ -414,6 +429,25 @@ __device__ void safe_solve_one(double* W, const T* __restrict__ H, int k, double
     if (!done) {
         load_sym<T>(W, H, k, diag, scale, base);
         __syncthreads();
+        // Every |lambda_i| <= ||H||_F.  Below the clamp level all eigenvalues are raised to `pert`, so S(H) = I / pert
+        // EXACTLY and no decomposition is needed -- the regime of the first iterations of a sampled logit fit (C4), where the
+        // weighted Grams of small factors have trace << pert and every row used to pay ten Jacobi sweeps for it.
+        {
+            const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+            double f2 = 0.0;
+            for (int e = threadIdx.x; e < k * k; e += blockDim.x) f2 = fma(W[e], W[e], f2);
+            f2 = warp_sum(f2);
+            if (lane == 0) xpart[warp] = f2;
+            __syncthreads();
+            double tot = 0.0;
+            for (int wv = 0; wv < nwarps; wv++) tot += xpart[wv];
+            __syncthreads();
+            if (tot < pert * pert) {
+                for (int r = threadIdx.x; r < k; r += blockDim.x) x[r] = g[r] / pert;
+                __syncthreads();
+                return;
+            }
+        }
         // rotations stop at |w_p . w_q| <= tol |w_p| |w_q|: float64 inputs to working precision; float32 inputs carry 6e-8
         // relative noise already, 1e-11 leaves the clamped solve exact to far below that and saves the last sweep
         jacobi_clamped_solve(W, k, g, x, xpart, sh, pert, sizeof(T) == 4 ? 1e-11 : 1e-15);

@@ -46,8 +46,9 @@ newton_finish_small_kernel(int64_t rows, int l, int k, T* __restrict__ F, const 
     constexpr int ZLD = KT + 4;       // row stride of Z in shared memory: 16-byte aligned rows, conflict-free columns
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double* Wall = reinterpret_cast<double*>(smem_raw);          // WARPS solve tiles
-    double* Hs = Wall + WARPS * TILE;                            // KT x KT float64 (shared Hessian part, if hx_stride == 0)
-    T* Zs = reinterpret_cast<T*>(Hs + KT * KT);                  // l x ZLD (columns >= k zero)
+    constexpr int HLD = KT + 1;       // odd pitch: lane r reads row r, so the 32 lanes of a warp hit 32 different banks
+    double* Hs = Wall + WARPS * TILE;                            // KT x HLD float64 (shared Hessian part, if hx_stride == 0)
+    T* Zs = reinterpret_cast<T*>(Hs + KT * HLD);                 // l x ZLD (columns >= k zero); KT (KT + 1) is even: 16-byte aligned
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     for (int e = threadIdx.x; e < l * ZLD + 32; e += blockDim.x) {
         const int r = e / ZLD, c = e % ZLD;
@@ -56,7 +57,7 @@ newton_finish_small_kernel(int64_t rows, int l, int k, T* __restrict__ F, const 
     if (hx_stride == 0)
         for (int e = threadIdx.x; e < KT * KT; e += blockDim.x) {
             const int r = e / KT, c = e % KT;
-            Hs[e] = (r < k && c < k) ? Hx64[(r > c ? r : c) * k + (r > c ? c : r)] : 0.0;   // lower triangle, like eigh
+            Hs[r * HLD + c] = (r < k && c < k) ? Hx64[(r > c ? r : c) * k + (r > c ? c : r)] : 0.0;   // lower triangle, like eigh
         }
     __syncthreads();
     double* W = Wall + warp * TILE;
@@ -127,7 +128,7 @@ newton_finish_small_kernel(int64_t rows, int l, int k, T* __restrict__ F, const 
         // ---- the clamped solve in float64 (l2 on the diagonal)
         double a[KT], dinv;
         const bool fac = wsolve::safe_factor_warp<KT, T>(Wr, l2_diag, k, lane, pert, chol_fastpath, known_pd, W, a, &dinv,
-                                                         hx_stride == 0 ? Hs + (lane < KT ? lane : 0) * KT : nullptr);
+                                                         hx_stride == 0 ? Hs + (lane < KT ? lane : 0) * HLD : nullptr);
         const double x = wsolve::safe_apply_warp<KT>(fac, a, dinv, k, lane, gfull, pert, W);
         __syncwarp();
         if (act) {
@@ -232,7 +233,7 @@ bool newton_finish_small(pycmf_ctx* ctx, int64_t rows, int64_t l, int64_t k, T* 
     const T* Hx = hx_per_row ? static_cast<const T*>(Hx_any) : nullptr;                 // per-row Hessians: compute dtype
     const double* Hx64 = hx_per_row ? nullptr : static_cast<const double*>(Hx_any);     // shared Hessian: float64
     const int kt = wsolve::pick_kt(int(k));
-    const size_t smem = sizeof(double) * (size_t(WARPS) * TILE + size_t(kt) * kt) + sizeof(T) * (size_t(l) * (kt + 4) + 32);
+    const size_t smem = sizeof(double) * (size_t(WARPS) * TILE + size_t(kt) * (kt + 1)) + sizeof(T) * (size_t(l) * (kt + 4) + 32);
     if (smem > size_t(ctx->max_smem_optin)) return false;
     // Definiteness shortcut: H_j = Hx(_j) + wy Z^T D Z + l2 I with the label term PSD when wy >= 0.
     //   l2 >= pert                      -> every H_j has lambda_min >= pert (pd_mode 2, if Hx is PSD: weights >= 0)

@@ -213,6 +213,14 @@ void resid_pass(pycmf_ctx* ctx, int64_t ra, int64_t rb, int64_t k, const T* A, c
             return;
         }
     }
+    if constexpr (std::is_same<T, double>::value) {
+        if (dmma_resid_eligible(ctx, ra, rb, k)) {               // float64 on the DMMA pipe (dmma.cu)
+            if (outL != nullptr || (outR == nullptr && sq != nullptr))
+                dmma_resid(ctx, 0, ra, rb, k, A, B, Tgt, ldt, trans_t, link, outL, sq);
+            if (outR != nullptr) dmma_resid(ctx, 1, ra, rb, k, A, B, Tgt, ldt, trans_t, link, outR, outL == nullptr ? sq : nullptr);
+            return;
+        }
+    }
     if (outL != nullptr || (outR == nullptr && sq != nullptr))
         dispatch_kc<T, 0>(ctx, ra, rb, k, A, B, Tgt, ldt, trans_t, link, outL, sq);
     if (outR != nullptr)

@@ -396,8 +396,9 @@ class CudaBackend:
                                         link_code(link), _ptr(out)))
         return out
 
-    def resid_pass(self, A, B, T, link, want_left=True, want_right=True, want_sq=False):
-        """(R B, R^T A, sum R^2) with R = f(A B^T) - T for a dense target T (DenseMatrix)."""
+    def resid_pass(self, A, B, T, link, want_left=True, want_right=True, want_sq=False, trans_t=False):
+        """(R B, R^T A, sum R^2) with R = f(A B^T) - T for a dense target T (DenseMatrix; stored transposed,
+        rows(B) x rows(A), when `trans_t`)."""
         rows, k = A.shape
         m = B.shape[0]
         outL = self.empty(rows, k) if want_left else None
@@ -405,7 +406,7 @@ class CudaBackend:
         sq = self.zeros(1, dtype=self.torch.float64) if want_sq else None
         t = T.t
         _lib.check(self.lib.pycmf_resid_pass(self.ctx, self.code, rows, m, k, _ptr(A), _ptr(B), t.data_ptr(), t.stride(0),
-                                             0, link_code(link), _ptr(outL), _ptr(outR), _ptr(sq)))
+                                             int(bool(trans_t)), link_code(link), _ptr(outL), _ptr(outR), _ptr(sq)))
         return outL, outR, sq
 
     # ---- MU ------------------------------------------------------------------------------------

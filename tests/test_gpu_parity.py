@@ -192,6 +192,10 @@ def test_safe_solve_matches_eigh_clamp(k, chol):
             H[b] -= 0.7 * np.eye(k)                       # indefinite: abs() of negative eigenvalues
         if b == 5:
             H[b] += 3.0 * np.eye(k)                       # safely positive definite: Cholesky path
+        if b == 6:
+            H[b] *= 0.15 / np.linalg.norm(H[b])           # ||H||_F < pert: every eigenvalue clamped, S(H) = I / pert
+        if b == 7:
+            H[b] *= 0.21 / np.linalg.norm(H[b])           # just above the Frobenius shortcut: the full path
     g = rng.randn(batch, k)
     ref = np.einsum('bij,bj->bi', O.safe_invert(H, 0.2), g)
     got = be.to_host(be.safe_solve(be.to_device(H), be.to_device(g), 0.2))
@@ -532,3 +536,32 @@ def test_mu_fused_update_matches_the_unfused_path(dtype, tol, shape):
         outs.append(be.to_host(F))
     ref = F0 * ((T @ B) / np.where((d := F0 @ (B.T @ B) + 0.01 + 0.02 * F0) == 0, np.finfo(np.float32).eps, d))
     assert rel_fro(outs[0], outs[1]) < tol and rel_fro(outs[0], ref) < max(tol, 1e-6 if dtype == "float32" else 1e-12)
+
+
+@pytest.mark.parametrize("link", ["linear", "logit"])
+@pytest.mark.parametrize("shape", [(300, 200, 32), (1000, 130, 17), (64, 64, 128), (777, 333, 64), (129, 500, 10)])
+@pytest.mark.parametrize("trans", [False, True])
+def test_dmma_fused_residual_matches_numpy(be64, link, shape, trans):
+    """float64 fused residual pass on the DMMA pipe (dmma_resid_kernel): R = f(A B^T) - T never leaves the SM;
+    R B, R^T A and sum R^2 against NumPy, ragged tiles, odd k, transposed target, both links."""
+    ra, rb, k = shape
+    rng = np.random.RandomState(3)
+    A, B = 0.3 * rng.randn(ra, k), 0.3 * rng.randn(rb, k)
+    Tm = rng.rand(ra, rb)
+    est = A @ B.T
+    R = (O.expit(est) if link == "logit" else est) - Tm
+    from pycmf_b200.device import DenseMatrix
+    Td = DenseMatrix(be64.to_device(np.ascontiguousarray(Tm.T if trans else Tm)))
+    be64.profile(True); be64.profile_reset()
+    if trans:
+        # target stored transposed (rows(B) x rows(A)), as the Z update reads Y (cmf_solvers.py:497)
+        outL, outR, sq = be64.resid_pass(be64.to_device(A), be64.to_device(B), Td, link, want_sq=True, trans_t=True)
+        wantL, wantR = R @ B, R.T @ A
+    else:
+        outL, outR, sq = be64.resid_pass(be64.to_device(A), be64.to_device(B), Td, link, want_sq=True)
+        wantL, wantR = R @ B, R.T @ A
+    ran = be64.profile_query("dmma_resid_left")[1] + be64.profile_query("dmma_resid_right")[1]
+    be64.profile(False)
+    assert ran == 2, "the DMMA residual kernels did not run"
+    assert rel_fro(be64.to_host(outL), wantL) < 1e-12 and rel_fro(be64.to_host(outR), wantR) < 1e-12
+    assert abs(float(be64.to_host(sq)[0]) - (R * R).sum()) <= 1e-12 * (R * R).sum()
