@@ -373,7 +373,7 @@ def bench_workload(env, name, scale, col_scale, steps, warmup, args, headline):
         torch.cuda.synchronize()
 
     # ---- timed region A (the product path: fit_device's stepper = eager warm-up, then CUDA-graph replay)
-    step = solver.make_stepper(st)
+    step = solver.make_stepper(st, force_graph=True)
     for i in range(max(warmup, 3)):
         step()
     barrier()
@@ -499,7 +499,8 @@ def bench_workload(env, name, scale, col_scale, steps, warmup, args, headline):
         "config": W.bench_config(name, scale, col_scale, world),
         "details": {"objective_first": round(obj_first, 6), "objective_last": round(obj_last, 6),
                     "x_shard_mb": round(x_bytes_dev / 1e6, 1), "dense_path": args.dense_path,
-                    "cuda_graph": bool(solver._graphable(FitStateProbe(comm, be)))},
+                    "cuda_graph": bool(solver._graphable(FitStateProbe(comm, be), True)),
+                    "cuda_graph_in_e2e": bool(solver._graphable(FitStateProbe(comm, be)))},
         "clocks": clock_info, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
         "parity": parity,
     }

@@ -173,19 +173,26 @@ class _IterativeCMFSolver:
         st = self.prepare(X, Y, U, V, Z)
         return self.device_error(st)
 
-    def _graphable(self, st):
-        """One iteration can be replayed as a CUDA graph when it needs no host work: single rank, no sampling."""
+    # 'auto' captures the iteration only for fits long enough to pay for it: capture + instantiate + the graph's private
+    # allocations cost 13 - 32 ms (C2 / C3 / C5), the launch gaps they remove ~0.1 ms per iteration
+    GRAPH_MIN_ITERS = 64
+
+    def _graphable(self, st, force=False):
+        """One iteration can be replayed as a CUDA graph when it needs no host work: no sampling, capturable collectives."""
         if self.use_cuda_graph is False or self.sg_sample_ratio < 1.:
+            return False
+        if self.use_cuda_graph == "auto" and not force and self.max_iter < self.GRAPH_MIN_ITERS:
             return False
         if st.comm.world > 1 and not getattr(st.comm, "graph_capturable", False):
             return False
         return hasattr(st.be, "capture_step")
 
-    def make_stepper(self, st):
+    def make_stepper(self, st, force_graph=False):
         """Returns step(): one solver iteration. After two eager iterations (scratch arenas reach their final size)
-        the iteration is captured into a CUDA graph and replayed, which removes ~25 launch gaps per iteration."""
+        the iteration is captured into a CUDA graph and replayed, which removes ~25 launch gaps per iteration
+        (`force_graph`: also for short fits -- steady-state timing)."""
         state = {"eager": 0, "graph": None}
-        graphable = self._graphable(st)
+        graphable = self._graphable(st, force_graph)
 
         def step():
             st.iteration += 1

@@ -52,7 +52,9 @@ pycmf_ctx* fork_side(pycmf_ctx* ctx) {
     s->spmm_path = ctx->spmm_path;
     s->spmm_blocks_per_sm = ctx->spmm_blocks_per_sm;
     s->spmm_unroll = ctx->spmm_unroll;
+    s->spmm_lean = ctx->spmm_lean;
     s->mu_fused = ctx->mu_fused;
+    s->solve_path = ctx->solve_path;
     s->tc_max_splits = ctx->tc_max_splits;
     s->tc_ctas = ctx->tc_ctas;
     s->tc_chain = ctx->tc_chain;
@@ -164,7 +166,7 @@ void mu_v_partial_impl(pycmf_ctx* ctx, int64_t n, int64_t d, int64_t k, const T*
         if (!done) gemm<T>(ctx, true, d, k, n, X, ldx, U, k, out, k, T(1), T(0));
     } else {
         PYCMF_CHECK(colptr && rowidx && cvals, "mu_v_partial: neither dense X nor CSC arrays given");
-        spmm<T>(ctx, d, colptr, rowidx, cvals, U, k, k, out, k, T(1), T(0));
+        spmm<T>(ctx, d, colptr, rowidx, cvals, U, k, k, out, k, T(1), T(0), n);
     }
     join_side(ctx);
 }
@@ -218,7 +220,7 @@ void mu_left_impl(pycmf_ctx* ctx, int64_t rows, int64_t m, int64_t k, T* F, cons
         if (!done) gemm<T>(ctx, trans_t, rows, k, m, Tg, ldt, B, k, N, k, T(1), T(0));
     } else {
         PYCMF_CHECK(rowptr && colidx && vals, "mu_left: neither dense target nor CSR arrays given");
-        spmm<T>(ctx, rows, rowptr, colidx, vals, B, k, k, N, k, T(1), T(0));
+        spmm<T>(ctx, rows, rowptr, colidx, vals, B, k, k, N, k, T(1), T(0), m);
     }
     join_side(ctx);
     if (fused && mu_fused_apply<T>(ctx, rows, k, F, N, G, l1, l2)) return;
@@ -272,7 +274,7 @@ void newton_left_impl(pycmf_ctx* ctx, int64_t rows, int64_t m, int64_t k, T* F, 
                 resid_pass<T>(ctx, rows, m, k, F, B, nullptr, 0, false, link, g, nullptr, nullptr);
                 axpby<T>(ctx, rows * k, T(weight), g, T(0), nullptr, g);
             }
-            spmm<T>(ctx, rows, rowptr, colidx, vals, B, k, k, g, k, T(-weight), T(1));
+            spmm<T>(ctx, rows, rowptr, colidx, vals, B, k, k, g, k, T(-weight), T(1), m);
         }
         if (link == PYCMF_LINEAR) {
             join_side(ctx);
@@ -336,7 +338,7 @@ void newton_v_xpart_impl(pycmf_ctx* ctx, int64_t d_rows, int64_t n, int64_t k, c
             resid_pass<T>(ctx, n, d_rows, k, U, V, nullptr, 0, false, x_link, nullptr, gx, nullptr);
             axpby<T>(ctx, d_rows * k, T(alpha), gx, T(0), nullptr, gx);
         }
-        spmm<T>(ctx, d_rows, colptr, rowidx, cvals, U, k, k, gx, k, T(-alpha), T(1));
+        spmm<T>(ctx, d_rows, colptr, rowidx, cvals, U, k, k, gx, k, T(-alpha), T(1), n);
     }
     if (x_link == PYCMF_LINEAR) {
         join_side(ctx);
@@ -485,7 +487,9 @@ int pycmf_set_option(pycmf_ctx* ctx, const char* key, double value) {
         else if (k == "spmm_path") ctx->spmm_path = int(value);
         else if (k == "spmm_blocks_per_sm") ctx->spmm_blocks_per_sm = int(value);
         else if (k == "spmm_unroll") ctx->spmm_unroll = int(value);
+        else if (k == "spmm_lean") ctx->spmm_lean = int(value);
         else if (k == "mu_fused") ctx->mu_fused = int(value);
+        else if (k == "solve_path") ctx->solve_path = int(value);
         else if (k == "tc_trace") ctx->tc_trace = int(value);
         else if (k == "tc_ctas") ctx->tc_ctas = int(value);
         else if (k == "tc_chain") ctx->tc_chain = int(value);
@@ -557,9 +561,9 @@ int pycmf_spmm(pycmf_ctx* ctx, int dtype, int64_t rows, int64_t cols, const int3
     return guarded(ctx, [&] {
         DISPATCH(dtype,
                  spmm<float>(ctx, rows, rowptr, colidx, (const float*)vals, (const float*)B, ldb, k, (float*)C, ldc,
-                             float(alpha), float(beta)),
+                             float(alpha), float(beta), cols),
                  spmm<double>(ctx, rows, rowptr, colidx, (const double*)vals, (const double*)B, ldb, k, (double*)C,
-                              ldc, alpha, beta));
+                              ldc, alpha, beta, cols));
     });
 }
 

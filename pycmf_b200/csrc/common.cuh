@@ -39,7 +39,7 @@ struct pycmf_ctx {
     int tc_chain = 0;        // > 0: accumulation chain cap in tiles (default 16)
     size_t max_scratch = size_t(2) << 30;
     // scratch arenas (grown on demand; growth synchronises the stream)
-    pycmf::Scratch arena[8];
+    pycmf::Scratch arena[10];
     std::vector<void*> retired;   // outgrown arenas: kept until destroy (a CUDA graph captured earlier may still point at them)
     // optional per-kernel-family timers (cudaEvent pairs recorded on the stream around each launch)
     int profile = 0;
@@ -53,7 +53,10 @@ struct pycmf_ctx {
                                 // spills: 86 us on C2; 3: 168 registers: 91 us; 4: 128 registers, spills: 187 us)
     int spmm_path = 1;       // option: 0 = generic SpMM kernel only (tests), 1 = vector kernels for k = 32 / 64 / 128 / 256, 2 = without the sub-warp grouping
     int spmm_blocks_per_sm = 0;  // option: resident 256-thread CTAs per SM of the nonzero-balanced SpMM (0 = default 4)
+    int solve_path = 1;      // option: clamped solve with active clamp, k > 32: 1 = tridiagonalisation + bisection + inverse iteration
+                             // (tridiag_solve.cuh), 0 = one-sided Jacobi only
     int mu_fused = 1;        // option: 0 = separate F G GEMM + elementwise ratio launches (tests)
+    int spmm_lean = 1;       // option: 1 = shared-memory staged nonzeros + packed FMAs (spmm_nzb2_kernel), 0 = shuffle variant
     int spmm_unroll = 4;     // option: independent factor-row gathers per lane in flight (4 or 8)
     int side_streams = 1;    // option: 0 runs the side branches on the main stream (serial)
 };
@@ -200,7 +203,7 @@ void final_sum(pycmf_ctx* ctx, int nparts, const double* part, double scale, dou
 // sparse.cu
 template <typename T>
 void spmm(pycmf_ctx* ctx, int64_t rows, const int32_t* rowptr, const int32_t* colidx, const T* vals,
-          const T* B, int64_t ldb, int64_t k, T* C, int64_t ldc, T alpha, T beta);
+          const T* B, int64_t ldb, int64_t k, T* C, int64_t ldc, T alpha, T beta, int64_t b_rows = 0);
 // mode 0: out += scale * sum_nz t_ij (a_i . b_j)
 // mode 1: out += scale * sum_nz [ (t_ij - s_ij)^2 - s_ij^2 ],  s_ij = sigmoid(a_i . b_j)
 // mode 2: out += scale * sum_nz t_ij^2

@@ -6,6 +6,7 @@
 //   newton_solve_rows F_i <- F_i - (g_i + l1 sign F_i + l2 F_i) S(H_i + l2 I), optional clamp
 //   sample_indices    on-device per-row sampling without replacement (Feistel permutation prefix)
 #include "common.cuh"
+#include "tridiag_solve.cuh"
 
 namespace pycmf {
 namespace {
@@ -403,7 +404,8 @@ __device__ void jacobi_clamped_solve(double* W, int k, const double* g, double* 
 template <typename T>
 __device__ void safe_solve_one(double* W, const T* __restrict__ H, int k, double diag, const double* g,
                                double* x, double* xpart, SolveShared* sh, double pert, bool chol_fastpath,
-                               double scale, const double* __restrict__ base = nullptr) {
+                               double scale, const double* __restrict__ base = nullptr, double* tri_work = nullptr,
+                               double* tri_scratch = nullptr) {
     bool done = false;
     if (chol_fastpath) {
         // lambda_min(H) > pert  <=>  H - pert I is positive definite  <=>  its Cholesky succeeds
@@ -448,6 +450,13 @@ __device__ void safe_solve_one(double* W, const T* __restrict__ H, int k, double
                 return;
             }
         }
+        // clamp active on part of the spectrum: only the eigenpairs above the clamp level are needed (tridiag_solve.cuh);
+        // one-sided Jacobi is the fallback
+        if (tri_work != nullptr) {
+            if (tri::clamped_solve(W, k, g, x, tri_work, tri_scratch, pert)) return;
+            load_sym<T>(W, H, k, diag, scale, base);
+            __syncthreads();
+        }
         // rotations stop at |w_p . w_q| <= tol |w_p| |w_q|: float64 inputs to working precision; float32 inputs carry 6e-8
         // relative noise already, 1e-11 leaves the clamped solve exact to far below that and saves the last sweep
         jacobi_clamped_solve(W, k, g, x, xpart, sh, pert, sizeof(T) == 4 ? 1e-11 : 1e-15);
@@ -460,15 +469,17 @@ __global__ void __launch_bounds__(1024)
 safe_solve_kernel(int64_t batch, int k, const T* __restrict__ H, int64_t h_stride, const T* __restrict__ g,
                   T* __restrict__ out, double l1, double l2, double l2_diag, double pert, bool non_negative,
                   bool chol_fastpath, double* __restrict__ Wglobal, double h_scale,
-                  const double* __restrict__ Hbase) {
+                  const double* __restrict__ Hbase, double* __restrict__ tri_scratch) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int nwarps = blockDim.x >> 5;
     double* gv = reinterpret_cast<double*>(smem_raw);   // k
     double* xv = gv + k;                                // k
     double* xpart = xv + k;                             // nwarps * k
     SolveShared* sh = reinterpret_cast<SolveShared*>(xpart + nwarps * k);
+    double* tri_work = tri_scratch != nullptr ? reinterpret_cast<double*>(sh + 2) : nullptr;
     double* W = Wglobal != nullptr ? Wglobal + int64_t(blockIdx.x) * k * k
-                                   : reinterpret_cast<double*>(sh + 2);
+                                   : reinterpret_cast<double*>(sh + 2) + (tri_scratch != nullptr ? tri::work_doubles(k) : 0);
+    double* tri_zg = tri_scratch != nullptr ? tri_scratch + size_t(blockIdx.x) * tri::scratch_doubles(k) : nullptr;
     for (int64_t b = blockIdx.x; b < batch; b += gridDim.x) {
         __syncthreads();
         for (int r = threadIdx.x; r < k; r += blockDim.x) {
@@ -481,7 +492,8 @@ safe_solve_kernel(int64_t batch, int k, const T* __restrict__ H, int64_t h_strid
             gv[r] = gr;
         }
         __syncthreads();
-        safe_solve_one<T>(W, H + b * h_stride, k, l2_diag, gv, xv, xpart, sh, pert, chol_fastpath, h_scale, Hbase);
+        safe_solve_one<T>(W, H + b * h_stride, k, l2_diag, gv, xv, xpart, sh, pert, chol_fastpath, h_scale, Hbase, tri_work,
+                          tri_zg);
         __syncthreads();
         for (int r = threadIdx.x; r < k; r += blockDim.x) {
             if (MODE == 0) {
@@ -575,10 +587,11 @@ __global__ void sample_indices_kernel(int64_t rows, int64_t row0, int64_t N, int
     idx[e] = hi > lo ? ((int64_t(v) >= lo && int64_t(v) < hi) ? int32_t(int64_t(v) - lo) : -1) : int32_t(v);
 }
 
-size_t solve_smem_bytes(int k, int nthreads, bool w_in_smem) {
+size_t solve_smem_bytes(int k, int nthreads, bool w_in_smem, bool tri_path = false) {
     int nwarps = nthreads / 32;
     size_t b = sizeof(double) * (size_t(2) * k + size_t(nwarps) * k) + 2 * sizeof(SolveShared);
     b = (b + 15) & ~size_t(15);
+    if (tri_path) b += sizeof(double) * tri::work_doubles(k);
     if (w_in_smem) b += sizeof(double) * size_t(k) * k;
     return b + 16;
 }
@@ -596,22 +609,25 @@ void launch_solve(pycmf_ctx* ctx, int64_t batch, int64_t k, const T* H, int64_t 
         return;
     // one warp per Jacobi pair: k / 2 pairs per step, so wide matrices get a full CTA (k = 128: 64 pairs on 32 warps are two
     // rounds per step instead of eight on 8 warps)
-    int nthreads = k <= 32 ? 64 : (k <= 64 ? 128 : (k <= 96 ? 256 : 1024));
-    bool w_in_smem = solve_smem_bytes(int(k), nthreads, true) <= size_t(ctx->max_smem_optin);
-    size_t smem = solve_smem_bytes(int(k), nthreads, w_in_smem);
+    // tridiagonal path (default): one thread per wanted eigenvector, so at least k threads; Jacobi only: one warp per column pair
+    const bool tri_path = ctx->solve_path != 0 && k >= 8;
+    int nthreads = tri_path ? (k <= 64 ? 128 : (k <= 128 ? 256 : 512))
+                            : (k <= 32 ? 64 : (k <= 64 ? 128 : (k <= 96 ? 256 : 1024)));
+    bool w_in_smem = solve_smem_bytes(int(k), nthreads, true, tri_path) <= size_t(ctx->max_smem_optin);
+    size_t smem = solve_smem_bytes(int(k), nthreads, w_in_smem, tri_path);
     auto kern = safe_solve_kernel<T, MODE>;
     PYCMF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
     int64_t grid = batch;
     double* Wg = nullptr;
-    if (!w_in_smem) {
-        grid = std::min<int64_t>(batch, 2 * ctx->num_sms);
-        Wg = static_cast<double*>(scratch(ctx, 2, size_t(grid) * k * k * sizeof(double)));
-    } else {
-        grid = std::min<int64_t>(batch, int64_t(1) << 30);
-    }
+    double* tri_scratch = nullptr;
+    if (!w_in_smem || tri_path) grid = std::min<int64_t>(batch, 2 * ctx->num_sms);      // persistent: per-CTA scratch
+    else grid = std::min<int64_t>(batch, int64_t(1) << 30);
+    if (!w_in_smem) Wg = static_cast<double*>(scratch(ctx, 2, size_t(grid) * k * k * sizeof(double)));
+    if (tri_path) tri_scratch = static_cast<double*>(scratch(ctx, 8, size_t(grid) * tri::scratch_doubles(int(k)) * sizeof(double)));
     Timed timer(ctx, "safe_solve");
     kern<<<(unsigned)grid, nthreads, smem, ctx->stream>>>(batch, int(k), H, h_stride, g, out, l1, l2, l2_diag,
-                                                         pert, non_negative, ctx->chol_fastpath != 0, Wg, h_scale, Hbase);
+                                                         pert, non_negative, ctx->chol_fastpath != 0, Wg, h_scale, Hbase,
+                                                         tri_scratch);
     PYCMF_LAUNCH_CHECK(ctx);
 }
 

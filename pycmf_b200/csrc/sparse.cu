@@ -383,6 +383,128 @@ spmm_nzb_kernel(int64_t rows, const int32_t* __restrict__ rowptr, const int32_t*
     }
 }
 
+
+// ---- the same kernel on an instruction diet -----------------------------------------------------------------------------
+// ncu on the C3 shard put spmm_nzb_kernel at 12.9 warp instructions per nonzero with the issue slots 63 - 66 % busy and only
+// 57 % of the L2 throughput used (profiles/r02_ncu_c3_spmm_nzb_summary.txt): two shuffles, two selects and 64-bit address
+// arithmetic per gathered row, four scalar FMAs per 16 bytes.  Here a warp stages each 32-nonzero block in shared memory as
+// 16-byte records {row offset of the factor row (32-bit, elements), unused, value, value}: a sub-warp group fetches its
+// nonzero with ONE broadcast LDS.128, forms the address with one IMAD.WIDE, and feeds the value pair straight into two packed
+// FMAs (fma.rn.f32x2) per 16-byte factor segment -- 5 instructions per gathered row.  Masking (a row ending inside a batch)
+// lives in a separate tail batch.  Needs rows(B) * ldb < 2^31.
+__device__ __forceinline__ void ffma2(unsigned long long& acc, unsigned long long a, unsigned long long b) {
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(a), "l"(b));
+}
+
+template <int LPN, int UNROLL, int MINB>
+__global__ void __launch_bounds__(256, MINB)
+spmm_nzb2_kernel(int64_t rows, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx,
+                 const float* __restrict__ vals, const float* __restrict__ B, int ldb,
+                 float* __restrict__ C, int64_t ldc, float alpha, float beta) {
+    constexpr int NG = 32 / LPN;          // nonzeros per load instruction
+    constexpr int BATCH = NG * UNROLL;    // nonzeros per round trip
+    __shared__ uint4 stage[8][32];        // per warp: one record per nonzero of the current block
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int gl = lane % LPN, gid = lane / LPN;
+    const int64_t warp = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = (int64_t(gridDim.x) * blockDim.x) >> 5;
+    const int base = rowptr[0];
+    const int total = rowptr[rows] - base;
+    const int e0 = base + int(nzb_share_begin(warp, total, nwarps)), e1 = base + int(nzb_share_begin(warp + 1, total, nwarps));
+    if (e0 >= e1) return;
+    int lo = 0, hi = int(rows);
+    while (hi - lo > 1) {
+        const int mid = int((unsigned(lo) + unsigned(hi)) >> 1);
+        if (rowptr[mid] <= e0) lo = mid; else hi = mid;
+    }
+    int row = lo;
+    int row_begin = rowptr[row], row_end = rowptr[row + 1];
+    const float* Bl = B + gl * 4;
+    const int last = base + total - 1;
+    uint4* st = stage[wib];
+    int pos = e0;
+    int c = colidx[min(pos + lane, last)];
+    float v = pos + lane < e1 ? vals[pos + lane] : 0.0f;
+    unsigned long long acc0 = 0ull, acc1 = 0ull;        // (x, y) and (z, w) of this lane's 16-byte output segment
+    while (pos < e1) {
+        const int npos = pos + 32;
+        int cn = 0; float vn = 0.0f;
+        if (npos < e1) {                                     // prefetch the next block
+            cn = colidx[min(npos + lane, last)];
+            vn = npos + lane < e1 ? vals[npos + lane] : 0.0f;
+        }
+        __syncwarp();                                        // everybody finished reading the previous block's records
+        st[lane] = make_uint4(unsigned(c) * unsigned(ldb), 0u, __float_as_uint(v), __float_as_uint(v));
+        __syncwarp();
+        const int bend = min(32, e1 - pos);
+        int j0 = 0;
+        while (j0 < bend) {
+            const int j1 = min(bend, row_end - pos);         // this row's part of the block: [j0, j1)
+            int j = j0;
+            for (; j + BATCH <= j1; j += BATCH) {            // full batches: no masking
+                uint4 rec[UNROLL];
+                ulonglong2 bv[UNROLL];
+#pragma unroll
+                for (int u = 0; u < UNROLL; u++) rec[u] = st[j + u * NG + gid];
+#pragma unroll
+                for (int u = 0; u < UNROLL; u++) bv[u] = __ldg(reinterpret_cast<const ulonglong2*>(Bl + rec[u].x));
+#pragma unroll
+                for (int u = 0; u < UNROLL; u++) {
+                    const unsigned long long vv = (static_cast<unsigned long long>(rec[u].w) << 32) | rec[u].z;
+                    ffma2(acc0, vv, bv[u].x);
+                    ffma2(acc1, vv, bv[u].y);
+                }
+            }
+            if (j < j1) {                                    // tail batch of this row's part: masked
+                uint4 rec[UNROLL];
+                ulonglong2 bv[UNROLL];
+#pragma unroll
+                for (int u = 0; u < UNROLL; u++) {
+                    const int src = j + u * NG + gid;
+                    rec[u] = st[src < j1 ? src : j0];
+                    if (src >= j1) { rec[u].z = 0u; rec[u].w = 0u; }
+                }
+#pragma unroll
+                for (int u = 0; u < UNROLL; u++) bv[u] = __ldg(reinterpret_cast<const ulonglong2*>(Bl + rec[u].x));
+#pragma unroll
+                for (int u = 0; u < UNROLL; u++) {
+                    const unsigned long long vv = (static_cast<unsigned long long>(rec[u].w) << 32) | rec[u].z;
+                    ffma2(acc0, vv, bv[u].x);
+                    ffma2(acc1, vv, bv[u].y);
+                }
+            }
+            j0 = j1;
+            if (pos + j1 == row_end || pos + j1 == e1) {
+                float4 acc = make_float4(__uint_as_float(unsigned(acc0)), __uint_as_float(unsigned(acc0 >> 32)),
+                                         __uint_as_float(unsigned(acc1)), __uint_as_float(unsigned(acc1 >> 32)));
+#pragma unroll
+                for (int o = 16; o >= LPN; o >>= 1) {
+                    acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o); acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
+                    acc.z += __shfl_xor_sync(0xffffffffu, acc.z, o); acc.w += __shfl_xor_sync(0xffffffffu, acc.w, o);
+                }
+                const bool whole = row_begin >= e0 && row_end <= e1;
+                if (gid == 0) {
+                    float* crow = C + int64_t(row) * ldc + gl * 4;
+                    if (!whole) {
+                        atomicAdd(&crow[0], alpha * acc.x); atomicAdd(&crow[1], alpha * acc.y);
+                        atomicAdd(&crow[2], alpha * acc.z); atomicAdd(&crow[3], alpha * acc.w);
+                    } else {
+                        float4 prev = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (beta != 0.0f) prev = *reinterpret_cast<const float4*>(crow);
+                        *reinterpret_cast<float4*>(crow) = make_float4(alpha * acc.x + beta * prev.x, alpha * acc.y + beta * prev.y,
+                                                                       alpha * acc.z + beta * prev.z, alpha * acc.w + beta * prev.w);
+                    }
+                }
+                acc0 = 0ull; acc1 = 0ull;
+                if (pos + j1 == row_end && pos + j1 < e1) {
+                    do { row++; row_begin = row_end; row_end = rowptr[row + 1]; } while (row_end == row_begin);
+                }
+            }
+        }
+        pos = npos; c = cn; v = vn;
+    }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256)
 sddmm_reduce_kernel(int mode, int64_t rows, const int32_t* __restrict__ rowptr,
@@ -427,7 +549,7 @@ sddmm_reduce_kernel(int mode, int64_t rows, const int32_t* __restrict__ rowptr,
 
 template <typename T>
 void spmm(pycmf_ctx* ctx, int64_t rows, const int32_t* rowptr, const int32_t* colidx, const T* vals,
-          const T* B, int64_t ldb, int64_t k, T* C, int64_t ldc, T alpha, T beta) {
+          const T* B, int64_t ldb, int64_t k, T* C, int64_t ldc, T alpha, T beta, int64_t b_rows) {
     if (rows <= 0 || k <= 0) return;
     PYCMF_CHECK(k <= 32 * MAXT, "spmm: n_components > 256 is not supported");
     PYCMF_CHECK(rows < (int64_t(1) << 31) - 1, "spmm: too many rows");
@@ -443,11 +565,21 @@ void spmm(pycmf_ctx* ctx, int64_t rows, const int32_t* rowptr, const int32_t* co
             const int64_t nwarps = int64_t(nb) * 8;
             spmm_nzb_prologue_kernel<<<(unsigned)ceil_div(rows, 256), 256, 0, ctx->stream>>>(rows, rowptr, nwarps, C, ldc, int(k), beta);
             PYCMF_LAUNCH_CHECK(ctx);
+            // lean variant (shared-memory staged nonzeros, packed FMAs): needs 32-bit element offsets into B
+            const bool lean = ctx->spmm_lean != 0 && b_rows > 0 && b_rows * ldb < (int64_t(1) << 31);
 #define LAUNCHN(L, U, M) spmm_nzb_kernel<L, U, M><<<nb, 256, 0, ctx->stream>>>(rows, rowptr, colidx, vals, B, ldb, C, ldc, alpha, beta)
-            if (k == 32) { if (deep) LAUNCHN(8, 8, 3); else LAUNCHN(8, 4, 4); }
-            else if (k == 64) { if (deep) LAUNCHN(16, 8, 3); else LAUNCHN(16, 4, 4); }
-            else { if (deep) LAUNCHN(32, 8, 3); else LAUNCHN(32, 4, 4); }
+#define LAUNCHL(L, U, M) spmm_nzb2_kernel<L, U, M><<<nb, 256, 0, ctx->stream>>>(rows, rowptr, colidx, vals, B, int(ldb), C, ldc, alpha, beta)
+            if (lean) {
+                if (k == 32) { if (deep) LAUNCHL(8, 8, 3); else LAUNCHL(8, 4, 4); }
+                else if (k == 64) { if (deep) LAUNCHL(16, 8, 3); else LAUNCHL(16, 4, 4); }
+                else { if (deep) LAUNCHL(32, 8, 3); else LAUNCHL(32, 4, 4); }
+            } else {
+                if (k == 32) { if (deep) LAUNCHN(8, 8, 3); else LAUNCHN(8, 4, 4); }
+                else if (k == 64) { if (deep) LAUNCHN(16, 8, 3); else LAUNCHN(16, 4, 4); }
+                else { if (deep) LAUNCHN(32, 8, 3); else LAUNCHN(32, 4, 4); }
+            }
 #undef LAUNCHN
+#undef LAUNCHL
             PYCMF_LAUNCH_CHECK(ctx);
             return;
         }
@@ -512,7 +644,7 @@ void sddmm_reduce(pycmf_ctx* ctx, int mode, int64_t rows, const int32_t* rowptr,
 
 #define INSTANTIATE(T)                                                                                        \
     template void spmm<T>(pycmf_ctx*, int64_t, const int32_t*, const int32_t*, const T*, const T*, int64_t,   \
-                          int64_t, T*, int64_t, T, T);                                                        \
+                          int64_t, T*, int64_t, T, T, int64_t);                                                      \
     template void sddmm_reduce<T>(pycmf_ctx*, int, int64_t, const int32_t*, const int32_t*, const T*,         \
                                   const T*, const T*, int64_t, double, double*);
 INSTANTIATE(float)

@@ -1,0 +1,374 @@
+// Eigenvalue-clamped solve WITHOUT a full eigendecomposition, one CTA per matrix (float64):
+//     x = S(H) g,   S(H) = Q diag(1 / max(|lambda|, p)) Q^T                       (reference _safe_invert, cmf_solvers.py:346-356)
+//       = g / p + sum_{|lambda_i| >= p} (1 / |lambda_i| - 1 / p) (q_i . g) q_i
+// Only the eigenpairs ABOVE the clamp level enter, and the clamped part of the spectrum (the rank-deficient bulk of a
+// sampled weighted Gram) never has to be resolved.  Stages:
+//   1. Householder tridiagonalisation H = P T P^T in shared memory (reflectors kept in the rows they annihilate), with
+//      y = P^T g applied on the fly.  4/3 k^3 flop, column-owned updates (conflict-free), ~7 barriers per step.
+//   2. Sturm counts at -p and +p give the indices of the eigenvalues that matter; each gets its own thread and is bisected
+//      (three-term recurrence of the leading principal minors with rescaling: 2 dependent FMAs per element, no division).
+//   3. One thread per wanted eigenvector: inverse iteration with a pivoted LU of the shifted tridiagonal (EISPACK tinvit /
+//      LAPACK dstein scheme), three solves, vectors in an L2-resident scratch laid out [element][vector].
+//   4. Vectors whose eigenvalues are closer than 1e-5 ||T|| are orthonormalised (modified Gram-Schmidt, CTA-wide dots): a
+//      multiple eigenvalue needs an orthonormal basis of its eigenspace, nothing more.
+//   5. z = y / p + sum coef_i z_i, x = P z (reflectors applied in reverse).
+// ~16x fewer flops than the ten one-sided Jacobi sweeps this replaces at k = 128.  Any sign of trouble (a vector that does
+// not survive the orthogonalisation) returns false and the caller falls back to Jacobi.  Prototype with the same arithmetic:
+// scripts/tridiag_clamped_solve.py (1e-13 against eigh on rank-deficient, indefinite, clustered and clamp-level spectra).
+#pragma once
+#include "common.cuh"
+
+namespace pycmf {
+namespace tri {
+
+// both sums to every thread; red: 64 doubles of shared memory
+__device__ __forceinline__ void block_sum2(double& a, double& b, double* red) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    a = warp_sum(a);
+    b = warp_sum(b);
+    __syncthreads();
+    if (lane == 0) { red[warp] = a; red[32 + warp] = b; }
+    __syncthreads();
+    double sa = 0.0, sb = 0.0;
+    for (int w = 0; w < nwarps; w++) { sa += red[w]; sb += red[32 + w]; }
+    a = sa;
+    b = sb;
+}
+
+// number of eigenvalues of the (scaled) tridiagonal that are < x: sign changes of the leading principal minors
+__device__ __forceinline__ int sturm_count(const double* __restrict__ ds, const double* __restrict__ es2, int k, double x) {
+    double p0 = 1.0, p1 = ds[0] - x;
+    bool sp = p1 < 0.0;                          // p0 > 0; an exact zero takes the sign opposite to its predecessor
+    if (p1 == 0.0) sp = true;
+    int cnt = sp ? 1 : 0;
+    for (int i = 1; i < k; i++) {
+        const double p2 = fma(ds[i] - x, p1, -es2[i] * p0);
+        p0 = p1;
+        p1 = p2;
+        const bool s = p1 < 0.0 || (p1 == 0.0 && !sp);
+        cnt += (s != sp) ? 1 : 0;
+        sp = s;
+        if ((i & 7) == 7) {                      // entries are <= 1 in magnitude: growth <= 3.3 per step, decay unbounded
+            const double mx = fmax(fabs(p0), fabs(p1));
+            if (mx > 1e100) { p0 *= 1e-100; p1 *= 1e-100; }
+            else if (mx < 1e-100 && mx > 0.0) { p0 *= 1e100; p1 *= 1e100; }
+        }
+    }
+    return cnt;
+}
+
+// work (shared memory, doubles): 16 k + 72.  zg (global, doubles): 6 k^2 for this CTA.
+__host__ __device__ constexpr size_t work_doubles(int k) { return size_t(16) * k + 72; }
+__host__ __device__ constexpr size_t scratch_doubles(int k) { return size_t(6) * k * k; }
+
+__device__ bool clamped_solve(double* __restrict__ W, int k, const double* __restrict__ g, double* __restrict__ x,
+                              double* __restrict__ work, double* __restrict__ zg, double pert) {
+    const int tid = threadIdx.x, NT = blockDim.x;
+    double* d = work;                 // k   diagonal of T
+    double* e = d + k;                // k   e[i] couples i - 1 and i (e[0] = 0)
+    double* beta = e + k;             // k   reflector scalars
+    double* v = beta + k;             // k   current reflector / later: scaled diagonal
+    double* q = v + k;                // k   / later: squared scaled off-diagonal
+    double* pp = q + k;               // 4 k partial mat-vec sums / later: scaled off-diagonal
+    double* y = pp + 4 * k;           // k   P^T g, then the combined vector
+    double* lam = y + k;              // k   wanted eigenvalues (scaled)
+    double* coef = lam + k;           // k
+    int* cstart = reinterpret_cast<int*>(coef + k);   // 6 k + 2 ints in 3 k + 1 doubles: cluster starts, block of a vector,
+    int* vblk = cstart + k;                           //   block starts, per-block counts below -p / below +p, wanted offsets
+    int* bstart = vblk + k;                           // k + 1
+    int* bneg = bstart + k + 1;
+    int* blt = bneg + k;
+    int* woff = blt + k;                              // k + 1
+    double* red = coef + 4 * k + 1;   // 64
+    __shared__ int s_fail, s_nblk;
+    if (tid == 0) s_fail = 0;
+    for (int r = tid; r < k; r += NT) y[r] = g[r];
+    __syncthreads();
+
+    // ---- 1. tridiagonalisation ----------------------------------------------------------------------------------------
+    for (int j = 0; j < k - 2; j++) {
+        const int m = k - j - 1;
+        double* xr = W + size_t(j) * k + j + 1;              // row j right of the diagonal (= column j below it)
+        double s = 0.0, dummy = 0.0;
+        for (int c = tid; c < m; c += NT) s = fma(xr[c], xr[c], s);
+        block_sum2(s, dummy, red);
+        const double x0 = xr[0];
+        const double tail2 = s - x0 * x0;
+        if (!(tail2 > 0.0)) {                               // nothing to annihilate (uniform decision)
+            if (tid == 0) { d[j] = W[size_t(j) * k + j]; e[j + 1] = x0; beta[j] = 0.0; }
+            continue;
+        }
+        const double alpha = x0 >= 0.0 ? -sqrt(s) : sqrt(s);
+        const double v0 = x0 - alpha;
+        const double b = 2.0 / (tail2 + v0 * v0);
+        for (int c = tid; c < m; c += NT) v[c] = c == 0 ? v0 : xr[c];
+        __syncthreads();
+        // p = b S v, S = trailing m x m block (symmetric, kept in full): thread owns a column, row segments interleaved
+        const int mp = (m + 31) & ~31;
+        const int tpc = max(1, min(4, NT / mp));
+        const double* S = W + size_t(j + 1) * k + j + 1;
+        if (tid < tpc * mp) {
+            const int c = tid % mp, seg = tid / mp;
+            if (c < m) {
+                double a0 = 0.0, a1 = 0.0;
+                int r = seg;
+                for (; r + tpc < m; r += 2 * tpc) {
+                    a0 = fma(S[size_t(r) * k + c], v[r], a0);
+                    a1 = fma(S[size_t(r + tpc) * k + c], v[r + tpc], a1);
+                }
+                if (r < m) a0 = fma(S[size_t(r) * k + c], v[r], a0);
+                pp[seg * k + c] = a0 + a1;
+            }
+        }
+        __syncthreads();
+        double vp = 0.0, vy = 0.0;
+        for (int c = tid; c < m; c += NT) {
+            double pc = 0.0;
+            for (int sg = 0; sg < tpc; sg++) pc += pp[sg * k + c];
+            pc *= b;
+            q[c] = pc;
+            vp = fma(v[c], pc, vp);
+            vy = fma(v[c], y[j + 1 + c], vy);
+        }
+        block_sum2(vp, vy, red);
+        const double K = 0.5 * b * vp;
+        for (int c = tid; c < m; c += NT) {
+            q[c] -= K * v[c];
+            y[j + 1 + c] -= b * vy * v[c];                   // y <- H_j y
+        }
+        __syncthreads();
+        // S -= v q^T + q v^T
+        if (tid < tpc * mp) {
+            const int c = tid % mp, seg = tid / mp;
+            if (c < m) {
+                const double vc = v[c], qc = q[c];
+                double* Sc = W + size_t(j + 1) * k + j + 1 + c;
+                for (int r = seg; r < m; r += tpc) Sc[size_t(r) * k] -= fma(v[r], qc, q[r] * vc);
+            }
+        }
+        for (int c = tid; c < m; c += NT) xr[c] = v[c];      // the reflector lives in the row it annihilated
+        if (tid == 0) { d[j] = W[size_t(j) * k + j]; e[j + 1] = alpha; beta[j] = b; }
+        __syncthreads();
+    }
+    if (tid == 0) {
+        e[0] = 0.0;
+        if (k >= 2) {
+            d[k - 2] = W[size_t(k - 2) * k + k - 2];
+            e[k - 1] = W[size_t(k - 2) * k + k - 1];
+            beta[k - 2] = 0.0;
+        }
+        d[k - 1] = W[size_t(k - 1) * k + k - 1];
+        beta[k - 1] = 0.0;
+    }
+    __syncthreads();
+
+    // ---- 2. the eigenvalues above the clamp level ------------------------------------------------------------------------
+    double* ds = v;
+    double* es2 = q;
+    double* es = pp;
+    double tn = 0.0;
+    for (int i = 0; i < k; i++) tn = fmax(tn, fabs(d[i]) + fabs(e[i]) + (i + 1 < k ? fabs(e[i + 1]) : 0.0));   // every thread
+    __syncthreads();
+    if (!(tn > 0.0) || !(tn < 1e300)) {                       // zero matrix (everything clamped) or garbage
+        for (int r = tid; r < k; r += NT) y[r] = y[r] / pert;
+        __syncthreads();
+    } else {
+        const double inv = 1.0 / tn;
+        for (int i = tid; i < k; i += NT) {
+            ds[i] = d[i] * inv;
+            es[i] = e[i] * inv;
+            es2[i] = (e[i] * inv) * (e[i] * inv);
+        }
+        __syncthreads();
+        const double ps = pert * inv;
+        // ---- 2a. split T where an off-diagonal is negligible (LAPACK dstebz criterion): eigenvectors live on their block, so
+        //          a multiple eigenvalue of H (rank-deficient Gram + l2 I, ...) becomes one simple eigenvalue per block and the
+        //          vectors of different blocks are orthogonal by support
+        if (tid == 0) {
+            int nb = 0;
+            bstart[0] = 0;
+            for (int i = 1; i < k; i++)
+                if (es2[i] <= 4.930380657631324e-32 * fabs(ds[i - 1] * ds[i]) + 1e-300) { es[i] = 0.0; es2[i] = 0.0; bstart[++nb] = i; }
+            bstart[++nb] = k;
+            s_nblk = nb;
+        }
+        __syncthreads();
+        const int nblk = s_nblk;
+        for (int bI = tid; bI < nblk; bI += NT) {             // wanted eigenvalues of every block: below -p and above +p
+            const int s0 = bstart[bI], sz = bstart[bI + 1] - s0;
+            const int nn = sturm_count(ds + s0, es2 + s0, sz, -ps), nl = sturm_count(ds + s0, es2 + s0, sz, ps);
+            bneg[bI] = nn;
+            blt[bI] = nl;
+            woff[bI + 1] = nn + (sz - nl);
+        }
+        __syncthreads();
+        if (tid == 0) {
+            woff[0] = 0;
+            for (int bI = 0; bI < nblk; bI++) woff[bI + 1] += woff[bI];
+        }
+        __syncthreads();
+        const int nw = woff[nblk];                            // wanted (uniform); <= k <= NT
+        // ---- 2b / 3. one thread per wanted eigenpair: bisection inside its block, then inverse iteration ---------------------
+        double* Z = zg;                        // arrays [element * k + vector]
+        double* U0 = Z + size_t(k) * k;        // reciprocal pivots
+        double* U1 = U0 + size_t(k) * k;
+        double* U2 = U1 + size_t(k) * k;
+        double* L = U2 + size_t(k) * k;
+        double* PV = L + size_t(k) * k;        // 1.0 where rows were swapped
+        const int t = tid;
+        int s0 = 0, sz = 0;
+        double *Zb = Z, *U0b = U0, *U1b = U1, *U2b = U2, *Lb = L, *PVb = PV;
+        if (tid < nw) {
+            int bI = 0;
+            while (woff[bI + 1] <= t) bI++;
+            s0 = bstart[bI];
+            sz = bstart[bI + 1] - s0;
+            const int jl = t - woff[bI];
+            const int idx = jl < bneg[bI] ? jl : blt[bI] + (jl - bneg[bI]);
+            vblk[t] = bI;
+            const double* bd = ds + s0;
+            const double* be = es + s0;        // be[i] couples i - 1 and i inside the block (be[0] is never used)
+            const double* be2 = es2 + s0;
+            double lo = -1.0009765625, hi = 1.0009765625;
+            if (sz == 1) { lo = hi = bd[0]; }
+            for (int it = 0; it < 64 && sz > 1; it++) {
+                const double mid = 0.5 * (lo + hi);
+                if (mid <= lo || mid >= hi) break;
+                if (sturm_count(bd, be2, sz, mid) > idx) hi = mid; else lo = mid;
+            }
+            const double lm = 0.5 * (lo + hi);
+            lam[t] = lm;
+            for (int i = 0; i < s0; i++) Z[size_t(i) * k + t] = 0.0;
+            for (int i = s0 + sz; i < k; i++) Z[size_t(i) * k + t] = 0.0;
+            Zb = Z + size_t(s0) * k + t;                   // element i of the block at Zb[i * k]
+            U0b = U0 + size_t(s0) * k + t; U1b = U1 + size_t(s0) * k + t; U2b = U2 + size_t(s0) * k + t;
+            Lb = L + size_t(s0) * k + t; PVb = PV + size_t(s0) * k + t;
+            if (sz == 1) {
+                Zb[0] = 1.0;
+            } else {
+                const double tiny = 2.220446049250313e-16;
+                double r0 = bd[0] - lm, r1 = be[1], r2 = 0.0;
+                for (int i = 0; i < sz - 1; i++) {
+                    const double q0 = be[i + 1], q1 = bd[i + 1] - lm, q2 = i + 2 < sz ? be[i + 2] : 0.0;
+                    double u0, u1, u2, l, pv;
+                    if (fabs(q0) > fabs(r0)) {
+                        pv = 1.0; u0 = q0; u1 = q1; u2 = q2;
+                        l = r0 / q0;
+                        r0 = r1 - l * q1; r1 = r2 - l * q2; r2 = 0.0;
+                    } else {
+                        if (r0 == 0.0) r0 = tiny;
+                        pv = 0.0; u0 = r0; u1 = r1; u2 = r2;
+                        l = q0 / r0;
+                        r0 = q1 - l * r1; r1 = q2 - l * r2; r2 = 0.0;
+                    }
+                    U0b[size_t(i) * k] = 1.0 / u0; U1b[size_t(i) * k] = u1; U2b[size_t(i) * k] = u2;
+                    Lb[size_t(i) * k] = l; PVb[size_t(i) * k] = pv;
+                }
+                if (r0 == 0.0) r0 = tiny;
+                U0b[size_t(sz - 1) * k] = 1.0 / r0; U1b[size_t(sz - 1) * k] = 0.0; U2b[size_t(sz - 1) * k] = 0.0;
+                uint32_t st = 0x9e3779b9u * uint32_t(t + 1) + 0x7f4a7c15u;     // start vector: positive pseudo-random entries
+                for (int i = 0; i < sz; i++) {
+                    st = st * 1664525u + 1013904223u;
+                    Zb[size_t(i) * k] = 0.5 + double(st >> 8) * (1.0 / 16777216.0);
+                }
+            }
+        }
+        __syncthreads();
+        // clusters of close eigenvalues of the SAME block: their vectors are re-orthogonalised after EVERY sweep (as dstein does;
+        // orthogonalising only at the end lets the amplification ratios inside a multiple eigenvalue compound: 1e-9 instead of 1e-12)
+        if (tid == 0) {
+            int start = 0;
+            for (int u = 0; u < nw; u++) {
+                // separately computed vectors of eigenvalues a gap delta ||T|| apart overlap by ~eps / delta (2e-11 here)
+                if (u > 0 && (vblk[u] != vblk[u - 1] || !(lam[u] - lam[u - 1] < 1e-5))) start = u;
+                cstart[u] = start;
+            }
+        }
+        __syncthreads();
+        for (int it = 0; it < 3; it++) {
+            if (tid < nw && sz > 1) {
+                if (it > 0) {                                  // apply L^-1 P; the running element stays in a register, so the
+                    double cur = Zb[0];                        // loads of one step do not wait for the stores of the previous
+#pragma unroll 8
+                    for (int i = 0; i < sz - 1; i++) {
+                        const double xn = Zb[size_t(i + 1) * k], l = Lb[size_t(i) * k], pv = PVb[size_t(i) * k];
+                        if (pv != 0.0) { Zb[size_t(i) * k] = xn; cur = cur - l * xn; }
+                        else { Zb[size_t(i) * k] = cur; cur = xn - l * cur; }
+                    }
+                    Zb[size_t(sz - 1) * k] = cur;
+                }
+                double x1 = 0.0, x2 = 0.0, nrm = 0.0;          // back substitution with U (bandwidth 2)
+#pragma unroll 8
+                for (int i = sz - 1; i >= 0; i--) {
+                    const double zi = Zb[size_t(i) * k], a1 = U1b[size_t(i) * k], a2 = U2b[size_t(i) * k], a0 = U0b[size_t(i) * k];
+                    const double tv = (zi - a1 * x1 - a2 * x2) * a0;
+                    Zb[size_t(i) * k] = tv;
+                    x2 = x1; x1 = tv;
+                    nrm = fmax(nrm, fabs(tv));
+                }
+                // rescale by the max norm first (the solve amplifies by ~1e16), then to unit 2-norm
+                const double sc = nrm > 0.0 ? 1.0 / nrm : 1.0;
+                double s2 = 0.0;
+#pragma unroll 8
+                for (int i = 0; i < sz; i++) { const double tv = Zb[size_t(i) * k] * sc; s2 = fma(tv, tv, s2); }
+                const double sc2 = sc / sqrt(s2);
+#pragma unroll 8
+                for (int i = 0; i < sz; i++) Zb[size_t(i) * k] *= sc2;
+            }
+            __syncthreads();
+            for (int u = 1; u < nw; u++) {
+                const int c0 = cstart[u];
+                if (c0 == u) continue;                        // uniform
+                for (int i = c0; i < u; i++) {
+                    double dot = 0.0, dummy = 0.0;
+                    for (int el = tid; el < k; el += NT) dot = fma(Z[size_t(el) * k + i], Z[size_t(el) * k + u], dot);
+                    block_sum2(dot, dummy, red);
+                    for (int el = tid; el < k; el += NT) Z[size_t(el) * k + u] -= dot * Z[size_t(el) * k + i];
+                    __syncthreads();
+                }
+                double n2 = 0.0, dummy = 0.0;
+                for (int el = tid; el < k; el += NT) n2 = fma(Z[size_t(el) * k + u], Z[size_t(el) * k + u], n2);
+                block_sum2(n2, dummy, red);
+                if (!(n2 > 1e-8)) { if (tid == 0 && it == 2) s_fail = 1; if (!(n2 > 0.0)) n2 = 1.0; }   // a copy of an earlier vector
+                const double sc = 1.0 / sqrt(n2);
+                for (int el = tid; el < k; el += NT) Z[size_t(el) * k + u] *= sc;
+                __syncthreads();
+            }
+        }
+        // ---- 5. combine --------------------------------------------------------------------------------------------------
+        if (tid < nw) {
+            double c = 0.0;
+            for (int i = 0; i < k; i++) c = fma(Z[size_t(i) * k + tid], y[i], c);
+            coef[tid] = (1.0 / (fabs(lam[tid]) * tn) - 1.0 / pert) * c;
+        }
+        __syncthreads();
+        for (int el = tid; el < k; el += NT) {
+            double acc = y[el] / pert;
+            const double* zr = Z + size_t(el) * k;
+            for (int t = 0; t < nw; t++) acc = fma(coef[t], zr[t], acc);
+            x[el] = acc;
+        }
+        __syncthreads();
+        for (int el = tid; el < k; el += NT) y[el] = x[el];
+        __syncthreads();
+    }
+    // ---- x = P y: reflectors in reverse -------------------------------------------------------------------------------------
+    for (int j = k - 3; j >= 0; j--) {
+        const double b = beta[j];
+        if (b == 0.0) continue;                               // uniform
+        const int m = k - j - 1;
+        const double* vj = W + size_t(j) * k + j + 1;
+        double s = 0.0, dummy = 0.0;
+        for (int c = tid; c < m; c += NT) s = fma(vj[c], y[j + 1 + c], s);
+        block_sum2(s, dummy, red);
+        for (int c = tid; c < m; c += NT) y[j + 1 + c] -= b * s * vj[c];
+        __syncthreads();                                      // the next step's partial sums read the updated y
+    }
+    __syncthreads();
+    for (int el = tid; el < k; el += NT) x[el] = y[el];
+    __syncthreads();
+    return s_fail == 0;
+}
+
+}  // namespace tri
+}  // namespace pycmf

@@ -61,7 +61,7 @@ for a, b in ((U1, U2), (V1, V2), (Z1, Z2)):
 # the same fit through the default stepper: two eager iterations, then CUDA-graph replay with the NCCL collectives (and the
 # communication-stream overlap of the V update) captured inside the graph -- must equal the eager, per-iteration run
 case["iters"] = 7
-_, Ug, Vg, Zg = run(case, "float32", TorchComm(), dense_path=1, history=False)
+_, Ug, Vg, Zg = run(case, "float32", TorchComm(), dense_path=1, history=False, use_cuda_graph=True)
 _, Ue, Ve, Ze = run(case, "float32", TorchComm(), dense_path=1)
 for a, b in ((Ug, Ue), (Vg, Ve), (Zg, Ze)):
     assert rel_fro(a, b) < 1e-6, "graph replay vs eager on 2 ranks"

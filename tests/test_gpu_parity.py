@@ -177,12 +177,15 @@ def test_spmm_and_transpose(be64, k):
 
 
 @pytest.mark.parametrize("k", [1, 2, 7, 32, 33, 64, 128, 150])
-@pytest.mark.parametrize("chol", [0, 1])
-def test_safe_solve_matches_eigh_clamp(k, chol):
+@pytest.mark.parametrize("chol,path", [(0, 1), (1, 1), (0, 0), (1, 0)])
+def test_safe_solve_matches_eigh_clamp(k, chol, path):
+    """x = S(H) g against eigh: Cholesky fast path, Frobenius shortcut, and the clamp-active solvers (path 1 = tridiagonalisation
+    + bisection + inverse iteration, path 0 = one-sided Jacobi) on rank-deficient, indefinite, multiple-eigenvalue, clustered and
+    clamp-level spectra."""
     from pycmf_b200.device import CudaBackend
-    be = CudaBackend(dtype="float64", options={"chol_fastpath": chol})
+    be = CudaBackend(dtype="float64", options={"chol_fastpath": chol, "solve_path": path})
     rng = np.random.RandomState(k)
-    batch = 9
+    batch = 13
     H = np.empty((batch, k, k))
     for b in range(batch):
         r = max(1, (b * k) // batch)                      # ranks from deficient to full
@@ -196,6 +199,14 @@ def test_safe_solve_matches_eigh_clamp(k, chol):
             H[b] *= 0.15 / np.linalg.norm(H[b])           # ||H||_F < pert: every eigenvalue clamped, S(H) = I / pert
         if b == 7:
             H[b] *= 0.21 / np.linalg.norm(H[b])           # just above the Frobenius shortcut: the full path
+        if b >= 9:
+            Q, _ = np.linalg.qr(rng.randn(k, k))
+            lam = [np.where(np.arange(k) % 2 == 0, 1.0, 0.05),                       # a k/2-fold eigenvalue above the clamp
+                   0.2 + 1e-9 * rng.randn(k),                                        # everything at the clamp level
+                   np.repeat(np.linspace(0.3, 5, (k + 1) // 2), 2)[:k] + 1e-8 * rng.randn(k),     # tight pairs
+                   np.concatenate([np.linspace(0.25, 40, k - k // 3), 1e-4 * rng.rand(k // 3)])][b - 9]   # bulk below the clamp
+            H[b] = (Q * lam) @ Q.T
+            H[b] = 0.5 * (H[b] + H[b].T)
     g = rng.randn(batch, k)
     ref = np.einsum('bij,bj->bi', O.safe_invert(H, 0.2), g)
     got = be.to_host(be.safe_solve(be.to_device(H), be.to_device(g), 0.2))
@@ -417,15 +428,15 @@ def test_tc_mu_wide_fit_matches_oracle():
     for _ in range(30):
         O.mu_step(X, Y, Uo, Vo, Zo, 0.0, 0.0)
     U, V, Z = U0.copy(), V0.copy(), Z0.copy()
-    s = MUSolver(tol=0, max_iter=30, dtype="float32", backend_options={"dense_path": 1})
+    s = MUSolver(tol=0, max_iter=30, dtype="float32", backend_options={"dense_path": 1}, use_cuda_graph=True)
     s.fit_iterative_update(X, Y, U, V, Z)
     assert rel_fro(U, Uo) < 1e-3 and rel_fro(V, Vo) < 1e-3 and rel_fro(Z, Zo) < 1e-3
 
 
 @pytest.mark.parametrize("k", [32, 64, 128])
-@pytest.mark.parametrize("unroll", [4, 8])
+@pytest.mark.parametrize("unroll,lean", [(4, 1), (8, 1), (4, 0), (8, 0)])
 @pytest.mark.parametrize("shape", [(3000, 2500, 0.01), (40, 70, 0.2), (5000, 300, 0.002), (257, 4000, 0.05)])
-def test_spmm_nonzero_balanced_kernel(k, unroll, shape):
+def test_spmm_nonzero_balanced_kernel(k, unroll, lean, shape):
     """The nonzero-balanced fp32 SpMM: shares that cut rows (atomics), whole rows (stores), empty rows (prologue), more
     warps than nonzeros, hot rows / columns, alpha / beta -- against scipy in float64."""
     from pycmf_b200.device import CudaBackend
@@ -438,7 +449,7 @@ def test_spmm_nonzero_balanced_kernel(k, unroll, shape):
     S[n - 1, :] = 0                     # trailing empty row
     S = sp.csr_matrix(S)
     S.eliminate_zeros()
-    be = CudaBackend(dtype="float32", options={"spmm_path": 1, "spmm_unroll": unroll})
+    be = CudaBackend(dtype="float32", options={"spmm_path": 1, "spmm_unroll": unroll, "spmm_lean": lean})
     Sd = be.ingest(S)
     B, A, C0 = rng.randn(d, k), rng.randn(n, k), rng.randn(n, k)
     got = be.to_host(be.spmm(Sd, be.to_device(B), alpha=0.5, beta=2.0, out=be.to_device(C0)))
