@@ -55,6 +55,7 @@ pycmf_ctx* fork_side(pycmf_ctx* ctx) {
     s->spmm_lean = ctx->spmm_lean;
     s->mu_fused = ctx->mu_fused;
     s->solve_path = ctx->solve_path;
+    s->solve_threads = ctx->solve_threads;
     s->tc_max_splits = ctx->tc_max_splits;
     s->tc_ctas = ctx->tc_ctas;
     s->tc_chain = ctx->tc_chain;
@@ -123,7 +124,11 @@ void sqerr_impl(pycmf_ctx* ctx, int64_t rows, int64_t m, int64_t k, const T* A, 
         gram_f64<T>(ctx, m, k, B, G + k * k);
         dot_f64<double>(ctx, k * k, G, G + k * k, 1.0, out, true);
         sddmm_reduce<T>(ctx, 2, rows, rowptr, colidx, vals, A, B, k, 1.0, out);
-        sddmm_reduce<T>(ctx, 0, rows, rowptr, colidx, vals, A, B, k, -2.0, out);
+        // cross term sum_nz t_ij a_i . b_j = <A, T B>: one SpMM (the nonzero-balanced kernel) and a dot product in float64;
+        // the warp-per-row SDDMM reduction it replaces cost 1.18 ms on the C3 shard against 0.41 ms for the SpMM
+        T* N = static_cast<T*>(scratch(ctx, SLOT_T1, sizeof(T) * size_t(rows) * k));
+        spmm<T>(ctx, rows, rowptr, colidx, vals, B, k, k, N, k, T(1), T(0), m);
+        dot_f64<T>(ctx, rows * k, A, N, -2.0, out, true);
     } else {
         // sum_all sigma^2 + sum_nz [ (t - sigma)^2 - sigma^2 ]
         resid_pass<T>(ctx, rows, m, k, A, B, nullptr, 0, false, link, nullptr, nullptr, out);
@@ -490,6 +495,7 @@ int pycmf_set_option(pycmf_ctx* ctx, const char* key, double value) {
         else if (k == "spmm_lean") ctx->spmm_lean = int(value);
         else if (k == "mu_fused") ctx->mu_fused = int(value);
         else if (k == "solve_path") ctx->solve_path = int(value);
+        else if (k == "solve_threads") ctx->solve_threads = int(value);
         else if (k == "tc_trace") ctx->tc_trace = int(value);
         else if (k == "tc_ctas") ctx->tc_ctas = int(value);
         else if (k == "tc_chain") ctx->tc_chain = int(value);

@@ -55,6 +55,7 @@ struct pycmf_ctx {
     int spmm_blocks_per_sm = 0;  // option: resident 256-thread CTAs per SM of the nonzero-balanced SpMM (0 = default 4)
     int solve_path = 1;      // option: clamped solve with active clamp, k > 32: 1 = tridiagonalisation + bisection + inverse iteration
                              // (tridiag_solve.cuh), 0 = one-sided Jacobi only
+    int solve_threads = 0;   // option (tuning): CTA size of the tridiagonal clamped solve (0 = by k; must be >= k, multiple of 32)
     int mu_fused = 1;        // option: 0 = separate F G GEMM + elementwise ratio launches (tests)
     int spmm_lean = 1;       // option: 1 = shared-memory staged nonzeros + packed FMAs (spmm_nzb2_kernel), 0 = shuffle variant
     int spmm_unroll = 4;     // option: independent factor-row gathers per lane in flight (4 or 8)

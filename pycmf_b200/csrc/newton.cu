@@ -611,7 +611,7 @@ void launch_solve(pycmf_ctx* ctx, int64_t batch, int64_t k, const T* H, int64_t 
     // rounds per step instead of eight on 8 warps)
     // tridiagonal path (default): one thread per wanted eigenvector, so at least k threads; Jacobi only: one warp per column pair
     const bool tri_path = ctx->solve_path != 0 && k >= 8;
-    int nthreads = tri_path ? (k <= 64 ? 128 : (k <= 128 ? 256 : 512))
+    int nthreads = tri_path ? (ctx->solve_threads > 0 ? ctx->solve_threads : (k <= 64 ? 128 : (k <= 128 ? 256 : 512)))
                             : (k <= 32 ? 64 : (k <= 64 ? 128 : (k <= 96 ? 256 : 1024)));
     bool w_in_smem = solve_smem_bytes(int(k), nthreads, true, tri_path) <= size_t(ctx->max_smem_optin);
     size_t smem = solve_smem_bytes(int(k), nthreads, w_in_smem, tri_path);

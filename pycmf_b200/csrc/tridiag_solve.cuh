@@ -57,8 +57,8 @@ __device__ __forceinline__ int sturm_count(const double* __restrict__ ds, const 
     return cnt;
 }
 
-// work (shared memory, doubles): 16 k + 72.  zg (global, doubles): 6 k^2 for this CTA.
-__host__ __device__ constexpr size_t work_doubles(int k) { return size_t(16) * k + 72; }
+// work (shared memory, doubles): 16 k + 328.  zg (global, doubles): 6 k^2 for this CTA.
+__host__ __device__ constexpr size_t work_doubles(int k) { return size_t(16) * k + 72 + 256; }
 __host__ __device__ constexpr size_t scratch_doubles(int k) { return size_t(6) * k * k; }
 
 __device__ bool clamped_solve(double* __restrict__ W, int k, const double* __restrict__ g, double* __restrict__ x,
@@ -80,6 +80,7 @@ __device__ bool clamped_solve(double* __restrict__ W, int k, const double* __res
     int* blt = bneg + k;
     int* woff = blt + k;                              // k + 1
     double* red = coef + 4 * k + 1;   // 64
+    int* flags = reinterpret_cast<int*>(red + 64);    // blockDim.x ints (<= 512)
     __shared__ int s_fail, s_nblk;
     if (tid == 0) s_fail = 0;
     for (int r = tid; r < k; r += NT) y[r] = g[r];
@@ -215,28 +216,61 @@ __device__ bool clamped_solve(double* __restrict__ W, int k, const double* __res
         double* U2 = U1 + size_t(k) * k;
         double* L = U2 + size_t(k) * k;
         double* PV = L + size_t(k) * k;        // 1.0 where rows were swapped
+        // 2b. multi-section: the CTA's threads are dealt out G per wanted eigenvalue and cut its bracket into G + 1 parts per
+        //     round (log2(G + 1) bits per Sturm evaluation instead of 1: with 16 wanted eigenvalues and 256 threads, 14 rounds
+        //     instead of 55).  Brackets live in the (now dead) unscaled d / e arrays.
+        {
+            double* blo = d;
+            double* bhi = e;
+            const int G = max(1, min(32, NT / max(nw, 1)));
+            const int rounds = nw > 0 ? int(56.0f / log2f(float(G + 1))) + 2 : 0;     // bracket 2 -> 2^-54
+            const int tq = tid / G, gq = tid % G;
+            int qs0 = 0, qsz = 0, qidx = 0;
+            if (tq < nw) {
+                int bI = 0;
+                while (woff[bI + 1] <= tq) bI++;
+                qs0 = bstart[bI];
+                qsz = bstart[bI + 1] - qs0;
+                const int jl = tq - woff[bI];
+                qidx = jl < bneg[bI] ? jl : blt[bI] + (jl - bneg[bI]);
+                if (gq == 0) {
+                    vblk[tq] = bI;
+                    blo[tq] = qsz == 1 ? ds[qs0] : -1.0009765625;
+                    bhi[tq] = qsz == 1 ? ds[qs0] : 1.0009765625;
+                }
+            }
+            __syncthreads();
+            for (int rd = 0; rd < rounds; rd++) {
+                if (tq < nw) {
+                    const double lo = blo[tq], hi = bhi[tq];
+                    const double xq = lo + (hi - lo) * (double(gq + 1) / double(G + 1));
+                    int above = 1;                                    // "more than idx eigenvalues below xq"
+                    if (qsz > 1 && hi > lo) above = sturm_count(ds + qs0, es2 + qs0, qsz, xq) > qidx ? 1 : 0;
+                    flags[tid] = above;
+                }
+                __syncthreads();
+                if (tq < nw && gq == 0 && qsz > 1) {
+                    const double lo = blo[tq], hi = bhi[tq];
+                    int j = 0;
+                    while (j < G && flags[tid + j] == 0) j++;          // first interior point with the eigenvalue below it
+                    const double nlo = j > 0 ? lo + (hi - lo) * (double(j) / double(G + 1)) : lo;
+                    const double nhi = j < G ? lo + (hi - lo) * (double(j + 1) / double(G + 1)) : hi;
+                    blo[tq] = fmax(lo, fmin(nlo, hi));
+                    bhi[tq] = fmin(hi, fmax(nhi, lo));
+                }
+                __syncthreads();
+            }
+        }
         const int t = tid;
         int s0 = 0, sz = 0;
         double *Zb = Z, *U0b = U0, *U1b = U1, *U2b = U2, *Lb = L, *PVb = PV;
         if (tid < nw) {
-            int bI = 0;
-            while (woff[bI + 1] <= t) bI++;
+            const int bI = vblk[t];
             s0 = bstart[bI];
             sz = bstart[bI + 1] - s0;
-            const int jl = t - woff[bI];
-            const int idx = jl < bneg[bI] ? jl : blt[bI] + (jl - bneg[bI]);
-            vblk[t] = bI;
             const double* bd = ds + s0;
             const double* be = es + s0;        // be[i] couples i - 1 and i inside the block (be[0] is never used)
-            const double* be2 = es2 + s0;
-            double lo = -1.0009765625, hi = 1.0009765625;
-            if (sz == 1) { lo = hi = bd[0]; }
-            for (int it = 0; it < 64 && sz > 1; it++) {
-                const double mid = 0.5 * (lo + hi);
-                if (mid <= lo || mid >= hi) break;
-                if (sturm_count(bd, be2, sz, mid) > idx) hi = mid; else lo = mid;
-            }
-            const double lm = 0.5 * (lo + hi);
+            const double lm = 0.5 * (d[t] + e[t]);
             lam[t] = lm;
             for (int i = 0; i < s0; i++) Z[size_t(i) * k + t] = 0.0;
             for (int i = s0 + sz; i < k; i++) Z[size_t(i) * k + t] = 0.0;
