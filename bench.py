@@ -35,6 +35,7 @@ sys.path.insert(0, ROOT)
 
 METRIC = "cmf_fit_iterations_per_sec"
 UNIT = "it/s"
+DEFAULT_OTHERS = "c1,c2,c3,c4"
 LTS_CAP_BYTES_PER_CLK = 6300.0      # measured full-chip L2 -> SM throughput cap (guides/B300_MICROARCH.md, "LTS throughput cap")
 
 
@@ -430,12 +431,15 @@ def bench_workload(env, name, scale, col_scale, steps, warmup, args, headline):
     e2e = None
     host = None
     x_host_dtype = torch.float32 if (not cfg["sparse"] and n_loc * d * 8 > 16e9) else torch.float64
-    want_cpu = world == 1 and not args.no_cpu
-    if not args.no_e2e or want_cpu:
+    # C4: the reference draws a fresh permutation and copies X[:, mask] for every one of the 44000 rows of an iteration
+    # (cmf_solvers.py:328-344): minutes per iteration even on this slice -- no CPU arm for it
+    want_cpu = world == 1 and not args.no_cpu and name != "c4"
+    do_e2e = not args.no_e2e and name != "c4"          # (C4: the device-resident figure only)
+    if do_e2e or want_cpu:
         host = host_problem(torch, data, U0, V0, Z0, x_dtype=x_host_dtype)
     del st, step, U, V, Z
     x_bytes_dev = (nnz_loc * (sb + 4) * 2 if cfg["sparse"] else n_loc * d * sb)
-    if not args.no_e2e:
+    if do_e2e:
         del data
         torch.cuda.empty_cache()
         Xh, Yh, Uh, Vh, Zh = host
@@ -640,11 +644,14 @@ def run_ours(args):
     others = []
     names = args.others
     if names is None:
-        names = "c1,c2,c3" if args.workload == "c5" and args.scale is None else "none"
+        names = DEFAULT_OTHERS if args.workload == "c5" and args.scale is None else "none"
     for nm in [x for x in names.split(",") if x and x != "none"]:
         s, cs = default_scale(nm, world)
         # short steps: more of them, so that the timed region spans several clock samples
+        # (c4: a 0.35 s iteration -- a quarter of the steps)
         k_steps = args.steps * (25 if nm == "c1" else 5 if nm == "c2" else 2 if nm == "c3" else 1)
+        if nm == "c4":
+            k_steps = max(3, args.steps // 4)
         res = bench_workload(env, nm, s, cs, k_steps, args.warmup, args, False)
         if rank == 0:
             others.append(res)
@@ -717,11 +724,11 @@ def run_reference(args):
         else torch.device("cpu")
     names = args.others
     if names is None:
-        names = "c1,c2,c3" if args.workload == "c5" and args.scale is None else "none"
+        names = DEFAULT_OTHERS if args.workload == "c5" and args.scale is None else "none"
     try:
         head = reference_workload(W, torch, device, args.workload, world, args.steps, args.warmup, 60.0)
         others = [reference_workload(W, torch, device, nm, world, args.steps, args.warmup, 30.0)
-                  for nm in names.split(",") if nm and nm != "none"]
+                  for nm in names.split(",") if nm and nm not in ("none", "c4")]      # c4: minutes per reference iteration
     except Exception as e:  # noqa: BLE001
         print(json.dumps({"impl": "reference", "unavailable": "reference arm failed: %r" % (e,)}))
         return

@@ -468,7 +468,9 @@ bool mu_fused_apply(pycmf_ctx* ctx, int64_t rows, int64_t k, T* F, const T* N, c
     if (smem > size_t(ctx->max_smem_optin)) return false;
     auto kern = vec ? mu_fused_kernel<T, true> : mu_fused_kernel<T, false>;
     PYCMF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-    const int64_t grid = std::min<int64_t>(ceil_div(rows, MUF_ROWS), int64_t(4) * ctx->num_sms);
+    int per_sm = 2;                                            // one resident wave: the row loop is grid-strided
+    PYCMF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, smem));
+    const int64_t grid = std::min<int64_t>(ceil_div(rows, MUF_ROWS), int64_t(std::max(per_sm, 1)) * ctx->num_sms);
     Timed timer(ctx, "mu_fused");
     kern<<<(unsigned)grid, 256, smem, ctx->stream>>>(rows, int(k), F, N, G, T(l1), T(l2), T(kEpsF32));
     PYCMF_LAUNCH_CHECK(ctx);
