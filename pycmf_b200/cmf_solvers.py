@@ -167,6 +167,19 @@ class _IterativeCMFSolver:
         ex, ey = np.sqrt(np.maximum(be.to_host(parts), 0.0))
         return float(self.alpha * ex + (1 - self.alpha) * ey)
 
+    def device_error_parts(self, st, x_link, y_link):
+        """(||X - f1(U V^T)||_F, ||Y - f2(V Z^T)||_F) on the resident state, with the given links (cmf.py:697-698 evaluates
+        the final reconstruction error with the estimator's links, whatever the solver)."""
+        be = st.be
+        parts = be.zeros(2, dtype=be.torch.float64)
+        if st.X is not None:
+            parts[0:1] = be.sqerr(st.U, st.V, st.X, x_link)
+        st.comm.all_reduce_sum(parts[0:1])
+        if st.Y is not None:
+            parts[1:2] = be.sqerr(st.V, st.Z, st.Y, y_link)
+        ex, ey = np.sqrt(np.maximum(be.to_host(parts), 0.0))
+        return float(ex), float(ey)
+
     def compute_error(self, X, Y, U, V, Z):
         if isinstance(X, FitState):
             return self.device_error(X)
@@ -249,6 +262,12 @@ class _IterativeCMFSolver:
         st = self.prepare(X, Y, U, V, Z)
         n_iter = self.fit_device(st)
         be = st.be
+        # final reconstruction errors while X / Y are still resident (CMF.fit_transform, cmf.py:697-698): evaluating them
+        # afterwards from the host arrays would upload X a second time (40 GB on C5)
+        self.final_errors_ = None
+        links = getattr(self, "final_error_links", None)
+        if links is not None:
+            self.final_errors_ = self.device_error_parts(st, links[0], links[1])
         # only the factors that were updated come back: a factor held fixed (update_V=False in transform(), cmf.py:741)
         # stays bit-identical on the host, as in the reference (tests/test_cmf.py:408) -- a float32 round trip would not
         pairs = []

@@ -107,18 +107,24 @@ __device__ bool clamped_solve(double* __restrict__ W, int k, const double* __res
         // p = b S v, S = trailing m x m block (symmetric, kept in full): thread owns a column, row segments interleaved
         const int mp = (m + 31) & ~31;
         const int tpc = max(1, min(4, NT / mp));
-        const double* S = W + size_t(j + 1) * k + j + 1;
+        // (32-bit indices -- k^2 <= 65536 -- and four independent loads per trip: with 8 warps per SM these loops are latency-
+        //  bound, ncu put 57 % of the kernel here while they walked one dependent generic load at a time)
         if (tid < tpc * mp) {
             const int c = tid % mp, seg = tid / mp;
             if (c < m) {
-                double a0 = 0.0, a1 = 0.0;
-                int r = seg;
-                for (; r + tpc < m; r += 2 * tpc) {
-                    a0 = fma(S[size_t(r) * k + c], v[r], a0);
-                    a1 = fma(S[size_t(r + tpc) * k + c], v[r + tpc], a1);
+                const double* Sc = W + (j + 1) * k + j + 1 + c;
+                const int st = tpc * k;
+                double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+                int r = seg, o = seg * k;
+                for (; r + 3 * tpc < m; r += 4 * tpc, o += 4 * st) {
+                    const double s0 = Sc[o], s1 = Sc[o + st], s2 = Sc[o + 2 * st], s3 = Sc[o + 3 * st];
+                    a0 = fma(s0, v[r], a0);
+                    a1 = fma(s1, v[r + tpc], a1);
+                    a2 = fma(s2, v[r + 2 * tpc], a2);
+                    a3 = fma(s3, v[r + 3 * tpc], a3);
                 }
-                if (r < m) a0 = fma(S[size_t(r) * k + c], v[r], a0);
-                pp[seg * k + c] = a0 + a1;
+                for (; r < m; r += tpc, o += st) a0 = fma(Sc[o], v[r], a0);
+                pp[seg * k + c] = (a0 + a1) + (a2 + a3);
             }
         }
         __syncthreads();
@@ -143,8 +149,18 @@ __device__ bool clamped_solve(double* __restrict__ W, int k, const double* __res
             const int c = tid % mp, seg = tid / mp;
             if (c < m) {
                 const double vc = v[c], qc = q[c];
-                double* Sc = W + size_t(j + 1) * k + j + 1 + c;
-                for (int r = seg; r < m; r += tpc) Sc[size_t(r) * k] -= fma(v[r], qc, q[r] * vc);
+                double* Sc = W + (j + 1) * k + j + 1 + c;
+                const int st = tpc * k;
+                int r = seg, o = seg * k;
+                for (; r + 3 * tpc < m; r += 4 * tpc, o += 4 * st) {
+                    double s0 = Sc[o], s1 = Sc[o + st], s2 = Sc[o + 2 * st], s3 = Sc[o + 3 * st];
+                    s0 -= fma(v[r], qc, q[r] * vc);
+                    s1 -= fma(v[r + tpc], qc, q[r + tpc] * vc);
+                    s2 -= fma(v[r + 2 * tpc], qc, q[r + 2 * tpc] * vc);
+                    s3 -= fma(v[r + 3 * tpc], qc, q[r + 3 * tpc] * vc);
+                    Sc[o] = s0; Sc[o + st] = s1; Sc[o + 2 * st] = s2; Sc[o + 3 * st] = s3;
+                }
+                for (; r < m; r += tpc, o += st) Sc[o] -= fma(v[r], qc, q[r] * vc);
             }
         }
         for (int c = tid; c < m; c += NT) xr[c] = v[c];      // the reflector lives in the row it annihilated
