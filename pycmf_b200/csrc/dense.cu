@@ -375,10 +375,13 @@ template <typename T> __device__ __forceinline__ Vec4<T> ld4s(const T* p) {     
 
 // VEC4: k % 4 == 0 -- a thread owns a 4 x 4 block of F G (4 rows, 4 columns) and walks the contraction four steps at a
 // time with 128-bit shared-memory reads of both operands (16 FMAs per 2 loads); otherwise the scalar form (k = 10 on C1).
-template <typename T, bool VEC4>
+// KC > 0: n_components known at compile time (32 / 64 / 128): the index divisions of the staging loops become shifts and the
+// contraction unrolls (they were 40 % of the instructions with a run-time k).
+template <typename T, bool VEC4, int KC>
 __global__ void __launch_bounds__(256)
-mu_fused_kernel(int64_t rows, int k, T* __restrict__ F, const T* __restrict__ N, const T* __restrict__ G, T l1, T l2,
+mu_fused_kernel(int64_t rows, int k_rt, T* __restrict__ F, const T* __restrict__ N, const T* __restrict__ G, T l1, T l2,
                 T eps) {
+    const int k = KC > 0 ? KC : k_rt;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int ldg = VEC4 ? k + 4 : k + 1;                    // pitch of G: 16-byte aligned rows / odd (conflict-free columns)
     const int ldf = VEC4 ? k + 4 : k;
@@ -466,7 +469,10 @@ bool mu_fused_apply(pycmf_ctx* ctx, int64_t rows, int64_t k, T* F, const T* N, c
     const bool vec = k % 4 == 0;
     const size_t smem = sizeof(T) * (size_t(k) * (k + 4) + size_t(MUF_ROWS) * (k + 4));
     if (smem > size_t(ctx->max_smem_optin)) return false;
-    auto kern = vec ? mu_fused_kernel<T, true> : mu_fused_kernel<T, false>;
+    auto kern = k == 32 ? mu_fused_kernel<T, true, 32>
+              : k == 64 ? mu_fused_kernel<T, true, 64>
+              : k == 128 ? mu_fused_kernel<T, true, 128>
+              : vec ? mu_fused_kernel<T, true, 0> : mu_fused_kernel<T, false, 0>;
     PYCMF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
     int per_sm = 2;                                            // one resident wave: the row loop is grid-strided
     PYCMF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, smem));

@@ -36,6 +36,7 @@ row_grad_hess_kernel(int64_t rows, int64_t m, int k, const T* __restrict__ A, co
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int ta = tid >> 4, tb = tid & 15;
     const bool want_g = g != nullptr, want_h = H != nullptr;
+    const bool sym = a_off == b_off;      // the CTA covers a diagonal block of H (always, unless k needs several register passes)
 
     for (int c = tid; c < k; c += 256) a_s[c] = A[i * k + c];
     T gacc = T(0);
@@ -127,10 +128,13 @@ row_grad_hess_kernel(int64_t rows, int64_t m, int k, const T* __restrict__ A, co
                     int b = b_off + tb + 16 * y;
                     bb[y] = b < k ? B_s[jj * kp + b] : T(0);
                 }
+                // H_i is symmetric: only the register tiles on and below the diagonal are accumulated (x > y: every element of
+                // the tile has a > b when a_off == b_off), 36 of 64 at HB = 8; the mirror images are written out at the end
 #pragma unroll
                 for (int x = 0; x < HB; x++)
 #pragma unroll
-                    for (int y = 0; y < HB; y++) hacc[x][y] = fma(wa[x], bb[y], hacc[x][y]);
+                    for (int y = 0; y < HB; y++)
+                        if (x >= y || !sym) hacc[x][y] = fma(wa[x], bb[y], hacc[x][y]);
             }
         }
     }
@@ -148,8 +152,13 @@ row_grad_hess_kernel(int64_t rows, int64_t m, int k, const T* __restrict__ A, co
             for (int y = 0; y < HB; y++) {
                 int b = b_off + tb + 16 * y;
                 if (b >= k) continue;
+                if (sym && x < y) continue;                      // written as the mirror image of tile (y, x)
                 T prev = accumulate ? Hi[a * k + b] : T(0);
                 Hi[a * k + b] = prev + hacc[x][y];
+                if (sym && x > y) {
+                    prev = accumulate ? Hi[b * k + a] : T(0);
+                    Hi[b * k + a] = prev + hacc[x][y];
+                }
             }
         }
     }
