@@ -426,6 +426,25 @@ def bench_workload(env, name, scale, col_scale, steps, warmup, args, headline):
     n_loc, d, l, k = r1 - r0, cfg["d"], cfg["l"], cfg["k"]
     nnz_loc = data["X"].nnz if cfg["sparse"] else None
     roofline = build_roofline(env, name, cfg, fams, n_prof, ms_prof, n_loc, nnz_loc, sb, scale, args, clock_info)
+    if roofline is not None and name != "c4":
+        # the whole iteration against the same peak: SURVEY 8d's algorithmic flops / bytes of ONE iteration of the full
+        # problem (all ranks) over the measured time per iteration (region A), per GPU
+        cfull = dict(cfg)
+        nnz_all = None
+        if cfg["sparse"]:
+            tnnz = torch.tensor([float(nnz_loc)], dtype=torch.float64, device=be.device)
+            comm.all_reduce_sum(tnnz)
+            nnz_all = float(tnnz.item())
+        fl, by = W.algorithmic_work(cfull, sb, nnz_all)
+        sec = ms / steps / 1e3
+        if roofline["bound"] == "tensor":
+            ach = fl / sec / 1e12 / world
+            roofline["step_level"] = {"achieved": round(ach, 1), "unit": "TFLOP/s per GPU", "frac": round(ach / roofline["peak"], 4)
+                                      if roofline.get("peak") else None, "algorithmic_flops_per_iteration": fl}
+        else:
+            ach = by / sec / 1e9 / world
+            roofline["step_level"] = {"achieved": round(ach, 1), "unit": "GB/s per GPU", "frac": round(ach / roofline["peak"], 4)
+                                      if roofline.get("peak") else None, "algorithmic_bytes_per_iteration": by}
 
     # ---- e2e through the solver seam with host buffers
     e2e = None
