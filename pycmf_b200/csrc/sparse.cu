@@ -571,6 +571,7 @@ void spmm(pycmf_ctx* ctx, int64_t rows, const int32_t* rowptr, const int32_t* co
 #define LAUNCHL(L, U, M) spmm_nzb2_kernel<L, U, M><<<nb, 256, 0, ctx->stream>>>(rows, rowptr, colidx, vals, B, int(ldb), C, ldc, alpha, beta)
             if (lean) {
                 if (k == 32) { if (deep) LAUNCHL(8, 8, 3); else LAUNCHL(8, 4, 4); }
+                // (five / six resident CTAs per SM at 48 / 40 registers were measured slower: 0.45 / 0.53 ms against 0.41)
                 else if (k == 64) { if (deep) LAUNCHL(16, 8, 3); else LAUNCHL(16, 4, 4); }
                 else { if (deep) LAUNCHL(32, 8, 3); else LAUNCHL(32, 4, 4); }
             } else {
