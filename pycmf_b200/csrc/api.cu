@@ -55,6 +55,7 @@ pycmf_ctx* fork_side(pycmf_ctx* ctx) {
     s->spmm_lean = ctx->spmm_lean;
     s->mu_fused = ctx->mu_fused;
     s->solve_path = ctx->solve_path;
+    s->hess_mma = ctx->hess_mma;
     s->solve_threads = ctx->solve_threads;
     s->tc_max_splits = ctx->tc_max_splits;
     s->tc_ctas = ctx->tc_ctas;
@@ -495,6 +496,7 @@ int pycmf_set_option(pycmf_ctx* ctx, const char* key, double value) {
         else if (k == "spmm_lean") ctx->spmm_lean = int(value);
         else if (k == "mu_fused") ctx->mu_fused = int(value);
         else if (k == "solve_path") ctx->solve_path = int(value);
+        else if (k == "hess_mma") ctx->hess_mma = int(value);
         else if (k == "solve_threads") ctx->solve_threads = int(value);
         else if (k == "tc_trace") ctx->tc_trace = int(value);
         else if (k == "tc_ctas") ctx->tc_ctas = int(value);

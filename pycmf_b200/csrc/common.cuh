@@ -56,6 +56,7 @@ struct pycmf_ctx {
     int solve_path = 1;      // option: clamped solve with active clamp, k > 32: 1 = tridiagonalisation + bisection + inverse iteration
                              // (tridiag_solve.cuh), 0 = one-sided Jacobi only
     int solve_threads = 0;   // option (tuning): CTA size of the tridiagonal clamped solve (0 = by k; must be >= k, multiple of 32)
+    int hess_mma = 1;        // option: 0 = per-row Hessian builds on the FMA pipes only (tests), 1 = mma.sync 3xTF32 for k = 64 / 128
     int mu_fused = 1;        // option: 0 = separate F G GEMM + elementwise ratio launches (tests)
     int spmm_lean = 1;       // option: 1 = shared-memory staged nonzeros + packed FMAs (spmm_nzb2_kernel), 0 = shuffle variant
     int spmm_unroll = 4;     // option: independent factor-row gathers per lane in flight (4 or 8)

@@ -5,6 +5,8 @@
 //                     one-sided Jacobi otherwise; always float64
 //   newton_solve_rows F_i <- F_i - (g_i + l1 sign F_i + l2 F_i) S(H_i + l2 I), optional clamp
 //   sample_indices    on-device per-row sampling without replacement (Feistel permutation prefix)
+#include <type_traits>
+
 #include "common.cuh"
 #include "tridiag_solve.cuh"
 
@@ -162,6 +164,185 @@ row_grad_hess_kernel(int64_t rows, int64_t m, int k, const T* __restrict__ A, co
             }
         }
     }
+}
+
+// =============================================================================================
+// row_grad_hess on the tensor cores (fp32, n_components 64 / 128, non-negative weight)
+// =============================================================================================
+// Same contract as row_grad_hess_kernel; the weighted Gram  H_i += sum_j ww_j b_j b_j^T  (2 s k^2 flop per row: 2.65e15 per
+// iteration at C4's full size, the wall of the sampled logit Newton step) runs as warp-level MMAs.  The sample sets differ from
+// row to row, so the operand is built per CTA: the tile of TJ gathered factor rows is scaled by sqrt(ww_j) and split ONCE into
+// tf32 hi / lo parts in shared memory (C = C_hi + C_lo); then H += C_hi^T C_hi + C_hi^T C_lo + C_lo^T C_hi (3xTF32: fp32
+// products) with mma.sync.m16n8k8 -- A and B fragments both come from the same two tiles, pitch = 8 (mod 32) words so that
+// the fragment loads are conflict-free.  Eight warps, each 1/4 of the rows x 1/2 of the columns of H in registers.
+// (Legacy warp-level path on purpose: 279 TFLOP/s TF32 measured on B200, scripts/hmma_rate.cu; tcgen05 wants its operands
+// behind shared-memory descriptors with a 128-row M, which a per-row gathered 32-sample tile does not fill.)
+__device__ __forceinline__ uint32_t to_tf32(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+constexpr int TJM = 32;    // sampled rows per tile of the tensor-core kernel (64 measured slower: 51 vs 31.5 ms on the C4 slice)
+
+template <int K>
+__global__ void __launch_bounds__(256)
+row_grad_hess_mma_kernel(int64_t rows, int64_t m, const float* __restrict__ A, const float* __restrict__ B,
+                         const float* __restrict__ Tgt, int64_t ldt, bool trans_t,
+                         const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx,
+                         const float* __restrict__ vals, int link, float w,
+                         const int32_t* __restrict__ idx, int64_t n_sample,
+                         float* __restrict__ g, float* __restrict__ H, bool accumulate,
+                         int64_t samples_per_split, int64_t g_split_stride, int64_t h_split_stride) {
+    constexpr int k = K;
+    constexpr int KP = K + 8;                 // = 8 (mod 32) words
+    constexpr int MT = K / 64;                // 16-row MMA tiles per warp (warp owns K / 4 rows)
+    constexpr int NT = K / 16;                // 8-column MMA tiles per warp (warp owns K / 2 columns)
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float* a_s = reinterpret_cast<float*>(smem_raw);     // K
+    float* B_s = a_s + K;                                 // TJM x KP  gathered rows (fp32)
+    uint32_t* Chi = reinterpret_cast<uint32_t*>(B_s + TJM * KP);   // TJM x KP  tf32(sqrt(ww) b)
+    uint32_t* Clo = Chi + TJM * KP;                        // TJM x KP  tf32(remainder)
+    float* r_s = reinterpret_cast<float*>(Clo + TJM * KP); // TJM   (w * residual)
+    float* w_s = r_s + TJM;                                // TJM   sqrt(w * f')
+    float* t_s = w_s + TJM;                                // TJM   targets of the staged samples
+    const int64_t i = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int gq = lane >> 2, tq = lane & 3;
+    const int m0 = (warp >> 1) * (K / 4), n0 = (warp & 1) * (K / 2);
+    const bool want_g = g != nullptr;
+
+    for (int c = tid; c < k; c += 256) a_s[c] = A[i * k + c];
+    float gacc = 0.f;
+    float acc[MT][NT][4];
+#pragma unroll
+    for (int x = 0; x < MT; x++)
+#pragma unroll
+        for (int y = 0; y < NT; y++)
+#pragma unroll
+            for (int z = 0; z < 4; z++) acc[x][y][z] = 0.f;
+
+    const int64_t total_all = idx != nullptr ? n_sample : m;
+    const int64_t t_first = int64_t(blockIdx.y) * samples_per_split;
+    const int64_t total = t_first + samples_per_split < total_all ? t_first + samples_per_split : total_all;
+    if (g != nullptr) g += int64_t(blockIdx.y) * g_split_stride;
+    H += int64_t(blockIdx.y) * h_split_stride;
+    int lo = 0, hi = 0;
+    if (rowptr != nullptr) { lo = rowptr[i]; hi = rowptr[i + 1]; }
+
+    for (int64_t t0 = t_first; t0 < total; t0 += TJM) {
+        const int64_t rem_t = total - t0;
+        const int cnt = rem_t < TJM ? int(rem_t) : TJM;
+        __syncthreads();
+        // stage the sampled rows of B (16-byte loads: 4 columns per thread and trip)
+        for (int e = tid; e < TJM * (K / 4); e += 256) {
+            const int jj = e / (K / 4), c4 = (e % (K / 4)) * 4;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (jj < cnt) {
+                const int64_t j = idx != nullptr ? int64_t(idx[i * n_sample + t0 + jj]) : t0 + jj;
+                if (j >= 0) v = *reinterpret_cast<const float4*>(B + j * k + c4);       // j < 0: sample on another shard
+            }
+            *reinterpret_cast<float4*>(B_s + jj * KP + c4) = v;
+        }
+        if (want_g && tid < TJM) {
+            float tg = 0.f;
+            if (tid < cnt) {
+                const int64_t j = idx != nullptr ? int64_t(idx[i * n_sample + t0 + tid]) : t0 + tid;
+                if (j >= 0) {
+                    if (Tgt != nullptr) {
+                        tg = trans_t ? Tgt[j * ldt + i] : Tgt[i * ldt + j];
+                    } else if (rowptr != nullptr) {
+                        int l = lo, h = hi;
+                        while (l < h) {
+                            const int mid = (l + h) >> 1;
+                            if (colidx[mid] < int(j)) l = mid + 1; else h = mid;
+                        }
+                        if (l < hi && colidx[l] == int(j)) tg = vals[l];
+                    }
+                }
+            }
+            t_s[tid] = tg;
+        }
+        __syncthreads();
+        // estimates: each warp takes TJM / 8 sampled rows
+        for (int jj = warp; jj < TJM; jj += 8) {
+            float d = 0.f;
+            for (int c = lane; c < k; c += 32) d = fmaf(a_s[c], B_s[jj * KP + c], d);
+            d = warp_sum(d);
+            if (lane == 0) {
+                float rr = 0.f, ww = 0.f;
+                int64_t j = -1;
+                if (jj < cnt) j = idx != nullptr ? int64_t(idx[i * n_sample + t0 + jj]) : t0 + jj;
+                if (j >= 0) {
+                    float est = d, fp = 1.f;
+                    if (link == PYCMF_LOGIT) { est = sigmoid_<float>(d); fp = est * (1.f - est); }
+                    const float tg = want_g ? t_s[jj] : 0.f;
+                    rr = w * (est - tg);
+                    ww = w * fp;
+                }
+                r_s[jj] = rr;
+                w_s[jj] = sqrtf(fmaxf(ww, 0.f));
+            }
+        }
+        __syncthreads();
+        if (want_g && tid < k) {
+#pragma unroll 8
+            for (int jj = 0; jj < TJM; jj++) gacc = fmaf(r_s[jj], B_s[jj * KP + tid], gacc);
+        }
+        // C = sqrt(ww) b, split into tf32 hi / lo once per element
+        for (int e = tid; e < TJM * K; e += 256) {
+            const int jj = e / K, c = e % K;
+            const float x = w_s[jj] * B_s[jj * KP + c];
+            const uint32_t h32 = to_tf32(x);
+            Chi[jj * KP + c] = h32;
+            Clo[jj * KP + c] = to_tf32(x - __uint_as_float(h32));
+        }
+        __syncthreads();
+        // H += C_hi^T C_hi + C_hi^T C_lo + C_lo^T C_hi   (contraction over the TJM samples, 8 per MMA)
+#pragma unroll
+        for (int kb = 0; kb < TJM; kb += 8) {
+            uint32_t ah[MT][4], al[MT][4];
+#pragma unroll
+            for (int x = 0; x < MT; x++) {
+                const int r0 = (kb + tq) * KP + m0 + x * 16 + gq, r1 = (kb + tq + 4) * KP + m0 + x * 16 + gq;
+                ah[x][0] = Chi[r0]; ah[x][1] = Chi[r0 + 8]; ah[x][2] = Chi[r1]; ah[x][3] = Chi[r1 + 8];
+                al[x][0] = Clo[r0]; al[x][1] = Clo[r0 + 8]; al[x][2] = Clo[r1]; al[x][3] = Clo[r1 + 8];
+            }
+#pragma unroll
+            for (int y = 0; y < NT; y++) {
+                const int c0 = (kb + tq) * KP + n0 + y * 8 + gq, c1 = (kb + tq + 4) * KP + n0 + y * 8 + gq;
+                const uint32_t bh0 = Chi[c0], bh1 = Chi[c1], bl0 = Clo[c0], bl1 = Clo[c1];
+#pragma unroll
+                for (int x = 0; x < MT; x++) {
+                    mma_tf32(acc[x][y], al[x], bh0, bh1);        // corrections first, the large term last
+                    mma_tf32(acc[x][y], ah[x], bl0, bl1);
+                    mma_tf32(acc[x][y], ah[x], bh0, bh1);
+                }
+            }
+        }
+    }
+    if (want_g && tid < k) {
+        const float prev = accumulate ? g[i * k + tid] : 0.f;
+        g[i * k + tid] = prev + gacc;
+    }
+    float* Hi = H + i * int64_t(k) * k;
+#pragma unroll
+    for (int x = 0; x < MT; x++)
+#pragma unroll
+        for (int y = 0; y < NT; y++) {
+            const int r = m0 + x * 16 + gq, c = n0 + y * 8 + 2 * tq;
+            float2* p0 = reinterpret_cast<float2*>(Hi + r * k + c);
+            float2* p1 = reinterpret_cast<float2*>(Hi + (r + 8) * k + c);
+            float2 v0 = make_float2(acc[x][y][0], acc[x][y][1]), v1 = make_float2(acc[x][y][2], acc[x][y][3]);
+            if (accumulate) { const float2 q0 = *p0, q1 = *p1; v0.x += q0.x; v0.y += q0.y; v1.x += q1.x; v1.y += q1.y; }
+            *p0 = v0;
+            *p1 = v1;
+        }
 }
 
 // =============================================================================================
@@ -686,6 +867,31 @@ void row_grad_hess(pycmf_ctx* ctx, int64_t rows, int64_t m, int64_t k, const T* 
         if (g) { g_out = reinterpret_cast<T*>(part); g_stride = rows * k; }
         if (H) { H_out = reinterpret_cast<T*>(part + gbytes); h_stride = rows * k * k; }
         acc_kernel = false;
+    }
+    if constexpr (std::is_same<T, float>::value) {
+        // tensor-core weighted Gram (mma.sync 3xTF32) for the wide factors of the sampled / logit Newton step
+        if (H != nullptr && (k == 64 || k == 128) && w >= 0.0 && ctx->hess_mma != 0 &&
+            (reinterpret_cast<uintptr_t>(B) & 15) == 0 && (reinterpret_cast<uintptr_t>(H_out) & 7) == 0) {
+            const size_t sm = sizeof(float) * (size_t(k) + size_t(3) * TJM * (k + 8) + 3 * TJM);
+            dim3 grid((unsigned)rows, (unsigned)nsplit);
+            Timed timer(ctx, "row_grad_hess");
+#define LAUNCHM(KK)                                                                                              \
+    do {                                                                                                         \
+        auto kern = row_grad_hess_mma_kernel<KK>;                                                                \
+        PYCMF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(sm)));            \
+        kern<<<grid, 256, sm, ctx->stream>>>(rows, m, A, B, Tgt, ldt, trans_t, rowptr, colidx, vals, link,       \
+                                             float(w), idx, n_sample, g_out, H_out, acc_kernel, per_split,        \
+                                             g_stride, h_stride);                                                \
+    } while (0)
+            if (k == 64) LAUNCHM(64); else LAUNCHM(128);
+#undef LAUNCHM
+            PYCMF_LAUNCH_CHECK(ctx);
+            if (nsplit > 1) {
+                if (g) reduce_parts<T>(ctx, rows, k, int(nsplit), g_out, g, k, T(1), accumulate ? T(1) : T(0));
+                reduce_parts<T>(ctx, rows, k * k, int(nsplit), H_out, H, k * k, T(1), accumulate ? T(1) : T(0));
+            }
+            return;
+        }
     }
     {
         Timed timer(ctx, "row_grad_hess");

@@ -576,3 +576,29 @@ def test_dmma_fused_residual_matches_numpy(be64, link, shape, trans):
     assert ran == 2, "the DMMA residual kernels did not run"
     assert rel_fro(be64.to_host(outL), wantL) < 1e-12 and rel_fro(be64.to_host(outR), wantR) < 1e-12
     assert abs(float(be64.to_host(sq)[0]) - (R * R).sum()) <= 1e-12 * (R * R).sum()
+
+
+@pytest.mark.parametrize("k", [64, 128])
+@pytest.mark.parametrize("link", ["logit", "linear"])
+@pytest.mark.parametrize("sparse", [False, True])
+def test_hessian_mma_matches_fma_and_oracle(k, link, sparse):
+    """Per-row weighted Grams on the tensor cores (row_grad_hess_mma_kernel, mma.sync 3xTF32) against the FMA kernel and
+    the float64 oracle: one sampled Newton update of the left factor (gradient + Hessian + clamped solve per row)."""
+    from pycmf_b200.device import CudaBackend
+    rng = np.random.RandomState(17)
+    rows, m, ns = 150, 700, 230
+    F0, B = 0.2 * rng.randn(rows, k), 0.3 * rng.randn(m, k)
+    T = O.expit(rng.randn(rows, m)) if link == "logit" else rng.randn(rows, m)
+    if sparse:
+        T = sp.csr_matrix(T * (rng.rand(rows, m) < 0.1))
+    idx = np.stack([rng.permutation(m)[:ns] for _ in range(rows)]).astype(np.int32)
+    ref = F0.copy()
+    O._rows_newton(ref, B, T, 0.6, 0.0, 0.1, link, False, 0.2, l2_in_logit_hessian=True, idx=idx)
+    outs = []
+    for mma in (1, 0):
+        be = CudaBackend(dtype="float32", options={"hess_mma": mma})
+        F = be.to_device(F0)
+        be.newton_left(F, be.to_device(B), be.ingest(T), 0.6, 0.0, 0.1, link, False, 0.2, True, idx=be.to_device(idx, np.int32))
+        outs.append(be.to_host(F))
+    assert rel_fro(outs[0], outs[1]) < 2e-5
+    assert rel_fro(outs[0], ref) < 1e-4 and rel_fro(outs[1], ref) < 1e-4
