@@ -1,4 +1,9 @@
-// Experiment harness (diagnostics, NOT product code) for the next round: the eigenvalue-clamped Newton solve
+// RUN IN ROUND 2 (profiles/r02_experiments_pair_lanczos.txt): correct to 4e-14, but SLOWER than the Jacobi kernel it was meant to
+// replace (4096 matrices of 128 x 128: 318 ms against 124 ms; the QL stage is a 16M-clock sequential chain per matrix).  Not
+// adopted: the product's clamped solve became tridiagonalisation + Sturm multi-section + inverse iteration instead
+// (pycmf_b200/csrc/tridiag_solve.cuh).  Kept as the record of the experiment.
+//
+// Experiment harness (diagnostics, NOT product code): the eigenvalue-clamped Newton solve
 //   x = S(H) g,  S(H) = Q diag(1 / max(|lambda|, p)) Q^T        (reference _safe_invert, cmf_solvers.py:346-356)
 // WITHOUT an eigendecomposition of H (NumPy prototype: scripts/lanczos_clamped_solve.py):
 //   stage 1  k Lanczos steps on (H, g) with full reorthogonalisation (classical Gram-Schmidt twice):  H Q = Q T,  Q^T g = |g| e_1
@@ -9,7 +14,7 @@
 // The numerical core (stage 2 and a sequential version of stage 1) is __host__ __device__ and is checked ON THE HOST by this
 // program against a plain Jacobi eigendecomposition -- that part runs without a GPU and passed when this file was written.
 // The CUDA kernel (one CTA per matrix for stage 1, thread 0 for stage 2 in this first version) was written when the round's GPU
-// budget was spent and HAS NOT RUN YET; with a GPU present the program compares it with the product's Jacobi solve
+// budget was spent; with a GPU present the program compares it with the product's Jacobi solve
 // (pycmf_safe_solve from pycmf_b200/libpycmf_b200.so, loaded with dlopen) and times both.
 //
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -o scripts/lanczos_solve.bin scripts/lanczos_solve.cu -ldl

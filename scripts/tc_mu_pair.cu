@@ -1,5 +1,7 @@
-// Experiment harness (diagnostics, NOT product code; NOT YET RUN ON HARDWARE -- written at the end of round 1 when the GPU
-// budget was spent): the MU tensor-core contraction of pycmf_b200/csrc/tc_mu.cu on CTA PAIRS (tcgen05 cta_group::2).
+// Experiment harness (diagnostics, NOT product code): the MU tensor-core contraction of pycmf_b200/csrc/tc_mu.cu on CTA PAIRS
+// (tcgen05 cta_group::2).  RUN IN ROUND 2 (profiles/r02_experiments_pair_lanczos.txt): correct (7e-6 against float64) but
+// SLOWER than the shipping kernel -- 147 / 153 TFLOP/s fp32-equivalent against 197 on the same 20000 x 50000, k = 256 slice.
+// Not adopted; kept as the record of the experiment.
 //
 // Why: the round-1 trace (profiles/r01_tc_mu_trace.txt) shows tc_mu_kernel at k = 256 sitting on the per-SM L2 -> SM ingest
 // rate: every 128 x 32 tile of X (16 KB) needs the whole K-major Q^T tile (k x 32, tf32 hi + lo = 64 KB).  With
