@@ -1,5 +1,5 @@
 #!/bin/bash
-OUT=gpurun_out/r2x
+OUT=gpurun_out/r2y
 mkdir -p $OUT
 N=${1:-8}
 ( time timeout 1200 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --steps 20 --warmup 5 > $OUT/bench_n$N.json 2> $OUT/bench_n$N.err ) 2> $OUT/bench_n$N.time; echo "bench rc=$?"

@@ -173,3 +173,70 @@ def test_topic_terms_format(capsys):
     _print_topic_terms_with_importances_from_matrices(U, Z, np.array(["a", "b", "c"]), topn_words=2)
     out = capsys.readouterr().out.strip().splitlines()
     assert out == ["Topic 1 [0.500]: c,b", "Topic 2 [0.250]: b,a"]
+
+
+_RNG_WORKER = r'''
+import os, sys
+sys.path.insert(0, sys.argv[1]); sys.path.insert(0, os.path.join(sys.argv[1], "tests"))
+import numpy as np, torch, torch.distributed as dist
+from fake_backend import FakeBackend
+from pycmf_b200.cmf_solvers import NewtonSolver, FitState
+from pycmf_b200.sharding import TorchComm
+rank = int(sys.argv[3])
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%s" % sys.argv[2], rank=rank, world_size=2)
+np.random.seed(1000 + rank)                       # the ranks' global NumPy streams start DIFFERENT (random_state=None)
+be, comm = FakeBackend(), TorchComm()
+n, d, l, k = 12, 9, 4, 3
+st = FitState(be, comm, None, None, torch.zeros(n // 2, k, dtype=torch.float64), torch.zeros(d, k, dtype=torch.float64),
+              torch.zeros(l, k, dtype=torch.float64), n, (rank * n // 2, (rank + 1) * n // 2))
+s = NewtonSolver(sg_sample_ratio=0.5, random_state=None, sampler="numpy", backend=be, comm=comm)
+st.iteration = 1
+m = s._masks(st)
+# replicated masks (Z, Vy) must be identical on both ranks; Vx is localised to the rank's rows (-1 elsewhere)
+for key in ("Z", "Vy"):
+    mine = m[key].to(torch.float64).clone(); other = mine.clone()
+    dist.broadcast(other, src=0)
+    assert torch.equal(mine, other), key
+full = torch.where(m["Vx"] >= 0, m["Vx"] + st.r0, torch.zeros_like(m["Vx"])).to(torch.float64)
+dist.all_reduce(full)
+assert int((m["Vx"] >= 0).sum()) > 0 and float(full.max()) < n
+dist.destroy_process_group()
+print("OK")
+'''
+
+
+def test_numpy_sampler_is_synchronised_across_ranks_without_an_integer_seed(tmp_path):
+    """ADVICE r1: with random_state=None every rank owns a different global NumPy stream; the solver re-seeds all ranks from
+    rank 0 before the first draw, otherwise the replicated V / Z masks silently diverge."""
+    script = tmp_path / "rng_worker.py"
+    script.write_text(_RNG_WORKER)
+    port = str(31500 + os.getpid() % 2000)
+    procs = [subprocess.Popen([sys.executable, str(script), ROOT, port, str(r)],
+                              stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True) for r in range(2)]
+    outs = [p.communicate(timeout=300)[0] for p in procs]
+    for p, o in zip(procs, outs):
+        assert p.returncode == 0 and "OK" in o, o[-3000:]
+
+
+def test_bench_config_and_algorithmic_work_follow_the_survey():
+    """bench.py's `config` object is built by ONE function for both arms, and the step-level roofline uses SURVEY 8d's figures."""
+    from pycmf_b200 import workloads as W
+    c5 = W.describe("c5")
+    fl, by = W.algorithmic_work(c5, 4)
+    assert abs(fl - 1.036e13) / 1.036e13 < 5e-3 and abs(by - 8.12e10) / 8.12e10 < 5e-3        # SURVEY 8d
+    c3 = W.describe("c3")
+    fl3, by3 = W.algorithmic_work(c3, 4)
+    assert abs(fl3 - 8.7e10) / 8.7e10 < 0.03 and abs(by3 - 5.06e9) / 5.06e9 < 0.03
+    shard = W.describe("c3", 0.125)
+    assert (shard["n"], shard["d"]) == (250000, 200000)            # a row shard keeps every column
+    cfg = W.bench_config("c5", 1.0, 1.0, 8)
+    assert cfg["workload"].startswith("c5: dense X 200000x50000") and "larger than L2" in cfg["l2_policy"]
+    assert "L2-resident" in W.bench_config("c1", 1.0, 1.0, 1)["l2_policy"]
+    assert W.bench_config("c2", 1.0, 1.0, 1)["deviation_from_SURVEY_8d"]
+
+
+def test_n_components_above_the_backend_limit_is_rejected_before_any_device_work():
+    from pycmf_b200.cmf_solvers import MUSolver
+    s = MUSolver(max_iter=1)
+    with pytest.raises(ValueError, match="n_components"):
+        s.prepare(np.ones((4, 300)), np.ones((300, 2)), np.ones((4, 300)), np.ones((300, 300)), np.ones((2, 300)))
