@@ -188,6 +188,7 @@ __device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], 
                  : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
+constexpr int RCM = 1024;  // CSR nonzeros of the row kept in shared memory for the target lookups
 constexpr int TJM = 32;    // sampled rows per tile of the tensor-core kernel (64 measured slower: 51 vs 31.5 ms on the C4 slice)
 
 template <int K>
@@ -211,6 +212,9 @@ row_grad_hess_mma_kernel(int64_t rows, int64_t m, const float* __restrict__ A, c
     float* r_s = reinterpret_cast<float*>(Clo + TJM * KP); // TJM   (w * residual)
     float* w_s = r_s + TJM;                                // TJM   sqrt(w * f')
     float* t_s = w_s + TJM;                                // TJM   targets of the staged samples
+    int* idx_s = reinterpret_cast<int*>(t_s + TJM);        // TJM   sample indices of the tile (-1 = none / other shard)
+    int* rc_col = idx_s + TJM;                             // RCM   this row's CSR column indices ...
+    float* rc_val = reinterpret_cast<float*>(rc_col + RCM);// RCM   ... and values (target lookups stay on chip)
     const int64_t i = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int gq = lane >> 2, tq = lane & 3;
@@ -234,39 +238,54 @@ row_grad_hess_mma_kernel(int64_t rows, int64_t m, const float* __restrict__ A, c
     H += int64_t(blockIdx.y) * h_split_stride;
     int lo = 0, hi = 0;
     if (rowptr != nullptr) { lo = rowptr[i]; hi = rowptr[i + 1]; }
+    // the row's nonzeros on chip (when they fit): every tile looks its 32 targets up by binary search, and seven dependent
+    // global loads per lookup were a third of a tile's latency chain
+    const bool row_cached = want_g && rowptr != nullptr && hi - lo <= RCM;
+    if (row_cached)
+        for (int e = tid; e < hi - lo; e += 256) { rc_col[e] = colidx[lo + e]; rc_val[e] = vals[lo + e]; }
 
     for (int64_t t0 = t_first; t0 < total; t0 += TJM) {
         const int64_t rem_t = total - t0;
         const int cnt = rem_t < TJM ? int(rem_t) : TJM;
         __syncthreads();
-        // stage the sampled rows of B (16-byte loads: 4 columns per thread and trip)
-        for (int e = tid; e < TJM * (K / 4); e += 256) {
-            const int jj = e / (K / 4), c4 = (e % (K / 4)) * 4;
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (jj < cnt) {
-                const int64_t j = idx != nullptr ? int64_t(idx[i * n_sample + t0 + jj]) : t0 + jj;
-                if (j >= 0) v = *reinterpret_cast<const float4*>(B + j * k + c4);       // j < 0: sample on another shard
-            }
-            *reinterpret_cast<float4*>(B_s + jj * KP + c4) = v;
-        }
-        if (want_g && tid < TJM) {
-            float tg = 0.f;
-            if (tid < cnt) {
-                const int64_t j = idx != nullptr ? int64_t(idx[i * n_sample + t0 + tid]) : t0 + tid;
+        // the tile's sample indices, read from global memory ONCE (they used to be re-read by the staging loop, the target
+        // lookup and lane 0 of every estimate: three dependent round trips per tile), and the targets of the samples
+        if (tid < TJM) {
+            int j = -1;
+            if (tid < cnt) j = idx != nullptr ? idx[i * n_sample + t0 + tid] : int(t0 + tid);
+            idx_s[tid] = j;
+            if (want_g) {
+                float tg = 0.f;
                 if (j >= 0) {
                     if (Tgt != nullptr) {
-                        tg = trans_t ? Tgt[j * ldt + i] : Tgt[i * ldt + j];
+                        tg = trans_t ? Tgt[int64_t(j) * ldt + i] : Tgt[i * ldt + j];
+                    } else if (row_cached) {
+                        int l = 0, h = hi - lo;
+                        while (l < h) {
+                            const int mid = (l + h) >> 1;
+                            if (rc_col[mid] < j) l = mid + 1; else h = mid;
+                        }
+                        if (l < hi - lo && rc_col[l] == j) tg = rc_val[l];
                     } else if (rowptr != nullptr) {
                         int l = lo, h = hi;
                         while (l < h) {
                             const int mid = (l + h) >> 1;
-                            if (colidx[mid] < int(j)) l = mid + 1; else h = mid;
+                            if (colidx[mid] < j) l = mid + 1; else h = mid;
                         }
-                        if (l < hi && colidx[l] == int(j)) tg = vals[l];
+                        if (l < hi && colidx[l] == j) tg = vals[l];
                     }
                 }
+                t_s[tid] = tg;
             }
-            t_s[tid] = tg;
+        }
+        __syncthreads();
+        // stage the sampled rows of B (16-byte loads: 4 columns per thread and trip)
+        for (int e = tid; e < TJM * (K / 4); e += 256) {
+            const int jj = e / (K / 4), c4 = (e % (K / 4)) * 4;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            const int j = idx_s[jj];
+            if (j >= 0) v = *reinterpret_cast<const float4*>(B + int64_t(j) * k + c4);   // j < 0: none / sample on another shard
+            *reinterpret_cast<float4*>(B_s + jj * KP + c4) = v;
         }
         __syncthreads();
         // estimates: each warp takes TJM / 8 sampled rows
@@ -276,9 +295,7 @@ row_grad_hess_mma_kernel(int64_t rows, int64_t m, const float* __restrict__ A, c
             d = warp_sum(d);
             if (lane == 0) {
                 float rr = 0.f, ww = 0.f;
-                int64_t j = -1;
-                if (jj < cnt) j = idx != nullptr ? int64_t(idx[i * n_sample + t0 + jj]) : t0 + jj;
-                if (j >= 0) {
+                if (idx_s[jj] >= 0) {
                     float est = d, fp = 1.f;
                     if (link == PYCMF_LOGIT) { est = sigmoid_<float>(d); fp = est * (1.f - est); }
                     const float tg = want_g ? t_s[jj] : 0.f;
@@ -872,7 +889,7 @@ void row_grad_hess(pycmf_ctx* ctx, int64_t rows, int64_t m, int64_t k, const T* 
         // tensor-core weighted Gram (mma.sync 3xTF32) for the wide factors of the sampled / logit Newton step
         if (H != nullptr && (k == 64 || k == 128) && w >= 0.0 && ctx->hess_mma != 0 &&
             (reinterpret_cast<uintptr_t>(B) & 15) == 0 && (reinterpret_cast<uintptr_t>(H_out) & 7) == 0) {
-            const size_t sm = sizeof(float) * (size_t(k) + size_t(3) * TJM * (k + 8) + 3 * TJM);
+            const size_t sm = sizeof(float) * (size_t(k) + size_t(3) * TJM * (k + 8) + 4 * TJM + 2 * RCM);
             dim3 grid((unsigned)rows, (unsigned)nsplit);
             Timed timer(ctx, "row_grad_hess");
 #define LAUNCHM(KK)                                                                                              \
