@@ -53,8 +53,9 @@ struct pycmf_ctx {
                                 // spills: 86 us on C2; 3: 168 registers: 91 us; 4: 128 registers, spills: 187 us)
     int spmm_path = 1;       // option: 0 = generic SpMM kernel only (tests), 1 = vector kernels for k = 32 / 64 / 128 / 256, 2 = without the sub-warp grouping
     int spmm_blocks_per_sm = 0;  // option: resident 256-thread CTAs per SM of the nonzero-balanced SpMM (0 = default 4)
-    int solve_path = 1;      // option: clamped solve with active clamp, k > 32: 1 = tridiagonalisation + bisection + inverse iteration
-                             // (tridiag_solve.cuh), 0 = one-sided Jacobi only
+    int solve_path = 2;      // option: clamped solve with active clamp, k > 32: 1 = tridiagonalisation + bisection + inverse iteration
+                             // (tridiag_solve.cuh), 2 = the same with the Householder steps on a register-resident matrix
+                             // for k = 64 / 128, 0 = one-sided Jacobi only
     int solve_threads = 0;   // option (tuning): CTA size of the tridiagonal clamped solve (0 = by k; must be >= k, multiple of 32)
     int hess_mma = 1;        // option: 0 = per-row Hessian builds on the FMA pipes only (tests), 1 = mma.sync 3xTF32 for k = 64 / 128
     int mu_fused = 1;        // option: 0 = separate F G GEMM + elementwise ratio launches (tests)

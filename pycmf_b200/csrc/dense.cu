@@ -372,6 +372,14 @@ template <typename T> __device__ __forceinline__ Vec4<T> ld4s(const T* p) {     
     load4<T>(p, o.v);
     return o;
 }
+template <typename T> __device__ __forceinline__ void st4s(T* p, const Vec4<T>& v);
+template <> __device__ __forceinline__ void st4s<float>(float* p, const Vec4<float>& v) {
+    *reinterpret_cast<float4*>(p) = make_float4(v.v[0], v.v[1], v.v[2], v.v[3]);
+}
+template <> __device__ __forceinline__ void st4s<double>(double* p, const Vec4<double>& v) {
+    *reinterpret_cast<double2*>(p) = make_double2(v.v[0], v.v[1]);
+    *reinterpret_cast<double2*>(p + 2) = make_double2(v.v[2], v.v[3]);
+}
 
 // VEC4: k % 4 == 0 -- a thread owns a 4 x 4 block of F G (4 rows, 4 columns) and walks the contraction four steps at a
 // time with 128-bit shared-memory reads of both operands (16 FMAs per 2 loads); otherwise the scalar form (k = 10 on C1).
@@ -392,14 +400,34 @@ mu_fused_kernel(int64_t rows, int k_rt, T* __restrict__ F, const T* __restrict__
     for (int64_t r0 = int64_t(blockIdx.x) * MUF_ROWS; r0 < rows; r0 += int64_t(gridDim.x) * MUF_ROWS) {
         __syncthreads();
         const int nr = int(min(int64_t(MUF_ROWS), rows - r0));
-        for (int e = threadIdx.x; e < MUF_ROWS * k; e += blockDim.x) {
-            const int r = e / k, c = e % k;
-            Fs[r * ldf + c] = r < nr ? F[(r0 + r) * k + c] : T(0);
+        if (VEC4) {                                          // 16-byte (float) / 2 x 16-byte (double) loads and stores
+            for (int e = threadIdx.x; e < MUF_ROWS * cgroups; e += blockDim.x) {
+                const int r = e / cgroups, c = (e % cgroups) * 4;
+                Vec4<T> f;
+#pragma unroll
+                for (int w = 0; w < 4; w++) f.v[w] = T(0);
+                if (r < nr) f = ld4s<T>(F + (r0 + r) * k + c);
+                st4s<T>(Fs + r * ldf + c, f);
+            }
+        } else {
+            for (int e = threadIdx.x; e < MUF_ROWS * k; e += blockDim.x) {
+                const int r = e / k, c = e % k;
+                Fs[r * ldf + c] = r < nr ? F[(r0 + r) * k + c] : T(0);
+            }
         }
         __syncthreads();
         if (VEC4) {
             for (int item = threadIdx.x; item < (MUF_ROWS / 4) * cgroups; item += blockDim.x) {
                 const int rg = item / cgroups, c0 = (item % cgroups) * 4;
+                // the numerator entries of this 4 x 4 block are requested before the contraction: their HBM latency
+                // hides behind the k FMAs per entry instead of following them
+                Vec4<T> nv[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+#pragma unroll
+                    for (int w = 0; w < 4; w++) nv[u].v[w] = T(0);
+                    if (rg * 4 + u < nr) nv[u] = ld4s<T>(N + (r0 + rg * 4 + u) * k + c0);
+                }
                 T d[4][4];
 #pragma unroll
                 for (int u = 0; u < 4; u++)
@@ -423,16 +451,17 @@ mu_fused_kernel(int64_t rows, int k_rt, T* __restrict__ F, const T* __restrict__
                 for (int u = 0; u < 4; u++) {
                     const int r = rg * 4 + u;
                     if (r >= nr) break;
+                    const Vec4<T> fv = ld4s<T>(f0 + u * ldf + c0);
+                    Vec4<T> o;
 #pragma unroll
                     for (int w = 0; w < 4; w++) {
-                        const int c = c0 + w;
-                        const T fv = f0[u * ldf + c];
                         T dd = d[u][w];
                         if (l1 > T(0)) dd += l1;
-                        if (l2 > T(0)) dd = dd + l2 * fv;
+                        if (l2 > T(0)) dd = dd + l2 * fv.v[w];
                         if (dd == T(0)) dd = eps;
-                        F[(r0 + r) * k + c] = fv * (N[(r0 + r) * k + c] / dd);
+                        o.v[w] = fv.v[w] * (nv[u].v[w] / dd);
                     }
+                    st4s<T>(F + (r0 + r) * k + c0, o);
                 }
             }
         } else {

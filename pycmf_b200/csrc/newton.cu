@@ -608,7 +608,7 @@ __device__ void jacobi_clamped_solve(double* W, int k, const double* g, double* 
 }
 
 // The whole clamped solve for one matrix; H is (re)loaded from global memory as needed.
-template <typename T>
+template <typename T, int KR = 0>
 __device__ void safe_solve_one(double* W, const T* __restrict__ H, int k, double diag, const double* g,
                                double* x, double* xpart, SolveShared* sh, double pert, bool chol_fastpath,
                                double scale, const double* __restrict__ base = nullptr, double* tri_work = nullptr,
@@ -660,7 +660,7 @@ __device__ void safe_solve_one(double* W, const T* __restrict__ H, int k, double
         // clamp active on part of the spectrum: only the eigenpairs above the clamp level are needed (tridiag_solve.cuh);
         // one-sided Jacobi is the fallback
         if (tri_work != nullptr) {
-            if (tri::clamped_solve(W, k, g, x, tri_work, tri_scratch, pert)) return;
+            if (tri::clamped_solve<KR>(W, k, g, x, tri_work, tri_scratch, pert)) return;
             load_sym<T>(W, H, k, diag, scale, base);
             __syncthreads();
         }
@@ -671,8 +671,9 @@ __device__ void safe_solve_one(double* W, const T* __restrict__ H, int k, double
 }
 
 // MODE 0: x_b = S(H_b) g_b (all float64).  MODE 1: Newton row update on F.
-template <typename T, int MODE>
-__global__ void __launch_bounds__(1024)
+// KR > 0: k == KR, blockDim.x == 2 KR, the tridiagonalisation keeps the matrix in registers (tridiag_solve.cuh, tridiag_reg).
+template <typename T, int MODE, int KR = 0>
+__global__ void __launch_bounds__(KR > 0 ? 2 * KR : 1024)
 safe_solve_kernel(int64_t batch, int k, const T* __restrict__ H, int64_t h_stride, const T* __restrict__ g,
                   T* __restrict__ out, double l1, double l2, double l2_diag, double pert, bool non_negative,
                   bool chol_fastpath, double* __restrict__ Wglobal, double h_scale,
@@ -699,7 +700,7 @@ safe_solve_kernel(int64_t batch, int k, const T* __restrict__ H, int64_t h_strid
             gv[r] = gr;
         }
         __syncthreads();
-        safe_solve_one<T>(W, H + b * h_stride, k, l2_diag, gv, xv, xpart, sh, pert, chol_fastpath, h_scale, Hbase, tri_work,
+        safe_solve_one<T, KR>(W, H + b * h_stride, k, l2_diag, gv, xv, xpart, sh, pert, chol_fastpath, h_scale, Hbase, tri_work,
                           tri_zg);
         __syncthreads();
         for (int r = threadIdx.x; r < k; r += blockDim.x) {
@@ -823,6 +824,11 @@ void launch_solve(pycmf_ctx* ctx, int64_t batch, int64_t k, const T* H, int64_t 
     bool w_in_smem = solve_smem_bytes(int(k), nthreads, true, tri_path) <= size_t(ctx->max_smem_optin);
     size_t smem = solve_smem_bytes(int(k), nthreads, w_in_smem, tri_path);
     auto kern = safe_solve_kernel<T, MODE>;
+    // solve_path 2: Householder steps on a register-resident matrix (k = 64 / 128 with the matrix in shared memory and 2 k threads)
+    if (tri_path && ctx->solve_path >= 2 && w_in_smem && nthreads == 2 * k) {
+        if (k == 64) kern = safe_solve_kernel<T, MODE, 64>;
+        else if (k == 128) kern = safe_solve_kernel<T, MODE, 128>;
+    }
     PYCMF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
     int64_t grid = batch;
     double* Wg = nullptr;

@@ -61,6 +61,138 @@ __device__ __forceinline__ int sturm_count(const double* __restrict__ ds, const 
 __host__ __device__ constexpr size_t work_doubles(int k) { return size_t(16) * k + 72 + 256; }
 __host__ __device__ constexpr size_t scratch_doubles(int k) { return size_t(6) * k * k; }
 
+
+// shared-memory store of v when x == y.  Inline PTX on purpose: written as `if (u == sel) val = a[u]` over the unrolled
+// register array, the compiler turns the select chain into an indexed load and moves the whole array to local memory.
+__device__ __forceinline__ void st_shared_if_eq(uint32_t saddr, int x, int y, double v) {
+    asm volatile("{\n .reg .pred p;\n setp.eq.s32 p, %1, %2;\n @p st.shared.f64 [%0], %3;\n}"
+                 :: "r"(saddr), "r"(x), "r"(y), "d"(v) : "memory");
+}
+
+// ---- 1'. tridiagonalisation with the trailing matrix in REGISTERS (k = KR = 64 / 128, blockDim.x = 2 KR) --------------------
+// The shared-memory form above is latency-bound: 8 warps walk dependent shared-memory loads and ~10 barriers per Householder
+// step (ncu: 57 % of the kernel's samples, issue slots 22 % busy).  Here the symmetric matrix lives in registers, column-owned:
+// the lane pair (2c, 2c + 1) holds column c, lane h = tid & 1 its rows r = 2 i + h as a[i] (KR / 2 doubles per thread, every
+// index a compile-time constant).  Per step: row j (published to shared memory by the previous step's update) gives the
+// reflector; p = S v is KR / 2 register FMAs per thread against broadcast reads of v, the pair combines by one shuffle;
+// S -= v q^T + q v^T is two FMAs per element against broadcast reads of v and q.  Four barriers per step, no traffic on the
+// matrix.  Blocks of 8 register elements whose rows are all <= j and warps whose columns are all <= j are skipped (uniform
+// branches).  Same arithmetic as the loop above (reflectors in the rows of W they annihilate, y = P^T g on the fly).
+// buf: 3 KR + 8 doubles of shared memory, 16-byte aligned.  red: 64 doubles.
+template <int KR>
+__device__ __forceinline__ void tridiag_reg(double* __restrict__ W, double* __restrict__ d, double* __restrict__ e,
+                                            double* __restrict__ beta, double* __restrict__ y, double* __restrict__ buf,
+                                            double* __restrict__ red) {
+    constexpr int k = KR, HN = KR / 2, VP = HN + 2, NB = HN / 8, NW = KR / 16;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int c = tid >> 1, h = tid & 1;
+    double* colbuf = buf;                 // KR      row j of the current matrix
+    double* vd = buf + KR;                // 2 x VP  reflector, de-interleaved: v[r] at vd[(r & 1) * VP + (r >> 1)]
+    double* qd = vd + 2 * VP;             // 2 x VP  q, same layout
+    const uint32_t col_c = uint32_t(__cvta_generic_to_shared(colbuf + c));
+    double a[HN];
+#pragma unroll
+    for (int i = 0; i < HN; i++) a[i] = W[(2 * i + h) * k + c];
+    if (h == 0) colbuf[c] = a[0];
+    // The step loop is unrolled over blocks of 16 steps (jb) so that every register index below is a compile-time constant:
+    // during steps 16 jb .. 16 jb + 15 the register blocks b < jb are dead, and the row to publish sits in block jb (or is
+    // element 0 of block jb + 1).
+#pragma unroll
+    for (int jb = 0; jb < NB; jb++) {
+        const int jend = jb == NB - 1 ? 14 : 16;                           // steps j = 0 .. k - 3
+        for (int jj = 0; jj < jend; jj++) {
+            const int j = 16 * jb + jj;
+            __syncthreads();                                               // (A) colbuf = row j
+            double s = 0.0;
+#pragma unroll
+            for (int u = 0; u < KR / 32; u++) {
+                const int r = lane + 32 * u;
+                const double x = colbuf[r];
+                s = r > j ? fma(x, x, s) : s;
+            }
+            s = warp_sum(s);                                               // same operations in every warp: uniform value
+            const double x0 = colbuf[j + 1], dj = colbuf[j];
+            const double tail2 = s - x0 * x0;
+            const int selx = h == ((j + 1) & 1) ? (j + 1) >> 1 : -1;       // row j + 1 is a[(j + 1) / 2] of the lanes h == (j + 1) % 2
+            if (!(tail2 > 0.0)) {                                          // nothing to annihilate (uniform decision)
+                if (tid == 0) { d[j] = dj; e[j + 1] = x0; beta[j] = 0.0; }
+                __syncthreads();                                           // everyone is done with colbuf
+#pragma unroll
+                for (int u = 0; u < 8; u++) st_shared_if_eq(col_c, selx, 8 * jb + u, a[8 * jb + u]);
+                if (jb + 1 < NB) st_shared_if_eq(col_c, selx, 8 * (jb + 1), a[jb + 1 < NB ? 8 * (jb + 1) : 0]);
+                continue;
+            }
+            const double alpha = x0 >= 0.0 ? -sqrt(s) : sqrt(s);
+            const double v0 = x0 - alpha;
+            const double bq = 2.0 / (tail2 + v0 * v0);
+            if (tid < k) {
+                const int r = tid;
+                const double vr = r <= j ? 0.0 : (r == j + 1 ? v0 : colbuf[r]);
+                vd[(r & 1) * VP + (r >> 1)] = vr;
+                if (r > j) W[j * k + r] = vr;                              // the reflector lives in the row it annihilated
+            }
+            if (tid == 0) { d[j] = dj; e[j + 1] = alpha; beta[j] = bq; }
+            __syncthreads();                                               // (B) v
+            const bool live = 16 * warp + 15 > j;                          // this warp still owns a column of the trailing block
+            double p0 = 0.0, p1 = 0.0, p2 = 0.0, p3 = 0.0;
+            if (live) {
+#pragma unroll
+                for (int b = jb; b < NB; b++) {                            // rows <= j inside block jb meet v = 0
+                    const double2* vv = reinterpret_cast<const double2*>(vd + h * VP + 8 * b);
+                    const double2 v01 = vv[0], v23 = vv[1], v45 = vv[2], v67 = vv[3];
+                    p0 = fma(a[8 * b + 0], v01.x, p0); p1 = fma(a[8 * b + 1], v01.y, p1);
+                    p2 = fma(a[8 * b + 2], v23.x, p2); p3 = fma(a[8 * b + 3], v23.y, p3);
+                    p0 = fma(a[8 * b + 4], v45.x, p0); p1 = fma(a[8 * b + 5], v45.y, p1);
+                    p2 = fma(a[8 * b + 6], v67.x, p2); p3 = fma(a[8 * b + 7], v67.y, p3);
+                }
+            }
+            double pc = (p0 + p1) + (p2 + p3);
+            pc += __shfl_xor_sync(0xffffffffu, pc, 1);                     // both lanes of the pair: p_c = (S v)_c
+            const double vc = vd[(c & 1) * VP + (c >> 1)];                 // 0 for c <= j
+            double qc = c > j ? bq * pc : 0.0;
+            double vp = h == 0 ? vc * qc : 0.0;
+            double vy = h == 0 ? vc * y[c] : 0.0;
+            vp = warp_sum(vp);
+            vy = warp_sum(vy);
+            if (lane == 0) { red[warp] = vp; red[32 + warp] = vy; }
+            __syncthreads();                                               // (C) partial sums
+            double svp = 0.0, svy = 0.0;
+#pragma unroll
+            for (int w = 0; w < NW; w++) { svp += red[w]; svy += red[32 + w]; }
+            const double Kc = 0.5 * bq * svp;
+            qc -= Kc * vc;
+            if (h == 0) {
+                qd[(c & 1) * VP + (c >> 1)] = qc;
+                y[c] -= bq * svy * vc;                                     // y <- H_j y
+            }
+            __syncthreads();                                               // (D) q
+            if (live) {
+                // S -= v q^T + q v^T on the elements this thread owns
+#pragma unroll
+                for (int b = jb; b < NB; b++) {
+                    const double2* vv = reinterpret_cast<const double2*>(vd + h * VP + 8 * b);
+                    const double2* qq = reinterpret_cast<const double2*>(qd + h * VP + 8 * b);
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {
+                        const double2 v2 = vv[u], q2 = qq[u];
+                        a[8 * b + 2 * u] = fma(-q2.x, vc, fma(-v2.x, qc, a[8 * b + 2 * u]));
+                        a[8 * b + 2 * u + 1] = fma(-q2.y, vc, fma(-v2.y, qc, a[8 * b + 2 * u + 1]));
+                    }
+                }
+                // publish row j + 1 of the updated matrix for the next step
+#pragma unroll
+                for (int u = 0; u < 8; u++) st_shared_if_eq(col_c, selx, 8 * jb + u, a[8 * jb + u]);
+                if (jb + 1 < NB) st_shared_if_eq(col_c, selx, 8 * (jb + 1), a[jb + 1 < NB ? 8 * (jb + 1) : 0]);
+            }
+        }
+    }
+    __syncthreads();
+    W[(k - 2 + h) * k + c] = a[HN - 1];                                    // rows k - 2, k - 1: the last 2 x 2 block
+    __syncthreads();
+}
+
+// KR > 0: k == KR and blockDim.x == 2 KR, tridiagonalisation in registers (tridiag_reg)
+template <int KR = 0>
 __device__ bool clamped_solve(double* __restrict__ W, int k, const double* __restrict__ g, double* __restrict__ x,
                               double* __restrict__ work, double* __restrict__ zg, double pert) {
     const int tid = threadIdx.x, NT = blockDim.x;
@@ -87,6 +219,9 @@ __device__ bool clamped_solve(double* __restrict__ W, int k, const double* __res
     __syncthreads();
 
     // ---- 1. tridiagonalisation ----------------------------------------------------------------------------------------
+    if constexpr (KR > 0) {
+        tridiag_reg<KR>(W, d, e, beta, y, pp, red);
+    } else
     for (int j = 0; j < k - 2; j++) {
         const int m = k - j - 1;
         double* xr = W + size_t(j) * k + j + 1;              // row j right of the diagonal (= column j below it)

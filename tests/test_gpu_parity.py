@@ -177,11 +177,12 @@ def test_spmm_and_transpose(be64, k):
 
 
 @pytest.mark.parametrize("k", [1, 2, 7, 32, 33, 64, 128, 150])
-@pytest.mark.parametrize("chol,path", [(0, 1), (1, 1), (0, 0), (1, 0)])
+@pytest.mark.parametrize("chol,path", [(0, 2), (1, 2), (0, 1), (1, 1), (0, 0), (1, 0)])
 def test_safe_solve_matches_eigh_clamp(k, chol, path):
     """x = S(H) g against eigh: Cholesky fast path, Frobenius shortcut, and the clamp-active solvers (path 1 = tridiagonalisation
-    + bisection + inverse iteration, path 0 = one-sided Jacobi) on rank-deficient, indefinite, multiple-eigenvalue, clustered and
-    clamp-level spectra."""
+    + bisection + inverse iteration, path 2 = the same with the Householder steps on a register-resident matrix for k = 64 / 128
+    (the default), path 0 = one-sided Jacobi) on rank-deficient, indefinite, multiple-eigenvalue, clustered and clamp-level
+    spectra."""
     from pycmf_b200.device import CudaBackend
     be = CudaBackend(dtype="float64", options={"chol_fastpath": chol, "solve_path": path})
     rng = np.random.RandomState(k)
@@ -528,7 +529,7 @@ def test_dense_ingest_pads_the_row_pitch_to_128_bytes():
 
 
 @pytest.mark.parametrize("dtype,tol", [("float64", 1e-12), ("float32", 2e-6)])
-@pytest.mark.parametrize("shape", [(1000, 64), (77, 10), (300, 128), (5000, 33)])
+@pytest.mark.parametrize("shape", [(1000, 64), (77, 10), (300, 128), (5000, 33), (131, 20), (257, 32)])
 def test_mu_fused_update_matches_the_unfused_path(dtype, tol, shape):
     """F <- F * N / (F G + l1 + l2 F) with the denominator product inside the kernel (mu_fused_kernel) against the
     separate GEMM + elementwise launches, through the MU left update (zero denominators included)."""
