@@ -8,7 +8,8 @@
 //   2. Sturm counts at -p and +p give the indices of the eigenvalues that matter; each gets its own thread and is bisected
 //      (three-term recurrence of the leading principal minors with rescaling: 2 dependent FMAs per element, no division).
 //   3. One thread per wanted eigenvector: inverse iteration with a pivoted LU of the shifted tridiagonal (EISPACK tinvit /
-//      LAPACK dstein scheme), three solves, vectors in an L2-resident scratch laid out [element][vector].
+//      LAPACK dstein scheme), three solves, vectors and LU factors in a per-CTA global scratch laid out [vector][element]
+//      (each thread streams its own rows through L1).
 //   4. Vectors whose eigenvalues are closer than 1e-5 ||T|| are orthonormalised (modified Gram-Schmidt, CTA-wide dots): a
 //      multiple eigenvalue needs an orthonormal basis of its eigenspace, nothing more.
 //   5. z = y / p + sum coef_i z_i, x = P z (reflectors applied in reverse).
@@ -57,10 +58,16 @@ __device__ __forceinline__ int sturm_count(const double* __restrict__ ds, const 
     return cnt;
 }
 
-// work (shared memory, doubles): 16 k + 328.  zg (global, doubles): 6 k^2 for this CTA.
+// work (shared memory, doubles): 16 k + 328.  zg (global, doubles): 6 k (k + 16) for this CTA.
 __host__ __device__ constexpr size_t work_doubles(int k) { return size_t(16) * k + 72 + 256; }
-__host__ __device__ constexpr size_t scratch_doubles(int k) { return size_t(6) * k * k; }
+// per-CTA global scratch of the inverse iteration: six arrays [vector][element], row pitch k + 16 doubles (an odd number of
+// 128-byte lines, so that the rows of different vectors spread over all L1 sets)
+__host__ __device__ constexpr int vec_pitch(int k) { return k + 16; }
+__host__ __device__ constexpr size_t scratch_doubles(int k) { return size_t(6) * k * vec_pitch(k); }
 
+
+// request the line of p into L1 (the inverse-iteration sweeps walk per-thread rows of the global scratch)
+__device__ __forceinline__ void pf_l1(const double* p) { asm volatile("prefetch.global.L1 [%0];" :: "l"(p)); }
 
 // shared-memory store of v when x == y.  Inline PTX on purpose: written as `if (u == sel) val = a[u]` over the unrolled
 // register array, the compiler turns the select chain into an indexed load and moves the whole array to local memory.
@@ -212,7 +219,6 @@ __device__ bool clamped_solve(double* __restrict__ W, int k, const double* __res
     int* blt = bneg + k;
     int* woff = blt + k;                              // k + 1
     double* red = coef + 4 * k + 1;   // 64
-    int* flags = reinterpret_cast<int*>(red + 64);    // blockDim.x ints (<= 512)
     __shared__ int s_fail, s_nblk;
     if (tid == 0) s_fail = 0;
     for (int r = tid; r < k; r += NT) y[r] = g[r];
@@ -361,22 +367,36 @@ __device__ bool clamped_solve(double* __restrict__ W, int k, const double* __res
         __syncthreads();
         const int nw = woff[nblk];                            // wanted (uniform); <= k <= NT
         // ---- 2b / 3. one thread per wanted eigenpair: bisection inside its block, then inverse iteration ---------------------
-        double* Z = zg;                        // arrays [element * k + vector]
-        double* U0 = Z + size_t(k) * k;        // reciprocal pivots
-        double* U1 = U0 + size_t(k) * k;
-        double* U2 = U1 + size_t(k) * k;
-        double* L = U2 + size_t(k) * k;
-        double* PV = L + size_t(k) * k;        // 1.0 where rows were swapped
+        // arrays [vector * ZP + element]: a thread walks ITS vector through consecutive addresses (one L2 round trip per 16
+        // elements, then L1 hits).  The [element][vector] layout this replaces was coalesced across the threads, but with at most
+        // k threads per SM in these chains every element paid the L2 latency: ncu put 26 % of the kernel's samples on the
+        // barrier behind the sweeps.
+        const int ZP = vec_pitch(k);
+        double* Z = zg;
+        double* U0 = Z + size_t(k) * ZP;       // reciprocal pivots
+        double* U1 = U0 + size_t(k) * ZP;
+        double* U2 = U1 + size_t(k) * ZP;
+        double* L = U2 + size_t(k) * ZP;
+        double* PV = L + size_t(k) * ZP;       // 1.0 where rows were swapped
         // 2b. multi-section: the CTA's threads are dealt out G per wanted eigenvalue and cut its bracket into G + 1 parts per
         //     round (log2(G + 1) bits per Sturm evaluation instead of 1: with 16 wanted eigenvalues and 256 threads, 14 rounds
-        //     instead of 55).  Brackets live in the (now dead) unscaled d / e arrays.
+        //     instead of 55).  G is a power of two <= 32, so a group sits inside one warp: the G answers are combined by a
+        //     ballot, every lane of the group keeps the bracket in registers and the rounds need no barrier (the two barriers
+        //     and the leader's serial scan of a flag array per round were 20 % of the kernel's samples).  The final brackets
+        //     go to the (now dead) unscaled d / e arrays.
         {
             double* blo = d;
             double* bhi = e;
-            const int G = max(1, min(32, NT / max(nw, 1)));
+            int G = 1;
+            while (2 * G <= min(32, NT / max(nw, 1))) G *= 2;
             const int rounds = nw > 0 ? int(56.0f / log2f(float(G + 1))) + 2 : 0;     // bracket 2 -> 2^-54
             const int tq = tid / G, gq = tid % G;
+            const int lane = tid & 31;
+            const unsigned gmask = G == 32 ? 0xffffffffu : ((1u << G) - 1u);
+            const int gshift = lane & ~(G - 1);
+            const double inv = 1.0 / double(G + 1);
             int qs0 = 0, qsz = 0, qidx = 0;
+            double lo = 0.0, hi = 0.0;
             if (tq < nw) {
                 int bI = 0;
                 while (woff[bI + 1] <= tq) bI++;
@@ -384,33 +404,26 @@ __device__ bool clamped_solve(double* __restrict__ W, int k, const double* __res
                 qsz = bstart[bI + 1] - qs0;
                 const int jl = tq - woff[bI];
                 qidx = jl < bneg[bI] ? jl : blt[bI] + (jl - bneg[bI]);
-                if (gq == 0) {
-                    vblk[tq] = bI;
-                    blo[tq] = qsz == 1 ? ds[qs0] : -1.0009765625;
-                    bhi[tq] = qsz == 1 ? ds[qs0] : 1.0009765625;
-                }
+                lo = qsz == 1 ? ds[qs0] : -1.0009765625;
+                hi = qsz == 1 ? ds[qs0] : 1.0009765625;
+                if (gq == 0) vblk[tq] = bI;
             }
-            __syncthreads();
+            __syncthreads();                                          // (d / e are read above by nobody any more)
             for (int rd = 0; rd < rounds; rd++) {
-                if (tq < nw) {
-                    const double lo = blo[tq], hi = bhi[tq];
-                    const double xq = lo + (hi - lo) * (double(gq + 1) / double(G + 1));
-                    int above = 1;                                    // "more than idx eigenvalues below xq"
-                    if (qsz > 1 && hi > lo) above = sturm_count(ds + qs0, es2 + qs0, qsz, xq) > qidx ? 1 : 0;
-                    flags[tid] = above;
-                }
-                __syncthreads();
-                if (tq < nw && gq == 0 && qsz > 1) {
-                    const double lo = blo[tq], hi = bhi[tq];
-                    int j = 0;
-                    while (j < G && flags[tid + j] == 0) j++;          // first interior point with the eigenvalue below it
-                    const double nlo = j > 0 ? lo + (hi - lo) * (double(j) / double(G + 1)) : lo;
-                    const double nhi = j < G ? lo + (hi - lo) * (double(j + 1) / double(G + 1)) : hi;
-                    blo[tq] = fmax(lo, fmin(nlo, hi));
-                    bhi[tq] = fmin(hi, fmax(nhi, lo));
-                }
-                __syncthreads();
+                // interior point m = gq + 1 of the bracket: x_m = lo + (hi - lo) (m / (G + 1)), the same expression below
+                const double xq = lo + (hi - lo) * (double(gq + 1) * inv);
+                int above = 1;                                        // "more than idx eigenvalues below xq"
+                if (tq < nw && qsz > 1 && hi > lo) above = sturm_count(ds + qs0, es2 + qs0, qsz, xq) > qidx ? 1 : 0;
+                const unsigned grp = (__ballot_sync(0xffffffffu, above != 0) >> gshift) & gmask;
+                const int j = grp != 0u ? __ffs(int(grp)) - 1 : G;    // first interior point with the eigenvalue below it
+                const double nlo = j > 0 ? lo + (hi - lo) * (double(j) * inv) : lo;
+                const double nhi = j < G ? lo + (hi - lo) * (double(j + 1) * inv) : hi;
+                const double l2 = fmax(lo, fmin(nlo, hi)), h2 = fmin(hi, fmax(nhi, lo));
+                lo = l2;
+                hi = h2;
             }
+            if (tq < nw && gq == 0) { blo[tq] = lo; bhi[tq] = hi; }
+            __syncthreads();
         }
         const int t = tid;
         int s0 = 0, sz = 0;
@@ -423,11 +436,11 @@ __device__ bool clamped_solve(double* __restrict__ W, int k, const double* __res
             const double* be = es + s0;        // be[i] couples i - 1 and i inside the block (be[0] is never used)
             const double lm = 0.5 * (d[t] + e[t]);
             lam[t] = lm;
-            for (int i = 0; i < s0; i++) Z[size_t(i) * k + t] = 0.0;
-            for (int i = s0 + sz; i < k; i++) Z[size_t(i) * k + t] = 0.0;
-            Zb = Z + size_t(s0) * k + t;                   // element i of the block at Zb[i * k]
-            U0b = U0 + size_t(s0) * k + t; U1b = U1 + size_t(s0) * k + t; U2b = U2 + size_t(s0) * k + t;
-            Lb = L + size_t(s0) * k + t; PVb = PV + size_t(s0) * k + t;
+            for (int i = 0; i < s0; i++) Z[size_t(t) * ZP + i] = 0.0;
+            for (int i = s0 + sz; i < k; i++) Z[size_t(t) * ZP + i] = 0.0;
+            Zb = Z + size_t(t) * ZP + s0;                  // element i of the block at Zb[i]
+            U0b = U0 + size_t(t) * ZP + s0; U1b = U1 + size_t(t) * ZP + s0; U2b = U2 + size_t(t) * ZP + s0;
+            Lb = L + size_t(t) * ZP + s0; PVb = PV + size_t(t) * ZP + s0;
             if (sz == 1) {
                 Zb[0] = 1.0;
             } else {
@@ -446,15 +459,15 @@ __device__ bool clamped_solve(double* __restrict__ W, int k, const double* __res
                         l = q0 / r0;
                         r0 = q1 - l * r1; r1 = q2 - l * r2; r2 = 0.0;
                     }
-                    U0b[size_t(i) * k] = 1.0 / u0; U1b[size_t(i) * k] = u1; U2b[size_t(i) * k] = u2;
-                    Lb[size_t(i) * k] = l; PVb[size_t(i) * k] = pv;
+                    U0b[i] = 1.0 / u0; U1b[i] = u1; U2b[i] = u2;
+                    Lb[i] = l; PVb[i] = pv;
                 }
                 if (r0 == 0.0) r0 = tiny;
-                U0b[size_t(sz - 1) * k] = 1.0 / r0; U1b[size_t(sz - 1) * k] = 0.0; U2b[size_t(sz - 1) * k] = 0.0;
+                U0b[sz - 1] = 1.0 / r0; U1b[sz - 1] = 0.0; U2b[sz - 1] = 0.0;
                 uint32_t st = 0x9e3779b9u * uint32_t(t + 1) + 0x7f4a7c15u;     // start vector: positive pseudo-random entries
                 for (int i = 0; i < sz; i++) {
                     st = st * 1664525u + 1013904223u;
-                    Zb[size_t(i) * k] = 0.5 + double(st >> 8) * (1.0 / 16777216.0);
+                    Zb[i] = 0.5 + double(st >> 8) * (1.0 / 16777216.0);
                 }
             }
         }
@@ -474,20 +487,27 @@ __device__ bool clamped_solve(double* __restrict__ W, int k, const double* __res
             if (tid < nw && sz > 1) {
                 if (it > 0) {                                  // apply L^-1 P; the running element stays in a register, so the
                     double cur = Zb[0];                        // loads of one step do not wait for the stores of the previous
+                    if (sz > 16) { pf_l1(Zb + 16); pf_l1(Lb + 16); pf_l1(PVb + 16); }
 #pragma unroll 8
                     for (int i = 0; i < sz - 1; i++) {
-                        const double xn = Zb[size_t(i + 1) * k], l = Lb[size_t(i) * k], pv = PVb[size_t(i) * k];
-                        if (pv != 0.0) { Zb[size_t(i) * k] = xn; cur = cur - l * xn; }
-                        else { Zb[size_t(i) * k] = cur; cur = xn - l * cur; }
+                        // the rows are walked at one dependent FMA per element: the next lines are requested two ahead
+                        if ((i & 15) == 0 && i + 32 < sz) { pf_l1(Zb + i + 32); pf_l1(Lb + i + 32); pf_l1(PVb + i + 32); }
+                        const double xn = Zb[i + 1], l = Lb[i], pv = PVb[i];
+                        if (pv != 0.0) { Zb[i] = xn; cur = cur - l * xn; }
+                        else { Zb[i] = cur; cur = xn - l * cur; }
                     }
-                    Zb[size_t(sz - 1) * k] = cur;
+                    Zb[sz - 1] = cur;
                 }
                 double x1 = 0.0, x2 = 0.0, nrm = 0.0;          // back substitution with U (bandwidth 2)
+                if (sz > 16) { pf_l1(Zb + sz - 17); pf_l1(U0b + sz - 17); pf_l1(U1b + sz - 17); pf_l1(U2b + sz - 17); }
 #pragma unroll 8
                 for (int i = sz - 1; i >= 0; i--) {
-                    const double zi = Zb[size_t(i) * k], a1 = U1b[size_t(i) * k], a2 = U2b[size_t(i) * k], a0 = U0b[size_t(i) * k];
+                    if (((sz - 1 - i) & 15) == 0 && i >= 32) {
+                        pf_l1(Zb + i - 32); pf_l1(U0b + i - 32); pf_l1(U1b + i - 32); pf_l1(U2b + i - 32);
+                    }
+                    const double zi = Zb[i], a1 = U1b[i], a2 = U2b[i], a0 = U0b[i];
                     const double tv = (zi - a1 * x1 - a2 * x2) * a0;
-                    Zb[size_t(i) * k] = tv;
+                    Zb[i] = tv;
                     x2 = x1; x1 = tv;
                     nrm = fmax(nrm, fabs(tv));
                 }
@@ -495,10 +515,17 @@ __device__ bool clamped_solve(double* __restrict__ W, int k, const double* __res
                 const double sc = nrm > 0.0 ? 1.0 / nrm : 1.0;
                 double s2 = 0.0;
 #pragma unroll 8
-                for (int i = 0; i < sz; i++) { const double tv = Zb[size_t(i) * k] * sc; s2 = fma(tv, tv, s2); }
+                for (int i = 0; i < sz; i++) {
+                    if ((i & 15) == 0 && i + 32 < sz) pf_l1(Zb + i + 32);
+                    const double tv = Zb[i] * sc;
+                    s2 = fma(tv, tv, s2);
+                }
                 const double sc2 = sc / sqrt(s2);
 #pragma unroll 8
-                for (int i = 0; i < sz; i++) Zb[size_t(i) * k] *= sc2;
+                for (int i = 0; i < sz; i++) {
+                    if ((i & 15) == 0 && i + 32 < sz) pf_l1(Zb + i + 32);
+                    Zb[i] *= sc2;
+                }
             }
             __syncthreads();
             for (int u = 1; u < nw; u++) {
@@ -506,31 +533,30 @@ __device__ bool clamped_solve(double* __restrict__ W, int k, const double* __res
                 if (c0 == u) continue;                        // uniform
                 for (int i = c0; i < u; i++) {
                     double dot = 0.0, dummy = 0.0;
-                    for (int el = tid; el < k; el += NT) dot = fma(Z[size_t(el) * k + i], Z[size_t(el) * k + u], dot);
+                    for (int el = tid; el < k; el += NT) dot = fma(Z[size_t(i) * ZP + el], Z[size_t(u) * ZP + el], dot);
                     block_sum2(dot, dummy, red);
-                    for (int el = tid; el < k; el += NT) Z[size_t(el) * k + u] -= dot * Z[size_t(el) * k + i];
+                    for (int el = tid; el < k; el += NT) Z[size_t(u) * ZP + el] -= dot * Z[size_t(i) * ZP + el];
                     __syncthreads();
                 }
                 double n2 = 0.0, dummy = 0.0;
-                for (int el = tid; el < k; el += NT) n2 = fma(Z[size_t(el) * k + u], Z[size_t(el) * k + u], n2);
+                for (int el = tid; el < k; el += NT) n2 = fma(Z[size_t(u) * ZP + el], Z[size_t(u) * ZP + el], n2);
                 block_sum2(n2, dummy, red);
                 if (!(n2 > 1e-8)) { if (tid == 0 && it == 2) s_fail = 1; if (!(n2 > 0.0)) n2 = 1.0; }   // a copy of an earlier vector
                 const double sc = 1.0 / sqrt(n2);
-                for (int el = tid; el < k; el += NT) Z[size_t(el) * k + u] *= sc;
+                for (int el = tid; el < k; el += NT) Z[size_t(u) * ZP + el] *= sc;
                 __syncthreads();
             }
         }
         // ---- 5. combine --------------------------------------------------------------------------------------------------
         if (tid < nw) {
             double c = 0.0;
-            for (int i = 0; i < k; i++) c = fma(Z[size_t(i) * k + tid], y[i], c);
+            for (int i = 0; i < k; i++) c = fma(Z[size_t(tid) * ZP + i], y[i], c);
             coef[tid] = (1.0 / (fabs(lam[tid]) * tn) - 1.0 / pert) * c;
         }
         __syncthreads();
         for (int el = tid; el < k; el += NT) {
             double acc = y[el] / pert;
-            const double* zr = Z + size_t(el) * k;
-            for (int t = 0; t < nw; t++) acc = fma(coef[t], zr[t], acc);
+            for (int t = 0; t < nw; t++) acc = fma(coef[t], Z[size_t(t) * ZP + el], acc);
             x[el] = acc;
         }
         __syncthreads();
