@@ -351,6 +351,9 @@ __device__ bool clamped_solve(double* __restrict__ W, int k, const double* __res
             s_nblk = nb;
         }
         __syncthreads();
+        // reciprocals of the off-diagonals that survived the split: the LU factorisations below divide by them when they pivot
+        double* esi = pp + k;
+        for (int i = tid; i < k; i += NT) esi[i] = es[i] != 0.0 ? 1.0 / es[i] : 0.0;
         const int nblk = s_nblk;
         for (int bI = tid; bI < nblk; bI += NT) {             // wanted eigenvalues of every block: below -p and above +p
             const int s0 = bstart[bI], sz = bstart[bI + 1] - s0;
@@ -434,6 +437,7 @@ __device__ bool clamped_solve(double* __restrict__ W, int k, const double* __res
             sz = bstart[bI + 1] - s0;
             const double* bd = ds + s0;
             const double* be = es + s0;        // be[i] couples i - 1 and i inside the block (be[0] is never used)
+            const double* bei = esi + s0;      // 1 / be[i]
             const double lm = 0.5 * (d[t] + e[t]);
             lam[t] = lm;
             for (int i = 0; i < s0; i++) Z[size_t(t) * ZP + i] = 0.0;
@@ -446,20 +450,24 @@ __device__ bool clamped_solve(double* __restrict__ W, int k, const double* __res
             } else {
                 const double tiny = 2.220446049250313e-16;
                 double r0 = bd[0] - lm, r1 = be[1], r2 = 0.0;
+                // One division per row at most, and only when the running pivot is kept (the reciprocal of an off-diagonal pivot
+                // comes from shared memory); U is stored with its rows already divided by the pivot, so that the back substitution
+                // carries ONE dependent FMA per element.  (Two divisions per row, one of them on the dependent chain, made this
+                // loop 17 % of the kernel's samples.)
                 for (int i = 0; i < sz - 1; i++) {
                     const double q0 = be[i + 1], q1 = bd[i + 1] - lm, q2 = i + 2 < sz ? be[i + 2] : 0.0;
-                    double u0, u1, u2, l, pv;
+                    double ui, u1, u2, l, pv;
                     if (fabs(q0) > fabs(r0)) {
-                        pv = 1.0; u0 = q0; u1 = q1; u2 = q2;
-                        l = r0 / q0;
+                        pv = 1.0; ui = bei[i + 1]; u1 = q1; u2 = q2;
+                        l = r0 * ui;
                         r0 = r1 - l * q1; r1 = r2 - l * q2; r2 = 0.0;
                     } else {
                         if (r0 == 0.0) r0 = tiny;
-                        pv = 0.0; u0 = r0; u1 = r1; u2 = r2;
-                        l = q0 / r0;
+                        pv = 0.0; ui = 1.0 / r0; u1 = r1; u2 = r2;
+                        l = q0 * ui;
                         r0 = q1 - l * r1; r1 = q2 - l * r2; r2 = 0.0;
                     }
-                    U0b[i] = 1.0 / u0; U1b[i] = u1; U2b[i] = u2;
+                    U0b[i] = ui; U1b[i] = u1 * ui; U2b[i] = u2 * ui;
                     Lb[i] = l; PVb[i] = pv;
                 }
                 if (r0 == 0.0) r0 = tiny;
@@ -498,7 +506,7 @@ __device__ bool clamped_solve(double* __restrict__ W, int k, const double* __res
                     }
                     Zb[sz - 1] = cur;
                 }
-                double x1 = 0.0, x2 = 0.0, nrm = 0.0;          // back substitution with U (bandwidth 2)
+                double x1 = 0.0, x2 = 0.0, nrm = 0.0, s2 = 0.0; // back substitution with U (bandwidth 2, rows divided by the pivot)
                 if (sz > 16) { pf_l1(Zb + sz - 17); pf_l1(U0b + sz - 17); pf_l1(U1b + sz - 17); pf_l1(U2b + sz - 17); }
 #pragma unroll 8
                 for (int i = sz - 1; i >= 0; i--) {
@@ -506,21 +514,23 @@ __device__ bool clamped_solve(double* __restrict__ W, int k, const double* __res
                         pf_l1(Zb + i - 32); pf_l1(U0b + i - 32); pf_l1(U1b + i - 32); pf_l1(U2b + i - 32);
                     }
                     const double zi = Zb[i], a1 = U1b[i], a2 = U2b[i], a0 = U0b[i];
-                    const double tv = (zi - a1 * x1 - a2 * x2) * a0;
+                    const double tv = fma(-a1, x1, fma(-a2, x2, zi * a0));   // the inner FMA does not wait for x1
                     Zb[i] = tv;
                     x2 = x1; x1 = tv;
                     nrm = fmax(nrm, fabs(tv));
-                }
-                // rescale by the max norm first (the solve amplifies by ~1e16), then to unit 2-norm
-                const double sc = nrm > 0.0 ? 1.0 / nrm : 1.0;
-                double s2 = 0.0;
-#pragma unroll 8
-                for (int i = 0; i < sz; i++) {
-                    if ((i & 15) == 0 && i + 32 < sz) pf_l1(Zb + i + 32);
-                    const double tv = Zb[i] * sc;
                     s2 = fma(tv, tv, s2);
                 }
-                const double sc2 = sc / sqrt(s2);
+                // to unit 2-norm.  The solve amplifies by up to ~1e16 per tiny pivot: when the plain sum of squares left the
+                // representable range, rescale by the max norm first
+                double sc2;
+                if (s2 > 1e-280 && s2 < 1e280) {
+                    sc2 = 1.0 / sqrt(s2);
+                } else {
+                    const double sc = nrm > 0.0 ? 1.0 / nrm : 1.0;
+                    s2 = 0.0;
+                    for (int i = 0; i < sz; i++) { const double tv = Zb[i] * sc; s2 = fma(tv, tv, s2); }
+                    sc2 = sc / sqrt(s2);
+                }
 #pragma unroll 8
                 for (int i = 0; i < sz; i++) {
                     if ((i & 15) == 0 && i + 32 < sz) pf_l1(Zb + i + 32);
