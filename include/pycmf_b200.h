@@ -50,8 +50,12 @@ int pycmf_set_stream(pycmf_ctx* ctx, void* stream);
 /* options: "chol_fastpath" (0/1, default 1), "dense_path" (0 = generic FMA kernels, 1 = tcgen05
  * 3xTF32 for n_components 32 / 64 / 128 / 192 / 256, 2 = tcgen05 1xTF32 (k = 32 only); default 1),
  * "spmm_path" (0 = generic CSR kernel, 1 = vector / sub-warp-grouped kernels for k = 32 / 64 / 128 / 256,
- * default 1), "max_scratch_mb", "side_streams" (0/1), and for tests and tuning: "tc_max_splits", "tc_ctas",
- * "tc_chain", "tc_x_promotion", "tc_prefetch", "tc_trace", "finish_minblocks" */
+ * default 1), "solve_path" (clamped solve with the clamp active, k > 32: 0 = one-sided Jacobi, 1 = tridiagonalisation +
+ * multi-section + inverse iteration, 2 = the same with the Householder steps on a register-resident matrix for
+ * k = 64 / 128; default 2), "hess_mma" (0 = per-row weighted Grams on the FMA pipes, 1 = mma.sync 3xTF32 for k = 64 / 128;
+ * default 1), "mu_fused" (0 = separate denominator GEMM + elementwise MU step, default 1), "max_scratch_mb",
+ * "side_streams" (0/1), and for tests and tuning: "tc_max_splits", "tc_ctas", "tc_chain", "tc_x_promotion",
+ * "tc_prefetch", "tc_trace", "finish_minblocks", "solve_threads", "spmm_blocks_per_sm", "spmm_unroll", "spmm_lean" */
 int pycmf_set_option(pycmf_ctx* ctx, const char* key, double value);
 /* number of kernels this context launched since creation (bench.py's gpu_launches) */
 int64_t pycmf_launch_count(pycmf_ctx* ctx);
