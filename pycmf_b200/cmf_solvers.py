@@ -41,12 +41,15 @@ def _beta_loss_to_float(beta_loss):
 class FitState:
     """Everything one rank keeps in HBM during a fit: its row shard of X and U, replicated Y / V / Z."""
 
-    def __init__(self, backend, comm, X, Y, U, V, Z, n_total, rows):
+    def __init__(self, backend, comm, X, Y, U, V, Z, n_total, rows, Xcol=None, cols=None):
         self.be, self.comm = backend, comm
         self.X, self.Y = X, Y
         self.U, self.V, self.Z = U, V, Z
         self.n_total = n_total
         self.r0, self.r1 = rows
+        # column block [c0, c1) of X over ALL rows (second copy; the column-sharded Newton V phase, SURVEY 8e)
+        self.Xcol = Xcol
+        self.c0, self.c1 = cols if cols is not None else (0, 0)
         self.iteration = 0
 
     @property
@@ -64,7 +67,7 @@ class _IterativeCMFSolver:
                  x_link="linear", y_link="linear", hessian_pertubation=0.2,
                  sg_sample_ratio=1., random_state=None,
                  dtype="float32", device=None, comm=None, sampler="auto", backend=None, backend_options=None,
-                 sharded_input=False, use_cuda_graph="auto"):
+                 sharded_input=False, use_cuda_graph="auto", v_phase="auto"):
         self.max_iter = max_iter
         self.tol = tol
         self.beta_loss = _beta_loss_to_float(beta_loss)
@@ -95,6 +98,7 @@ class _IterativeCMFSolver:
         self._backend = backend
         self.sharded_input = sharded_input   # X / U handed in are already this rank's row block
         self.use_cuda_graph = use_cuda_graph # replay one captured iteration (single GPU, no per-iteration host work)
+        self.v_phase = v_phase               # Newton V update with per-row Hessians on several ranks: 'rows' | 'columns'
         self.masks_per_iter = None     # test hook: list of per-iteration mask dicts (global indices)
         self.history = None            # test hook: list receiving the objective after every iteration
 
@@ -141,7 +145,12 @@ class _IterativeCMFSolver:
         Ud = be.to_device(np.asarray(U)[take])
         Vd = be.to_device(np.asarray(V))
         Zd = be.to_device(np.asarray(Z))
-        return FitState(be, comm, Xd, Yd, Ud, Vd, Zd, n_total, (r0, r1))
+        Xcol, cols = self._prepare_column_block(be, comm, X, np.shape(V)[0])
+        return FitState(be, comm, Xd, Yd, Ud, Vd, Zd, n_total, (r0, r1), Xcol, cols)
+
+    def _prepare_column_block(self, be, comm, X, d):
+        """Only the Newton solver re-partitions (NewtonSolver._prepare_column_block)."""
+        return None, None
 
     # ---- seam ------------------------------------------------------------------------------------
     def update_step(self, X, Y, U, V, Z, l1_reg, l2_reg, alpha):
@@ -471,10 +480,13 @@ class NewtonSolver(_IterativeCMFSolver):
             self._sync_numpy_rng(st)
             host = _draw_masks_numpy(n, d, l, ratio, self.update_U, self.update_Z, self.update_V)
         dev = {}
+        by_columns = st.Xcol is not None
         for key, val in host.items():
             val = np.asarray(val)
             if key == "U":
                 val = val[st.r0:st.r1]
+            elif key in ("Vx", "Vy") and by_columns:
+                val = val[st.c0:st.c1]                   # this rank's rows of V; sampled rows of U stay GLOBAL indices
             elif key == "Vx" and st.comm.world > 1:
                 val = localize_indices(val, st.r0, st.r1)
             dev[key] = be.to_device(val, np.int32)
@@ -510,11 +522,66 @@ class NewtonSolver(_IterativeCMFSolver):
             out["U"] = be.sample_indices(st.r1 - st.r0, d, s_d, seed, 4 * it + 0, row0=st.r0)
         if self.update_Z:
             out["Z"] = be.sample_indices(l, d, s_d, seed, 4 * it + 1)
-        if self.update_V:
+        if self.update_V and st.Xcol is not None:
+            # column-sharded V phase: the sets of this rank's rows of V only, sampled rows of U as global indices
+            out["Vx"] = be.sample_indices(st.c1 - st.c0, n, s_n, seed, 4 * it + 2, row0=st.c0)
+            out["Vy"] = be.sample_indices(st.c1 - st.c0, l, s_l, seed, 4 * it + 3, row0=st.c0)
+        elif self.update_V:
             out["Vx"] = be.sample_indices(d, n, s_n, seed, 4 * it + 2,
                                           window=(st.r0, st.r1) if st.comm.world > 1 else None)
             out["Vy"] = be.sample_indices(d, l, s_l, seed, 4 * it + 3)
         return out
+
+    # ---- column-sharded V phase ("Newton, logit x-link / sg<1") ---------------------------------------
+    def _wants_columns(self, world):
+        """Per-row Hessians of the V update sum over ALL rows of U: row shards would have to all-reduce d k^2 numbers per
+        iteration (13 GB at C4).  'columns' re-partitions for the V phase instead: every rank owns d / G rows of V and the
+        matching column block of X over all rows (a second copy), U is all-gathered (n k), the new rows of V are
+        all-gathered (d k).  'rows' keeps the chunked all-reduce of the partial Hessians (no second copy of X)."""
+        import os
+        mode = self.v_phase
+        if mode == "auto":
+            mode = os.environ.get("PYCMF_B200_V_PHASE", "rows")
+        if mode not in ("rows", "columns"):
+            raise ValueError("v_phase must be 'rows', 'columns' or 'auto', got %r" % (mode,))
+        per_row = self.x_link == "logit" or self.sg_sample_ratio < 1.
+        return mode == "columns" and world > 1 and self.update_V and per_row
+
+    def _prepare_column_block(self, be, comm, X, d):
+        if X is None or not self._wants_columns(comm.world):
+            return None, None
+        if self.sharded_input or getattr(X, "is_sparse", None) is not None:
+            raise ValueError("v_phase='columns' needs the whole host matrix X on every rank (each rank uploads its "
+                             "column block); with sharded_input=True or a device-resident X use v_phase='rows'")
+        c0, c1 = row_range(d, comm.rank, comm.world)
+        if sp.issparse(X):
+            block = sp.csc_matrix(X)[:, c0:c1].tocsr()
+        else:
+            block = np.ascontiguousarray(np.asarray(X)[:, c0:c1])
+        return be.ingest(block), (c0, c1)
+
+    def _step_v_columns(self, st, idx_x, idx_y, join_z):
+        """_newton_update_V (:432-486) for this rank's rows [c0, c1) of V against all rows of U_new."""
+        be, comm = st.be, st.comm
+        alpha, l1, l2, pert = self.alpha, self.l1_reg, self.l2_reg, self.hessian_pertubation
+        d, k = st.V.shape
+        c0, c1 = st.c0, st.c1
+        U_all = comm.all_gather_rows(st.U, st.n_total)
+        V_loc = st.V[c0:c1]
+        Y_loc = be.row_slice(st.Y, c0, c1)
+        step = be.v_chunk_rows(max(1, c1 - c0), k, True)
+        for j0 in range(0, c1 - c0, step):
+            j1 = min(c1 - c0, j0 + step)
+            gx, Hx, pr = be.newton_v_xpart(V_loc, U_all, st.Xcol, j0, j1, self.x_link, alpha,
+                                           idx=None if idx_x is None else idx_x[j0:j1])
+            join_z()
+            be.newton_v_finish(V_loc, st.Z, Y_loc, j0, j1, self.y_link, alpha, l1, l2, gx, Hx, pr,
+                               self.V_non_negative, pert, idx=None if idx_y is None else idx_y[j0:j1])
+        join_z()
+        if d % comm.world == 0:
+            comm.all_gather_into(st.V, V_loc.clone())
+        else:
+            st.V.copy_(comm.all_gather_rows(V_loc, d))
 
     def _step(self, st):
         be = st.be
@@ -547,6 +614,9 @@ class NewtonSolver(_IterativeCMFSolver):
             idx_x, idx_y = m.get("Vx"), m.get("Vy")
             per_row = be.newton_v_needs_per_row(self.x_link, idx_x is not None)
             world = st.comm.world
+            if st.Xcol is not None:
+                self._step_v_columns(st, idx_x, idx_y, join_z)
+                return
             if world > 1 and not per_row and idx_y is None and d % world == 0:
                 # Shared X-side Hessian: the gradient partial is reduce-scattered by rows of V, every rank finishes its
                 # d / G rows (the per-row solves are the expensive, replicated part otherwise) and the new rows are

@@ -97,3 +97,69 @@ def test_two_gpu_row_sharding_matches_single_gpu(tmp_path):
     out = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900)
     errors = [ln for ln in out.stdout.splitlines() if "Error" in ln and "ChildFailed" not in ln]
     assert out.returncode == 0 and "MULTI_OK" in out.stdout, "\n".join(errors[:6]) or out.stdout[-3000:]
+
+
+_COLUMNS_WORKER = r"""
+import os, sys
+sys.path.insert(0, sys.argv[1]); sys.path.insert(0, os.path.join(sys.argv[1], "tests"))
+import numpy as np, torch, torch.distributed as dist
+rank = int(os.environ["RANK"]); torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
+dist.init_process_group("nccl")
+from helpers import load_golden, draw_masks_for_case, rel_fro
+from test_gpu_parity import _mid_case, MID
+from pycmf_b200.cmf_solvers import NewtonSolver
+from pycmf_b200.sharding import TorchComm, Comm
+
+def run(case, dtype, comm, masks=None, **extra):
+    p = dict(case["params"]); p.pop("solver"); p.update(extra)
+    s = NewtonSolver(max_iter=case["iters"], tol=0, random_state=case["rng_seed"], dtype=dtype, comm=comm, **p)
+    s.history = []; s.masks_per_iter = masks
+    U, V, Z = case["U0"].copy(), case["V0"].copy(), case["Z0"].copy()
+    s.fit_iterative_update(case["X"], case["Y"], U, V, Z)
+    return np.asarray(s.history), U, V, Z
+
+# the reference's trajectories (golden = unmodified reference), float64, per-row Hessians: dense / CSR, logit x link, sampled
+for name in ["nt_logit_logit", "nt_csr_logit_lin", "nt_sg_logit_logit", "nt_sg_csr_lin_logit", "nt_sg_zero_ysample"]:
+    case, g = load_golden(name)
+    hist, U, V, Z = run(case, "float64", TorchComm(), draw_masks_for_case(case), v_phase="columns")
+    assert np.allclose(hist, g["objective"][1:], rtol=1e-9, atol=1e-11), name
+    for got, ref in ((U, g["U"]), (V, g["V"]), (Z, g["Z"])):
+        assert rel_fro(got, ref) < 1e-9, name
+# mid-size float32 (k = 72: tensor-core Hessians, tridiagonal clamped solve): column-sharded == row-sharded == one rank
+solver, n, d, l, k, sparse, params = MID["nt_logit_lin_k72"]
+case = _mid_case(solver, n, d, l, k, sparse, seed=11, **params); case["iters"] = 3
+hc, Uc, Vc, Zc = run(case, "float32", TorchComm(), v_phase="columns")
+hr, Ur, Vr, Zr = run(case, "float32", TorchComm(), v_phase="rows")
+h1, U1, V1, Z1 = run(case, "float32", Comm())
+for h in (hc, hr):                          # the float32 parity bars (objective 1e-4, factors 1e-3)
+    assert np.abs(h - h1).max() / np.abs(h1).max() < 1e-4, ("columns / rows vs one rank", h1, hr, hc)
+for a, b in ((Uc, U1), (Vc, V1), (Zc, Z1), (Ur, U1), (Vr, V1), (Zr, Z1)):
+    assert rel_fro(a, b) < 1e-3, "column- / row-sharded V phase vs one rank"
+# device sampler: the sets are keyed by the GLOBAL row of V, so the column-sharded phase draws what one rank draws
+solver, n, d, l, k, sparse, params = MID["nt_signed_l1_lin_logit_k32"]
+case = _mid_case(solver, 600, 201, 6, 16, False, seed=3, **params); case["iters"] = 3      # d odd: uneven column blocks
+case["params"]["sg_sample_ratio"] = 0.5
+h2, U2, V2, Z2 = run(case, "float64", TorchComm(), sampler="device", v_phase="columns")
+h1, U1, V1, Z1 = run(case, "float64", Comm(), sampler="device")
+assert np.abs(h2 - h1).max() / np.abs(h1).max() < 1e-9, ("device sampler, columns on 2 ranks vs 1", h1, h2)
+for a, b in ((U1, U2), (V1, V2), (Z1, Z2)):
+    assert rel_fro(a, b) < 1e-9, "device sampler, columns on 2 ranks vs 1"
+dist.barrier(); dist.destroy_process_group()
+if rank == 0: print("COLUMNS_OK")
+"""
+
+
+def test_two_gpu_column_sharded_newton_v_phase(tmp_path):
+    """for per-row Hessians (logit x link / sg < 1) the V phase re-partitions -- all-gather U, every rank updates
+    its d / G rows of V against its column block of X, all-gather V -- instead of all-reducing d k^2 Hessian entries."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    script = tmp_path / "worker_columns.py"
+    script.write_text(_COLUMNS_WORKER)
+    port = str(27600 + os.getpid() % 2000)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+           "--master-addr", "127.0.0.1", "--master-port", port, str(script), ROOT]
+    out = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900)
+    errors = [ln for ln in out.stdout.splitlines() if "Error" in ln and "ChildFailed" not in ln]
+    assert out.returncode == 0 and "COLUMNS_OK" in out.stdout, "\n".join(errors[:6]) or out.stdout[-3000:]

@@ -48,14 +48,14 @@ def test_product_never_imports_the_oracle():
             assert not re.search(r"^\s*(from|import)\s+oracle|import_module\(.oracle|/oracle", src, re.M), fn
 
 
-def _run_fake(case, masks=None, comm=None):
+def _run_fake(case, masks=None, comm=None, **extra):
     from pycmf_b200.cmf_solvers import MUSolver, NewtonSolver
     MUSolver.SHARD_V_MIN = 0          # exercise the row-sharded V update on the small test shapes
     p = dict(case["params"])
     solver = p.pop("solver")
     cls = MUSolver if solver == "mu" else NewtonSolver
     s = cls(max_iter=case["iters"], tol=0, random_state=case["rng_seed"], dtype="float64", backend=FakeBackend(),
-            comm=comm, **p)
+            comm=comm, **p, **extra)
     s.history, s.masks_per_iter = [], masks
     U, V, Z = case["U0"].copy(), case["V0"].copy(), case["Z0"].copy()
     e0 = s.compute_error(case["X"], case["Y"], U, V, Z)
@@ -89,9 +89,21 @@ from helpers import load_golden, draw_masks_for_case, rel_fro
 from test_host_logic import _run_fake
 from pycmf_b200.sharding import TorchComm
 dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%s" % sys.argv[2], rank=int(sys.argv[3]), world_size=2)
+extra = {"v_phase": sys.argv[5]} if len(sys.argv) > 5 else {}
+from pycmf_b200.cmf_solvers import NewtonSolver
+calls, inner = [0], NewtonSolver._step_v_columns
+def counted(self, *a):
+    calls[0] += 1
+    return inner(self, *a)
+NewtonSolver._step_v_columns = counted
 for name in sys.argv[4].split(","):
     case, g = load_golden(name)
-    hist, U, V, Z = _run_fake(case, draw_masks_for_case(case), comm=TorchComm())
+    calls[0] = 0
+    hist, U, V, Z = _run_fake(case, draw_masks_for_case(case), comm=TorchComm(), **extra)
+    p = case["params"]
+    per_row = p["solver"] == "newton" and p.get("update_V", True) and \
+        (p.get("x_link", "linear") == "logit" or p.get("sg_sample_ratio", 1.) < 1.)
+    assert calls[0] == (case["iters"] if extra and per_row else 0), (name, calls[0])
     assert np.allclose(hist, g["objective"], rtol=1e-9, atol=1e-11), name
     for got, ref in ((U, g["U"]), (V, g["V"]), (Z, g["Z"])):
         assert rel_fro(got, ref) < 1e-9, name
@@ -110,6 +122,49 @@ def test_row_sharding_world2_gloo_is_shard_count_invariant(tmp_path):
     outs = [p.communicate(timeout=600)[0] for p in procs]
     for p, o in zip(procs, outs):
         assert p.returncode == 0 and "OK" in o, o[-3000:]
+
+
+def test_column_sharded_newton_v_phase_world2_gloo(tmp_path):
+    """SURVEY 8e, Newton with a logit x link / sg < 1: for the V phase every rank owns d / 2 rows of V and the matching
+    column block of X over all rows, U is all-gathered and the new V rows are all-gathered (v_phase='columns').  Must
+    reproduce the reference trajectories exactly like the row-sharded partial-Hessian all-reduce does; the cases with a
+    shared Hessian (linear x link, sg = 1) must not re-partition at all."""
+    names = ("nt_logit_logit,nt_logit_lin,nt_csr_logit_lin,nt_sg_logit_logit,nt_sg_lin_lin,nt_sg_csr_lin_logit,"
+             "nt_sg_zero_ysample,nt_lin_logit,nt_no_V,mu_dense")
+    script = tmp_path / "worker.py"
+    script.write_text(_WORKER)
+    port = str(33500 + os.getpid() % 2000)
+    procs = [subprocess.Popen([sys.executable, str(script), ROOT, port, str(r), names, "columns"],
+                              stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True) for r in range(2)]
+    outs = [p.communicate(timeout=600)[0] for p in procs]
+    for p, o in zip(procs, outs):
+        assert p.returncode == 0 and "OK" in o, o[-3000:]
+
+
+def test_column_phase_selection_and_errors():
+    from pycmf_b200.cmf_solvers import MUSolver, NewtonSolver
+    be = FakeBackend()
+    assert NewtonSolver(x_link="logit", v_phase="columns", backend=be)._wants_columns(2)
+    assert NewtonSolver(sg_sample_ratio=0.5, v_phase="columns", backend=be)._wants_columns(4)
+    assert not NewtonSolver(x_link="logit", v_phase="columns", backend=be)._wants_columns(1)      # one rank: nothing to do
+    assert not NewtonSolver(x_link="linear", v_phase="columns", backend=be)._wants_columns(2)     # shared Hessian
+    assert not NewtonSolver(x_link="logit", v_phase="columns", update_V=False, backend=be)._wants_columns(2)
+    assert not NewtonSolver(x_link="logit", backend=be)._wants_columns(2)                         # default: rows
+    with pytest.raises(ValueError, match="v_phase"):
+        NewtonSolver(x_link="logit", v_phase="diagonal", backend=be)._wants_columns(2)
+
+    class TwoRanks:
+        rank, world = 1, 2
+    s = NewtonSolver(x_link="logit", v_phase="columns", backend=be, sharded_input=True)
+    with pytest.raises(ValueError, match="whole host matrix"):
+        s._prepare_column_block(be, TwoRanks(), np.zeros((4, 6)), 6)
+    s = NewtonSolver(x_link="logit", v_phase="columns", backend=be)
+    blk, (c0, c1) = s._prepare_column_block(be, TwoRanks(), np.arange(24.).reshape(4, 6), 6)
+    assert (c0, c1) == (3, 6) and np.array_equal(blk.a, np.arange(24.).reshape(4, 6)[:, 3:6])
+    import scipy.sparse as sp
+    blk, _ = s._prepare_column_block(be, TwoRanks(), sp.csr_matrix(np.arange(24.).reshape(4, 6)), 6)
+    assert blk.is_sparse and np.array_equal(blk.a.toarray(), np.arange(24.).reshape(4, 6)[:, 3:6])
+    assert MUSolver(backend=be)._prepare_column_block(be, TwoRanks(), np.zeros((4, 6)), 6) == (None, None)
 
 
 def test_row_range_and_localize():
