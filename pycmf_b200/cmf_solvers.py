@@ -533,24 +533,31 @@ class NewtonSolver(_IterativeCMFSolver):
         return out
 
     # ---- column-sharded V phase ("Newton, logit x-link / sg<1") ---------------------------------------
-    def _wants_columns(self, world):
-        """Per-row Hessians of the V update sum over ALL rows of U: row shards would have to all-reduce d k^2 numbers per
-        iteration (13 GB at C4).  'columns' re-partitions for the V phase instead: every rank owns d / G rows of V and the
-        matching column block of X over all rows (a second copy), U is all-gathered (n k), the new rows of V are
-        all-gathered (d k).  'rows' keeps the chunked all-reduce of the partial Hessians (no second copy of X)."""
+    def _v_phase_mode(self):
         import os
         mode = self.v_phase
         if mode == "auto":
-            mode = os.environ.get("PYCMF_B200_V_PHASE", "rows")
-        if mode not in ("rows", "columns"):
+            mode = os.environ.get("PYCMF_B200_V_PHASE", "auto")
+        if mode not in ("rows", "columns", "auto"):
             raise ValueError("v_phase must be 'rows', 'columns' or 'auto', got %r" % (mode,))
+        return mode
+
+    def _wants_columns(self, world):
+        """Per-row Hessians of the V update sum over ALL rows of U: row shards have to all-reduce d k^2 numbers per
+        iteration (13 GB at C4) and every rank repeats all d clamped solves.  'columns' re-partitions for the V phase
+        instead: every rank owns d / G rows of V and the matching column block of X over all rows (a second copy), U is
+        all-gathered (n k), the new rows of V are all-gathered (d k), and the solves shrink by G.  'rows' keeps the chunked
+        all-reduce of the partial Hessians (no second copy of X).  'auto': columns whenever every rank holds the whole
+        host matrix (so it can upload its column block), rows otherwise."""
         per_row = self.x_link == "logit" or self.sg_sample_ratio < 1.
-        return mode == "columns" and world > 1 and self.update_V and per_row
+        return self._v_phase_mode() != "rows" and world > 1 and self.update_V and per_row
 
     def _prepare_column_block(self, be, comm, X, d):
         if X is None or not self._wants_columns(comm.world):
             return None, None
         if self.sharded_input or getattr(X, "is_sparse", None) is not None:
+            if self._v_phase_mode() == "auto":
+                return None, None
             raise ValueError("v_phase='columns' needs the whole host matrix X on every rank (each rank uploads its "
                              "column block); with sharded_input=True or a device-resident X use v_phase='rows'")
         c0, c1 = row_range(d, comm.rank, comm.world)

@@ -28,8 +28,10 @@ def run(case, dtype, comm, masks=None, dense_path=0, history=True, **extra):
     cls = MUSolver if solver == "mu" else NewtonSolver
     # dense_path 0: both shard counts use the same (FMA) arithmetic, so only the summation order differs; the tcgen05
     # path switches on above a size threshold and would be compared against the FMA path on the smaller shards
+    # v_phase='rows': this worker covers the row-sharded partial-Hessian exchange; the column-sharded V phase ('auto' picks
+    # it for per-row Hessians when every rank holds the whole host X) has its own worker below
     s = cls(max_iter=case["iters"], tol=0, random_state=case["rng_seed"], dtype=dtype, comm=comm,
-            backend_options={"dense_path": dense_path}, **p)
+            backend_options={"dense_path": dense_path}, v_phase="rows", **p)
     s.history = [] if history else None; s.masks_per_iter = masks
     U, V, Z = case["U0"].copy(), case["V0"].copy(), case["Z0"].copy()
     s.fit_iterative_update(case["X"], case["Y"], U, V, Z)
