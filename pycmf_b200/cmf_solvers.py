@@ -109,8 +109,9 @@ class _IterativeCMFSolver:
             self._backend = CudaBackend(device=self.device, dtype=self.dtype, options=self.backend_options)
         return self._backend
 
-    def prepare(self, X, Y, U, V, Z):
-        """Host inputs -> FitState in HBM (row shard of X / U for this rank)."""
+    def prepare(self, X, Y, U, V, Z, column_block=True):
+        """Host inputs -> FitState in HBM (row shard of X / U for this rank; `column_block`: also the rank's column block
+        of X when the solver's V phase re-partitions -- not needed to evaluate the objective)."""
         k = np.shape(V)[1]
         if k > MAX_COMPONENTS:
             raise ValueError("n_components = %d: the B200 backend keeps a factor row in registers / tensor memory and "
@@ -145,7 +146,7 @@ class _IterativeCMFSolver:
         Ud = be.to_device(np.asarray(U)[take])
         Vd = be.to_device(np.asarray(V))
         Zd = be.to_device(np.asarray(Z))
-        Xcol, cols = self._prepare_column_block(be, comm, X, np.shape(V)[0])
+        Xcol, cols = self._prepare_column_block(be, comm, X, np.shape(V)[0]) if column_block else (None, None)
         return FitState(be, comm, Xd, Yd, Ud, Vd, Zd, n_total, (r0, r1), Xcol, cols)
 
     def _prepare_column_block(self, be, comm, X, d):
@@ -192,7 +193,7 @@ class _IterativeCMFSolver:
     def compute_error(self, X, Y, U, V, Z):
         if isinstance(X, FitState):
             return self.device_error(X)
-        st = self.prepare(X, Y, U, V, Z)
+        st = self.prepare(X, Y, U, V, Z, column_block=False)
         return self.device_error(st)
 
     # 'auto' captures the iteration only for fits long enough to pay for it: capture + instantiate + the graph's private
