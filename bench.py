@@ -52,6 +52,9 @@ def parse_args():
     ap.add_argument("--dtype", default="float32", choices=["float32", "float64"])
     ap.add_argument("--dense-path", type=int, default=None, help="0 generic FMA, 1 tcgen05 3xTF32, 2 tcgen05 1xTF32")
     ap.add_argument("--opt", action="append", default=[], help="backend option key=value (repeatable)")
+    ap.add_argument("--v-phase", default="rows", choices=["rows", "columns"],
+                    help="N > 1, Newton with per-row Hessians (c4): 'columns' re-partitions the resident row shards into "
+                         "column blocks (all-to-all) and runs the column-sharded V phase; default 'rows' = the measured path")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-parity", action="store_true")
@@ -364,8 +367,12 @@ def bench_workload(env, name, scale, col_scale, steps, warmup, args, headline):
     x_sum = float(xs.item())
     U, V, Z = W.finish_init(be, data, x_sum)
     U0, V0, Z0 = U.clone(), V.clone(), Z.clone()
-    st = FitState(be, comm, data["X"], data["Y"], U, V, Z, n, (r0, r1))
-    solver = make_solver(cfg, params, dtype=args.dtype, backend=be, comm=comm, max_iter=steps)
+    solver = make_solver(cfg, params, dtype=args.dtype, backend=be, comm=comm, max_iter=steps, sharded_input=True,
+                         v_phase=args.v_phase)
+    xcol, cols = solver._prepare_column_block(be, comm, data["X"], data["X"], cfg["d"], r0)   # None unless --v-phase columns
+    st = FitState(be, comm, data["X"], data["Y"], U, V, Z, n, (r0, r1), xcol, cols)
+    v_phase_used = "columns" if xcol is not None else "rows"
+    del xcol
     obj_first = solver.device_error(st)
 
     def barrier():
@@ -523,7 +530,8 @@ def bench_workload(env, name, scale, col_scale, steps, warmup, args, headline):
         "details": {"objective_first": round(obj_first, 6), "objective_last": round(obj_last, 6),
                     "x_shard_mb": round(x_bytes_dev / 1e6, 1), "dense_path": args.dense_path,
                     "cuda_graph": bool(solver._graphable(FitStateProbe(comm, be), True)),
-                    "cuda_graph_in_e2e": bool(solver._graphable(FitStateProbe(comm, be)))},
+                    "cuda_graph_in_e2e": bool(solver._graphable(FitStateProbe(comm, be))),
+                    "v_phase": v_phase_used},
         "clocks": clock_info, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
         "parity": parity,
     }
@@ -671,7 +679,11 @@ def run_ours(args):
         k_steps = args.steps * (25 if nm == "c1" else 5 if nm == "c2" else 2 if nm == "c3" else 1)
         if nm == "c4":
             k_steps = max(3, args.steps // 4)
-        res = bench_workload(env, nm, s, cs, k_steps, args.warmup, args, False)
+        try:
+            res = bench_workload(env, nm, s, cs, k_steps, args.warmup, args, False)
+        except Exception as e:  # noqa: BLE001 -- a secondary entry must not cost the headline line
+            res = {"workload": nm, "error": "%s: %s" % (type(e).__name__, str(e)[:300])}
+            print("bench: workload %s failed on rank %d: %r" % (nm, rank, e), file=sys.stderr, flush=True)
         if rank == 0:
             others.append(res)
 

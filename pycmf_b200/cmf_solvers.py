@@ -146,10 +146,10 @@ class _IterativeCMFSolver:
         Ud = be.to_device(np.asarray(U)[take])
         Vd = be.to_device(np.asarray(V))
         Zd = be.to_device(np.asarray(Z))
-        Xcol, cols = self._prepare_column_block(be, comm, X, np.shape(V)[0]) if column_block else (None, None)
+        Xcol, cols = self._prepare_column_block(be, comm, X, Xd, np.shape(V)[0], r0) if column_block else (None, None)
         return FitState(be, comm, Xd, Yd, Ud, Vd, Zd, n_total, (r0, r1), Xcol, cols)
 
-    def _prepare_column_block(self, be, comm, X, d):
+    def _prepare_column_block(self, be, comm, X, Xd, d, r0):
         """Only the Newton solver re-partitions (NewtonSolver._prepare_column_block)."""
         return None, None
 
@@ -548,20 +548,24 @@ class NewtonSolver(_IterativeCMFSolver):
         iteration (13 GB at C4) and every rank repeats all d clamped solves.  'columns' re-partitions for the V phase
         instead: every rank owns d / G rows of V and the matching column block of X over all rows (a second copy), U is
         all-gathered (n k), the new rows of V are all-gathered (d k), and the solves shrink by G.  'rows' keeps the chunked
-        all-reduce of the partial Hessians (no second copy of X).  'auto': columns whenever every rank holds the whole
-        host matrix (so it can upload its column block), rows otherwise."""
+        all-reduce of the partial Hessians (no second copy of X).  'auto' = 'columns' (PYCMF_B200_V_PHASE overrides)."""
         per_row = self.x_link == "logit" or self.sg_sample_ratio < 1.
         return self._v_phase_mode() != "rows" and world > 1 and self.update_V and per_row
 
-    def _prepare_column_block(self, be, comm, X, d):
+    def _prepare_column_block(self, be, comm, X, Xd, d, r0):
+        """This rank's column block of X over all rows (None when the V phase stays row-sharded).  Three sources:
+        the whole host matrix (every rank uploads its block: a second PCIe transfer the size of the row shard), the whole
+        matrix already in HBM (device initialisation: a view, nothing moves), or -- `sharded_input=True`, a rank holds its
+        rows only -- the row shards resident on the ranks, re-partitioned by one all-to-all over NVLink."""
         if X is None or not self._wants_columns(comm.world):
             return None, None
-        if self.sharded_input or getattr(X, "is_sparse", None) is not None:
-            if self._v_phase_mode() == "auto":
-                return None, None
-            raise ValueError("v_phase='columns' needs the whole host matrix X on every rank (each rank uploads its "
-                             "column block); with sharded_input=True or a device-resident X use v_phase='rows'")
-        c0, c1 = row_range(d, comm.rank, comm.world)
+        ranges = [row_range(d, g, comm.world) for g in range(comm.world)]
+        c0, c1 = ranges[comm.rank]
+        on_device = getattr(X, "is_sparse", None) is not None
+        if self.sharded_input:
+            return be.column_block(Xd, comm, r0, ranges), (c0, c1)
+        if on_device:
+            return be.col_slice(X, c0, c1), (c0, c1)
         if sp.issparse(X):
             block = sp.csc_matrix(X)[:, c0:c1].tocsr()
         else:

@@ -51,6 +51,54 @@ def _ptr(t):
     return 0 if t is None else t.data_ptr()
 
 
+def column_block_from_row_shards(M, comm, r0, col_ranges):
+    """Row shards -> column blocks on the device, for the column-sharded Newton V phase: every rank holds the
+    rows [r0, r0 + M.shape[0]) of X and ends up with the columns `col_ranges[rank]` of X over ALL rows.  One all-to-all
+    (NCCL over NVLink) of what already is in HBM; nothing crosses PCIe.  torch only (plumbing).
+
+    Dense: the column slabs of the row shard are sent to their owners, who stack the received slabs by source rank.
+    Sparse: in the CSC arrays of a row shard the nonzeros of the columns a rank owns are one contiguous segment, so the
+    shard's (row index, value) arrays are the send buffer as they lie; the receiver merges the segments column by column
+    with a stable sort on the column id (source ranks, and the rows inside each, stay ascending: sorted CSC).  Only the
+    column access path of the block is built (that is all newton_v_xpart reads)."""
+    import torch
+    world, rank = comm.world, comm.rank
+    c0, c1 = col_ranges[rank]
+    widths = [b - a for a, b in col_ranges]
+    n_loc = M.shape[0]
+    if not M.is_sparse:
+        dev = M.t.device
+        rows_of = [v[0] for v in comm.all_gather_ints([n_loc], dev)]
+        send = torch.cat([M.t[:, a:b].reshape(-1) for a, b in col_ranges])
+        got = comm.all_to_all_chunks(send, [n_loc * w for w in widths], [r * (c1 - c0) for r in rows_of])
+        del send
+        block = got.view(sum(rows_of), c1 - c0)       # source blocks are row blocks in rank order
+        return DenseMatrix(block)
+    dev = M.colptr.device
+    colptr = M.colptr.to(torch.int64)
+    bounds = [(int(colptr[a]), int(colptr[b])) for a, b in col_ranges]
+    seg = [hi - lo for lo, hi in bounds]
+    info = comm.all_gather_ints([n_loc] + seg, dev)                       # per source: its rows, its segment sizes
+    rows_of = [v[0] for v in info]
+    recv_seg = [v[1 + rank] for v in info]
+    counts = (colptr[1:] - colptr[:-1]).to(torch.int32)                     # nonzeros per column of this row shard
+    got_counts = comm.all_to_all_chunks(counts, widths, [c1 - c0] * world).view(world, c1 - c0)
+    got_rows = comm.all_to_all_chunks(M.rowidx + int(r0), seg, recv_seg)    # global row numbers
+    got_vals = comm.all_to_all_chunks(M.cvals, seg, recv_seg)
+    col_of = torch.repeat_interleave(torch.arange(c1 - c0, device=dev, dtype=torch.int32).repeat(world),
+                                     got_counts.reshape(-1).to(torch.int64))
+    order = torch.sort(col_of, stable=True).indices
+    out = SparseMatrix.__new__(SparseMatrix)
+    out.shape = (sum(rows_of), c1 - c0)
+    out.rowptr = out.colidx = out.vals = None                               # row access is not defined on a column block
+    out.colptr = torch.zeros(c1 - c0 + 1, dtype=torch.int32, device=dev)
+    out.colptr[1:] = torch.cumsum(got_counts.sum(0).to(torch.int64), 0).to(torch.int32)
+    out.rowidx = got_rows[order].to(torch.int32).contiguous()
+    out.cvals = got_vals[order].contiguous()
+    out.nnz = int(out.cvals.shape[0])
+    return out
+
+
 class CudaBackend:
     """One context (= one rank, one GPU, one stream)."""
 
@@ -350,6 +398,11 @@ class CudaBackend:
         colidx, vals = M.colidx[lo:hi].clone(), M.vals[lo:hi].clone()
         colptr, rowidx, cvals = self._csc_from_csr(rp, colidx, vals, r1 - r0, M.shape[1])
         return SparseMatrix((r1 - r0, M.shape[1]), rp, colidx, vals, colptr, rowidx, cvals)
+
+    def column_block(self, M, comm, r0, col_ranges):
+        """This rank's column block of X over all rows, from the row shards resident on the ranks (all-to-all)."""
+        blk = column_block_from_row_shards(M, comm, r0, col_ranges)
+        return blk if blk.is_sparse else self.dense(blk.t)        # same (padded-pitch) layout as an ingested matrix
 
     def col_slice(self, M, c0, c1):
         """Columns [c0, c1) of an ingested matrix as the operand of a V-side pass (X^T U over a column slab): a strided

@@ -40,6 +40,15 @@ class Comm:
             out.copy_(block)
         return out
 
+    def all_to_all_chunks(self, t, send_counts, recv_counts):
+        """t = the chunks for rank 0, 1, ... back to back (send_counts[g] leading-dimension entries for rank g); returns
+        the chunks received from rank 0, 1, ... back to back (recv_counts[g] entries from rank g)."""
+        return t
+
+    def all_gather_ints(self, values, device=None):
+        """(world x len(values)) nested list: every rank's host integers (exchanged through a tensor on `device`)."""
+        return [[int(v) for v in values]]
+
     def barrier(self):
         pass
 
@@ -113,6 +122,25 @@ class TorchComm(Comm):
         for r, p in enumerate(parts):
             out[r * rows:(r + 1) * rows] = p
         return out
+
+    def all_to_all_chunks(self, t, send_counts, recv_counts):
+        if self.world == 1:
+            return t
+        import torch
+        t = t.contiguous()
+        out = torch.empty((int(sum(recv_counts)),) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+        self.dist.all_to_all_single(out, t, [int(c) for c in recv_counts], [int(c) for c in send_counts],
+                                    group=self.group)
+        return out
+
+    def all_gather_ints(self, values, device=None):
+        if self.world == 1:
+            return Comm.all_gather_ints(self, values)
+        import torch
+        mine = torch.tensor([int(v) for v in values], dtype=torch.int64, device=device)
+        parts = [torch.empty_like(mine) for _ in range(self.world)]
+        self.dist.all_gather(parts, mine, group=self.group)
+        return [[int(v) for v in p.tolist()] for p in parts]
 
     def barrier(self):
         if self.world > 1:

@@ -37,6 +37,17 @@ class FakeBackend:
     def row_slice(self, T, r0, r1):
         return M(T.a[r0:r1])
 
+    def col_slice(self, T, c0, c1):
+        return M(T.a[:, c0:c1])
+
+    def column_block(self, T, comm, r0, col_ranges):
+        """Test stand-in of CudaBackend.column_block: every rank's row shard is gathered as an object."""
+        shards = [None] * comm.world
+        comm.dist.all_gather_object(shards, T.a, group=comm.group)
+        c0, c1 = col_ranges[comm.rank]
+        full = sp.vstack(shards).tocsr() if T.is_sparse else np.vstack(shards)
+        return M(full[:, c0:c1])
+
     def synchronize(self):
         pass
 

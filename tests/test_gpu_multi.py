@@ -165,3 +165,60 @@ def test_two_gpu_column_sharded_newton_v_phase(tmp_path):
     out = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900)
     errors = [ln for ln in out.stdout.splitlines() if "Error" in ln and "ChildFailed" not in ln]
     assert out.returncode == 0 and "COLUMNS_OK" in out.stdout, "\n".join(errors[:6]) or out.stdout[-3000:]
+
+
+_REPART_WORKER = r"""
+import os, sys
+sys.path.insert(0, sys.argv[1]); sys.path.insert(0, os.path.join(sys.argv[1], "tests"))
+import numpy as np, torch, torch.distributed as dist
+rank = int(os.environ["RANK"]); torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
+dist.init_process_group("nccl")
+from helpers import load_golden, draw_masks_for_case, rel_fro
+from pycmf_b200.cmf_solvers import NewtonSolver
+from pycmf_b200.device import CudaBackend
+from pycmf_b200.sharding import TorchComm, row_range
+comm = TorchComm()
+world = comm.world
+for name in ["nt_logit_logit", "nt_sg_csr_lin_logit", "nt_csr_logit_lin"]:
+    case, g = load_golden(name)
+    p = dict(case["params"]); p.pop("solver")
+    n, d = case["X"].shape
+    r0, r1 = row_range(n, rank, world)
+    # (a) every rank holds its rows only: the resident row shards are re-partitioned by one all-to-all over NVLink
+    s = NewtonSolver(max_iter=case["iters"], tol=0, random_state=case["rng_seed"], dtype="float64", comm=comm,
+                     sharded_input=True, v_phase="columns", **p)
+    s.history, s.masks_per_iter = [], draw_masks_for_case(case)
+    U, V, Z = case["U0"][r0:r1].copy(), case["V0"].copy(), case["Z0"].copy()
+    s.fit_iterative_update(case["X"][r0:r1], case["Y"], U, V, Z)
+    assert np.allclose(s.history, g["objective"][1:], rtol=1e-9, atol=1e-11), (name, "all-to-all")
+    for got, ref in ((U, g["U"][r0:r1]), (V, g["V"]), (Z, g["Z"])):
+        assert rel_fro(got, ref) < 1e-9, (name, "all-to-all")
+    # (b) the whole matrix already in HBM on every rank (device initialisation): the column block is a view
+    be = CudaBackend(dtype="float64")
+    s = NewtonSolver(max_iter=case["iters"], tol=0, random_state=case["rng_seed"], dtype="float64", comm=comm,
+                     backend=be, v_phase="columns", **p)
+    s.history, s.masks_per_iter = [], draw_masks_for_case(case)
+    U, V, Z = case["U0"].copy(), case["V0"].copy(), case["Z0"].copy()
+    s.fit_iterative_update(be.ingest(case["X"]), case["Y"], U, V, Z)
+    assert np.allclose(s.history, g["objective"][1:], rtol=1e-9, atol=1e-11), (name, "resident")
+    for got, ref in ((U, g["U"]), (V, g["V"]), (Z, g["Z"])):
+        assert rel_fro(got, ref) < 1e-9, (name, "resident")
+dist.barrier(); dist.destroy_process_group()
+if rank == 0: print("REPART_OK")
+"""
+
+
+def test_two_gpu_column_phase_from_resident_row_shards(tmp_path):
+    """The device-side sources of the column block (explicit v_phase='columns'): per-rank row shards re-partitioned by an
+    all-to-all under NCCL (sharded_input=True), and a matrix already resident on every rank (a view)."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    script = tmp_path / "worker_repart.py"
+    script.write_text(_REPART_WORKER)
+    port = str(25600 + os.getpid() % 2000)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+           "--master-addr", "127.0.0.1", "--master-port", port, str(script), ROOT]
+    out = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900)
+    errors = [ln for ln in out.stdout.splitlines() if "Error" in ln and "ChildFailed" not in ln]
+    assert out.returncode == 0 and "REPART_OK" in out.stdout, "\n".join(errors[:6]) or out.stdout[-3000:]

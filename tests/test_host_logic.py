@@ -142,6 +142,84 @@ def test_column_sharded_newton_v_phase_world2_gloo(tmp_path, mode):
         assert p.returncode == 0 and "OK" in o, o[-3000:]
 
 
+_REPART_WORKER = r'''
+import os, sys
+sys.path.insert(0, sys.argv[1]); sys.path.insert(0, os.path.join(sys.argv[1], "tests"))
+import numpy as np, scipy.sparse as sp, torch, torch.distributed as dist
+rank, world = int(sys.argv[3]), int(sys.argv[4])
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%s" % sys.argv[2], rank=rank, world_size=world)
+from pycmf_b200.device import DenseMatrix, SparseMatrix, column_block_from_row_shards
+from pycmf_b200.sharding import TorchComm, row_range
+from helpers import load_golden, draw_masks_for_case, rel_fro
+from fake_backend import FakeBackend
+from pycmf_b200.cmf_solvers import NewtonSolver
+comm = TorchComm()
+
+def csc_arrays(A):                       # the column access path of a SparseMatrix, as device.py builds it
+    C = sp.csc_matrix(A); C.sort_indices()
+    return (torch.from_numpy(C.indptr.astype(np.int32)), torch.from_numpy(C.indices.astype(np.int32)),
+            torch.from_numpy(C.data.astype(np.float64)))
+
+# 1. the torch-level re-partition itself (CPU tensors): dense and CSR, uneven row and column blocks, an empty column
+rng = np.random.RandomState(5)
+for n, d in ((23, 11), (8, 5), (6, 3)):
+    A = rng.randn(n, d) * (rng.rand(n, d) < 0.4)
+    A[:, d // 2] = 0.0
+    r0, r1 = row_range(n, rank, world)
+    ranges = [row_range(d, g, world) for g in range(world)]
+    c0, c1 = ranges[rank]
+    blk = column_block_from_row_shards(DenseMatrix(torch.from_numpy(A[r0:r1].copy())), comm, r0, ranges)
+    assert blk.shape == (n, c1 - c0) and np.array_equal(blk.t.numpy(), A[:, c0:c1]), "dense"
+    S = SparseMatrix.__new__(SparseMatrix)
+    S.shape = (r1 - r0, d)
+    S.rowptr = S.colidx = S.vals = None
+    S.colptr, S.rowidx, S.cvals = csc_arrays(A[r0:r1])
+    blk = column_block_from_row_shards(S, comm, r0, ranges)
+    want = csc_arrays(A[:, c0:c1])
+    assert blk.shape == (n, c1 - c0) and blk.nnz == want[2].numel(), "sparse shape"
+    for got, ref in zip((blk.colptr, blk.rowidx, blk.cvals), want):
+        assert got.dtype == ref.dtype and torch.equal(got, ref), "sparse arrays"
+
+# 2. the solver on per-rank row blocks (sharded_input=True): explicit v_phase='columns' re-partitions the resident shards
+for name in sys.argv[5].split(","):
+    case, g = load_golden(name)
+    p = dict(case["params"]); p.pop("solver")
+    n, d = case["X"].shape
+    r0, r1 = row_range(n, rank, world)
+    for mode in ("columns", "auto"):
+        s = NewtonSolver(max_iter=case["iters"], tol=0, random_state=case["rng_seed"], dtype="float64",
+                         backend=FakeBackend(), comm=comm, sharded_input=True, v_phase=mode, **p)
+        s.history, s.masks_per_iter = [], draw_masks_for_case(case)
+        seen = []
+        inner = s._step_v_columns
+        s._step_v_columns = lambda *a: (seen.append(1), inner(*a))[1]
+        U, V, Z = case["U0"][r0:r1].copy(), case["V0"].copy(), case["Z0"].copy()
+        s.fit_iterative_update(case["X"][r0:r1], case["Y"], U, V, Z)
+        assert len(seen) == case["iters"], (name, mode, len(seen))
+        assert np.allclose(s.history, g["objective"][1:], rtol=1e-9, atol=1e-11), (name, mode)
+        for got, ref in ((U, g["U"][r0:r1]), (V, g["V"]), (Z, g["Z"])):
+            assert rel_fro(got, ref) < 1e-9, (name, mode)
+dist.destroy_process_group()
+print("OK")
+'''
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_row_shards_to_column_blocks_all_to_all_gloo(tmp_path, world):
+    """The device-side source of the column-sharded V phase: row shards resident on the ranks are re-partitioned into
+    column blocks by one all-to-all (pycmf_b200.device.column_block_from_row_shards, torch only) -- checked on CPU tensors
+    against scipy slicing -- and the solver takes it for per-rank inputs (sharded_input=True) with v_phase='columns'."""
+    script = tmp_path / "repart_worker.py"
+    script.write_text(_REPART_WORKER)
+    port = str(35500 + os.getpid() % 2000 + world)
+    names = "nt_logit_logit,nt_sg_csr_lin_logit,nt_sg_zero_ysample"
+    procs = [subprocess.Popen([sys.executable, str(script), ROOT, port, str(r), str(world), names],
+                              stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True) for r in range(world)]
+    outs = [p.communicate(timeout=600)[0] for p in procs]
+    for p, o in zip(procs, outs):
+        assert p.returncode == 0 and "OK" in o, o[-3000:]
+
+
 def test_column_phase_selection_and_errors():
     from pycmf_b200.cmf_solvers import MUSolver, NewtonSolver
     be = FakeBackend()
@@ -157,19 +235,19 @@ def test_column_phase_selection_and_errors():
 
     class TwoRanks:
         rank, world = 1, 2
-    s = NewtonSolver(x_link="logit", v_phase="columns", backend=be, sharded_input=True)
-    with pytest.raises(ValueError, match="whole host matrix"):
-        s._prepare_column_block(be, TwoRanks(), np.zeros((4, 6)), 6)
-    # 'auto' falls back to the row-sharded phase when a rank only holds its own rows
-    assert NewtonSolver(x_link="logit", backend=be, sharded_input=True)._prepare_column_block(
-        be, TwoRanks(), np.zeros((4, 6)), 6) == (None, None)
+    A = np.arange(24.).reshape(4, 6)
+    assert NewtonSolver(x_link="logit", backend=be, v_phase="rows", sharded_input=True)._prepare_column_block(
+        be, TwoRanks(), A, be.ingest(A), 6, 4) == (None, None)
+    blk, (c0, c1) = NewtonSolver(x_link="logit", backend=be)._prepare_column_block(
+        be, TwoRanks(), be.ingest(A), be.ingest(A[2:]), 6, 2)                 # matrix already resident: a view of it
+    assert (c0, c1) == (3, 6) and np.array_equal(blk.a, A[:, 3:6])
     s = NewtonSolver(x_link="logit", backend=be)
-    blk, (c0, c1) = s._prepare_column_block(be, TwoRanks(), np.arange(24.).reshape(4, 6), 6)
-    assert (c0, c1) == (3, 6) and np.array_equal(blk.a, np.arange(24.).reshape(4, 6)[:, 3:6])
+    blk, (c0, c1) = s._prepare_column_block(be, TwoRanks(), A, be.ingest(A[2:]), 6, 2)
+    assert (c0, c1) == (3, 6) and np.array_equal(blk.a, A[:, 3:6])
     import scipy.sparse as sp
-    blk, _ = s._prepare_column_block(be, TwoRanks(), sp.csr_matrix(np.arange(24.).reshape(4, 6)), 6)
-    assert blk.is_sparse and np.array_equal(blk.a.toarray(), np.arange(24.).reshape(4, 6)[:, 3:6])
-    assert MUSolver(backend=be)._prepare_column_block(be, TwoRanks(), np.zeros((4, 6)), 6) == (None, None)
+    blk, _ = s._prepare_column_block(be, TwoRanks(), sp.csr_matrix(A), be.ingest(A[2:]), 6, 2)
+    assert blk.is_sparse and np.array_equal(blk.a.toarray(), A[:, 3:6])
+    assert MUSolver(backend=be)._prepare_column_block(be, TwoRanks(), A, be.ingest(A), 6, 0) == (None, None)
 
 
 def test_row_range_and_localize():
