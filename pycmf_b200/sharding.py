@@ -82,6 +82,11 @@ class TorchComm(Comm):
         import torch
         k = t.shape[1]
         sizes = [row_range(n_total, r, self.world) for r in range(self.world)]
+        if n_total % self.world == 0 and self.dist.get_backend(self.group) == "nccl":
+            # equal blocks: one all-gather straight into the result (the call all_gather_into makes), no padding, no list
+            out = torch.empty(n_total, k, dtype=t.dtype, device=t.device)
+            self.dist.all_gather_into_tensor(out, t.contiguous(), group=self.group)
+            return out
         maxr = max(b - a for a, b in sizes)
         pad = torch.zeros(maxr, k, dtype=t.dtype, device=t.device)
         pad[:t.shape[0]] = t
