@@ -378,3 +378,26 @@ def test_n_components_above_the_backend_limit_is_rejected_before_any_device_work
     s = MUSolver(max_iter=1)
     with pytest.raises(ValueError, match="n_components"):
         s.prepare(np.ones((4, 300)), np.ones((300, 2)), np.ones((4, 300)), np.ones((300, 300)), np.ones((2, 300)))
+
+
+def _edge_names():
+    from test_oracle_vs_reference import EDGE
+    return sorted(EDGE)
+
+
+@pytest.mark.parametrize("name", _edge_names())
+def test_solver_orchestration_on_degenerate_shapes(name):
+    """One row, one label column, rank one, an all-zero CSR row, sample sets of one / zero indices, single-factor updates:
+    the host orchestration (phases, chunked V rows, write-back of the updated factors only) against the oracle."""
+    from helpers import run_oracle
+    from test_oracle_vs_reference import EDGE, _edge_case
+    n, d, l, k, sparse, params = EDGE[name]
+    case = _edge_case(sorted(EDGE).index(name), n, d, l, k, sparse, **params)
+    masks = draw_masks_for_case(case)
+    hist_o, Uo, Vo, Zo = run_oracle(case, masks)
+    hist, U, V, Z = _run_fake(case, masks)
+    assert np.allclose(hist, hist_o, rtol=1e-9, atol=1e-11)
+    for got, ref, upd in ((U, Uo, "update_U"), (V, Vo, "update_V"), (Z, Zo, "update_Z")):
+        assert np.allclose(got, ref, rtol=1e-9, atol=1e-12)
+        if not params.get(upd, True):
+            assert np.array_equal(got, case[upd[-1] + "0"])            # a factor held fixed is never written back
