@@ -54,6 +54,6 @@ def test_fits_on_degenerate_shapes_match_the_oracle(tmp_path):
     script = tmp_path / "edge_worker.py"
     script.write_text(_WORKER)
     out = subprocess.run([sys.executable, str(script), ROOT], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True,
-                         timeout=600).stdout
+                         timeout=150).stdout
     print(out[-4000:])
     assert "EDGE_DONE bad=0" in out, "\n".join(ln for ln in out.splitlines() if ln.startswith("FAIL"))[:3000] or out[-2000:]
