@@ -20,13 +20,12 @@ import os, sys
 sys.path.insert(0, sys.argv[1]); sys.path.insert(0, os.path.join(sys.argv[1], "tests"))
 import numpy as np
 from helpers import run_oracle, draw_masks_for_case, rel_fro
-from test_oracle_vs_reference import EDGE, _edge_case
+from oracle.cases import EDGE, make_edge_case
 from pycmf_b200.cmf_solvers import MUSolver, NewtonSolver
 
 bad = 0
 for name in sorted(EDGE):
-    n, d, l, k, sparse, params = EDGE[name]
-    case = _edge_case(sorted(EDGE).index(name), n, d, l, k, sparse, **params)
+    case = make_edge_case(name)
     masks = draw_masks_for_case(case)
     hist_o, Uo, Vo, Zo = run_oracle(case, masks)
     for dtype, obj_tol, fac_tol in (("float64", 1e-9, 1e-9), ("float32", 1e-4, 1e-3)):

@@ -381,7 +381,7 @@ def test_n_components_above_the_backend_limit_is_rejected_before_any_device_work
 
 
 def _edge_names():
-    from test_oracle_vs_reference import EDGE
+    from oracle.cases import EDGE
     return sorted(EDGE)
 
 
@@ -390,9 +390,9 @@ def test_solver_orchestration_on_degenerate_shapes(name):
     """One row, one label column, rank one, an all-zero CSR row, sample sets of one / zero indices, single-factor updates:
     the host orchestration (phases, chunked V rows, write-back of the updated factors only) against the oracle."""
     from helpers import run_oracle
-    from test_oracle_vs_reference import EDGE, _edge_case
-    n, d, l, k, sparse, params = EDGE[name]
-    case = _edge_case(sorted(EDGE).index(name), n, d, l, k, sparse, **params)
+    from oracle.cases import EDGE, make_edge_case
+    params = EDGE[name][-1]
+    case = make_edge_case(name)
     masks = draw_masks_for_case(case)
     hist_o, Uo, Vo, Zo = run_oracle(case, masks)
     hist, U, V, Z = _run_fake(case, masks)

@@ -10,7 +10,7 @@ import numpy as np
 import pytest
 
 from oracle import cmf_oracle as O
-from oracle.cases import CASES, make_case
+from oracle.cases import CASES, EDGE, make_case, make_edge_case
 from oracle.make_golden import run_reference
 from oracle.ref_loader import load_reference
 
@@ -61,49 +61,12 @@ def test_fit_loop_with_early_stop_matches_reference(solver):
         assert rel_fro(got, ref) < 1e-9
 
 
-def _edge_case(seed, n, d, l, k, sparse, **params):
-    """A tiny problem with degenerate dimensions (the generator of oracle/cases.py needs n, d, l > 1)."""
-    import scipy.sparse as sp
-    rng = np.random.RandomState(seed)
-    logit_x, logit_y = params.get("x_link") == "logit", params.get("y_link") == "logit"
-    X = rng.rand(n, d) if logit_x else np.abs(rng.randn(n, d))
-    if sparse:
-        X = X * (rng.rand(n, d) < 0.5)
-        X[n // 2, :] = 0.0                                   # an empty row (and, when n == 1, an all-zero matrix)
-        X = sp.csr_matrix(X)
-    Y = rng.rand(d, l) if logit_y else np.abs(rng.randn(d, l))
-    signed = params.get("U_non_negative", True) is False
-    f = (lambda a: a) if signed else np.abs
-    U0, V0, Z0 = f(0.3 * rng.randn(n, k)), f(0.3 * rng.randn(d, k)), f(0.3 * rng.randn(l, k))
-    return dict(name="edge", X=X, Y=Y, U0=U0, V0=V0, Z0=Z0, params=dict(params), iters=4, rng_seed=100 + seed)
-
-
-_NT = dict(solver="newton", alpha=0.4, l1_reg=0.01, l2_reg=0.1, hessian_pertubation=0.2, U_non_negative=True,
-           V_non_negative=True, Z_non_negative=True, sg_sample_ratio=1.0)
-EDGE = {
-    "mu_one_row": (1, 9, 3, 2, False, dict(solver="mu")),
-    "mu_one_label_column": (7, 5, 1, 3, False, dict(solver="mu", l1_reg=0.05)),
-    "mu_rank_one": (6, 5, 4, 1, False, dict(solver="mu", l2_reg=0.1)),
-    "mu_csr_empty_matrix_row": (1, 6, 2, 2, True, dict(solver="mu")),
-    "mu_only_U": (5, 4, 3, 2, False, dict(solver="mu", update_V=False, update_Z=False)),
-    "nt_one_row": (1, 7, 3, 2, False, dict(_NT, y_link="logit")),
-    "nt_one_label_column": (8, 6, 1, 3, False, dict(_NT, x_link="logit", y_link="logit")),
-    "nt_rank_one_signed": (9, 5, 3, 1, False, dict(_NT, U_non_negative=False, V_non_negative=False,
-                                                   Z_non_negative=False)),
-    "nt_csr_two_columns": (6, 2, 3, 2, True, dict(_NT, x_link="logit")),
-    "nt_only_Z": (6, 5, 3, 2, False, dict(_NT, y_link="logit", update_U=False, update_V=False)),
-    "nt_sg_samples_of_one": (6, 5, 3, 2, False, dict(_NT, sg_sample_ratio=0.3)),       # int(5*.3) = 1, int(3*.3) = 0
-    "nt_sg_csr_logit": (5, 7, 4, 2, True, dict(_NT, x_link="logit", y_link="logit", sg_sample_ratio=0.5)),
-}
-
-
 @pytest.mark.parametrize("name", sorted(EDGE))
 def test_oracle_matches_the_live_reference_on_degenerate_shapes(name):
     """Ragged / minimal inputs (one row, one label column, rank one, an all-zero CSR row, two columns, sample sets of one
     and of zero indices, single-factor updates): the oracle must follow the reference here too, NumPy's global RNG in
     lock-step for the sampled cases."""
-    n, d, l, k, sparse, params = EDGE[name]
-    case = _edge_case(sorted(EDGE).index(name), n, d, l, k, sparse, **params)
+    case = make_edge_case(name)
     hist_ref, U_ref, V_ref, Z_ref = run_reference(case)
     hist, U, V, Z = run_oracle(case)
     assert np.isfinite(hist_ref).all()
