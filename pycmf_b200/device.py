@@ -42,13 +42,20 @@ class SparseMatrix:
 
     def __init__(self, shape, rowptr, colidx, vals, colptr, rowidx, cvals):
         self.shape = tuple(shape)
+        self.nnz = int(vals.shape[0])
+        # a matrix (or a rank's shard) without nonzeros still hands non-NULL index / value pointers to the C ABI
+        colidx, vals, rowidx, cvals = (_non_null(t) for t in (colidx, vals, rowidx, cvals))
         self.rowptr, self.colidx, self.vals = rowptr, colidx, vals
         self.colptr, self.rowidx, self.cvals = colptr, rowidx, cvals
-        self.nnz = int(vals.shape[0])
 
 
 def _ptr(t):
     return 0 if t is None else t.data_ptr()
+
+
+def _non_null(t):
+    """t, or one zero element of its kind when t is empty (never read: the row / column pointers say so)."""
+    return t if t is None or t.numel() > 0 else t.new_zeros(1)
 
 
 def column_block_from_row_shards(M, comm, r0, col_ranges):
@@ -83,8 +90,9 @@ def column_block_from_row_shards(M, comm, r0, col_ranges):
     recv_seg = [v[1 + rank] for v in info]
     counts = (colptr[1:] - colptr[:-1]).to(torch.int32)                     # nonzeros per column of this row shard
     got_counts = comm.all_to_all_chunks(counts, widths, [c1 - c0] * world).view(world, c1 - c0)
-    got_rows = comm.all_to_all_chunks(M.rowidx + int(r0), seg, recv_seg)    # global row numbers
-    got_vals = comm.all_to_all_chunks(M.cvals, seg, recv_seg)
+    nnz_loc = sum(seg)                                                      # (an empty shard holds one dummy element)
+    got_rows = comm.all_to_all_chunks(M.rowidx[:nnz_loc] + int(r0), seg, recv_seg)    # global row numbers
+    got_vals = comm.all_to_all_chunks(M.cvals[:nnz_loc], seg, recv_seg)
     col_of = torch.repeat_interleave(torch.arange(c1 - c0, device=dev, dtype=torch.int32).repeat(world),
                                      got_counts.reshape(-1).to(torch.int64))
     order = torch.sort(col_of, stable=True).indices
@@ -96,6 +104,7 @@ def column_block_from_row_shards(M, comm, r0, col_ranges):
     out.rowidx = got_rows[order].to(torch.int32).contiguous()
     out.cvals = got_vals[order].contiguous()
     out.nnz = int(out.cvals.shape[0])
+    out.rowidx, out.cvals = _non_null(out.rowidx), _non_null(out.cvals)
     return out
 
 

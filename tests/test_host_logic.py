@@ -165,6 +165,8 @@ rng = np.random.RandomState(5)
 for n, d in ((23, 11), (8, 5), (6, 3)):
     A = rng.randn(n, d) * (rng.rand(n, d) < 0.4)
     A[:, d // 2] = 0.0
+    if n == 8:
+        A[:row_range(n, 0, world)[1]] = 0.0                  # rank 0's shard has no nonzeros at all
     r0, r1 = row_range(n, rank, world)
     ranges = [row_range(d, g, world) for g in range(world)]
     c0, c1 = ranges[rank]
@@ -174,10 +176,12 @@ for n, d in ((23, 11), (8, 5), (6, 3)):
     S.shape = (r1 - r0, d)
     S.rowptr = S.colidx = S.vals = None
     S.colptr, S.rowidx, S.cvals = csc_arrays(A[r0:r1])
+    if S.cvals.numel() == 0:                                 # as SparseMatrix stores an empty shard: one dummy element
+        S.rowidx, S.cvals = torch.zeros(1, dtype=torch.int32), torch.zeros(1, dtype=torch.float64)
     blk = column_block_from_row_shards(S, comm, r0, ranges)
     want = csc_arrays(A[:, c0:c1])
     assert blk.shape == (n, c1 - c0) and blk.nnz == want[2].numel(), "sparse shape"
-    for got, ref in zip((blk.colptr, blk.rowidx, blk.cvals), want):
+    for got, ref in zip((blk.colptr, blk.rowidx[:blk.nnz], blk.cvals[:blk.nnz]), want):
         assert got.dtype == ref.dtype and torch.equal(got, ref), "sparse arrays"
 
 # 2. the solver on per-rank row blocks (sharded_input=True): explicit v_phase='columns' re-partitions the resident shards
