@@ -50,6 +50,7 @@ class FitState:
         # column block [c0, c1) of X over ALL rows (second copy; the column-sharded Newton V phase)
         self.Xcol = Xcol
         self.c0, self.c1 = cols if cols is not None else (0, 0)
+        self.row_counts = None      # rows held by every rank when the caller handed in its own blocks (sharded_input)
         self.iteration = 0
 
     @property
@@ -128,10 +129,12 @@ class _IterativeCMFSolver:
             r0 = int(counts[:comm.rank].sum())
             r1 = r0 + n_local
             take = slice(None)
+            row_counts = [int(c) for c in counts]
         else:
             n_total = n_local
             r0, r1 = row_range(n_total, comm.rank, comm.world)
             take = slice(r0, r1)
+            row_counts = None
         Xd = None
         if X is not None:
             if getattr(X, "is_sparse", None) is not None:        # already ingested (device initialisation, bench)
@@ -147,7 +150,9 @@ class _IterativeCMFSolver:
         Vd = be.to_device(np.asarray(V))
         Zd = be.to_device(np.asarray(Z))
         Xcol, cols = self._prepare_column_block(be, comm, X, Xd, np.shape(V)[0], r0) if column_block else (None, None)
-        return FitState(be, comm, Xd, Yd, Ud, Vd, Zd, n_total, (r0, r1), Xcol, cols)
+        st = FitState(be, comm, Xd, Yd, Ud, Vd, Zd, n_total, (r0, r1), Xcol, cols)
+        st.row_counts = row_counts
+        return st
 
     def _prepare_column_block(self, be, comm, X, Xd, d, r0):
         """Only the Newton solver re-partitions (NewtonSolver._prepare_column_block)."""
@@ -578,7 +583,7 @@ class NewtonSolver(_IterativeCMFSolver):
         alpha, l1, l2, pert = self.alpha, self.l1_reg, self.l2_reg, self.hessian_pertubation
         d, k = st.V.shape
         c0, c1 = st.c0, st.c1
-        U_all = comm.all_gather_rows(st.U, st.n_total)
+        U_all = comm.all_gather_rows(st.U, st.n_total, st.row_counts)
         V_loc = st.V[c0:c1]
         Y_loc = be.row_slice(st.Y, c0, c1)
         step = be.v_chunk_rows(max(1, c1 - c0), k, True)

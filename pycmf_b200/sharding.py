@@ -23,7 +23,7 @@ class Comm:
     def all_reduce_sum(self, t):
         return t
 
-    def all_gather_rows(self, t, n_total):
+    def all_gather_rows(self, t, n_total, counts=None):
         return t
 
     def reduce_scatter_rows(self, t, out=None):
@@ -75,14 +75,19 @@ class TorchComm(Comm):
             self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM, group=self.group)
         return t
 
-    def all_gather_rows(self, t, n_total):
-        """Concatenate the row blocks of every rank (blocks follow row_range)."""
+    def all_gather_rows(self, t, n_total, counts=None):
+        """Concatenate the row blocks of every rank (blocks follow row_range, or have `counts[r]` rows when the caller
+        handed in its own blocks: sharded_input)."""
         if self.world == 1:
             return t
         import torch
         k = t.shape[1]
-        sizes = [row_range(n_total, r, self.world) for r in range(self.world)]
-        if n_total % self.world == 0 and self.dist.get_backend(self.group) == "nccl":
+        if counts is None:
+            sizes = [row_range(n_total, r, self.world) for r in range(self.world)]
+        else:
+            ends = np.cumsum([int(c) for c in counts])
+            sizes = [(int(e - c), int(e)) for e, c in zip(ends, counts)]
+        if len({b - a for a, b in sizes}) == 1 and self.dist.get_backend(self.group) == "nccl":
             # equal blocks: one all-gather straight into the result (the call all_gather_into makes), no padding, no list
             out = torch.empty(n_total, k, dtype=t.dtype, device=t.device)
             self.dist.all_gather_into_tensor(out, t.contiguous(), group=self.group)

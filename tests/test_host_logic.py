@@ -189,7 +189,9 @@ for name in sys.argv[5].split(","):
     case, g = load_golden(name)
     p = dict(case["params"]); p.pop("solver")
     n, d = case["X"].shape
-    r0, r1 = row_range(n, rank, world)
+    # the caller's own, UNEVEN row blocks (sharded_input does not require row_range's balanced split)
+    cuts = [0] + [int(n * f) for f in ((0.65,) if world == 2 else (0.5, 0.6))] + [n]
+    r0, r1 = cuts[rank], cuts[rank + 1]
     for mode in ("columns", "auto"):
         s = NewtonSolver(max_iter=case["iters"], tol=0, random_state=case["rng_seed"], dtype="float64",
                          backend=FakeBackend(), comm=comm, sharded_input=True, v_phase=mode, **p)
