@@ -682,6 +682,8 @@ def run_ours(args):
         try:
             res = bench_workload(env, nm, s, cs, k_steps, args.warmup, args, False)
         except Exception as e:  # noqa: BLE001 -- a secondary entry must not cost the headline line
+            if world > 1:       # several ranks: the others may be inside a collective of this workload -- fail fast
+                raise
             res = {"workload": nm, "error": "%s: %s" % (type(e).__name__, str(e)[:300])}
             print("bench: workload %s failed on rank %d: %r" % (nm, rank, e), file=sys.stderr, flush=True)
         if rank == 0:
